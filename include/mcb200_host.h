@@ -1,0 +1,48 @@
+/* mcb200_host.h — C entry points of the host-side problem setup (libmcbhost.so).
+ *
+ * Replaces the reference's `Simulator::Simulator(const std::string io_dir)`
+ * (src/simulator/setup.cpp:30-1069, include/simulator.h:144): input.xml +
+ * xs_library text files -> the flattened `mcb_problem` that mcb_create() and the
+ * CPU oracle consume.  No GPU is needed for anything in this header.
+ */
+#ifndef MCB200_HOST_H
+#define MCB200_HOST_H
+
+#include "mcb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcbh_deck mcbh_deck;
+
+enum { MCBH_IGNORE_TRMM = 1 }; /* accept <trmm> but build no TRMM tallies (transport + k only) */
+
+/* io_dir: directory holding input.xml (a trailing '/' is added when missing, like Main.cpp:16);
+ * xs_dir: directory holding <ZAID>.txt (reference: "./xs_library" relative to the CWD, setup.cpp:326).
+ * Returns NULL on error; the message (the reference's own wording where it has one) is in mcbh_last_error(). */
+mcbh_deck* mcbh_load_deck(const char* io_dir, const char* xs_dir, int flags);
+/* same, from XML text */
+mcbh_deck* mcbh_load_deck_string(const char* xml_text, const char* xs_dir, int flags);
+void mcbh_free_deck(mcbh_deck* d);
+const char* mcbh_last_error(void);
+
+/* the flattened problem; pointers stay valid until mcbh_free_deck. n_sample / n_cycle / n_passive / seed may be
+ * overridden through mcbh_set_run (0 keeps the deck's value) — the reference has no such knobs */
+const mcb_problem* mcbh_problem(mcbh_deck* d);
+void mcbh_set_run(mcbh_deck* d, uint64_t n_sample, uint64_t n_cycle, uint64_t n_passive, uint64_t seed);
+
+/* scalar facts about the problem: out[0..15] = n_sample, n_cycle, n_passive, ksearch, n_nuclides, n_materials,
+ * n_surfaces, n_cells, n_estimators, n_tallies, n_sources, entropy_on, n_xs_rows, n_scores, n_filters, trmm_present */
+void mcbh_info(mcbh_deck* d, int64_t out[16]);
+
+/* names for reporting (Estimator::report): kind 0 nuclide, 1 material, 2 surface, 3 cell; NULL when out of range */
+const char* mcbh_name(const mcbh_deck* d, int kind, int index);
+const char* mcbh_mode(const mcbh_deck* d);            /* "fixed source" | "k-eigenvalue" */
+const char* mcbh_simulation_name(const mcbh_deck* d);
+int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z); /* general.cpp:26-34; -1 = lost */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_HOST_H */

@@ -1,0 +1,64 @@
+// C entry points of libmcbhost.so (include/mcb200_host.h).
+#include <string>
+
+#include "deck.h"
+#include "mcb200_host.h"
+
+struct mcbh_deck { mcb::Deck deck; };
+
+static thread_local std::string g_error;
+
+extern "C" {
+
+mcbh_deck* mcbh_load_deck(const char* io_dir, const char* xs_dir, int flags)
+{
+    std::string dir = io_dir ? io_dir : "";
+    if (dir.empty() || dir.back() != '/') dir += "/";
+    mcbh_deck* d = new mcbh_deck;
+    if (!d->deck.load(dir, xs_dir ? xs_dir : "./xs_library", flags, g_error)) { delete d; return nullptr; }
+    d->deck.view();
+    return d;
+}
+mcbh_deck* mcbh_load_deck_string(const char* xml_text, const char* xs_dir, int flags)
+{
+    mcbh_deck* d = new mcbh_deck;
+    if (!d->deck.load_string(xml_text ? xml_text : "", xs_dir ? xs_dir : "./xs_library", flags, g_error)) { delete d; return nullptr; }
+    d->deck.view();
+    return d;
+}
+void mcbh_free_deck(mcbh_deck* d) { delete d; }
+const char* mcbh_last_error(void) { return g_error.c_str(); }
+const mcb_problem* mcbh_problem(mcbh_deck* d) { return d ? d->deck.view() : nullptr; }
+void mcbh_set_run(mcbh_deck* d, uint64_t n_sample, uint64_t n_cycle, uint64_t n_passive, uint64_t seed)
+{
+    if (!d) return;
+    if (n_sample) d->deck.p.n_sample = n_sample;
+    if (n_cycle) { d->deck.p.n_cycle = n_cycle; d->deck.p.n_passive = n_passive; }
+    if (seed) d->deck.p.seed = seed;
+}
+void mcbh_info(mcbh_deck* d, int64_t out[16])
+{
+    const mcb_problem* p = d->deck.view();
+    const int64_t v[16] = {(int64_t)p->n_sample, (int64_t)p->n_cycle, (int64_t)p->n_passive, p->ksearch, p->n_nuclides,
+                           p->n_materials, p->n_surfaces, p->n_cells, p->n_estimators, p->n_tallies, p->n_sources,
+                           p->entropy_on, p->n_xs_rows, p->n_scores, p->n_filters, d->deck.trmm_present ? 1 : 0};
+    for (int i = 0; i < 16; i++) out[i] = v[i];
+}
+const char* mcbh_name(const mcbh_deck* d, int kind, int index)
+{
+    if (!d || index < 0) return nullptr;
+    const std::vector<std::string>* v = nullptr;
+    switch (kind) {
+    case 0: v = &d->deck.nuclide_names; break;
+    case 1: v = &d->deck.material_names; break;
+    case 2: v = &d->deck.surface_names; break;
+    case 3: v = &d->deck.cell_names; break;
+    default: return nullptr;
+    }
+    return index < (int)v->size() ? (*v)[index].c_str() : nullptr;
+}
+const char* mcbh_mode(const mcbh_deck* d) { return d ? d->deck.mode.c_str() : nullptr; }
+const char* mcbh_simulation_name(const mcbh_deck* d) { return d ? d->deck.simulation_name.c_str() : nullptr; }
+int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z) { return d ? d->deck.search_cell(x, y, z) : -1; }
+
+}  // extern "C"

@@ -1,0 +1,372 @@
+"""Deck writers for tests and the bench: they emit input.xml text in the reference's deck grammar
+ for the physics of BASELINE.json's configs, with the history counts as parameters.
+The physics values (densities, radii, source) are those of the reference's example decks
+(examples/<name>/input.xml, cited per function) so results can be compared with its documented numbers.
+"""
+import os
+
+HEAD = "<?xml version = '1.0' encoding = 'UTF-8'?>\n\n"
+
+
+def slab(samples=100000):
+    """examples/slab_analytic/input.xml: two purely absorbing slabs, leak through x=5 = exp(-4.2)."""
+    return HEAD + f"""
+<simulation>
+    <description name="Simple Slabs" samples="{samples:g}"/>
+</simulation>
+<nuclides>
+    <nuclide name="nuc1"> <capture xs="1.0"/> </nuclide>
+    <nuclide name="nuc2"> <capture xs="0.5"/> </nuclide>
+    <nuclide name="nuc3"> <capture xs="2.0"/> </nuclide>
+</nuclides>
+<materials>
+    <material name="mat1">
+        <nuclide name="nuc1" density="0.5"/>
+        <nuclide name="nuc2" density="1.0"/>
+        <nuclide name="nuc3" density="0.1"/>
+    </material>
+    <material name="mat2">
+        <nuclide name="nuc1" density="0.5"/>
+        <nuclide name="nuc2" density="0.5"/>
+    </material>
+</materials>
+<surfaces>
+    <plane_x name="px1" x="0.0"/>
+    <plane_x name="px2" x="1.0"/>
+    <plane_x name="px3" x="5.0"/>
+</surfaces>
+<cells>
+    <cell name="slab1" material="mat1">
+        <surface name="px1" sense="+1"/>
+        <surface name="px2" sense="-1"/>
+    </cell>
+    <cell name="slab2" material="mat2">
+        <surface name="px2" sense="+1"/>
+        <surface name="px3" sense="-1"/>
+    </cell>
+    <cell name="left outside" importance="0.0">
+        <surface name="px1" sense="-1"/>
+    </cell>
+    <cell name="right outside" importance="0.0">
+        <surface name="px3" sense="+1"/>
+    </cell>
+</cells>
+<distributions>
+    <delta name="dir" datatype="point" x = "1.0" y = "0.0" z = "0.0"/>
+</distributions>
+<sources>
+    <point x="1e-9" y="0.0" z="0.0" direction="dir"/>
+</sources>
+<estimators>
+    <estimator name="leak_rate" scores="cross">
+        <surface name="px3"/>
+    </estimator>
+</estimators>
+"""
+
+
+def heu_sphere(samples=1000, active=5, passive=3, source_tag="point", entropy=False, estimators=False):
+    """examples/HEU_sphere_criticality/input.xml: bare HEU sphere r=7.68 cm, k-eigenvalue.
+    source_tag="source" writes the deck's own <source position=...> form (rejected by the reference, F6)."""
+    src = ('<point x="0.0" y="0.0" z="0.0" direction="dir" energy="enrg"/>' if source_tag == "point"
+           else '<source position="pos" direction="dir" energy="enrg"/>')
+    ent = """
+    <entropy>
+        <x min="-7.68" max="7.68" step="8"/>
+        <y min="-7.68" max="7.68" step="8"/>
+        <z min="-7.68" max="7.68" step="8"/>
+    </entropy>""" if entropy else ""
+    est = """
+<estimators>
+    <estimator name="sphere_rates" scores="flux fission nu-fission absorption">
+        <cell name="sphere"/>
+        <filter type="energy" grid="1e-5 1.0 1e3 1e5 1e6 2e6 5e6 2e7"/>
+    </estimator>
+    <estimator name="sphere_coll" type="C" scores="flux total">
+        <cell name="sphere"/>
+    </estimator>
+    <estimator name="leak" scores="cross">
+        <surface name="suspicious_sphere"/>
+    </estimator>
+</estimators>""" if estimators else ""
+    return HEAD + f"""
+<simulation>
+    <description name="HEU Sphere" samples="{samples:g}"/>
+    <ksearch active_cycles="{active}" passive_cycles="{passive}"/>{ent}
+</simulation>
+<distributions>
+    <delta name="pos" datatype="point" x="0.0" y="0.0" z="0.0" />
+    <isotropic name="dir" datatype="point" />
+    <delta name="enrg" datatype="double" val="14.0e6"/>
+</distributions>
+<nuclides>
+    <nuclide name="U-235" ZAID="092235"/>
+    <nuclide name="U-238" ZAID="092238"/>
+</nuclides>
+<materials>
+    <material name="HEU">
+        <nuclide name="U-235" density="0.0455112"/>
+        <nuclide name="U-238" density="0.0033823"/>
+    </material>
+</materials>
+<surfaces>
+    <sphere name="suspicious_sphere"  x="0.0" y="0.0" z="0.0" r="7.68"/>
+</surfaces>
+<cells>
+    <cell name="sphere" material="HEU">
+        <surface name="suspicious_sphere" sense="-1" />
+    </cell>
+    <cell name="graveyard" importance="0.0">
+        <surface name="suspicious_sphere" sense="+1" />
+    </cell>
+</cells>
+<sources>
+    {src}
+</sources>{est}
+"""
+
+
+def ucube(samples=1000, active=5, passive=3):
+    """examples/UCube/input.xml: U-235 box with reflective/vacuum planes and the only <entropy> mesh."""
+    return HEAD + f"""
+<simulation>
+    <description name="Infinite U235 Cube" samples="{samples:g}"/>
+    <ksearch active_cycles="{active}" passive_cycles="{passive}"/>
+    <entropy>
+        <x min="0.0" max="12.0" step="12"/>
+        <y min="0.0" max="5.0" step="5"/>
+        <z min="0.0" max="6.0" step="6"/>
+    </entropy>
+</simulation>
+<distributions>
+    <isotropic name="dir" datatype="point" />
+    <delta name="enrg" datatype="double" val="14.0e6"/>
+</distributions>
+<nuclides>
+    <nuclide name="U-235" ZAID="092235"/>
+</nuclides>
+<materials>
+    <material name="Fuel">
+        <nuclide name="U-235" density="0.0508"/>
+    </material>
+</materials>
+<surfaces>
+    <plane_x name="px1" x="12.0" bc="vacuum"/>
+    <plane_x name="px2" x="-0.0" bc="reflective"/>
+    <plane_y name="py1" y="5.0" bc="vacuum"/>
+    <plane_y name="py2" y="-0.0" bc="reflective"/>
+    <plane_z name="pz1" z="6.0" bc="vacuum"/>
+    <plane_z name="pz2" z="-0.0" bc="reflective"/>
+</surfaces>
+<cells>
+    <cell name="UCube" material="Fuel">
+        <surface name="px1" sense="-1" />
+        <surface name="px2" sense="+1" />
+        <surface name="py1" sense="-1" />
+        <surface name="py2" sense="+1" />
+        <surface name="pz1" sense="-1" />
+        <surface name="pz2" sense="+1" />
+    </cell>
+</cells>
+<sources>
+    <point x="6.0" y="2.5" z="3.0" direction="dir" energy="enrg"/>
+</sources>
+"""
+
+
+def gcr(samples=400, active=5, passive=2, trmm=False):
+    """examples/infinite_GCR_TRMM/input.xml: infinite graphite-moderated medium (4 nuclides), reflective planes."""
+    t = """
+<trmm>
+    <cell name="infinity"/>
+    <filter type="energy" grid_lethargy="1E-5 2E7 20"/>
+</trmm>""" if trmm else ""
+    return HEAD + f"""
+<simulation>
+    <description name="Infinite GCR" samples="{samples:g}"/>
+    <ksearch active_cycles="{active}" passive_cycles="{passive}"/>
+</simulation>
+<distributions>
+    <isotropic name="dir" datatype="point" />
+    <delta name="enrg" datatype="double" val="14.0e6"/>
+</distributions>
+<nuclides>
+    <nuclide name="U-235" ZAID="092235"/>
+    <nuclide name="U-238" ZAID="092238"/>
+    <nuclide name="O-16"  ZAID="008016"/>
+    <nuclide name="C"     ZAID="006000"/>
+</nuclides>
+<materials>
+    <material name="Fuel">
+        <nuclide name="U-235" density="0.0000402"/>
+        <nuclide name="U-238" density="0.0009061"/>
+        <nuclide name="O-16"  density="0.0018927"/>
+        <nuclide name="C"     density="0.0757080"/>
+    </material>
+</materials>
+<surfaces>
+    <plane_x name="px1" x="100.0"  bc="reflective"/>
+    <plane_x name="px2" x="-100.0" bc="reflective"/>
+</surfaces>
+<cells>
+    <cell name="infinity" material="Fuel">
+        <surface name="px1" sense="-1" />
+        <surface name="px2" sense="+1" />
+    </cell>
+</cells>
+<sources>
+    <point x="0.0" y="0.0" z="0.0" direction="dir" energy="enrg"/>
+</sources>{t}
+"""
+
+
+def shielding(samples=20000, split=False):
+    """examples/shielding_vReduction/input.xml: water/B4C shield with a He-3 detector (6 nuclides, 10 cells).
+    split=True raises the importance of the cells towards the detector so that splitting is exercised."""
+    i3, i4, idet = ("2.0", "4.0", "4.0") if split else ("1.0", "1.0", "1.0")
+    return HEAD + f"""
+<simulation>
+    <description name="Shielding w/ Variance Reduction - 1" samples="{samples:g}"/>
+</simulation>
+<nuclides>
+    <nuclide name="O16" ZAID="008016"/>
+    <nuclide name="H1"  ZAID="001001"/>
+    <nuclide name="He3" ZAID="002003"/>
+    <nuclide name="C0"  ZAID="006000"/>
+    <nuclide name="B10" ZAID="005010"/>
+    <nuclide name="B11" ZAID="005011"/>
+</nuclides>
+<materials>
+    <material name="B4C">
+        <nuclide name="B10" density="0.0219716"/>
+        <nuclide name="B11" density="0.0878864"/>
+        <nuclide name="C0"  density="0.027468"/>
+    </material>
+    <material name="H2O">
+        <nuclide name="H1"  density="0.066733"/>
+        <nuclide name="O16" density="0.033368"/>
+    </material>
+    <material name="mat_detector">
+        <nuclide name="He3" density="0.00002501"/>
+    </material>
+</materials>
+<surfaces>
+    <plane_x    name="px1" x="0.0"/>
+    <plane_x    name="px2" x="4.0"/>
+    <plane_x    name="px3" x="5.0"/>
+    <plane_x    name="px4" x="9.0"/>
+    <plane_y    name="py1" y="0.0"/>
+    <plane_y    name="py2" y="3.0"/>
+    <plane_y    name="py3" y="6.0"/>
+    <cylinder_z name="cz1" x="6.5" y="1.5" r="0.5"/>
+</surfaces>
+<cells>
+    <cell name="water1" material="H2O" importance="1.0">
+        <surface name="px1" sense="+1"/> <surface name="px2" sense="-1"/>
+        <surface name="py1" sense="+1"/> <surface name="py2" sense="-1"/>
+    </cell>
+    <cell name="water2" material="H2O" importance="1.0">
+        <surface name="px1" sense="+1"/> <surface name="px2" sense="-1"/>
+        <surface name="py2" sense="+1"/> <surface name="py3" sense="-1"/>
+    </cell>
+    <cell name="water3" material="H2O" importance="{i3}">
+        <surface name="px2" sense="+1"/> <surface name="px4" sense="-1"/>
+        <surface name="py2" sense="+1"/> <surface name="py3" sense="-1"/>
+    </cell>
+    <cell name="water4" material="H2O" importance="{i4}">
+        <surface name="px3" sense="+1"/> <surface name="px4" sense="-1"/>
+        <surface name="py1" sense="+1"/> <surface name="py2" sense="-1"/>
+        <surface name="cz1" sense="+1"/>
+    </cell>
+    <cell name="shield" material="B4C" importance="{i3}">
+        <surface name="px2" sense="+1"/> <surface name="px3" sense="-1"/>
+        <surface name="py1" sense="+1"/> <surface name="py2" sense="-1"/>
+    </cell>
+    <cell name="detector" material="mat_detector" importance="{idet}">
+        <surface name="cz1" sense="-1"/>
+    </cell>
+    <cell name="left outside" importance="0.0"> <surface name="px1" sense="-1"/> </cell>
+    <cell name="right outside" importance="0.0"> <surface name="px4" sense="+1"/> </cell>
+    <cell name="down outside" importance="0.0"> <surface name="py1" sense="-1"/> </cell>
+    <cell name="up outside" importance="0.0"> <surface name="py3" sense="+1"/> </cell>
+</cells>
+<estimators>
+    <estimator name="detector_response" scores="flux absorption">
+        <cell  name="detector"/>
+    </estimator>
+</estimators>
+<distributions>
+    <delta name="enrg" datatype="double" val="2.0e6"/>
+</distributions>
+<sources>
+    <point x="1.5"  y="1.5"  z="0.0" energy="enrg"/>
+</sources>
+"""
+
+
+def fixed_source_fissile(samples=2000):
+    """A fixed-source deck in fissile material (same-history fission secondaries, fixed_source.cpp:12-22),
+    generic plane + cylinder_x surfaces, a uniform source energy and an independentXYZ direction, with
+    TL / collision / surface estimators and an energy filter — exercises the paths the example decks leave out."""
+    return HEAD + f"""
+<simulation>
+    <description name="subcritical block" samples="{samples:g}"/>
+</simulation>
+<distributions>
+    <uniform name="ux" datatype="double" a="0.2" b="0.9"/>
+    <uniform name="uy" datatype="double" a="-0.3" b="0.3"/>
+    <delta   name="uz" datatype="double" val="0.1"/>
+    <independentXYZ name="dir" datatype="point" x="ux" y="uy" z="uz"/>
+    <uniform name="enrg" datatype="double" a="1.0e5" b="3.0e6"/>
+</distributions>
+<nuclides>
+    <nuclide name="U-235" ZAID="092235"/>
+    <nuclide name="C"     ZAID="006000"/>
+</nuclides>
+<materials>
+    <material name="fuel">
+        <nuclide name="U-235" density="0.02"/>
+        <nuclide name="C"     density="0.04"/>
+    </material>
+    <material name="graphite">
+        <nuclide name="C" density="0.08"/>
+    </material>
+</materials>
+<surfaces>
+    <plane name="p1" a="1.0" b="0.0" c="0.0" d="-4.0" bc="vacuum"/>
+    <plane name="p2" a="1.0" b="0.2" c="0.0" d="5.0" bc="vacuum"/>
+    <cylinder_x name="cx" y="0.0" z="0.0" r="3.0"/>
+    <cylinder_x name="cxo" y="0.0" z="0.0" r="6.0" bc="vacuum"/>
+</surfaces>
+<cells>
+    <cell name="core" material="fuel">
+        <surface name="p1" sense="+1"/> <surface name="p2" sense="-1"/> <surface name="cx" sense="-1"/>
+    </cell>
+    <cell name="refl" material="graphite">
+        <surface name="p1" sense="+1"/> <surface name="p2" sense="-1"/>
+        <surface name="cx" sense="+1"/> <surface name="cxo" sense="-1"/>
+    </cell>
+</cells>
+<sources>
+    <point x="0.0" y="0.0" z="0.0" direction="dir" energy="enrg"/>
+</sources>
+<estimators>
+    <estimator name="core_tl" scores="flux fission nu-fission capture scatter total absorption">
+        <cell name="core"/> <cell name="refl"/>
+        <filter type="energy" grid_lethargy="1e-3 2e7 6"/>
+    </estimator>
+    <estimator name="core_c" type="C" scores="flux absorption">
+        <cell name="core"/>
+    </estimator>
+    <estimator name="interface" scores="cross flux">
+        <surface name="cx"/> <surface name="p2"/>
+    </estimator>
+</estimators>
+"""
+
+
+def write(dirpath, text):
+    os.makedirs(dirpath, exist_ok=True)
+    with open(os.path.join(dirpath, "input.xml"), "w") as f:
+        f.write(text)
+    return dirpath
