@@ -215,6 +215,14 @@ void mcb_reset_stage_times(mcb_ctx* ctx);
 /* fission bank of the last cycle on this rank, canonical order: out = n x 8 doubles (x,y,z,u,v,w,E,t), cells = n */
 int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n);
 
+/* source bank of the next cycle from HOST memory (n x 8 doubles x,y,z,u,v,w,E,t + n cells), replacing the bank the
+ * last cycle produced: the host-buffer form of `Sbank = Fbank` (handler.cpp:16).  With world > 1 every rank passes
+ * the same global bank. */
+int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells, int64_t n);
+/* per-history k scores of the last cycle on this rank, shard-local history order (EstimatorK::k_C / k_TL at
+ * end_history, Estimator.cpp:514-525): parity tests compare them with the oracle history by history */
+int64_t mcb_get_history_k(mcb_ctx* ctx, double* kC, double* kTL, int64_t max_n);
+
 /* parity / bench entry points on HOST buffers (H2D + kernel + D2H inside) */
 /* Material::Sigma{T,S,C,F}, nuSigmaF (Material.cpp:18-65): out5 = n x {SigmaT,SigmaS,SigmaC,SigmaF,nuSigmaF} */
 int mcb_xs_lookup_batch(mcb_ctx* ctx, int32_t material, const double* E, int64_t n, double* out5);
@@ -223,6 +231,8 @@ int mcb_xs_lookup_device(mcb_ctx* ctx, int32_t material, const double* dE, int64
 /* Material::nuclide_scatter (kind 0) / nuclide_nufission (kind 1) (Material.cpp:106-125): nuclide index or -1 */
 int mcb_select_channel_batch(mcb_ctx* ctx, int32_t material, int32_t kind, const double* E, const double* xi,
                              int64_t n, int32_t* nuclide);
+/* Nuclide::beta (Nuclide.cpp:74-77) of the material's local_nuclide-th nuclide */
+int mcb_beta_batch(mcb_ctx* ctx, int32_t material, int32_t local_nuclide, const double* E, int64_t n, double* out);
 /* Urand stream of history nps (Random.cpp:121-149,196-204): seeds_out[n*ndraw] raw 63-bit states after each draw */
 int mcb_rng_batch(mcb_ctx* ctx, const uint64_t* nps, int64_t n, int32_t ndraw, uint64_t* seeds_out);
 /* surface_intersect + Surface::eval (general.cpp:54-67, Geometry.cpp): per particle in cell[i]:

@@ -117,6 +117,11 @@ def cuda_lib():
         L.mcb_reset_stage_times.argtypes = [vp]
         L.mcb_get_fission_bank.restype = i64
         L.mcb_get_fission_bank.argtypes = [vp, vp, vp, i64]
+        L.mcb_set_source_bank.argtypes = [vp, vp, vp, i64]
+        L.mcb_get_history_k.restype = i64
+        L.mcb_get_history_k.argtypes = [vp, vp, vp, i64]
+        L.mcb_beta_batch.argtypes = [vp, i32, i32, vp, i64, vp]
+        L.mcb_device_count.restype = C.c_int
         L.mcb_xs_lookup_batch.argtypes = [vp, i32, vp, i64, vp]
         L.mcb_xs_lookup_device.argtypes = [vp, i32, vp, i64, vp, C.POINTER(C.c_float)]
         L.mcb_select_channel_batch.argtypes = [vp, i32, i32, vp, vp, i64, vp]
@@ -196,10 +201,10 @@ class Context:
     """Device context of one rank (mcb_ctx): owns tables, banks and tallies on one GPU."""
 
     def __init__(self, deck: Deck, device: int = 0, rank: int = 0, world: int = 1, bank_capacity: int = 0,
-                 site_capacity: int = 0, stream: int = 0):
+                 site_capacity: int = 0, stream: int = 0, stage_times: bool = False):
         L = cuda_lib()
         self.deck = deck
-        cfg = Config(device, rank, world, 0, bank_capacity, site_capacity, stream or None)
+        cfg = Config(device, rank, world, 1 if stage_times else 0, bank_capacity, site_capacity, stream or None)
         h = C.c_void_p()
         rc = L.mcb_create(deck.problem, C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -267,6 +272,24 @@ class Context:
         if n < 0:
             self._check(int(n))
         return sites[:n], cells[:n]
+
+    def set_source_bank(self, sites: np.ndarray, cells: np.ndarray):
+        sites = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, 8)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self._check(cuda_lib().mcb_set_source_bank(self._h, _ptr(sites), _ptr(cells), sites.shape[0]))
+
+    def history_k(self, n: int):
+        kC = np.zeros(max(n, 1)); kTL = np.zeros(max(n, 1))
+        got = cuda_lib().mcb_get_history_k(self._h, _ptr(kC), _ptr(kTL), n)
+        if got < 0:
+            self._check(int(got))
+        return kC[:got], kTL[:got]
+
+    def beta(self, material: int, local_nuclide: int, E: np.ndarray) -> np.ndarray:
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        out = np.empty(E.size)
+        self._check(cuda_lib().mcb_beta_batch(self._h, material, local_nuclide, _ptr(E), E.size, _ptr(out)))
+        return out
 
     # -- parity / bench entry points (host buffers) --
     def xs_lookup(self, material: int, E: np.ndarray) -> np.ndarray:

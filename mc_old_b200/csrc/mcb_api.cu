@@ -1,0 +1,962 @@
+// mcb_api.cu — the C-ABI of include/mcb200.h: device context, generation driver, parity entry points.
+//
+// mcb_run_cycle() is the body of the reference's cycle loop (Simulator::start(), handler.cpp:14-44) for the
+// histories this rank owns: source resampling -> event loop on the GPU -> fission bank in canonical order ->
+// per-history close-outs -> (multi-GPU) NCCL all-reduce of the sums and all-gather of the bank -> k update.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mcb_kernels.h"
+#include "mcb_tables.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL is bound at run time so that a process that already holds a libnccl (e.g. torch's) shares it ----
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err)
+    {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (lib) break; }
+        if (!lib && getenv("MCB_NCCL_LIB")) lib = dlopen(getenv("MCB_NCCL_LIB"), RTLD_NOW | RTLD_GLOBAL);
+        for (const char* n : names) { if (lib) break; lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); }
+        if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define MCB_SYM(field, name) field = (decltype(field))dlsym(lib, name); if (!field) { err = std::string("libnccl lacks ") + name; return false; }
+        MCB_SYM(GetUniqueId, "ncclGetUniqueId") MCB_SYM(CommInitRank, "ncclCommInitRank") MCB_SYM(CommDestroy, "ncclCommDestroy")
+        MCB_SYM(AllReduce, "ncclAllReduce") MCB_SYM(AllGather, "ncclAllGather") MCB_SYM(Broadcast, "ncclBroadcast")
+        MCB_SYM(GroupStart, "ncclGroupStart") MCB_SYM(GroupEnd, "ncclGroupEnd") MCB_SYM(GetErrorString, "ncclGetErrorString")
+#undef MCB_SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T* src, size_t count)
+    {
+        cudaError_t e = alloc(count);
+        if (e != cudaSuccess || count == 0) return e;
+        return cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+struct StageTimer {  // CUDA-event pairs per kernel class; resolved at the end of a generation
+    bool on = false;
+    struct Rec { int stage; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(cudaStream_t st, int stage)
+    {
+        if (!on) return;
+        Rec r{stage, get(), get()};
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEventRecord(recs.back().b, st);
+    }
+    void resolve(double* ms, uint64_t* count)
+    {
+        for (Rec& r : recs) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.stage] += t; count[r.stage]++; }
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    ~StageTimer() { for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }
+};
+enum { ST_SOURCE = 0, ST_LOOKUP, ST_FLIGHT, ST_CROSS, ST_COLLIDE, ST_CLOSEOUT, ST_BANK, ST_N };
+
+}  // namespace
+
+struct mcb_ctx {
+    std::string error;
+    int device = 0, rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // problem (host copies of what the close-out needs)
+    int ksearch = 0, entropy_on = 0;
+    uint64_t n_sample = 0, n_cycle = 0, n_passive = 0, seed = 1;
+    int64_t n_tallies = 0;
+    int n_materials = 0, n_nuclides = 0, n_cells = 0, n_surfaces = 0;
+    std::vector<int> mat_n_nuc;
+    // device problem
+    DevProblem P{};
+    DevBuf<DevMaterial> d_materials;
+    DevBuf<DevNuclide> d_nuclides;
+    DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid;
+    DevBuf<int32_t> d_map, d_hash, d_mat_nuclide, d_cell_surface, d_cell_sense, d_attach_begin[3], d_attach_list[3];
+    DevBuf<mcb_surface> d_surfaces;
+    DevBuf<mcb_cell> d_cells;
+    DevBuf<mcb_source> d_sources;
+    DevBuf<mcb_estimator> d_estimators;
+    DevBuf<mcb_score> d_scores;
+    DevBuf<mcb_filter> d_filters;
+    // shard
+    uint64_t shard_begin = 0, shard_count = 0;
+    // banks
+    uint32_t n_slots = 0, batch_hist = 0;
+    DevBuf<double> d_bank_f64;       // 15 double arrays of n_slots
+    DevBuf<uint64_t> d_bank_rng;
+    DevBuf<int32_t> d_bank_i32;      // 4 int arrays of n_slots
+    Bank B{};
+    DevBuf<uint32_t> d_queue;        // active, next, evq
+    uint32_t *q_active = nullptr, *q_next = nullptr, *q_ev = nullptr;
+    DevBuf<Counters> d_counters;
+    Counters* h_counters = nullptr;  // pinned
+    // per-history accumulators
+    DevBuf<double> d_hist_k;         // kC, kTL
+    DevBuf<int32_t> d_nsite;
+    DevBuf<uint32_t> d_site_offset;
+    DevBuf<unsigned char> d_scan_temp;
+    HistoryAcc H{};
+    // fission bank
+    uint64_t site_cap = 0, global_cap = 0;
+    DevBuf<Site> d_tmp_sites, d_local_bank, d_global_bank;
+    DevBuf<int32_t> d_tmp_hist;
+    uint64_t n_local_sites = 0, n_source_sites = 0;  // local bank of the last cycle; global source bank for the next
+    bool source_is_bank = false;
+    // tallies
+    DevBuf<double> d_tally_acc, d_tally_partial, d_tally_sum, d_tally_sq;
+    std::vector<double> tally_mean, tally_uncer;     // Tally::mean / uncer accumulated over active cycles
+    bool tallies_final = false;
+    // entropy
+    DevBuf<unsigned long long> d_entropy_bins;
+    // EstimatorK state (include/Estimator.h:466-502)
+    uint64_t icycle = 0, Navg = 0;
+    double k = 1.0, mean_accumulator = 0.0, uncer_sq_accumulator = 0.0;
+    // comm
+    ncclComm_t comm = nullptr;
+    DevBuf<unsigned long long> d_comm;               // reduction buffer
+    DevBuf<unsigned long long> d_counts;             // all-gather of per-rank site counts
+    // timing
+    StageTimer timer;
+    mcb_stage_times stage{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // scratch for the host-buffer entry points
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return ctx->fail(MCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) return ctx->fail(MCB_ERR_COMM, "%s: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+extern "C" {
+
+void mcb_shard_range(uint64_t n, int32_t rank, int32_t world, uint64_t* begin, uint64_t* count)
+{
+    // contiguous slices in rank order: the concatenation of the ranks' canonical fission banks is the canonical
+    // global bank
+    if (world < 1) world = 1;
+    const unsigned __int128 N = n;
+    const uint64_t b = (uint64_t)(N * (unsigned)rank / (unsigned)world);
+    const uint64_t e = (uint64_t)(N * (unsigned)(rank + 1) / (unsigned)world);
+    if (begin) *begin = b;
+    if (count) *count = e - b;
+}
+
+int mcb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* mcb_last_error(const mcb_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg)
+{
+    if (p->abi_version != MCB_ABI_VERSION) return ctx->fail(MCB_ERR_ARG, "mcb_problem.abi_version %d != %d", p->abi_version, MCB_ABI_VERSION);
+    if (p->n_sample == 0) return ctx->fail(MCB_ERR_ARG, "n_sample is zero");
+    if (p->n_sources <= 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
+    for (int f = 0; f < p->n_filters; f++)
+        if (p->filters[f].type == MCB_FILTER_TIME || p->filters[f].type == MCB_FILTER_ENERGY_OLD)
+            return ctx->fail(MCB_ERR_ARG, "unsupported: time / energy_old filters (SURVEY §8f-3)");
+    for (int e = 0; e < p->n_estimators; e++)
+        if (p->estimators[e].simulate) return ctx->fail(MCB_ERR_ARG, "unsupported: TRMM simulate-then-score estimators (SURVEY §8f-2)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ctx->fail(MCB_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    ctx->device = cfg ? cfg->device : 0;
+    ctx->rank = cfg ? cfg->rank : 0;
+    ctx->world = cfg && cfg->world > 0 ? cfg->world : 1;
+    if (ctx->rank < 0 || ctx->rank >= ctx->world) return ctx->fail(MCB_ERR_ARG, "rank %d outside world %d", ctx->rank, ctx->world);
+    CK(cudaSetDevice(ctx->device));
+    if (cfg && cfg->stream) ctx->stream = (cudaStream_t)cfg->stream;
+    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    ctx->timer.on = (cfg && (cfg->reserved & 1)) || getenv("MCB_STAGE_TIMES");
+
+    ctx->ksearch = p->ksearch; ctx->entropy_on = p->entropy_on;
+    ctx->n_sample = p->n_sample; ctx->n_cycle = p->n_cycle; ctx->n_passive = p->n_passive;
+    ctx->seed = p->seed ? p->seed : 1;
+    ctx->n_tallies = p->n_tallies;
+    ctx->n_materials = p->n_materials; ctx->n_nuclides = p->n_nuclides; ctx->n_cells = p->n_cells; ctx->n_surfaces = p->n_surfaces;
+
+    // ---- nuclear data: rows + per-material union grid / map / hash ----
+    CK(ctx->d_xs_rows.upload(p->xs_rows, (size_t)p->n_xs_rows * MCB_XS_ROW));
+    std::vector<DevNuclide> nuc(p->n_nuclides);
+    for (int n = 0; n < p->n_nuclides; n++) {
+        const mcb_nuclide& N = p->nuclides[n];
+        DevNuclide& D = nuc[n];
+        D.rows = ctx->d_xs_rows.p + (size_t)N.row_begin * MCB_XS_ROW;
+        D.n_rows = N.n_rows; D.has_delayed = N.has_delayed; D.A = N.A;
+        memcpy(D.watt_a, N.watt_a, sizeof(D.watt_a)); memcpy(D.watt_b, N.watt_b, sizeof(D.watt_b)); memcpy(D.watt_g, N.watt_g, sizeof(D.watt_g));
+    }
+    CK(ctx->d_nuclides.upload(nuc.data(), nuc.size()));
+    std::vector<mcb::MaterialTables> tabs(p->n_materials);
+    size_t nU = 0, nmap = 0, nhash = 0;
+    for (int m = 0; m < p->n_materials; m++) {
+        mcb::build_material_tables(p, m, 12, tabs[m]);
+        nU += tabs[m].U.size(); nmap += tabs[m].map.size(); nhash += tabs[m].hash.size();
+        ctx->mat_n_nuc.push_back(tabs[m].n_nuc);
+    }
+    std::vector<double> U; std::vector<int32_t> map, hash;
+    U.reserve(nU); map.reserve(nmap); hash.reserve(nhash);
+    std::vector<DevMaterial> mats(p->n_materials);
+    std::vector<size_t> oU(p->n_materials), omap(p->n_materials), ohash(p->n_materials);
+    for (int m = 0; m < p->n_materials; m++) {
+        oU[m] = U.size(); omap[m] = map.size(); ohash[m] = hash.size();
+        U.insert(U.end(), tabs[m].U.begin(), tabs[m].U.end());
+        map.insert(map.end(), tabs[m].map.begin(), tabs[m].map.end());
+        hash.insert(hash.end(), tabs[m].hash.begin(), tabs[m].hash.end());
+    }
+    CK(ctx->d_union.upload(U.data(), U.size()));
+    CK(ctx->d_map.upload(map.data(), map.size()));
+    CK(ctx->d_hash.upload(hash.data(), hash.size()));
+    for (int m = 0; m < p->n_materials; m++) {
+        DevMaterial& M = mats[m];
+        M.nuc_begin = p->mat_begin[m]; M.n_nuc = tabs[m].n_nuc;
+        M.nU = (int32_t)tabs[m].U.size(); M.n_hash = tabs[m].n_hash; M.shift = tabs[m].shift; M.pad = 0;
+        M.key_min = tabs[m].key_min;
+        M.U = ctx->d_union.p + oU[m]; M.map = ctx->d_map.p + omap[m]; M.hash = ctx->d_hash.p + ohash[m];
+    }
+    CK(ctx->d_materials.upload(mats.data(), mats.size()));
+    const int n_mat_nuc = p->mat_begin[p->n_materials];
+    CK(ctx->d_mat_nuclide.upload(p->mat_nuclide, n_mat_nuc));
+    CK(ctx->d_mat_density.upload(p->mat_density, n_mat_nuc));
+    // ---- geometry, sources, estimators ----
+    CK(ctx->d_surfaces.upload(p->surfaces, p->n_surfaces));
+    CK(ctx->d_cells.upload(p->cells, p->n_cells));
+    CK(ctx->d_cell_surface.upload(p->cell_surface, p->n_cell_surface));
+    CK(ctx->d_cell_sense.upload(p->cell_sense, p->n_cell_surface));
+    CK(ctx->d_sources.upload(p->sources, p->n_sources));
+    CK(ctx->d_estimators.upload(p->estimators, p->n_estimators));
+    CK(ctx->d_scores.upload(p->scores, p->n_scores));
+    CK(ctx->d_filters.upload(p->filters, p->n_filters));
+    CK(ctx->d_filter_grid.upload(p->filter_grid, p->n_filter_grid));
+    bool splitting = false;
+    {
+        double imp = -1.0;
+        for (int c = 0; c < p->n_cells; c++) {
+            const double I = p->cells[c].importance;
+            if (I == 0.0) continue;
+            if (imp < 0) imp = I; else if (I != imp) splitting = true;
+        }
+    }
+    for (int kind = 0; kind < 3; kind++) {
+        const int n_ids = kind == MCB_ATTACH_SURFACE ? p->n_surfaces : p->n_cells;
+        std::vector<int32_t> begin(n_ids + 1, 0), list;
+        for (int id = 0; id < n_ids; id++) {
+            begin[id] = (int32_t)list.size();
+            for (int e = 0; e < p->n_estimators; e++) {
+                const mcb_estimator& E = p->estimators[e];
+                if (E.attach != kind) continue;
+                const mcb_filter& F0 = p->filters[E.filter_begin];
+                for (int i = 0; i < F0.grid_n; i++)
+                    if ((int)p->filter_grid[F0.grid_begin + i] == id) { list.push_back(e); break; }
+            }
+        }
+        begin[n_ids] = (int32_t)list.size();
+        CK(ctx->d_attach_begin[kind].upload(begin.data(), begin.size()));
+        CK(ctx->d_attach_list[kind].upload(list.data(), list.size()));
+    }
+    int entropy_bins = 0;
+    if (p->entropy_on) {
+        const int ng = p->entropy_n[0] + p->entropy_n[1] + p->entropy_n[2];
+        CK(ctx->d_entropy_grid.upload(p->entropy_grid, ng));
+        entropy_bins = (p->entropy_n[0] - 1) * (p->entropy_n[1] - 1) * (p->entropy_n[2] - 1);
+        CK(ctx->d_entropy_bins.alloc(entropy_bins));
+    }
+
+    DevProblem& P = ctx->P;
+    P.ksearch = p->ksearch; P.n_materials = p->n_materials; P.n_nuclides = p->n_nuclides; P.n_surfaces = p->n_surfaces;
+    P.n_cells = p->n_cells; P.n_sources = p->n_sources; P.n_estimators = p->n_estimators; P.entropy_on = p->entropy_on;
+    P.shared_histories = (!p->ksearch || splitting) ? 1 : 0;
+    P.wr = p->wr; P.ws = p->ws; P.seed0 = ctx->seed; P.n_sample = p->n_sample;
+    P.materials = ctx->d_materials.p; P.nuclides = ctx->d_nuclides.p; P.mat_nuclide = ctx->d_mat_nuclide.p; P.mat_density = ctx->d_mat_density.p;
+    P.surfaces = ctx->d_surfaces.p; P.cells = ctx->d_cells.p; P.cell_surface = ctx->d_cell_surface.p; P.cell_sense = ctx->d_cell_sense.p;
+    P.sources = ctx->d_sources.p; P.estimators = ctx->d_estimators.p; P.scores = ctx->d_scores.p; P.filters = ctx->d_filters.p;
+    P.filter_grid = ctx->d_filter_grid.p;
+    for (int kind = 0; kind < 3; kind++) { P.attach_begin[kind] = ctx->d_attach_begin[kind].p; P.attach_list[kind] = ctx->d_attach_list[kind].p; }
+    for (int a = 0; a < 3; a++) P.entropy_n[a] = p->entropy_n[a];
+    P.entropy_bins = entropy_bins; P.entropy_grid = ctx->d_entropy_grid.p;
+
+    // ---- shard and banks ----
+    mcb_shard_range(p->n_sample, ctx->rank, ctx->world, &ctx->shard_begin, &ctx->shard_count);
+    if (ctx->shard_count >= (1ull << 31)) return ctx->fail(MCB_ERR_ARG, "more than 2^31 histories per GPU per generation");
+    // secondaries (same-history fission neutrons, splitting) need free slots behind the primaries of a batch
+    const uint64_t per_hist = P.shared_histories ? 4 : 1;
+    uint64_t cap = cfg && cfg->bank_capacity > 0 ? (uint64_t)cfg->bank_capacity : (1ull << 26);
+    cap = std::min<uint64_t>(cap, (1ull << 31) - 1);
+    uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(ctx->shard_count, cap / per_hist));
+    if (p->n_tallies > 0) {
+        // dense per-history tally accumulators of a batch: keep them under ~8 GiB
+        const uint64_t lim = std::max<uint64_t>(1024, (8ull << 30) / (8ull * (uint64_t)p->n_tallies));
+        batch = std::min(batch, lim);
+    }
+    ctx->batch_hist = (uint32_t)batch;
+    ctx->n_slots = (uint32_t)std::min<uint64_t>(batch * per_hist + 1024, (1ull << 31) - 1);
+    const size_t ns = ctx->n_slots;
+    CK(ctx->d_bank_f64.alloc(15 * ns));
+    CK(ctx->d_bank_rng.alloc(ns));
+    CK(ctx->d_bank_i32.alloc(4 * ns));
+    {
+        double* f = ctx->d_bank_f64.p;
+        Bank& B = ctx->B;
+        B.x = f; B.y = f + ns; B.z = f + 2 * ns; B.u = f + 3 * ns; B.v = f + 4 * ns; B.w = f + 5 * ns; B.E = f + 6 * ns;
+        B.speed = f + 7 * ns; B.wgt = f + 8 * ns; B.t = f + 9 * ns;
+        B.St = f + 10 * ns; B.Ss = f + 11 * ns; B.Sc = f + 12 * ns; B.Sf = f + 13 * ns; B.nSf = f + 14 * ns;
+        B.rng = ctx->d_bank_rng.p;
+        int32_t* i = ctx->d_bank_i32.p;
+        B.cell = i; B.hist = i + ns; B.uidx = i + 2 * ns; B.surf = i + 3 * ns;
+    }
+    CK(ctx->d_queue.alloc(3 * ns));
+    ctx->q_active = ctx->d_queue.p; ctx->q_next = ctx->d_queue.p + ns; ctx->q_ev = ctx->d_queue.p + 2 * ns;
+    CK(ctx->d_counters.alloc(1));
+    CK(cudaMemset(ctx->d_counters.p, 0, sizeof(Counters)));
+    CK(cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)));
+    const size_t nh = std::max<uint64_t>(ctx->shard_count, 1);
+    CK(ctx->d_hist_k.alloc(2 * nh));
+    CK(ctx->d_nsite.alloc(nh));
+    CK(ctx->d_site_offset.alloc(nh + 1));
+    CK(ctx->d_scan_temp.alloc(mcbk::scan_temp_bytes((uint32_t)nh) + 256));
+    ctx->H.kC = ctx->d_hist_k.p; ctx->H.kTL = ctx->d_hist_k.p + nh; ctx->H.nsite = ctx->d_nsite.p;
+    if (p->ksearch) {
+        // the first generations of a badly converged source bank up to ~3 sites per history (k_cycle of a 14 MeV
+        // point source in HEU is 2.7); leave room for 4
+        ctx->site_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity : 4 * ctx->shard_count + 4096;
+        CK(ctx->d_tmp_sites.alloc(ctx->site_cap));
+        CK(ctx->d_tmp_hist.alloc(ctx->site_cap));
+        CK(ctx->d_local_bank.alloc(ctx->site_cap));
+        if (ctx->world > 1) {
+            ctx->global_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity * ctx->world : 4 * p->n_sample + 4096ull * ctx->world;
+            CK(ctx->d_global_bank.alloc(ctx->global_cap));
+        }
+    }
+    if (p->n_tallies > 0) {
+        CK(ctx->d_tally_acc.alloc((size_t)p->n_tallies * batch));
+        CK(cudaMemset(ctx->d_tally_acc.p, 0, (size_t)p->n_tallies * batch * sizeof(double)));
+        CK(ctx->d_tally_partial.alloc((size_t)p->n_tallies * mcbk::tally_chunks((uint32_t)batch) * 2));
+        CK(ctx->d_tally_sum.alloc(p->n_tallies));
+        CK(ctx->d_tally_sq.alloc(p->n_tallies));
+        CK(cudaMemset(ctx->d_tally_sum.p, 0, p->n_tallies * sizeof(double)));
+        CK(cudaMemset(ctx->d_tally_sq.p, 0, p->n_tallies * sizeof(double)));
+        ctx->tally_mean.assign(p->n_tallies, 0.0);
+        ctx->tally_uncer.assign(p->n_tallies, 0.0);
+    }
+    CK(ctx->d_comm.alloc(32 + 2 * (size_t)std::max<int64_t>(p->n_tallies, 0)));
+    CK(ctx->d_counts.alloc(ctx->world));
+    CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); CK(cudaEventCreate(&ctx->ev2));
+    // the cross-section tables are read by every lookup and fit in L2 many times over: ask for them to persist
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && ctx->d_xs_rows.n) {
+            const size_t bytes = std::min<size_t>(ctx->d_xs_rows.n * sizeof(double), (size_t)prop.accessPolicyMaxWindowSize);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize));
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = ctx->d_xs_rows.p;
+            attr.accessPolicyWindow.num_bytes = bytes;
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (!getenv("MCB_NO_L2_PERSIST")) cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError();
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+int mcb_create(const mcb_problem* problem, const mcb_config* config, mcb_ctx** out)
+{
+    if (!problem || !out) { g_create_error = "mcb_create: null argument"; return MCB_ERR_ARG; }
+    mcb_ctx* ctx = new mcb_ctx;
+    const int rc = create_impl(ctx, problem, config);
+    if (rc != MCB_OK) {
+        g_create_error = ctx->error;
+        mcb_destroy(ctx);
+        *out = nullptr;
+        return rc;
+    }
+    *out = ctx;
+    return MCB_OK;
+}
+
+void mcb_destroy(mcb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mcb_comm_unique_id(char id[128])
+{
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return MCB_ERR_COMM; }
+    ncclUniqueId uid;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (g_nccl.GetUniqueId(&uid) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return MCB_ERR_COMM; }
+    memcpy(id, &uid, 128);
+    return MCB_OK;
+}
+
+int mcb_comm_init(mcb_ctx* ctx, const char id[128])
+{
+    if (!ctx) return MCB_ERR_ARG;
+    if (ctx->world == 1) return MCB_OK;
+    std::string err;
+    if (!g_nccl.load(err)) return ctx->fail(MCB_ERR_COMM, "%s", err.c_str());
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    NK(g_nccl.CommInitRank(&ctx->comm, ctx->world, uid, ctx->rank));
+    return MCB_OK;
+}
+
+double mcb_get_k(const mcb_ctx* ctx) { return ctx ? ctx->k : 0.0; }
+void mcb_set_k(mcb_ctx* ctx, double k) { if (ctx) ctx->k = k; }
+
+static double fx_to_double(unsigned long long lo, unsigned long long hi)
+{
+    const long double v = (long double)hi * 4294967296.0L + (long double)lo;
+    return (double)(v / (long double)MCB_FX_SCALE);
+}
+
+// the event loop over one batch of histories [h0, h0+nb) of the shard
+static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on, int* n_iterations)
+{
+    cudaStream_t st = ctx->stream;
+    const DevProblem& P = ctx->P;
+    TallyAcc T;
+    T.acc = ctx->d_tally_acc.p; T.stride = ctx->batch_hist; T.first_hist = (int32_t)h0; T.on = tally_on && ctx->n_tallies > 0;
+    const uint64_t nps0 = ctx->icycle * ctx->n_sample + ctx->shard_begin;
+    const Site* sbank = nullptr;
+    if (ctx->source_is_bank) sbank = ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p;
+    ctx->timer.begin(st, ST_SOURCE);
+    mcbk::source(st, P, ctx->B, ctx->q_active, (int32_t)h0, nb, nps0, sbank, ctx->n_source_sites);
+    ctx->timer.end(st);
+    Counters* C = ctx->d_counters.p;
+    // slot cursor starts behind the primaries; queue cursors are cleared every iteration
+    unsigned int cur[4] = {0, 0, 0, nb};
+    CK(cudaMemcpyAsync(&C->q_collide, cur, sizeof(cur), cudaMemcpyHostToDevice, st));
+    uint32_t n_active = nb;
+    uint32_t* active = ctx->q_active;
+    uint32_t* next = ctx->q_next;
+    int iterations = 0;
+    while (n_active > 0) {
+        ctx->timer.begin(st, ST_LOOKUP);
+        mcbk::xs_stage(st, P, ctx->B, active, n_active, C);
+        ctx->timer.end(st);
+        ctx->timer.begin(st, ST_FLIGHT);
+        mcbk::flight(st, P, ctx->B, active, n_active, ctx->q_ev, C, ctx->H, T);
+        ctx->timer.end(st);
+        ctx->timer.begin(st, ST_COLLIDE);
+        mcbk::collide(st, P, ctx->B, ctx->q_ev, n_active, C, next, ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+                      ctx->site_cap, ctx->n_slots, ctx->k);
+        ctx->timer.end(st);
+        ctx->timer.begin(st, ST_CROSS);
+        mcbk::cross(st, P, ctx->B, ctx->q_ev, n_active, n_active, C, next, T, ctx->n_slots);
+        ctx->timer.end(st);
+        CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(&C->q_collide, 0, 3 * sizeof(unsigned int), st));
+        CK(cudaStreamSynchronize(st));
+        const Counters& hc = *ctx->h_counters;
+        if (hc.lost) {
+            return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
+        }
+        if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
+        if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
+        n_active = hc.q_next;
+        std::swap(active, next);
+        iterations++;
+    }
+    *n_iterations += iterations;
+    if (T.on) {
+        ctx->timer.begin(st, ST_CLOSEOUT);
+        mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
+        ctx->timer.end(st);
+    }
+    return MCB_OK;
+}
+
+int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
+{
+    if (!ctx) return MCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool tally_on = ctx->icycle >= ctx->n_passive;  // handler.cpp:15
+    if (ctx->source_is_bank && ctx->n_source_sites == 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
+    if (ctx->world > 1 && !ctx->comm) return ctx->fail(MCB_ERR_COMM, "world > 1 but mcb_comm_init was not called");
+    Counters* C = ctx->d_counters.p;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CK(cudaMemsetAsync(C, 0, sizeof(Counters), st));
+    const size_t nh = std::max<uint64_t>(ctx->shard_count, 1);
+    CK(cudaMemsetAsync(ctx->d_hist_k.p, 0, 2 * nh * sizeof(double), st));
+    CK(cudaMemsetAsync(ctx->d_nsite.p, 0, nh * sizeof(int32_t), st));
+    int iterations = 0;
+    for (uint64_t h0 = 0; h0 < ctx->shard_count; h0 += ctx->batch_hist) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(ctx->batch_hist, ctx->shard_count - h0);
+        const int rc = transport_batch(ctx, (uint32_t)h0, nb, tally_on, &iterations);
+        if (rc != MCB_OK) return rc;
+    }
+    // ---- close-out on this rank ----
+    ctx->timer.begin(st, ST_CLOSEOUT);
+    if (ctx->ksearch) mcbk::reduce_k(st, ctx->H.kC, ctx->H.kTL, (uint32_t)ctx->shard_count, C);
+    ctx->timer.end(st);
+    CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t n_local = ctx->h_counters->site_cursor;
+    if (ctx->ksearch) {
+        ctx->timer.begin(st, ST_BANK);
+        mcbk::scan_sites(st, ctx->d_scan_temp.p, ctx->d_scan_temp.n, ctx->H.nsite, ctx->d_site_offset.p, (uint32_t)ctx->shard_count);
+        mcbk::bank_order(st, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p, n_local, ctx->d_site_offset.p, ctx->d_local_bank.p);
+        ctx->timer.end(st);
+        if (ctx->entropy_on) {
+            ctx->timer.begin(st, ST_CLOSEOUT);
+            mcbk::entropy_history(st, ctx->P, ctx->d_local_bank.p, ctx->d_site_offset.p, ctx->H.nsite, (uint32_t)ctx->shard_count, C);
+            CK(cudaMemsetAsync(ctx->d_entropy_bins.p, 0, ctx->d_entropy_bins.n * sizeof(unsigned long long), st));
+            mcbk::entropy_histogram(st, ctx->P, ctx->d_local_bank.p, n_local, ctx->d_entropy_bins.p);
+            ctx->timer.end(st);
+        }
+    }
+    ctx->n_local_sites = n_local;
+    CK(cudaEventRecord(ctx->ev1, st));
+
+    // ---- gather the sums: [0..9] fixed-point limbs, [10..15] counters, then tally sum / squared (as doubles) ----
+    const size_t nt = (size_t)std::max<int64_t>(ctx->n_tallies, 0);
+    std::vector<unsigned long long> red(16 + ctx->d_entropy_bins.n, 0);
+    std::vector<double> tsum(nt, 0.0), tsq(nt, 0.0);
+    uint64_t n_global_sites = n_local;
+    {
+        CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const Counters& hc = *ctx->h_counters;
+        if (hc.overflow_fixed) return ctx->fail(MCB_ERR_ARG, "a per-history k score left the fixed-point range");
+        for (int j = 0; j < 5; j++) { red[2 * j] = hc.fx_lo[j]; red[2 * j + 1] = hc.fx_hi[j]; }
+        red[10] = n_local; red[11] = hc.n_tracks; red[12] = hc.n_collisions; red[13] = hc.n_lookups; red[14] = hc.n_crossings;
+        red[15] = ctx->shard_count;
+        if (ctx->d_entropy_bins.n) CK(cudaMemcpyAsync(red.data() + 16, ctx->d_entropy_bins.p, ctx->d_entropy_bins.n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (nt && tally_on) {
+            CK(cudaMemcpyAsync(tsum.data(), ctx->d_tally_sum.p, nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(tsq.data(), ctx->d_tally_sq.p, nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemsetAsync(ctx->d_tally_sum.p, 0, nt * sizeof(double), st));
+            CK(cudaMemsetAsync(ctx->d_tally_sq.p, 0, nt * sizeof(double), st));
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    if (ctx->world > 1) {
+        // integer sums are exact, so k does not depend on the number of GPUs; tally sums are doubles
+        DevBuf<unsigned long long> d_red;
+        DevBuf<double> d_t;
+        CK(d_red.upload(red.data(), red.size()));
+        NK(g_nccl.AllReduce(d_red.p, d_red.p, red.size(), ncclUint64, ncclSum, ctx->comm, st));
+        if (nt && tally_on) {
+            std::vector<double> both(2 * nt);
+            memcpy(both.data(), tsum.data(), nt * sizeof(double)); memcpy(both.data() + nt, tsq.data(), nt * sizeof(double));
+            CK(d_t.upload(both.data(), both.size()));
+            NK(g_nccl.AllReduce(d_t.p, d_t.p, both.size(), ncclDouble, ncclSum, ctx->comm, st));
+            CK(cudaMemcpyAsync(both.data(), d_t.p, both.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            memcpy(tsum.data(), both.data(), nt * sizeof(double)); memcpy(tsq.data(), both.data() + nt, nt * sizeof(double));
+        }
+        // fission bank: all ranks learn every rank's count, then each rank's slice is broadcast into place
+        if (ctx->ksearch) {
+            unsigned long long mine = n_local;
+            DevBuf<unsigned long long> d_mine;
+            CK(d_mine.upload(&mine, 1));
+            NK(g_nccl.AllGather(d_mine.p, ctx->d_counts.p, 1, ncclUint64, ctx->comm, st));
+            std::vector<unsigned long long> counts(ctx->world);
+            CK(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, ctx->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            uint64_t total = 0;
+            for (auto c : counts) total += c;
+            if (total > ctx->global_cap) return ctx->fail(MCB_ERR_CAPACITY, "global fission bank overflow: %llu sites", (unsigned long long)total);
+            NK(g_nccl.GroupStart());
+            uint64_t off = 0;
+            for (int r = 0; r < ctx->world; r++) {
+                if (counts[r]) NK(g_nccl.Broadcast(ctx->d_local_bank.p, ctx->d_global_bank.p + off, counts[r] * sizeof(Site), ncclChar, r, ctx->comm, st));
+                off += counts[r];
+            }
+            NK(g_nccl.GroupEnd());
+            n_global_sites = total;
+        }
+        CK(cudaMemcpyAsync(red.data(), d_red.p, red.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaEventRecord(ctx->ev2, st));
+    CK(cudaEventSynchronize(ctx->ev2));
+    {
+        double ms[ST_N] = {0}; uint64_t cnt[ST_N] = {0};
+        ctx->timer.resolve(ms, cnt);
+        mcb_stage_times& S = ctx->stage;
+        S.ms_source += ms[ST_SOURCE]; S.ms_lookup += ms[ST_LOOKUP]; S.ms_flight += ms[ST_FLIGHT]; S.ms_cross += ms[ST_CROSS];
+        S.ms_collide += ms[ST_COLLIDE]; S.ms_closeout += ms[ST_CLOSEOUT]; S.ms_bank += ms[ST_BANK];
+        S.n_source += cnt[ST_SOURCE]; S.n_lookup += cnt[ST_LOOKUP]; S.n_flight += cnt[ST_FLIGHT]; S.n_cross += cnt[ST_CROSS];
+        S.n_collide += cnt[ST_COLLIDE]; S.n_closeout += cnt[ST_CLOSEOUT]; S.n_bank += cnt[ST_BANK];
+        S.units_lookup += ctx->h_counters->n_lookups;
+    }
+
+    // ---- cycle close-out on the host (identical on every rank) ----
+    mcb_cycle_result r;
+    memset(&r, 0, sizeof(r));
+    const double Ns = (double)ctx->n_sample;
+    if (tally_on && nt) {  // Estimator::end_cycle (Estimator.cpp:347-360)
+        for (size_t t = 0; t < nt; t++) {
+            const double mean = tsum[t] / Ns;
+            const double uncer_squared = (tsq[t] / Ns - mean * mean) / (Ns - 1.0);
+            ctx->tally_mean[t] += mean;
+            ctx->tally_uncer[t] += uncer_squared;
+        }
+    }
+    r.k_sum_C = fx_to_double(red[0], red[1]); r.k_sum_TL = fx_to_double(red[2], red[3]);
+    r.k_sq_C = fx_to_double(red[4], red[5]); r.k_sq_TL = fx_to_double(red[6], red[7]);
+    const double H_sum = fx_to_double(red[8], red[9]);
+    if (ctx->ksearch) {  // EstimatorK::report_cycle (Estimator.cpp:526-561)
+        const double mean_C = r.k_sum_C / Ns, mean_TL = r.k_sum_TL / Ns;
+        const double mean = (mean_C + mean_TL) / 2;
+        r.H = H_sum / Ns;
+        r.k_cycle = mean;
+        ctx->k = mean;
+        if (tally_on) {
+            const double us_C = (r.k_sq_C / Ns - mean_C * mean_C) / (Ns - 1.0);
+            const double us_TL = (r.k_sq_TL / Ns - mean_TL * mean_TL) / (Ns - 1.0);
+            ctx->Navg++;
+            ctx->mean_accumulator += mean;
+            ctx->uncer_sq_accumulator += us_C + us_TL;
+            r.k_avg = ctx->mean_accumulator / ctx->Navg;
+            r.k_uncer = std::sqrt(ctx->uncer_sq_accumulator) / ctx->Navg / 2;
+        }
+        if (ctx->d_entropy_bins.n) {
+            unsigned long long tot = 0;
+            for (size_t b = 0; b < ctx->d_entropy_bins.n; b++) tot += red[16 + b];
+            double Hc = 0.0;
+            for (size_t b = 0; b < ctx->d_entropy_bins.n; b++) if (red[16 + b]) { const double pb = (double)red[16 + b] / (double)tot; Hc -= pb * std::log2(pb); }
+            r.H_cycle_conventional = Hc;
+        }
+        ctx->n_source_sites = n_global_sites;
+        ctx->source_is_bank = true;
+    }
+    r.n_sites = ctx->ksearch ? n_global_sites : 0;
+    r.n_tracks = red[11]; r.n_collisions = red[12]; r.n_lookups = red[13]; r.n_crossings = red[14]; r.n_histories = red[15];
+    float ms_t = 0, ms_x = 0;
+    cudaEventElapsedTime(&ms_t, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ms_x, ctx->ev1, ctx->ev2);
+    r.ms_transport = ms_t; r.ms_exchange = ms_x;
+    r.n_iterations = iterations;
+    r.lost = 0;
+    ctx->icycle++;
+    if (out) *out = r;
+    return MCB_OK;
+}
+
+int mcb_get_tallies(mcb_ctx* ctx, double* mean, double* uncer, int64_t n)
+{
+    if (!ctx) return MCB_ERR_ARG;
+    if (n > ctx->n_tallies) n = ctx->n_tallies;
+    // Estimator::end_simulation (Estimator.cpp:361-367); the stored accumulators are left untouched
+    uint64_t n_active = ctx->icycle > ctx->n_passive ? ctx->icycle - ctx->n_passive : 0;
+    if (n_active == 0) n_active = 1;
+    const double Nactive = (double)n_active;
+    for (int64_t t = 0; t < n; t++) {
+        if (mean) mean[t] = ctx->tally_mean[t] / Nactive;
+        if (uncer) uncer[t] = std::sqrt(ctx->tally_uncer[t]) / Nactive;
+    }
+    return MCB_OK;
+}
+
+int mcb_get_stage_times(mcb_ctx* ctx, mcb_stage_times* out)
+{
+    if (!ctx || !out) return MCB_ERR_ARG;
+    *out = ctx->stage;
+    return MCB_OK;
+}
+void mcb_reset_stage_times(mcb_ctx* ctx)
+{
+    if (ctx) memset(&ctx->stage, 0, sizeof(ctx->stage));
+}
+
+int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
+{
+    if (!ctx) return MCB_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
+    const int64_t n = std::min<int64_t>((int64_t)ctx->n_local_sites, max_n);
+    if (n <= 0) return 0;
+    std::vector<Site> h((size_t)n);
+    if (cudaMemcpyAsync(h.data(), ctx->d_local_bank.p, (size_t)n * sizeof(Site), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return ctx->fail(MCB_ERR_CUDA, "fission bank read-back failed");
+    for (int64_t i = 0; i < n; i++) {
+        const Site& s = h[(size_t)i];
+        if (out) { double* o = out + 8 * i; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.u; o[4] = s.v; o[5] = s.w; o[6] = s.E; o[7] = s.t; }
+        if (cells) cells[i] = s.cell;
+    }
+    return n;
+}
+
+int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells, int64_t n)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (!ctx->ksearch) return ctx->fail(MCB_ERR_ARG, "mcb_set_source_bank: not a k-eigenvalue problem");
+    CK(cudaSetDevice(ctx->device));
+    Site* dst = ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p;
+    const uint64_t cap = ctx->world > 1 ? ctx->global_cap : ctx->site_cap;
+    if ((uint64_t)n > cap) return ctx->fail(MCB_ERR_CAPACITY, "source bank of %lld sites exceeds the capacity %llu", (long long)n, (unsigned long long)cap);
+    std::vector<Site> h((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        const double* s = sites8 + 8 * i;
+        Site& d = h[(size_t)i];
+        d.x = s[0]; d.y = s[1]; d.z = s[2]; d.u = s[3]; d.v = s[4]; d.w = s[5]; d.E = s[6]; d.t = s[7];
+        d.cell = cells[i]; d.seq = 0;
+    }
+    if (n) CK(cudaMemcpyAsync(dst, h.data(), (size_t)n * sizeof(Site), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_source_sites = (uint64_t)n;
+    ctx->source_is_bank = true;
+    return MCB_OK;
+}
+
+}  // extern "C"
+
+// ---- parity / bench entry points ----
+template <typename F>
+static int with_buffers(mcb_ctx* ctx, F f)
+{
+    CK(cudaSetDevice(ctx->device));
+    const int rc = f();
+    if (rc != MCB_OK) return rc;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MCB_OK;
+}
+
+extern "C" {
+#define H2D(buf, src, count) CK((buf).alloc(count)); if (count) CK(cudaMemcpyAsync((buf).p, src, (count) * sizeof(*(buf).p), cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, buf, count) if (count) CK(cudaMemcpyAsync(dst, (buf).p, (count) * sizeof(*(buf).p), cudaMemcpyDeviceToHost, ctx->stream))
+
+int mcb_xs_lookup_batch(mcb_ctx* ctx, int32_t material, const double* E, int64_t n, double* out5)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (material < 0 || material >= ctx->n_materials) return ctx->fail(MCB_ERR_ARG, "material %d out of range", material);
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<double> dE, dO;
+        H2D(dE, E, (size_t)n);
+        CK(dO.alloc((size_t)n * 5));
+        mcbk::xs_lookup(ctx->stream, ctx->P, material, dE.p, n, dO.p);
+        D2H(out5, dO, (size_t)n * 5);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_xs_lookup_device(mcb_ctx* ctx, int32_t material, const double* dE, int64_t n, double* dout5, float* ms)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (material < 0 || material >= ctx->n_materials) return ctx->fail(MCB_ERR_ARG, "material %d out of range", material);
+    CK(cudaSetDevice(ctx->device));
+    if (ms) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    mcbk::xs_lookup(ctx->stream, ctx->P, material, dE, n, dout5);
+    CK(cudaGetLastError());
+    if (ms) {
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    }
+    return MCB_OK;
+}
+
+int mcb_select_channel_batch(mcb_ctx* ctx, int32_t material, int32_t kind, const double* E, const double* xi, int64_t n,
+                             int32_t* nuclide)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (material < 0 || material >= ctx->n_materials) return ctx->fail(MCB_ERR_ARG, "material %d out of range", material);
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<double> dE, dX; DevBuf<int32_t> dO;
+        H2D(dE, E, (size_t)n); H2D(dX, xi, (size_t)n);
+        CK(dO.alloc((size_t)n));
+        mcbk::select_channel(ctx->stream, ctx->P, material, kind, dE.p, dX.p, n, dO.p);
+        D2H(nuclide, dO, (size_t)n);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_beta_batch(mcb_ctx* ctx, int32_t material, int32_t local_nuclide, const double* E, int64_t n, double* out)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (material < 0 || material >= ctx->n_materials) return ctx->fail(MCB_ERR_ARG, "material %d out of range", material);
+    if (local_nuclide < 0 || local_nuclide >= ctx->mat_n_nuc[material]) return ctx->fail(MCB_ERR_ARG, "nuclide %d out of range", local_nuclide);
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<double> dE, dO;
+        H2D(dE, E, (size_t)n);
+        CK(dO.alloc((size_t)n));
+        mcbk::beta(ctx->stream, ctx->P, material, local_nuclide, dE.p, n, dO.p);
+        D2H(out, dO, (size_t)n);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_rng_batch(mcb_ctx* ctx, const uint64_t* nps, int64_t n, int32_t ndraw, uint64_t* seeds_out)
+{
+    if (!ctx || n < 0 || ndraw < 0) return MCB_ERR_ARG;
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<uint64_t> dN, dO;
+        H2D(dN, nps, (size_t)n);
+        CK(dO.alloc((size_t)n * ndraw));
+        mcbk::rng(ctx->stream, ctx->seed, dN.p, n, ndraw, dO.p);
+        D2H(seeds_out, dO, (size_t)n * ndraw);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_geometry_batch(mcb_ctx* ctx, const int32_t* cell, const double* pos3, const double* dir3, int64_t n, double* out3)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    for (int64_t i = 0; i < n; i++) if (cell[i] < 0 || cell[i] >= ctx->n_cells) return ctx->fail(MCB_ERR_ARG, "cell %d out of range", cell[i]);
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<int32_t> dC; DevBuf<double> dP, dD, dO;
+        H2D(dC, cell, (size_t)n); H2D(dP, pos3, (size_t)n * 3); H2D(dD, dir3, (size_t)n * 3);
+        CK(dO.alloc((size_t)n * 3));
+        mcbk::geometry(ctx->stream, ctx->P, dC.p, dP.p, dD.p, n, dO.p);
+        D2H(out3, dO, (size_t)n * 3);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_search_cell_batch(mcb_ctx* ctx, const double* pos3, int64_t n, int32_t* cell)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<double> dP; DevBuf<int32_t> dO;
+        H2D(dP, pos3, (size_t)n * 3);
+        CK(dO.alloc((size_t)n));
+        mcbk::search_cell(ctx->stream, ctx->P, dP.p, n, dO.p);
+        D2H(cell, dO, (size_t)n);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_scatter_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, int64_t n, double* io5)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (nuclide < 0 || nuclide >= ctx->n_nuclides) return ctx->fail(MCB_ERR_ARG, "nuclide %d out of range", nuclide);
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<uint64_t> dN; DevBuf<double> dIO;
+        H2D(dN, nps, (size_t)n); H2D(dIO, io5, (size_t)n * 5);
+        mcbk::scatter(ctx->stream, ctx->P, nuclide, dN.p, n, dIO.p);
+        D2H(io5, dIO, (size_t)n * 5);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_watt_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, const double* E, int64_t n, double* Eout)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    if (nuclide < 0 || nuclide >= ctx->n_nuclides) return ctx->fail(MCB_ERR_ARG, "nuclide %d out of range", nuclide);
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<uint64_t> dN; DevBuf<double> dE, dO;
+        H2D(dN, nps, (size_t)n); H2D(dE, E, (size_t)n);
+        CK(dO.alloc((size_t)n));
+        mcbk::watt(ctx->stream, ctx->P, nuclide, dN.p, dE.p, n, dO.p);
+        D2H(Eout, dO, (size_t)n);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+// per-history k scores of the last cycle on this rank (k_C then k_TL, shard-local history order): parity tests
+int64_t mcb_get_history_k(mcb_ctx* ctx, double* kC, double* kTL, int64_t max_n)
+{
+    if (!ctx) return MCB_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
+    const int64_t n = std::min<int64_t>((int64_t)ctx->shard_count, max_n);
+    if (n <= 0) return 0;
+    if (cudaMemcpy(kC, ctx->H.kC, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(kTL, ctx->H.kTL, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return ctx->fail(MCB_ERR_CUDA, "history k read-back failed");
+    return n;
+}
+
+}  // extern "C"

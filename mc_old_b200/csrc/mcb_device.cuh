@@ -1,0 +1,310 @@
+// mcb_device.cuh — device-side data layout and the per-particle physics of the transport loop.
+//
+// Everything here is compiled with -fmad=false: the x86-64 reference build has no fused
+// multiply-add, and cross sections / channel selection are bit-exact against it.
+#ifndef MCB_DEVICE_CUH
+#define MCB_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mcb200.h"
+#include "mcb_physics.h"
+#include "mcb_tables.h"
+
+// ---------------------------------------------------------------------------------------------
+// flattened problem in device memory (built once by mcb_create; read-only afterwards)
+// ---------------------------------------------------------------------------------------------
+struct DevMaterial {
+    int32_t nuc_begin, n_nuc;    // range in mat_nuclide / mat_density (deck order = summation order)
+    int32_t nU, n_hash, shift, pad;
+    int64_t key_min;
+    const double* U;             // union grid
+    const int32_t* map;          // nU x n_nuc
+    const int32_t* hash;         // n_hash + 1
+};
+struct DevNuclide {
+    const double* rows;          // n_rows x {E, sigma_s, sigma_c, sigma_f, nu, beta}; 48-byte rows, 16-byte aligned
+    int32_t n_rows, has_delayed;
+    double A;
+    double watt_a[3], watt_b[3], watt_g[3];
+};
+struct DevProblem {
+    int32_t ksearch, n_materials, n_nuclides, n_surfaces, n_cells, n_sources, n_estimators, entropy_on;
+    int32_t shared_histories;    // several particles of one history can be in flight (secondaries / splitting)
+    int32_t pad;
+    double wr, ws;
+    uint64_t seed0, n_sample;
+    const DevMaterial* materials;
+    const DevNuclide* nuclides;
+    const int32_t* mat_nuclide;
+    const double* mat_density;
+    const mcb_surface* surfaces;
+    const mcb_cell* cells;
+    const int32_t* cell_surface;
+    const int32_t* cell_sense;
+    const mcb_source* sources;
+    const mcb_estimator* estimators;
+    const mcb_score* scores;
+    const mcb_filter* filters;
+    const double* filter_grid;
+    // estimators attached to surface s / cell c (TL) / cell c (C): CSR lists in deck order
+    const int32_t* attach_begin[3];
+    const int32_t* attach_list[3];
+    int32_t entropy_n[3];
+    int32_t entropy_bins;
+    const double* entropy_grid;
+};
+
+// SoA particle bank: one slot per particle in flight
+struct Bank {
+    double *x, *y, *z, *u, *v, *w, *E, *speed, *wgt, *t;
+    uint64_t* rng;
+    int32_t *cell, *hist;                 // hist = history index local to this rank's shard
+    double *St, *Ss, *Sc, *Sf, *nSf;      // macroscopic xs of the cell's material at E (stage: xs_lookup)
+    int32_t* uidx;                        // union-grid index of E in that material
+    int32_t* surf;                        // surface hit by the last flight (stage: flight)
+};
+
+// fission site / source site (AoS: sites are written and read by random index)
+struct Site {
+    double x, y, z, u, v, w, E, t;
+    int32_t cell, seq;                    // seq = order of banking within the parent history
+};
+
+struct Counters {
+    unsigned long long n_tracks, n_collisions, n_lookups, n_crossings, n_histories;
+    unsigned long long site_cursor;       // unordered fission sites banked this cycle
+    unsigned int q_collide, q_cross, q_next, slot_cursor;
+    int lost, overflow_sites, overflow_slots, overflow_fixed;
+    double lost_pos[3];
+    // exact (fixed-point, two-limb) sums over histories: k_C, k_TL, k_C^2, k_TL^2, H
+    unsigned long long fx_lo[5], fx_hi[5];
+};
+
+// per-history accumulators, indexed by the shard-local history index
+struct HistoryAcc {
+    double *kC, *kTL;                     // EstimatorK::k_C / k_TL of the history (Estimator.cpp:503-512)
+    int32_t* nsite;                       // fission sites banked by the history
+};
+
+// dense per-history tally accumulators of the current batch: acc[tally][batch history]
+struct TallyAcc {
+    double* acc;
+    int64_t stride;                       // histories per batch (row length)
+    int32_t first_hist;                   // shard-local index of the batch's first history
+    int32_t on;                           // tallies are being scored (active cycle, handler.cpp:15)
+};
+
+#define MCB_FX_SCALE 17592186044416.0     /* 2^44: fixed-point scale of the exact history sums */
+
+// ---------------------------------------------------------------------------------------------
+// cross sections
+// ---------------------------------------------------------------------------------------------
+struct MicroXS { double s, c, f, t, nu; };
+
+__device__ __forceinline__ double2 ld_row2(const double* p)
+{
+    return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// XSTable::xs for all tables of one nuclide at E (XSec.cpp:9-40, Algorithm.cpp:103-105); idx = #{n_E < E} - 1.
+// sigma_t / sigma_a are interpolated from their per-grid-point values (setup.cpp:371-372), not summed afterwards.
+__device__ __forceinline__ void micro_xs(const DevNuclide& N, int idx, double E, MicroXS& m)
+{
+    if (idx < 0 || idx >= N.n_rows - 1) {
+        const double* r = N.rows + (size_t)(idx < 0 ? 0 : N.n_rows - 1) * MCB_XS_ROW;
+        const double2 a = ld_row2(r), b = ld_row2(r + 2), c = ld_row2(r + 4);
+        m.s = a.y; m.c = b.x; m.f = b.y; m.nu = c.x;
+        m.t = a.y + b.x + b.y;
+        return;
+    }
+    const double* r = N.rows + (size_t)idx * MCB_XS_ROW;
+    const double2 a1 = ld_row2(r), b1 = ld_row2(r + 2), c1 = ld_row2(r + 4);
+    const double2 a2 = ld_row2(r + 6), b2 = ld_row2(r + 8), c2 = ld_row2(r + 10);
+    const double E1 = a1.x, E2 = a2.x;
+    const double f1 = (E - E2) / (E1 - E2);
+    const double f2 = (E - E1) / (E2 - E1);
+    m.s = f1 * a1.y + f2 * a2.y;
+    m.c = f1 * b1.x + f2 * b2.x;
+    m.f = f1 * b1.y + f2 * b2.y;
+    m.nu = f1 * c1.x + f2 * c2.x;
+    m.t = f1 * (a1.y + b1.x + b1.y) + f2 * (a2.y + b2.x + b2.y);
+}
+// one derived column: 0 sigma_a (= sigma_c + sigma_f per grid point), 1 beta
+__device__ __forceinline__ double micro_col(const DevNuclide& N, int idx, double E, int col)
+{
+    if (idx < 0 || idx >= N.n_rows - 1) {
+        const double* r = N.rows + (size_t)(idx < 0 ? 0 : N.n_rows - 1) * MCB_XS_ROW;
+        return col == 0 ? r[2] + r[3] : r[5];
+    }
+    const double* r1 = N.rows + (size_t)idx * MCB_XS_ROW;
+    const double* r2 = r1 + MCB_XS_ROW;
+    const double y1 = col == 0 ? r1[2] + r1[3] : r1[5];
+    const double y2 = col == 0 ? r2[2] + r2[3] : r2[5];
+    return mcb_interpolate(E, r1[0], r2[0], y1, y2);
+}
+
+__device__ __forceinline__ int union_index(const DevMaterial& M, double E)
+{
+    return mcb_union_count_less(M.U, M.hash, M.key_min, M.n_hash, M.shift, M.nU, E) - 1;
+}
+__device__ __forceinline__ int nuclide_index(const DevMaterial& M, int u, int n)
+{
+    return u < 0 ? -1 : __ldg(&M.map[(size_t)u * M.n_nuc + n]);
+}
+
+struct MacroXS { double t, s, c, f, nf; };
+
+// Material::SigmaT/S/C/F, nuSigmaF (Material.cpp:18-65): sums over nuclides in deck order, starting from 0.0
+__device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X)
+{
+    X.t = 0.0; X.s = 0.0; X.c = 0.0; X.f = 0.0; X.nf = 0.0;
+    for (int n = 0; n < M.n_nuc; n++) {
+        const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
+        const double dens = __ldg(&P.mat_density[M.nuc_begin + n]);
+        MicroXS m;
+        micro_xs(P.nuclides[gn], nuclide_index(M, u, n), E, m);
+        X.t += m.t * dens;
+        X.s += m.s * dens;
+        X.c += m.c * dens;
+        X.f += m.f * dens;
+        X.nf += (m.f * m.nu) * dens;   // Nuclide::nusigmaF = sigmaF*nu (Nuclide.cpp:57-61)
+    }
+}
+// Material::SigmaA (Material.cpp:34-41)
+__device__ __forceinline__ double macro_sigma_a(const DevProblem& P, const DevMaterial& M, int u, double E)
+{
+    double sum = 0.0;
+    for (int n = 0; n < M.n_nuc; n++) {
+        const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
+        sum += micro_col(P.nuclides[gn], nuclide_index(M, u, n), E, 0) * __ldg(&P.mat_density[M.nuc_begin + n]);
+    }
+    return sum;
+}
+// Material::nuclide_scatter (kind 0) / nuclide_nufission (kind 1) (Material.cpp:106-125): global nuclide index or -1.
+// `total` is the macroscopic xs the partial sums are compared against (SigmaS or nuSigmaF at the same E).
+__device__ __forceinline__ int select_nuclide(const DevProblem& P, const DevMaterial& M, int u, double E, int kind,
+                                              double total, double xi, int* local_n)
+{
+    const double thr = total * xi;
+    double s = 0.0;
+    for (int n = 0; n < M.n_nuc; n++) {
+        const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
+        MicroXS m;
+        micro_xs(P.nuclides[gn], nuclide_index(M, u, n), E, m);
+        s += (kind == 0 ? m.s : m.f * m.nu) * __ldg(&P.mat_density[M.nuc_begin + n]);
+        if (s > thr) { if (local_n) *local_n = n; return gn; }
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// distributions / reactions
+// ---------------------------------------------------------------------------------------------
+// DistributionWatt::sample (Distribution.cpp:34-73); returns eV
+__device__ __forceinline__ double watt_sample(const double* va, const double* vb, const double* vg, double E,
+                                              uint64_t& rng)
+{
+    double a, b, g;
+    if (E <= 1.0) { a = va[0]; b = vb[0]; g = vg[0]; }
+    else if (E <= 1.0e6) {
+        a = mcb_interpolate(E, 1.0, 1.0e6, va[0], va[1]);
+        b = mcb_interpolate(E, 1.0, 1.0e6, vb[0], vb[1]);
+        g = mcb_interpolate(E, 1.0, 1.0e6, vg[0], vg[1]);
+    } else {
+        a = mcb_interpolate(E, 1.0e6, 14.0e6, va[1], va[2]);
+        b = mcb_interpolate(E, 1.0e6, 14.0e6, vb[1], vb[2]);
+        g = mcb_interpolate(E, 1.0e6, 14.0e6, vg[1], vg[2]);
+    }
+    double Eout, C;
+    do {
+        const double lx = log(mcb_urand(rng));
+        Eout = -a * g * lx;
+        const double l2 = log(mcb_urand(rng));
+        C = (1.0 - g) * (1.0 - lx) - l2;
+    } while (C * C > b * Eout);
+    return Eout * 1.0e6;
+}
+// DistributionIsotropicDirection::sample (Distribution.cpp:78-92): x is the polar axis
+__device__ __forceinline__ void isotropic_direction(uint64_t& rng, double& dx, double& dy, double& dz)
+{
+    const double mu = 2.0 * mcb_urand(rng) - 1.0;
+    const double azi = MCB_PI_2 * mcb_urand(rng);
+    const double c = sqrt(1.0 - mu * mu);
+    double sa, ca;
+    sincos(azi, &sa, &ca);
+    dy = ca * c;
+    dz = sa * c;
+    dx = mu;
+}
+// Delta / Uniform (Distribution.cpp:30-33) / Watt at incident energy 0
+__device__ __forceinline__ double dist1_sample(const mcb_dist1& d, uint64_t& rng)
+{
+    switch (d.kind) {
+    case MCB_DIST_DELTA: return d.a;
+    case MCB_DIST_UNIFORM: return d.a + mcb_urand(rng) * (d.b - d.a);
+    default: return watt_sample(d.watt_a, d.watt_b, d.watt_g, 0.0, rng);
+    }
+}
+
+// ReactionScatter::sample (Reaction.cpp:27-118): elastic scatter off a free-gas target at 293.6 K, isotropic in
+// the centre of mass.  In/out: direction, energy and speed of the neutron.
+__device__ __forceinline__ void scatter_sample(double A, double& dx, double& dy, double& dz, double& E, double& speed,
+                                               uint64_t& rng)
+{
+    const double mu0 = 2.0 * mcb_urand(rng) - 1.0;  // DistributionIsotropicScatter (Distribution.cpp:74-77)
+    const double beta = sqrt(2.0659834e-11 * A);
+    const double y = beta * speed;
+    double V_tilda, mu_tilda, accept;
+    do {
+        double x;
+        if (mcb_urand(rng) < 2.0 / (2.0 + MCB_PI_SQRT * y)) {
+            const double r1 = mcb_urand(rng), r2 = mcb_urand(rng);
+            x = sqrt(-log(r1 * r2));
+        } else {
+            const double cos_val = cos(MCB_PI_HALF * mcb_urand(rng));
+            const double l1 = log(mcb_urand(rng));
+            const double l2 = log(mcb_urand(rng));
+            x = sqrt(-l1 - l2 * cos_val * cos_val);
+        }
+        V_tilda = x / beta;
+        mu_tilda = 2.0 * mcb_urand(rng) - 1.0;
+        accept = mcb_urand(rng);
+    } while (accept > sqrt(speed * speed + V_tilda * V_tilda - 2.0 * speed * V_tilda * mu_tilda) / (speed + V_tilda));
+    double nx, ny, nz;
+    mcb_scatter_direction(dx, dy, dz, mu_tilda, mcb_urand(rng), nx, ny, nz);
+    const double Vx = nx * V_tilda, Vy = ny * V_tilda, Vz = nz * V_tilda;
+    double vx = speed * dx, vy = speed * dy, vz = speed * dz;
+    const double ux = (vx + A * Vx) / (1.0 + A);
+    const double uy = (vy + A * Vy) / (1.0 + A);
+    const double uz = (vz + A * Vz) / (1.0 + A);
+    double cx = vx - ux, cy = vy - uy, cz = vz - uz;
+    const double speed_c = sqrt(cx * cx + cy * cy + cz * cz);
+    const double dcx = cx / speed_c, dcy = cy / speed_c, dcz = cz / speed_c;
+    double ex, ey, ez;
+    mcb_scatter_direction(dcx, dcy, dcz, mu0, mcb_urand(rng), ex, ey, ez);
+    cx = speed_c * ex; cy = speed_c * ey; cz = speed_c * ez;
+    vx = cx + ux; vy = cy + uy; vz = cz + uz;
+    speed = sqrt(vx * vx + vy * vy + vz * vz);  // Particle::set_speed (Particle.cpp:49-56)
+    E = mcb_energy_of_speed(speed);
+    dx = vx / speed; dy = vy / speed; dz = vz / speed;
+}
+
+// surface_intersect (general.cpp:54-67): nearest surface of the cell along the flight direction
+__device__ __forceinline__ int surface_intersect(const DevProblem& P, int cell, double x, double y, double z,
+                                                 double u, double v, double w, double& dist_out)
+{
+    const mcb_cell C = P.cells[cell];
+    double dist = MCB_MAX_FLOAT;
+    int S = -1;
+    for (int i = C.surf_begin; i < C.surf_end; i++) {
+        const int s = __ldg(&P.cell_surface[i]);
+        const double d = mcb_surf_distance(P.surfaces[s], x, y, z, u, v, w);
+        if (d < dist) { dist = d; S = s; }
+    }
+    dist_out = dist;
+    return S;
+}
+
+#endif

@@ -1,0 +1,47 @@
+// mcb_kernels.h — host-callable launchers of the kernels in mcb_kernels.cu (all asynchronous on `st`).
+#ifndef MCB_KERNELS_H
+#define MCB_KERNELS_H
+
+#include "mcb_device.cuh"
+
+namespace mcbk {
+
+// stages of one generation
+void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
+            uint64_t nps0, const Site* sbank, uint64_t n_sbank);
+void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, uint32_t n, Counters* C);
+void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, uint32_t n, uint32_t* evq,
+            Counters* C, const HistoryAcc& H, const TallyAcc& T);
+void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, uint32_t n_upper, Counters* C,
+             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+             uint64_t site_cap, uint32_t n_slots, double k_eff);
+void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, uint32_t n_active,
+           uint32_t n_upper, Counters* C, uint32_t* next, const TallyAcc& T, uint32_t n_slots);
+
+// generation close-out
+void bank_order(cudaStream_t st, const Site* tmp, const int32_t* tmp_hist, uint64_t n, const uint32_t* offset, Site* out);
+size_t scan_temp_bytes(uint32_t n);
+void scan_sites(cudaStream_t st, void* temp, size_t temp_bytes, const int32_t* nsite, uint32_t* offset, uint32_t n);
+void reduce_k(cudaStream_t st, const double* kC, const double* kTL, uint32_t n, Counters* C);
+void entropy_history(cudaStream_t st, const DevProblem& P, const Site* bank, const uint32_t* offset,
+                     const int32_t* nsite, uint32_t n_hist, Counters* C);
+void entropy_histogram(cudaStream_t st, const DevProblem& P, const Site* bank, uint64_t n, unsigned long long* bins);
+int tally_chunks(uint32_t n_hist);
+void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist, int64_t n_tallies, double* partial,
+                  double* sum, double* squared);
+void iota(cudaStream_t st, uint32_t* a, uint32_t n);
+
+// parity / bench kernels on plain device arrays
+void xs_lookup(cudaStream_t st, const DevProblem& P, int material, const double* E, int64_t n, double* out5);
+void select_channel(cudaStream_t st, const DevProblem& P, int material, int kind, const double* E, const double* xi,
+                    int64_t n, int32_t* out);
+void beta(cudaStream_t st, const DevProblem& P, int material, int local_n, const double* E, int64_t n, double* out);
+void rng(cudaStream_t st, uint64_t seed0, const uint64_t* nps, int64_t n, int ndraw, uint64_t* out);
+void geometry(cudaStream_t st, const DevProblem& P, const int32_t* cell, const double* pos, const double* dir,
+              int64_t n, double* out3);
+void search_cell(cudaStream_t st, const DevProblem& P, const double* pos, int64_t n, int32_t* out);
+void scatter(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, int64_t n, double* io5);
+void watt(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, const double* E, int64_t n, double* out);
+
+}  // namespace mcbk
+#endif

@@ -1,0 +1,62 @@
+#include "mcb_tables.h"
+
+#include <algorithm>
+
+namespace mcb {
+
+static int64_t key_of(double E, int shift)
+{
+    int64_t bits;
+    memcpy(&bits, &E, sizeof(bits));
+    return bits >> shift;
+}
+
+void build_material_tables(const mcb_problem* p, int material, int max_mant_bits, MaterialTables& T)
+{
+    const int nb = p->mat_begin[material], ne = p->mat_begin[material + 1];
+    T = MaterialTables();
+    T.n_nuc = ne - nb;
+    // union of the nuclide grids (column 0 of the xs rows)
+    for (int i = nb; i < ne; i++) {
+        const mcb_nuclide& N = p->nuclides[p->mat_nuclide[i]];
+        const double* rows = p->xs_rows + (size_t)N.row_begin * MCB_XS_ROW;
+        for (int r = 0; r < N.n_rows; r++) T.U.push_back(rows[(size_t)r * MCB_XS_ROW]);
+    }
+    std::sort(T.U.begin(), T.U.end());
+    T.U.erase(std::unique(T.U.begin(), T.U.end()), T.U.end());
+    const int nU = (int)T.U.size();
+    // map[u][n] = #{n_E <= U[u]} - 1 : one merge pass per nuclide
+    T.map.assign((size_t)nU * T.n_nuc, -1);
+    for (int i = nb; i < ne; i++) {
+        const mcb_nuclide& N = p->nuclides[p->mat_nuclide[i]];
+        const double* rows = p->xs_rows + (size_t)N.row_begin * MCB_XS_ROW;
+        int r = 0;
+        for (int u = 0; u < nU; u++) {
+            while (r < N.n_rows && rows[(size_t)r * MCB_XS_ROW] <= T.U[u]) r++;
+            T.map[(size_t)u * T.n_nuc + (i - nb)] = r - 1;
+        }
+    }
+    if (nU == 0) { T.hash.assign(1, 0); return; }
+    // hash on the bit pattern; keep the table at most ~4 entries per grid point
+    const int64_t cap = std::max<int64_t>(4 * (int64_t)nU + 1024, 4096);
+    int bits = std::min(std::max(max_mant_bits, 0), 20);
+    for (;; bits--) {
+        T.shift = 52 - bits;
+        T.key_min = key_of(T.U.front(), T.shift);
+        const int64_t n = key_of(T.U.back(), T.shift) - T.key_min + 1;
+        if (n <= cap || bits == 0) { T.n_hash = (int32_t)std::min<int64_t>(n, INT32_MAX - 2); break; }
+    }
+    // hash[b] = #{U < lower edge of bin b} = #{U with key < b}; keys are monotone in U (all U >= 0 here; a
+    // negative energy would sort before by key as well because the shift is arithmetic)
+    T.hash.assign((size_t)T.n_hash + 1, 0);
+    {
+        int u = 0;
+        for (int64_t b = 0; b <= T.n_hash; b++) {
+            while (u < nU && key_of(T.U[u], T.shift) - T.key_min < b) u++;
+            T.hash[(size_t)b] = u;
+        }
+    }
+    for (int64_t b = 0; b < T.n_hash; b++) T.max_bin = std::max(T.max_bin, T.hash[b + 1] - T.hash[b]);
+}
+
+}  // namespace mcb

@@ -1,0 +1,68 @@
+// mcb_tables.h — per-material unionized energy grid with a hashed bin index.
+//
+// Replaces the per-nuclide binary search of the reference (Nuclide::checkE ->
+// binary_search, src/Nuclide.cpp:18-24, src/Algorithm.cpp:46-64) by ONE search per
+// (particle, energy) on the union of the material's nuclide grids:
+//
+//   u      = #{U < E} - 1                        (strict <, like Algorithm.cpp:46-64)
+//   idx_n  = map[u*Nn + n] = #{n_E <= U[u]} - 1   (idx_n = -1 when u = -1)
+//
+// which equals the reference's idx_n = #{n_E < E} - 1 for every E, duplicates in n_E
+// included.  The search range is narrowed by a hash on the bit
+// pattern of E: key = (bits(E) >> shift) - key_min is an exactly monotone
+// piecewise-linear stand-in for lethargy (no libm, no rounding), and
+// hash[key] = #{U < lower edge of bin key}.
+#ifndef MCB_TABLES_H
+#define MCB_TABLES_H
+
+#include <stdint.h>
+#include <string.h>
+
+#include "mcb200.h"
+
+#if defined(__CUDACC__)
+#define MCB_THD __host__ __device__ __forceinline__
+#else
+#define MCB_THD inline
+#endif
+
+// #{U < E} restricted by the hash; works on host and device
+MCB_THD int mcb_union_count_less(const double* U, const int32_t* hash, int64_t key_min, int32_t n_hash, int32_t shift,
+                                 int32_t nU, double E)
+{
+    int64_t bits;
+#if defined(__CUDA_ARCH__)
+    bits = __double_as_longlong(E);
+#else
+    memcpy(&bits, &E, sizeof(bits));
+#endif
+    const int64_t key = (bits >> shift) - key_min;  // arithmetic shift: negative E -> negative key
+    if (key < 0) return 0;
+    if (key >= n_hash) return nU;
+    int lo = hash[key], hi = hash[key + 1];
+    while (lo < hi) {  // lower_bound: first element not < E
+        const int mid = (lo + hi) >> 1;
+        if (U[mid] < E) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+#ifdef __cplusplus
+#include <vector>
+namespace mcb {
+
+struct MaterialTables {
+    std::vector<double> U;       // distinct energies of all nuclides of the material, ascending
+    std::vector<int32_t> map;    // nU x n_nuc
+    std::vector<int32_t> hash;   // n_hash + 1
+    int64_t key_min = 0;
+    int32_t n_hash = 0, shift = 0, n_nuc = 0;
+    int32_t max_bin = 0;         // largest number of grid points in one hash bin (search depth statistics)
+};
+
+// max_mant_bits: mantissa bits kept in the key at most (bins per octave = 2^bits)
+void build_material_tables(const mcb_problem* p, int material, int max_mant_bits, MaterialTables& out);
+
+}  // namespace mcb
+#endif
+#endif
