@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py — histories/s of the B200 transport loop on the HEU-sphere k-eigenvalue problem.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU implementation, rank 0 only
+
+Workload (BASELINE.json north_star target): examples/HEU_sphere_criticality physics (bare HEU sphere r = 7.68 cm,
+U-235 + U-238, k-eigenvalue power iteration), scaled to --samples histories per generation PER GPU (weak scaling;
+default 1e7, i.e. 8e7 ~ the 1e8 target at 8 GPUs).  A "step" is one generation: source resampling from the fission
+bank, the event loop until every history is finished, fission-bank ordering, k close-out and, for N > 1, the NCCL
+all-reduce of the k sums and the all-gather of the fission bank.
+
+`value`  histories/s with the source bank resident in HBM (device time, CUDA events on the launch stream, max over
+         ranks).
+`e2e`    the same step driven through the C-ABI with HOST buffers: every step uploads the global source bank from
+         pinned host memory (mcb_set_source_bank), runs the generation, and reads the new global bank back
+         (mcb_get_source_bank).
+`roofline`  the dominant stage kernel of the timed loop: algorithmic bytes per launch / mean launch time (CUDA events
+         per launch in a separate pass, stage timing costs a few percent so it is off in the timed region).
+`cpu_baseline`  the compiled reference (oracle/_ref/MC_ref, single-threaded by construction) on the same deck at a
+         bounded history count, timed per generation from its own stdout on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "HEU_sphere_criticality"
+# algorithmic bytes per unit of each stage kernel; Nn = nuclides of the material (HEU: 2)
+BYTES_LOOKUP = lambda nn: 72 + 100 * nn   # E + mat 12, hash 4, bracket 16, Nn x (idx 4 + 2 rows x 48), 5 Sigma out 40
+BYTES_FLIGHT = 180                        # queue 4 + state in 112 + state out 44 + k_TL rmw 16 + event queue 4
+BYTES_COLLIDE = lambda nn: 220 + 2 * 96 * nn + 27  # state in 144 + out 76 + 2 selections x Nn x 2 rows + 0.35 sites x 76
+BYTES_CROSS = 140
+# fused step kernel: the whole-loop figure of SURVEY §8d per track = particle record in + out (224) + one xs lookup
+# (72 + 100 Nn) + 76-byte fission sites (one per ~3.8 tracks in HEU)
+BYTES_STEP = lambda nn: 224 + 72 + 100 * nn + 20
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference on the host CPU (test infrastructure under oracle/ is executed here, and only here)
+# ---------------------------------------------------------------------------------------------
+def run_reference_cpu(samples, warmup, steps):
+    """Runs oracle/_ref/MC_ref on the HEU deck; returns (histories/s over `steps` generations, cores, sample text).
+    Generation boundaries are timestamped from the reference's own per-cycle stdout lines (through a pty, so the
+    lines arrive unbuffered)."""
+    import pty
+    from mc_old_b200 import decks
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    exe = os.path.join(ref_dir, "MC_ref")
+    if not os.path.exists(exe):
+        return None
+    d = tempfile.mkdtemp(prefix="mcb_ref_")
+    decks.write(d, decks.heu_sphere(samples=samples, active=steps, passive=warmup))
+    master, slave = pty.openpty()
+    p = subprocess.Popen([exe, d], cwd=ref_dir, stdout=slave, stderr=subprocess.STDOUT, close_fds=True)
+    os.close(slave)
+    stamps, buf = [], b""
+    t_start = time.perf_counter()
+    while True:
+        try:
+            chunk = os.read(master, 4096)
+        except OSError:
+            break
+        if not chunk:
+            break
+        now = time.perf_counter()
+        buf += chunk
+        while b"\n" in buf:
+            line, buf = buf.split(b"\n", 1)
+            parts = line.strip().split()
+            if len(parts) >= 2 and parts[0].isdigit():
+                stamps.append(now)
+            elif b"running the simulation" in line:
+                t_start = now
+    p.wait()
+    os.close(master)
+    if p.returncode != 0 or len(stamps) < warmup + steps:
+        return None
+    t0 = stamps[warmup - 1] if warmup > 0 else t_start
+    dt = stamps[warmup + steps - 1] - t0
+    return steps * samples / dt, 1, ("MC_ref (g++ -O3, 1 thread: the reference is single-threaded and not re-entrant), "
+                                     "%d generations x %d histories after %d warm-up generations" % (steps, samples, warmup)), dt / steps
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    samples = args.ref_samples
+    r = run_reference_cpu(samples, args.warmup, args.steps)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/MC_ref is not built (run __graft_entry__.build() where /root/reference exists)"}))
+        return 0
+    value, cores, sample, s_per_step = r
+    line = {
+        "impl": "reference", "metric": "histories_per_second", "value": value, "unit": "histories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "histories_per_generation": samples, "note": "bounded sample of the same deck"},
+        "cpu_baseline": {"value": value, "unit": "histories/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = tempfile.mktemp(prefix="mcb_clocks_", suffix=".csv")
+        self.f = open(self.path, "w")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=float, default=1e7, help="histories per generation per GPU")
+    ap.add_argument("--ref-samples", type=float, default=2e5, help="histories per generation of the CPU reference runs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.ref_samples = int(args.ref_samples)
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mc_old_b200 as mcb
+    from mc_old_b200 import decks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()  # creates torch's NCCL communicator, so libnccl is loaded before ours binds it
+    per_gpu = int(args.samples)
+    n_sample = per_gpu * world
+    total_cycles = args.warmup + 3 * args.steps + 8
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n_sample, active=total_cycles, passive=args.warmup))
+    stream = torch.cuda.current_stream()
+    ctx = mcb.Context(deck, device=local_rank, rank=rank, world=world, stream=stream.cuda_stream)
+    if world > 1:
+        uid = [mcb.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        ctx.run_cycle()
+
+    # ---- timed region: K generations, device time on the launch stream ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = []
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        res.append(ctx.run_cycle())
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    hist = sum(r.n_histories for r in res)          # global counts (all-reduced inside the library)
+    coll = sum(r.n_collisions for r in res)
+    tracks = sum(r.n_tracks for r in res)
+    lookups = sum(r.n_lookups for r in res)
+    launches = sum(r.n_kernel_launches for r in res)
+    value = hist / (ms * 1e-3)
+
+    # ---- e2e: the same step with the source bank crossing the host boundary both ways ----
+    e2e = None
+    if not args.no_e2e:
+        cap = 4 * n_sample + 4096 * world
+        sites = torch.empty((cap, 8), dtype=torch.float64, pin_memory=True).numpy()
+        cells = torch.empty((cap,), dtype=torch.int32, pin_memory=True).numpy()
+        s, c = ctx.source_bank(cap, sites, cells)
+        n_bank = s.shape[0]
+        h2d = d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.set_source_bank(sites[:n_bank], cells[:n_bank])
+            h2d += n_bank * 68
+            r = ctx.run_cycle()
+            s, c = ctx.source_bank(cap, sites, cells)
+            n_bank = s.shape[0]
+            d2h += n_bank * 68 + 176
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": args.steps * n_sample / dt, "unit": "histories/s", "h2d_bytes_per_step": h2d // args.steps,
+               "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * dt / args.steps,
+               "what": "per step and per rank: mcb_set_source_bank (pinned host -> HBM) + mcb_run_cycle + mcb_get_source_bank (HBM -> pinned host)"}
+
+    # ---- per-stage pass: CUDA events around every stage launch (rank-local), for the roofline of the dominant kernel ----
+    ctx.reset_stage_times()
+    ctx.set_stage_timing(True)
+    for _ in range(2):
+        ctx.run_cycle()
+    ctx.set_stage_timing(False)
+    st = ctx.stage_times()
+    nn = 2
+    stage_bytes = {"lookup": st["units_lookup"] * BYTES_LOOKUP(nn)}
+    # units of the other stages on this rank over the two profiled generations (rank-local shares of the global counts)
+    frac = 1.0 / world
+    stages = {k: {"ms": st["ms_" + k], "launches": st["n_" + k]} for k in ("source", "lookup", "flight", "cross", "collide", "step", "finish", "closeout", "bank")}
+    dominant = max(("lookup", "flight", "collide", "cross", "step"), key=lambda k: stages[k]["ms"])
+    peak, peak_kind = peaks()
+    roofline = None
+    if stages[dominant]["ms"] > 0:
+        # unit counts of the profiled generations: scale the timed-region averages per generation
+        per_gen = {"lookup": st["units_lookup"] / 2.0, "flight": tracks / args.steps * frac, "collide": coll / args.steps * frac,
+                   "cross": (tracks - coll) / args.steps * frac, "step": tracks / args.steps * frac}
+        per_unit = {"lookup": BYTES_LOOKUP(nn), "flight": BYTES_FLIGHT, "collide": BYTES_COLLIDE(nn), "cross": BYTES_CROSS,
+                    "step": BYTES_STEP(nn)}
+        total_bytes = 2.0 * per_gen[dominant] * per_unit[dominant]
+        achieved = total_bytes / (stages[dominant]["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else dominant), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
+                    "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "bytes_per_unit": per_unit[dominant], "units_per_launch": 2.0 * per_gen[dominant] / max(stages[dominant]["launches"], 1),
+                    "avg_launch_ms": stages[dominant]["ms"] / max(stages[dominant]["launches"], 1),
+                    "note": "units of the tail kernel (k_finish) are counted with the dominant kernel's: its time is listed under stages"}
+    ctx.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = run_reference_cpu(args.ref_samples, 1, 4)
+        if r is not None:
+            cpu = {"value": r[0], "unit": "histories/s", "cores": r[1], "kind": "reference", "sample": r[2]}
+
+    if rank == 0:
+        line = {
+            "metric": "histories_per_second", "value": value, "unit": "histories/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "histories_per_generation": n_sample, "histories_per_gpu": per_gpu,
+                       "parallelism": "histories sharded over %d GPU(s); NCCL all-reduce of k sums + all-gather of the fission bank per generation" % world,
+                       "l2": "inputs larger than L2 (particle bank %.1f GB per GPU streams through HBM every stage)" % (per_gpu * 188 / 1e9)},
+            "collisions_per_second": coll / (ms * 1e-3), "tracks_per_second": tracks / (ms * 1e-3),
+            "xs_lookups_per_second": lookups / (ms * 1e-3),
+            "k_cycle_last": res[-1].k_cycle, "event_loop_iterations_per_step": sum(r.n_iterations for r in res) / args.steps,
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "stages_ms_2_generations": stages,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

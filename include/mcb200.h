@@ -169,7 +169,7 @@ typedef struct mcb_ctx mcb_ctx;
 typedef struct mcb_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t rank, world;       /* history sharding: this process owns histories [n*rank/world, n*(rank+1)/world) */
-    int32_t reserved;
+    int32_t reserved;          /* flags: 1 = time every stage launch with CUDA events; 2 = one kernel per event type */
     int64_t bank_capacity;     /* particle slots in flight on this GPU (0 = choose) */
     int64_t site_capacity;     /* fission sites this GPU can bank per cycle (0 = choose) */
     void* stream;              /* cudaStream_t to launch on (NULL = library-owned stream) */
@@ -186,12 +186,17 @@ typedef struct mcb_cycle_result {
     double ms_transport, ms_exchange; /* device time of the transport loop / the bank exchange+reductions */
     int32_t n_iterations;      /* event-loop iterations */
     int32_t lost;              /* particles lost on this rank */
+    uint64_t n_kernel_launches;/* kernels this library launched on this rank during the cycle */
 } mcb_cycle_result;
 
 typedef struct mcb_stage_times { /* accumulated CUDA-event time per kernel class since mcb_reset_stage_times */
     double ms_source, ms_lookup, ms_flight, ms_cross, ms_collide, ms_closeout, ms_bank;
     uint64_t n_source, n_lookup, n_flight, n_cross, n_collide, n_closeout, n_bank; /* launches */
     uint64_t units_lookup;     /* particles looked up (for the xs roofline) */
+    double ms_finish;          /* tail kernel: the last few particles of a batch followed to the end in registers */
+    uint64_t n_finish;
+    double ms_step;            /* fused step kernel: several events per particle and launch */
+    uint64_t n_step;
 } mcb_stage_times;
 
 /* lifecycle; replaces the object graph hand-over setup.cpp -> start() */
@@ -212,9 +217,13 @@ double mcb_get_k(const mcb_ctx* ctx);
 void mcb_set_k(mcb_ctx* ctx, double k);
 int mcb_get_stage_times(mcb_ctx* ctx, mcb_stage_times* out);
 void mcb_reset_stage_times(mcb_ctx* ctx);
+/* per-launch CUDA-event timing of the stage kernels on/off (off by default: the events cost a few percent) */
+void mcb_set_stage_timing(mcb_ctx* ctx, int on);
 /* fission bank of the last cycle on this rank, canonical order: out = n x 8 doubles (x,y,z,u,v,w,E,t), cells = n */
 int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n);
 
+/* the global source bank the next cycle will sample (after the all-gather), same layout; identical on every rank */
+int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n);
 /* source bank of the next cycle from HOST memory (n x 8 doubles x,y,z,u,v,w,E,t + n cells), replacing the bank the
  * last cycle produced: the host-buffer form of `Sbank = Fbank` (handler.cpp:16).  With world > 1 every rank passes
  * the same global bank. */

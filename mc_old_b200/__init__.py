@@ -22,7 +22,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 HOST_LIB = os.path.join(_HERE, "libmcbhost.so")
-CUDA_LIB = os.path.join(_HERE, "libmcb200.so")
+CUDA_LIB = os.environ.get("MCB200_LIB") or os.path.join(_HERE, "libmcb200.so")
 
 IGNORE_TRMM = 1
 
@@ -44,7 +44,7 @@ class CycleResult(C.Structure):
                 ("n_sites", C.c_uint64), ("n_histories", C.c_uint64), ("n_tracks", C.c_uint64),
                 ("n_collisions", C.c_uint64), ("n_lookups", C.c_uint64), ("n_crossings", C.c_uint64),
                 ("ms_transport", C.c_double), ("ms_exchange", C.c_double),
-                ("n_iterations", C.c_int32), ("lost", C.c_int32)]
+                ("n_iterations", C.c_int32), ("lost", C.c_int32), ("n_kernel_launches", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -54,7 +54,8 @@ class StageTimes(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_source", "ms_lookup", "ms_flight", "ms_cross", "ms_collide",
                                           "ms_closeout", "ms_bank")] + \
                [(n, C.c_uint64) for n in ("n_source", "n_lookup", "n_flight", "n_cross", "n_collide", "n_closeout",
-                                          "n_bank", "units_lookup")]
+                                          "n_bank", "units_lookup")] + \
+               [("ms_finish", C.c_double), ("n_finish", C.c_uint64), ("ms_step", C.c_double), ("n_step", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -115,9 +116,12 @@ def cuda_lib():
         L.mcb_set_k.argtypes = [vp, C.c_double]
         L.mcb_get_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
         L.mcb_reset_stage_times.argtypes = [vp]
+        L.mcb_set_stage_timing.argtypes = [vp, C.c_int]
         L.mcb_get_fission_bank.restype = i64
         L.mcb_get_fission_bank.argtypes = [vp, vp, vp, i64]
         L.mcb_set_source_bank.argtypes = [vp, vp, vp, i64]
+        L.mcb_get_source_bank.restype = i64
+        L.mcb_get_source_bank.argtypes = [vp, vp, vp, i64]
         L.mcb_get_history_k.restype = i64
         L.mcb_get_history_k.argtypes = [vp, vp, vp, i64]
         L.mcb_beta_batch.argtypes = [vp, i32, i32, vp, i64, vp]
@@ -201,10 +205,10 @@ class Context:
     """Device context of one rank (mcb_ctx): owns tables, banks and tallies on one GPU."""
 
     def __init__(self, deck: Deck, device: int = 0, rank: int = 0, world: int = 1, bank_capacity: int = 0,
-                 site_capacity: int = 0, stream: int = 0, stage_times: bool = False):
+                 site_capacity: int = 0, stream: int = 0, stage_times: bool = False, split_stages: bool = False):
         L = cuda_lib()
         self.deck = deck
-        cfg = Config(device, rank, world, 1 if stage_times else 0, bank_capacity, site_capacity, stream or None)
+        cfg = Config(device, rank, world, (1 if stage_times else 0) | (2 if split_stages else 0), bank_capacity, site_capacity, stream or None)
         h = C.c_void_p()
         rc = L.mcb_create(deck.problem, C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -263,12 +267,24 @@ class Context:
         self._check(cuda_lib().mcb_get_stage_times(self._h, C.byref(s)))
         return s.as_dict()
 
+    def set_stage_timing(self, on: bool):
+        cuda_lib().mcb_set_stage_timing(self._h, 1 if on else 0)
+
     def reset_stage_times(self):
         cuda_lib().mcb_reset_stage_times(self._h)
 
     def fission_bank(self, max_n: int):
         sites = np.zeros((max(max_n, 1), 8)); cells = np.zeros(max(max_n, 1), dtype=np.int32)
         n = cuda_lib().mcb_get_fission_bank(self._h, _ptr(sites), _ptr(cells), max_n)
+        if n < 0:
+            self._check(int(n))
+        return sites[:n], cells[:n]
+
+    def source_bank(self, max_n: int, sites: Optional[np.ndarray] = None, cells: Optional[np.ndarray] = None):
+        """Global source bank of the next cycle; pass preallocated (pinned) arrays to avoid allocations."""
+        if sites is None:
+            sites = np.zeros((max(max_n, 1), 8)); cells = np.zeros(max(max_n, 1), dtype=np.int32)
+        n = cuda_lib().mcb_get_source_bank(self._h, _ptr(sites), _ptr(cells), max_n)
         if n < 0:
             self._check(int(n))
         return sites[:n], cells[:n]

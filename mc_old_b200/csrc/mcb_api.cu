@@ -110,7 +110,8 @@ struct StageTimer {  // CUDA-event pairs per kernel class; resolved at the end o
     }
     ~StageTimer() { for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }
 };
-enum { ST_SOURCE = 0, ST_LOOKUP, ST_FLIGHT, ST_CROSS, ST_COLLIDE, ST_CLOSEOUT, ST_BANK, ST_N };
+enum { ST_SOURCE = 0, ST_LOOKUP, ST_FLIGHT, ST_CROSS, ST_COLLIDE, ST_CLOSEOUT, ST_BANK, ST_FINISH, ST_STEP, ST_N };
+constexpr int MCB_RING = 8;  // iterations the host may run ahead of the queue lengths it has seen
 
 }  // namespace
 
@@ -149,6 +150,11 @@ struct mcb_ctx {
     uint32_t *q_active = nullptr, *q_next = nullptr, *q_ev = nullptr;
     DevBuf<Counters> d_counters;
     Counters* h_counters = nullptr;  // pinned
+    unsigned long long* h_ring = nullptr;  // pinned: queue lengths of the last MCB_RING iterations
+    cudaEvent_t ev_ring[MCB_RING] = {};
+    uint64_t finish_below = 0;       // queue length under which the tail kernel takes over
+    bool split_stages = false;       // one kernel per event type (profiling mode) instead of the fused step kernel
+    int step_events = 2;             // events chained per particle and launch by the fused step kernel
     // per-history accumulators
     DevBuf<double> d_hist_k;         // kC, kTL
     DevBuf<int32_t> d_nsite;
@@ -159,6 +165,8 @@ struct mcb_ctx {
     uint64_t site_cap = 0, global_cap = 0;
     DevBuf<Site> d_tmp_sites, d_local_bank, d_global_bank;
     DevBuf<int32_t> d_tmp_hist;
+    DevBuf<double> d_io_sites;       // staging for host-facing bank I/O (n x 8 doubles)
+    DevBuf<int32_t> d_io_cells;
     uint64_t n_local_sites = 0, n_source_sites = 0;  // local bank of the last cycle; global source bank for the next
     bool source_is_bank = false;
     // tallies
@@ -385,6 +393,11 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     CK(ctx->d_counters.alloc(1));
     CK(cudaMemset(ctx->d_counters.p, 0, sizeof(Counters)));
     CK(cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)));
+    CK(cudaMallocHost((void**)&ctx->h_ring, MCB_RING * sizeof(unsigned long long)));
+    for (int i = 0; i < MCB_RING; i++) CK(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
+    ctx->finish_below = getenv("MCB_FINISH_BELOW") ? strtoull(getenv("MCB_FINISH_BELOW"), nullptr, 10) : 148ull * 256ull;
+    ctx->split_stages = (cfg && (cfg->reserved & 2)) || (getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "split"));
+    if (getenv("MCB_STEP_EVENTS")) ctx->step_events = std::max(1, atoi(getenv("MCB_STEP_EVENTS")));
     const size_t nh = std::max<uint64_t>(ctx->shard_count, 1);
     CK(ctx->d_hist_k.alloc(2 * nh));
     CK(ctx->d_nsite.alloc(nh));
@@ -460,6 +473,8 @@ void mcb_destroy(mcb_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    for (int i = 0; i < MCB_RING; i++) if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -510,45 +525,82 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     const uint64_t nps0 = ctx->icycle * ctx->n_sample + ctx->shard_begin;
     const Site* sbank = nullptr;
     if (ctx->source_is_bank) sbank = ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p;
-    ctx->timer.begin(st, ST_SOURCE);
-    mcbk::source(st, P, ctx->B, ctx->q_active, (int32_t)h0, nb, nps0, sbank, ctx->n_source_sites);
-    ctx->timer.end(st);
     Counters* C = ctx->d_counters.p;
-    // slot cursor starts behind the primaries; queue cursors are cleared every iteration
-    unsigned int cur[4] = {0, 0, 0, nb};
-    CK(cudaMemcpyAsync(&C->q_collide, cur, sizeof(cur), cudaMemcpyHostToDevice, st));
-    uint32_t n_active = nb;
-    uint32_t* active = ctx->q_active;
-    uint32_t* next = ctx->q_next;
-    int iterations = 0;
-    while (n_active > 0) {
-        ctx->timer.begin(st, ST_LOOKUP);
-        mcbk::xs_stage(st, P, ctx->B, active, n_active, C);
-        ctx->timer.end(st);
-        ctx->timer.begin(st, ST_FLIGHT);
-        mcbk::flight(st, P, ctx->B, active, n_active, ctx->q_ev, C, ctx->H, T);
-        ctx->timer.end(st);
-        ctx->timer.begin(st, ST_COLLIDE);
-        mcbk::collide(st, P, ctx->B, ctx->q_ev, n_active, C, next, ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
-                      ctx->site_cap, ctx->n_slots, ctx->k);
-        ctx->timer.end(st);
-        ctx->timer.begin(st, ST_CROSS);
-        mcbk::cross(st, P, ctx->B, ctx->q_ev, n_active, n_active, C, next, T, ctx->n_slots);
-        ctx->timer.end(st);
-        CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemsetAsync(&C->q_collide, 0, 3 * sizeof(unsigned int), st));
-        CK(cudaStreamSynchronize(st));
-        const Counters& hc = *ctx->h_counters;
-        if (hc.lost) {
-            return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
+    uint32_t* queue[2] = {ctx->q_active, ctx->q_next};
+    ctx->timer.begin(st, ST_SOURCE);
+    mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, sbank, ctx->n_source_sites, C);
+    ctx->timer.end(st);
+
+    // Event loop.  Queue lengths live on the device; the host launches iterations ahead of what it knows and
+    // learns the lengths from asynchronous copies into a pinned ring (an iteration on an empty queue is a no-op).
+    const int R = MCB_RING;
+    uint64_t known_n = nb;  // last length seen (sizes the grids)
+    int it = 0, seen = 0;
+    bool tail = nb <= ctx->finish_below;
+    const uint64_t finish_below = ctx->finish_below;
+    while (!tail) {
+        const int cur = it % 3, nxt = (it + 1) % 3;
+        uint32_t* q_in = queue[it & 1];
+        uint32_t* q_out = queue[(it + 1) & 1];
+        if (ctx->split_stages) {
+            ctx->timer.begin(st, ST_LOOKUP);
+            mcbk::xs_stage(st, P, ctx->B, q_in, cur, known_n, C);
+            ctx->timer.end(st);
+            ctx->timer.begin(st, ST_FLIGHT);
+            mcbk::flight(st, P, ctx->B, q_in, cur, known_n, ctx->q_ev, C, ctx->H, T);
+            ctx->timer.end(st);
+            ctx->timer.begin(st, ST_COLLIDE);
+            mcbk::collide(st, P, ctx->B, ctx->q_ev, cur, known_n, C, q_out, ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+                          ctx->site_cap, ctx->n_slots, ctx->k);
+            ctx->timer.end(st);
+            ctx->timer.begin(st, ST_CROSS);
+            mcbk::cross(st, P, ctx->B, ctx->q_ev, cur, known_n, C, q_out, T, ctx->n_slots);
+            ctx->timer.end(st);
+        } else {
+            ctx->timer.begin(st, ST_STEP);
+            mcbk::step(st, P, ctx->B, q_in, cur, ctx->step_events, known_n, C, q_out, ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+                       ctx->site_cap, ctx->n_slots, ctx->k);
+            ctx->timer.end(st);
         }
-        if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
-        if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
-        n_active = hc.q_next;
-        std::swap(active, next);
-        iterations++;
+        CK(cudaMemcpyAsync(&ctx->h_ring[it % R], &C->n_active[nxt], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_ring[it % R], st));
+        it++;
+        while (seen < it) {
+            if (it - seen >= R - 1) CK(cudaEventSynchronize(ctx->ev_ring[seen % R]));
+            else {
+                const cudaError_t q = cudaEventQuery(ctx->ev_ring[seen % R]);
+                if (q == cudaErrorNotReady) break;
+                if (q != cudaSuccess) return ctx->fail(MCB_ERR_CUDA, "event loop: %s", cudaGetErrorString(q));
+            }
+            known_n = ctx->h_ring[seen % R];
+            seen++;
+            if (known_n <= finish_below) { tail = true; break; }
+            // in problems with secondaries the queue can grow again: keep the grid hint generous
+            if (P.shared_histories) known_n = std::max<uint64_t>(2 * known_n, 4096);
+        }
     }
-    *n_iterations += iterations;
+    // drain: everything launched so far has to finish before the tail kernel picks up the current queue
+    CK(cudaStreamSynchronize(st));
+    uint64_t n_left = it ? ctx->h_ring[(it - 1) % R] : nb;
+    while (n_left > 0) {
+        const int cur = it % 3, nxt = (it + 1) % 3;
+        CK(cudaMemsetAsync(&C->n_active[nxt], 0, sizeof(unsigned long long), st));
+        ctx->timer.begin(st, ST_FINISH);
+        mcbk::finish(st, P, ctx->B, queue[it & 1], cur, n_left, C, queue[(it + 1) & 1], ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+                     ctx->site_cap, ctx->n_slots, ctx->k);
+        ctx->timer.end(st);
+        CK(cudaMemcpyAsync(&ctx->h_ring[0], &C->n_active[nxt], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_left = ctx->h_ring[0];
+        it++;
+    }
+    *n_iterations += it;
+    CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const Counters& hc = *ctx->h_counters;
+    if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
+    if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
+    if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
     if (T.on) {
         ctx->timer.begin(st, ST_CLOSEOUT);
         mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
@@ -563,6 +615,7 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const bool tally_on = ctx->icycle >= ctx->n_passive;  // handler.cpp:15
+    const uint64_t launches0 = mcbk::launch_count();
     if (ctx->source_is_bank && ctx->n_source_sites == 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
     if (ctx->world > 1 && !ctx->comm) return ctx->fail(MCB_ERR_COMM, "world > 1 but mcb_comm_init was not called");
     Counters* C = ctx->d_counters.p;
@@ -668,9 +721,9 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
         ctx->timer.resolve(ms, cnt);
         mcb_stage_times& S = ctx->stage;
         S.ms_source += ms[ST_SOURCE]; S.ms_lookup += ms[ST_LOOKUP]; S.ms_flight += ms[ST_FLIGHT]; S.ms_cross += ms[ST_CROSS];
-        S.ms_collide += ms[ST_COLLIDE]; S.ms_closeout += ms[ST_CLOSEOUT]; S.ms_bank += ms[ST_BANK];
+        S.ms_collide += ms[ST_COLLIDE]; S.ms_closeout += ms[ST_CLOSEOUT]; S.ms_bank += ms[ST_BANK]; S.ms_finish += ms[ST_FINISH]; S.ms_step += ms[ST_STEP];
         S.n_source += cnt[ST_SOURCE]; S.n_lookup += cnt[ST_LOOKUP]; S.n_flight += cnt[ST_FLIGHT]; S.n_cross += cnt[ST_CROSS];
-        S.n_collide += cnt[ST_COLLIDE]; S.n_closeout += cnt[ST_CLOSEOUT]; S.n_bank += cnt[ST_BANK];
+        S.n_collide += cnt[ST_COLLIDE]; S.n_closeout += cnt[ST_CLOSEOUT]; S.n_bank += cnt[ST_BANK]; S.n_finish += cnt[ST_FINISH]; S.n_step += cnt[ST_STEP];
         S.units_lookup += ctx->h_counters->n_lookups;
     }
 
@@ -721,6 +774,7 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     cudaEventElapsedTime(&ms_x, ctx->ev1, ctx->ev2);
     r.ms_transport = ms_t; r.ms_exchange = ms_x;
     r.n_iterations = iterations;
+    r.n_kernel_launches = mcbk::launch_count() - launches0;
     r.lost = 0;
     ctx->icycle++;
     if (out) *out = r;
@@ -752,23 +806,41 @@ void mcb_reset_stage_times(mcb_ctx* ctx)
 {
     if (ctx) memset(&ctx->stage, 0, sizeof(ctx->stage));
 }
+void mcb_set_stage_timing(mcb_ctx* ctx, int on)
+{
+    if (ctx) ctx->timer.on = on != 0;
+}
+
+static int64_t read_bank(mcb_ctx* ctx, const Site* bank, uint64_t have, double* out, int32_t* cells, int64_t max_n)
+{
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
+    const int64_t n = std::min<int64_t>((int64_t)have, max_n);
+    if (n <= 0) return 0;
+    // Site records -> the host-facing layout on the device, then straight into the caller's buffers
+    if (ctx->d_io_sites.n < (size_t)n * 8) {
+        if (ctx->d_io_sites.alloc((size_t)n * 8) != cudaSuccess || ctx->d_io_cells.alloc((size_t)n) != cudaSuccess)
+            return ctx->fail(MCB_ERR_CUDA, "out of device memory for the bank staging buffers");
+    }
+    mcbk::unpack_sites(ctx->stream, bank, (uint64_t)n, ctx->d_io_sites.p, ctx->d_io_cells.p);
+    cudaError_t e = cudaSuccess;
+    if (out) e = cudaMemcpyAsync(out, ctx->d_io_sites.p, (size_t)n * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && cells) e = cudaMemcpyAsync(cells, ctx->d_io_cells.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return ctx->fail(MCB_ERR_CUDA, "fission bank read-back failed: %s", cudaGetErrorString(e));
+    return n;
+}
 
 int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
 {
     if (!ctx) return MCB_ERR_ARG;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
-    const int64_t n = std::min<int64_t>((int64_t)ctx->n_local_sites, max_n);
-    if (n <= 0) return 0;
-    std::vector<Site> h((size_t)n);
-    if (cudaMemcpyAsync(h.data(), ctx->d_local_bank.p, (size_t)n * sizeof(Site), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-        return ctx->fail(MCB_ERR_CUDA, "fission bank read-back failed");
-    for (int64_t i = 0; i < n; i++) {
-        const Site& s = h[(size_t)i];
-        if (out) { double* o = out + 8 * i; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.u; o[4] = s.v; o[5] = s.w; o[6] = s.E; o[7] = s.t; }
-        if (cells) cells[i] = s.cell;
-    }
-    return n;
+    return read_bank(ctx, ctx->d_local_bank.p, ctx->n_local_sites, out, cells, max_n);
+}
+
+int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
+{
+    if (!ctx) return MCB_ERR_ARG;
+    if (!ctx->source_is_bank) return 0;
+    return read_bank(ctx, ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p, ctx->n_source_sites, out, cells, max_n);
 }
 
 int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells, int64_t n)
@@ -779,14 +851,12 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
     Site* dst = ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p;
     const uint64_t cap = ctx->world > 1 ? ctx->global_cap : ctx->site_cap;
     if ((uint64_t)n > cap) return ctx->fail(MCB_ERR_CAPACITY, "source bank of %lld sites exceeds the capacity %llu", (long long)n, (unsigned long long)cap);
-    std::vector<Site> h((size_t)n);
-    for (int64_t i = 0; i < n; i++) {
-        const double* s = sites8 + 8 * i;
-        Site& d = h[(size_t)i];
-        d.x = s[0]; d.y = s[1]; d.z = s[2]; d.u = s[3]; d.v = s[4]; d.w = s[5]; d.E = s[6]; d.t = s[7];
-        d.cell = cells[i]; d.seq = 0;
+    if (ctx->d_io_sites.n < (size_t)n * 8) { CK(ctx->d_io_sites.alloc((size_t)n * 8)); CK(ctx->d_io_cells.alloc((size_t)n)); }
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->d_io_sites.p, sites8, (size_t)n * 8 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_io_cells.p, cells, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        mcbk::pack_sites(ctx->stream, ctx->d_io_sites.p, ctx->d_io_cells.p, (uint64_t)n, dst);
     }
-    if (n) CK(cudaMemcpyAsync(dst, h.data(), (size_t)n * sizeof(Site), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_source_sites = (uint64_t)n;
     ctx->source_is_bank = true;

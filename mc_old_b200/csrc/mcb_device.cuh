@@ -75,7 +75,9 @@ struct Site {
 struct Counters {
     unsigned long long n_tracks, n_collisions, n_lookups, n_crossings, n_histories;
     unsigned long long site_cursor;       // unordered fission sites banked this cycle
-    unsigned int q_collide, q_cross, q_next, slot_cursor;
+    unsigned long long slot_cursor;       // bank slots in use (primaries + secondaries of the batch)
+    unsigned long long n_active[3];       // lengths of the particle queue: iteration i reads [i%3], fills [(i+1)%3], clears [(i+2)%3]
+    unsigned long long q_collide, q_cross;// lengths of the two halves of the event queue
     int lost, overflow_sites, overflow_slots, overflow_fixed;
     double lost_pos[3];
     // exact (fixed-point, two-limb) sums over histories: k_C, k_TL, k_C^2, k_TL^2, H
@@ -101,7 +103,7 @@ struct TallyAcc {
 // ---------------------------------------------------------------------------------------------
 // cross sections
 // ---------------------------------------------------------------------------------------------
-struct MicroXS { double s, c, f, t, nu; };
+struct MicroXS { double s, c, f, t, nu, beta; };
 
 __device__ __forceinline__ double2 ld_row2(const double* p)
 {
@@ -115,7 +117,7 @@ __device__ __forceinline__ void micro_xs(const DevNuclide& N, int idx, double E,
     if (idx < 0 || idx >= N.n_rows - 1) {
         const double* r = N.rows + (size_t)(idx < 0 ? 0 : N.n_rows - 1) * MCB_XS_ROW;
         const double2 a = ld_row2(r), b = ld_row2(r + 2), c = ld_row2(r + 4);
-        m.s = a.y; m.c = b.x; m.f = b.y; m.nu = c.x;
+        m.s = a.y; m.c = b.x; m.f = b.y; m.nu = c.x; m.beta = c.y;
         m.t = a.y + b.x + b.y;
         return;
     }
@@ -129,6 +131,7 @@ __device__ __forceinline__ void micro_xs(const DevNuclide& N, int idx, double E,
     m.c = f1 * b1.x + f2 * b2.x;
     m.f = f1 * b1.y + f2 * b2.y;
     m.nu = f1 * c1.x + f2 * c2.x;
+    m.beta = f1 * c1.y + f2 * c2.y;  // Nuclide::beta (Nuclide.cpp:74-77): the same interpolate() expression
     m.t = f1 * (a1.y + b1.x + b1.y) + f2 * (a2.y + b2.x + b2.y);
 }
 // one derived column: 0 sigma_a (= sigma_c + sigma_f per grid point), 1 beta
@@ -156,8 +159,18 @@ __device__ __forceinline__ int nuclide_index(const DevMaterial& M, int u, int n)
 
 struct MacroXS { double t, s, c, f, nf; };
 
+// per-nuclide by-products of one macroscopic lookup.  The running sums ARE the partial sums that
+// Material::nuclide_scatter / nuclide_nufission (Material.cpp:106-125) rebuild, so a kernel that keeps them can
+// pick the reaction nuclide without evaluating the tables again.
+struct XSDetail {
+    double cum_s[MCB_MAX_MAT_NUCLIDES];   // Sigma_s after nuclides 0..n
+    double cum_nf[MCB_MAX_MAT_NUCLIDES];  // nuSigma_f after nuclides 0..n
+    double beta[MCB_MAX_MAT_NUCLIDES];    // beta_n(E)
+};
+
 // Material::SigmaT/S/C/F, nuSigmaF (Material.cpp:18-65): sums over nuclides in deck order, starting from 0.0
-__device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X)
+template <bool DETAIL>
+__device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X, XSDetail* D)
 {
     X.t = 0.0; X.s = 0.0; X.c = 0.0; X.f = 0.0; X.nf = 0.0;
     for (int n = 0; n < M.n_nuc; n++) {
@@ -170,7 +183,21 @@ __device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial&
         X.c += m.c * dens;
         X.f += m.f * dens;
         X.nf += (m.f * m.nu) * dens;   // Nuclide::nusigmaF = sigmaF*nu (Nuclide.cpp:57-61)
+        if (DETAIL) { D->cum_s[n] = X.s; D->cum_nf[n] = X.nf; D->beta[n] = m.beta; }
     }
+}
+__device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X)
+{
+    macro_xs_impl<false>(P, M, u, E, X, nullptr);
+}
+// nuclide pick from kept partial sums: first n with cum[n] > total*xi (Material.cpp:106-125)
+__device__ __forceinline__ int select_from_detail(const DevProblem& P, const DevMaterial& M, const double* cum, double total,
+                                                  double xi, int* local_n)
+{
+    const double thr = total * xi;
+    for (int n = 0; n < M.n_nuc; n++)
+        if (cum[n] > thr) { *local_n = n; return __ldg(&P.mat_nuclide[M.nuc_begin + n]); }
+    return -1;
 }
 // Material::SigmaA (Material.cpp:34-41)
 __device__ __forceinline__ double macro_sigma_a(const DevProblem& P, const DevMaterial& M, int u, double E)

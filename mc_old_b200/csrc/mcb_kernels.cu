@@ -3,61 +3,76 @@
 // One generation (reference: one pass of the cycle body of Simulator::start(), handler.cpp:14-44) is
 //   source  -> { xs_lookup -> flight -> collide | cross } until the bank is empty -> close-out kernels.
 // Particles live in an SoA bank (Bank); each stage runs over an index queue of the particles whose next event it
-// is; queues are rebuilt every iteration with warp-ballot stream compaction.
+// is; the queues are rebuilt every iteration by stream compaction (warp prefix sums, ONE cursor atomic per block).
+// Queue lengths stay on the device: every stage kernel is a persistent tile loop that reads its length from
+// Counters, so the host never has to wait for an iteration before launching the next one.  When only a few
+// particles are left, k_finish runs each of them to the end of its history in registers.
 //
 // Nothing here is GEMM-shaped: the loop is FP64 scalar work, L2-resident table gathers and HBM streams of the
 // bank, so tensor cores are unused on purpose.
 #include "mcb_kernels.h"
+
+#include <algorithm>
 
 #include <cub/device/device_scan.cuh>
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int BLOCK = 256;
+constexpr int WARPS = BLOCK / 32;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
-// warp-ballot stream compaction: position of this lane's element in the queue behind *cursor (one atomic per warp).
-// Must be reached by all 32 lanes of the warp.
-__device__ __forceinline__ unsigned warp_append(unsigned int* cursor, bool pred)
+// ---------------------------------------------------------------------------------------------
+// block-level stream compaction: every thread asks for n[c] consecutive positions behind cursor c; one
+// atomicAdd per block and cursor (same-address atomics serialise in L2, so per-warp cursors were the bottleneck).
+// Must be reached by all threads of the block.  `S` is per-tile scratch; callers alternate two of them.
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+struct BlockScratch {
+    unsigned warp_tot[NC][WARPS];
+    unsigned long long base[NC];
+};
+template <int NC>
+__device__ __forceinline__ void block_reserve(BlockScratch<NC>& S, const unsigned (&n)[NC], unsigned long long* const (&cursor)[NC],
+                                              unsigned long long (&pos)[NC])
 {
-    const unsigned mask = __ballot_sync(FULL, pred);
-    if (mask == 0) return 0;
-    const int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if (lane_id() == leader) base = atomicAdd(cursor, __popc(mask));
-    base = __shfl_sync(FULL, base, leader);
-    return base + __popc(mask & ((1u << lane_id()) - 1));
-}
-// same with a per-lane element count (warp prefix sum); returns the first position of this lane's elements
-template <typename T>
-__device__ __forceinline__ T warp_reserve(T* cursor, unsigned n_mine)
-{
-    unsigned incl = n_mine;
+    unsigned incl[NC];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned t = __shfl_up_sync(FULL, incl, d);
-        if (lane_id() >= d) incl += t;
+    for (int c = 0; c < NC; c++) {
+        unsigned v = n[c];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL, v, d);
+            if (lane_id() >= d) v += t;
+        }
+        incl[c] = v;
+        if (lane_id() == 31) S.warp_tot[c][warp_id()] = v;
     }
-    const unsigned total = __shfl_sync(FULL, incl, 31);
-    T base = 0;
-    if (total == 0) return 0;
-    if (lane_id() == 31) base = atomicAdd(cursor, (T)total);
-    base = __shfl_sync(FULL, base, 31);
-    return base + (T)(incl - n_mine);
+    __syncthreads();
+    if (threadIdx.x < NC) {
+        const int c = threadIdx.x;
+        unsigned run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) { const unsigned t = S.warp_tot[c][w]; S.warp_tot[c][w] = run; run += t; }
+        S.base[c] = run ? atomicAdd(cursor[c], (unsigned long long)run) : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; c++) pos[c] = S.base[c] + S.warp_tot[c][warp_id()] + (incl[c] - n[c]);
+}
+// block-wide event counter: one atomic per block
+__device__ __forceinline__ void block_count(unsigned long long* dst, bool pred)
+{
+    const int c = __syncthreads_count(pred);
+    if (threadIdx.x == 0 && c) atomicAdd(dst, (unsigned long long)c);
 }
 
-__device__ __forceinline__ void hist_add(double* p, double v, int shared)
-{
-    if (shared) atomicAdd(p, v); else *p += v;
-}
-
-// block-wide sum of a counter into a global 64-bit counter (one atomic per warp)
-__device__ __forceinline__ void count_add(unsigned long long* dst, bool pred)
-{
-    const unsigned mask = __ballot_sync(FULL, pred);
-    if (mask && lane_id() == 0) atomicAdd(dst, (unsigned long long)__popc(mask));
-}
+// per-history accumulators are bumped with reductions at L2 (RED, no return value): a read-modify-write in the
+// thread would stall the warp for a DRAM round trip on every event
+__device__ __forceinline__ void hist_add(double* p, double v) { atomicAdd(p, v); }
 
 // ---------------------------------------------------------------------------------------------
 // tally scoring (Estimator::score, Estimator.cpp:298-336, for filters that yield one bin: surface, cell, energy)
@@ -94,7 +109,7 @@ __device__ __forceinline__ double score_value(const DevProblem& P, const mcb_sco
     default: return 0.0;
     }
 }
-__device__ void estimator_score(const DevProblem& P, const TallyAcc& T, int e, const ScoreState& s, double l, int hist)
+__device__ __noinline__ void estimator_score(const DevProblem& P, const TallyAcc& T, int e, const ScoreState& s, double l, int hist)
 {
     const mcb_estimator E = P.estimators[e];
     int64_t idx_1D = 0;
@@ -134,16 +149,231 @@ __device__ __forceinline__ bool has_attached(const DevProblem& P, int kind, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// the events of one particle, on registers.  Stage kernels load/store the fields an event needs; k_finish keeps
+// the whole particle in registers and chains the events.
+// ---------------------------------------------------------------------------------------------
+struct Particle {
+    double x, y, z, u, v, w, E, speed, wgt, t;
+    uint64_t rng;
+    int cell, hist;
+};
+
+// xs_lookup event
+template <bool DETAIL>
+__device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p, MacroXS& X, int& uidx, XSDetail* D)
+{
+    const int m = P.cells[p.cell].material;
+    if (m < 0) return false;
+    const DevMaterial M = P.materials[m];
+    uidx = union_index(M, p.E);
+    macro_xs_impl<DETAIL>(P, M, uidx, p.E, X, D);
+    return true;
+}
+
+// flight event: surface_intersect + collision_distance + move_particle (general.cpp:40-83,177-207).
+// Returns true when the flight ends on a surface (S_hit), false when it ends in a collision.
+__device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
+                                          const TallyAcc& T, int& S_hit)
+{
+    const int m = P.cells[p.cell].material;
+    double dsurf;
+    S_hit = surface_intersect(P, p.cell, p.x, p.y, p.z, p.u, p.v, p.w, dsurf);
+    double dcol;
+    if (m >= 0) dcol = -log(mcb_urand(p.rng)) / X.t;   // exponential_sample (Algorithm.cpp:123-126)
+    else dcol = MCB_MAX_FLOAT_LESS;                      // vacuum (general.cpp:44-46)
+    const bool to_cross = dcol > dsurf;
+    const double l = to_cross ? dsurf : dcol;
+    // Particle::move (Particle.cpp:66-76)
+    p.x += p.u * l; p.y += p.v * l; p.z += p.w * l;
+    p.t += l / p.speed;
+    if (P.ksearch && m >= 0) hist_add(&H.kTL[p.hist], X.nf * p.wgt * l);  // estimate_TL (Estimator.cpp:509-512)
+    if (T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
+        ScoreState s;
+        s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = -1; s.material = m; s.u = uidx; s.X = X;
+        score_attached(P, T, MCB_ATTACH_CELL_TL, p.cell, s, l, p.hist);
+    }
+    return to_cross;
+}
+
+// collide event, first half: Simulator::collision up to the fission dispatch (general.cpp:121-150): collision
+// tallies, bank_nu, fissioning nuclide, prompt/delayed draw.  Tells how many fission sites (k-eigenvalue) or
+// same-history secondaries (fixed source) the second half will write.
+struct CollideCtx {
+    int m, N_fission;
+    unsigned n_sites, n_second;
+};
+__device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
+                                               const TallyAcc& T, double k_eff, CollideCtx& c)
+{
+    c.m = P.cells[p.cell].material;
+    c.N_fission = -1; c.n_sites = 0; c.n_second = 0;
+    if (c.m < 0) { p.wgt = 0.0; return false; }  // vacuum: kill (general.cpp:124-128)
+    if (T.on && has_attached(P, MCB_ATTACH_CELL_C, p.cell)) {
+        ScoreState s;
+        s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = -1; s.material = c.m; s.u = uidx; s.X = X;
+        score_attached(P, T, MCB_ATTACH_CELL_C, p.cell, s, 0.0, p.hist);
+    }
+    // floor( w/k * nuSigmaF / SigmaT + xi ) (general.cpp:135-136)
+    const double a = p.wgt / k_eff * X.nf / X.t;
+    const double bn = floor(a + mcb_urand(p.rng));
+    const unsigned bank_nu = bn > 0.0 ? (unsigned)bn : 0u;
+    const DevMaterial& M = P.materials[c.m];
+    int ln = 0;
+    const double xi_f = mcb_urand(p.rng);
+    c.N_fission = D ? select_from_detail(P, M, D->cum_nf, X.nf, xi_f, &ln)
+                    : select_nuclide(P, M, uidx, p.E, 1, X.nf, xi_f, &ln);  // Material.cpp:116-125
+    if (c.N_fission >= 0) {
+        // prompt or delayed (ksearch.cpp:24-38, fixed_source.cpp:12,41-52)
+        const double beta = D ? D->beta[ln] : micro_col(P.nuclides[c.N_fission], nuclide_index(M, uidx, ln), p.E, 1);
+        const bool prompt = mcb_urand(p.rng) > beta;
+        if (P.ksearch) {
+            if (!prompt) (void)mcb_urand(p.rng);  // precursor group pick, result unused
+            c.n_sites = bank_nu;
+        } else if (prompt) {
+            c.n_second = bank_nu;
+        } else {
+            // delayed, non-TDMC branch: draws are consumed, no neutron is banked (fixed_source.cpp:41-63)
+            (void)mcb_urand(p.rng);
+            for (unsigned b = 0; b < bank_nu; b++) { (void)mcb_urand(p.rng); (void)mcb_urand(p.rng); }
+        }
+    }
+    return true;
+}
+// collide event, second half: bank the fission neutrons at [site0, ..) / [slot0, ..), k_C, implicit capture,
+// scatter, weight_roulette (general.cpp:139-163, ksearch.cpp:39-46, fixed_source.cpp:12-22, population_control.cpp:9-15).
+// Returns whether the particle survives; n_second_ok = secondaries that found a slot.
+__device__ __forceinline__ bool ev_collide_post(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx,
+                                                const XSDetail* D, const CollideCtx& c, const HistoryAcc& H, Counters* C, Site* tmp_sites,
+                                                int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots,
+                                                unsigned long long site0, unsigned long long slot0, unsigned& n_second_ok)
+{
+    n_second_ok = 0;
+    const double E_in = p.E;
+    if (c.n_sites) {
+        const int seq0 = atomicAdd(&H.nsite[p.hist], (int)c.n_sites);
+        const DevNuclide& N = P.nuclides[c.N_fission];
+        for (unsigned b = 0; b < c.n_sites; b++) {
+            Site s;
+            s.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, E_in, p.rng);   // energy first, then direction (App. D-4)
+            isotropic_direction(p.rng, s.u, s.v, s.w);
+            s.x = p.x; s.y = p.y; s.z = p.z; s.t = p.t; s.cell = p.cell; s.seq = seq0 + (int)b;
+            if (site0 + b < site_cap) { tmp_sites[site0 + b] = s; tmp_hist[site0 + b] = p.hist; }
+            else C->overflow_sites = 1;
+        }
+    }
+    if (c.n_second) {
+        const DevNuclide& N = P.nuclides[c.N_fission];
+        for (unsigned b = 0; b < c.n_second; b++) {
+            const double Es = watt_sample(N.watt_a, N.watt_b, N.watt_g, E_in, p.rng);
+            double du, dv, dw;
+            isotropic_direction(p.rng, du, dv, dw);
+            const unsigned long long j = slot0 + b;
+            if (j < n_slots) {
+                B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
+                B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = p.t;
+                B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
+                n_second_ok++;
+            } else C->overflow_slots = 1;
+        }
+    }
+    if (P.ksearch && c.N_fission >= 0) hist_add(&H.kC[p.hist], X.nf * p.wgt / X.t);  // estimate_C (Estimator.cpp:503-507)
+    // implicit absorption (general.cpp:154-156)
+    const double implicit = X.c + X.f;
+    p.wgt = p.wgt * (X.t - implicit) / X.t;
+    const double xi_s = mcb_urand(p.rng);
+    int ln_s = 0;
+    const int N_scatter = D ? select_from_detail(P, P.materials[c.m], D->cum_s, X.s, xi_s, &ln_s)
+                            : select_nuclide(P, P.materials[c.m], uidx, p.E, 0, X.s, xi_s, &ln_s);  // Material.cpp:106-115
+    if (N_scatter >= 0) scatter_sample(P.nuclides[N_scatter].A, p.u, p.v, p.w, p.E, p.speed, p.rng);
+    // weight_roulette (population_control.cpp:9-15)
+    if (p.wgt < P.wr) {
+        if (mcb_urand(p.rng) < p.wgt / P.ws) p.wgt = P.ws;
+        else { p.wgt = 0.0; return false; }
+    }
+    return true;
+}
+
+// cross event, first half: surface_hit + cell_importance up to the split (general.cpp:89-115,
+// population_control.cpp:21-43).  n_copy = split copies the second half will write.
+__device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, int S, const TallyAcc& T, Counters* C, unsigned& n_copy)
+{
+    n_copy = 0;
+    if (S < 0) { p.wgt = 0.0; return false; }  // no surface ahead: cannot happen in a closed geometry
+    const mcb_surface& Sf = P.surfaces[S];
+    const int cell_old = p.cell;
+    bool alive = true;
+    if (Sf.bc == MCB_BC_TRANSMISSION) {
+        p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
+        p.t += MCB_EPSILON_FLOAT / p.speed;
+        const int cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, p.x, p.y, p.z);
+        if (cn < 0) {  // "[WARNING] A particle is lost" (general.cpp:31-33)
+            if (atomicExch(&C->lost, 1) == 0) { C->lost_pos[0] = p.x; C->lost_pos[1] = p.y; C->lost_pos[2] = p.z; }
+            alive = false; p.wgt = 0.0;
+        } else p.cell = cn;
+    } else if (Sf.bc == MCB_BC_VACUUM) {
+        alive = false; p.wgt = 0.0;
+    } else {
+        mcb_surf_reflect(Sf, p.u, p.v, p.w);
+        p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
+        p.t += MCB_EPSILON_FLOAT / p.speed;
+    }
+    if (T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
+        ScoreState s;
+        s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = S; s.material = P.cells[p.cell].material;
+        s.u = -1; s.X = MacroXS{0, 0, 0, 0, 0};
+        if (s.material >= 0) { s.u = union_index(P.materials[s.material], p.E); macro_xs(P, P.materials[s.material], s.u, p.E, s.X); }
+        score_attached(P, T, MCB_ATTACH_SURFACE, S, s, 0.0, p.hist);
+    }
+    const double Iold = P.cells[cell_old].importance, Inew = P.cells[p.cell].importance;
+    if (Inew != Iold) {
+        const double rat = Inew / Iold;
+        if (rat < 1.0) {
+            if (mcb_urand(p.rng) < rat) p.wgt = p.wgt / rat;
+            else { alive = false; p.wgt = 0.0; }
+        } else {
+            const int ns = (int)floor(rat + mcb_urand(p.rng));
+            p.wgt = p.wgt / (double)ns;
+            n_copy = ns > 1 ? (unsigned)(ns - 1) : 0u;
+        }
+    }
+    return alive;
+}
+// cross event, second half: the split copies (population_control.cpp:44-48) and weight_roulette, which also
+// draws for a particle that was just killed (w = 0 < wr), like the reference
+__device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B, Particle& p, bool alive, unsigned n_copy,
+                                              unsigned long long slot0, uint32_t n_slots, Counters* C, unsigned& n_copy_ok)
+{
+    n_copy_ok = 0;
+    for (unsigned b = 0; b < n_copy; b++) {
+        const unsigned long long j = slot0 + b;
+        if (j < n_slots) {
+            B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = p.u; B.v[j] = p.v; B.w[j] = p.w;
+            B.E[j] = p.E; B.speed[j] = p.speed; B.wgt[j] = p.wgt; B.t[j] = p.t;
+            B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
+            n_copy_ok++;
+        } else C->overflow_slots = 1;
+    }
+    if (p.wgt < P.wr) {
+        if (mcb_urand(p.rng) < p.wgt / P.ws) p.wgt = P.ws;
+        else { p.wgt = 0.0; alive = false; }
+    }
+    return alive;
+}
+
+// ---------------------------------------------------------------------------------------------
 // stage kernels
 // ---------------------------------------------------------------------------------------------
 // source: SourceBank::get_source (Source.cpp:42-46) with j = floor(xi*N), SourcePoint / SourceDelta (Source.cpp:16-24)
 // History h (shard-local) of this cycle gets the stream of nps = cycle*Nsample + (shard_begin + h)
 // (RN_init_particle, Random.cpp:196-204).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BLOCK)
 k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint32_t count, uint64_t nps0,
-         const Site* sbank, uint64_t n_sbank)
+         const Site* sbank, uint64_t n_sbank, Counters* C)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) {  // queue state of the batch: `count` primaries in queue 0, slots behind them are free
+        C->n_active[0] = count; C->n_active[1] = 0; C->n_active[2] = 0; C->q_collide = 0; C->q_cross = 0; C->slot_cursor = count;
+    }
     if (q >= count) return;
     const int32_t h = first_hist + (int32_t)q;
     uint64_t rng = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)h);
@@ -172,284 +402,324 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     active[q] = q;
 }
 
-// xs_lookup stage: macroscopic cross sections of every queued particle at its energy in its cell's material
-__global__ void __launch_bounds__(256)
-k_xs_stage(const DevProblem P, Bank B, const uint32_t* __restrict__ active, uint32_t n, Counters* C)
+// xs_lookup stage: macroscopic cross sections of every queued particle at its energy in its cell's material.
+// As the first kernel of an iteration it also clears the queue lengths the iteration is going to fill.
+__global__ void __launch_bounds__(BLOCK)
+k_xs_stage(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, Counters* C)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = q < n;
-    bool looked = false;
-    if (valid) {
-        const uint32_t i = active[q];
-        const int m = P.cells[B.cell[i]].material;
-        if (m >= 0) {
-            const double E = B.E[i];
-            const DevMaterial M = P.materials[m];
-            const int u = union_index(M, E);
+    const unsigned long long n = C->n_active[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { C->n_active[(cur + 2) % 3] = 0; C->q_collide = 0; C->q_cross = 0; }
+    unsigned looked = 0;
+    for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x) {
+        const unsigned long long q = tile * BLOCK + threadIdx.x;
+        if (q < n) {
+            const uint32_t i = active[q];
+            Particle p;
+            p.cell = B.cell[i]; p.E = B.E[i];
             MacroXS X;
-            macro_xs(P, M, u, E, X);
-            B.St[i] = X.t; B.Ss[i] = X.s; B.Sc[i] = X.c; B.Sf[i] = X.f; B.nSf[i] = X.nf;
-            B.uidx[i] = u;
-            looked = true;
+            int u;
+            if (ev_lookup<false>(P, p, X, u, nullptr)) {
+                B.St[i] = X.t; B.Ss[i] = X.s; B.Sc[i] = X.c; B.Sf[i] = X.f; B.nSf[i] = X.nf;
+                B.uidx[i] = u;
+                looked++;
+            }
         }
     }
-    count_add(&C->n_lookups, looked);
+    // one counter atomic per block
+    for (int d = 16; d; d >>= 1) looked += __shfl_xor_sync(FULL, looked, d);
+    __shared__ unsigned s_cnt[WARPS];
+    if (lane_id() == 0) s_cnt[warp_id()] = looked;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < WARPS; w++) tot += s_cnt[w];
+        if (tot) atomicAdd(&C->n_lookups, (unsigned long long)tot);
+    }
 }
 
-// flight stage: surface_intersect + collision_distance + move_particle (general.cpp:40-83,177-207).
-// The event queue is split in place: collisions from the front, surface hits from the back.
-__global__ void __launch_bounds__(256)
-k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, uint32_t n, uint32_t* evq, Counters* C,
+// flight stage.  The event queue is split in place: collisions from the front, surface hits from the back.
+__global__ void __launch_bounds__(BLOCK)
+k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, uint32_t* evq, Counters* C,
          HistoryAcc H, TallyAcc T)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = q < n;
-    bool to_collide = false, to_cross = false;
-    uint32_t i = 0;
-    if (valid) {
-        i = active[q];
-        const int cell = B.cell[i];
-        const int m = P.cells[cell].material;
-        double x = B.x[i], y = B.y[i], z = B.z[i];
-        const double u = B.u[i], v = B.v[i], w = B.w[i];
-        uint64_t rng = B.rng[i];
-        double dsurf;
-        const int S = surface_intersect(P, cell, x, y, z, u, v, w, dsurf);
-        double dcol;
-        if (m >= 0) dcol = -log(mcb_urand(rng)) / B.St[i];   // exponential_sample (Algorithm.cpp:123-126)
-        else dcol = MCB_MAX_FLOAT_LESS;                        // vacuum (general.cpp:44-46)
-        const double l = (dcol > dsurf) ? dsurf : dcol;
-        to_cross = dcol > dsurf;
-        to_collide = !to_cross;
-        // Particle::move (Particle.cpp:66-76)
-        x += u * l; y += v * l; z += w * l;
-        const double speed = B.speed[i];
-        const double t = B.t[i] + l / speed;
-        B.x[i] = x; B.y[i] = y; B.z[i] = z; B.t[i] = t; B.rng[i] = rng;
-        B.surf[i] = S;
-        const int h = B.hist[i];
-        const double wgt = B.wgt[i];
-        if (P.ksearch && m >= 0) hist_add(&H.kTL[h], B.nSf[i] * wgt * l, P.shared_histories);  // estimate_TL (Estimator.cpp:509-512)
-        if (T.on && has_attached(P, MCB_ATTACH_CELL_TL, cell)) {
-            ScoreState s;
-            s.w = wgt; s.E = B.E[i]; s.speed = speed; s.cell = cell; s.surface_old = -1; s.material = m;
-            if (m >= 0) { s.u = B.uidx[i]; s.X.t = B.St[i]; s.X.s = B.Ss[i]; s.X.c = B.Sc[i]; s.X.f = B.Sf[i]; s.X.nf = B.nSf[i]; }
-            score_attached(P, T, MCB_ATTACH_CELL_TL, cell, s, l, h);
+    __shared__ BlockScratch<2> scratch[2];
+    const unsigned long long n = C->n_active[cur];
+    unsigned tracks = 0;
+    int it = 0;
+    for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x, it++) {
+        const unsigned long long q = tile * BLOCK + threadIdx.x;
+        const bool valid = q < n;
+        bool to_cross = false;
+        uint32_t i = 0;
+        if (valid) {
+            i = active[q];
+            Particle p;
+            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
+            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+            MacroXS X;
+            X.t = B.St[i]; X.nf = B.nSf[i];
+            int uidx = 0;
+            if (T.on) { X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; uidx = B.uidx[i]; }
+            int S;
+            to_cross = ev_flight(P, p, X, uidx, H, T, S);
+            B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.t[i] = p.t; B.rng[i] = p.rng; B.surf[i] = S;
+            tracks++;
         }
-        if (to_cross && S < 0) { to_cross = false; B.wgt[i] = 0.0; }  // no surface ahead: cannot happen in a closed geometry
+        const unsigned cnt[2] = {valid && !to_cross ? 1u : 0u, valid && to_cross ? 1u : 0u};
+        unsigned long long* const cur[2] = {&C->q_collide, &C->q_cross};
+        unsigned long long pos[2];
+        block_reserve<2>(scratch[it & 1], cnt, cur, pos);
+        if (cnt[0]) evq[pos[0]] = i;
+        if (cnt[1]) evq[n - 1 - pos[1]] = i;
     }
-    count_add(&C->n_tracks, valid);
-    const unsigned pc = warp_append(&C->q_collide, to_collide);
-    if (to_collide) evq[pc] = i;
-    const unsigned px = warp_append(&C->q_cross, to_cross);
-    if (to_cross) evq[n - 1 - px] = i;
+    for (int d = 16; d; d >>= 1) tracks += __shfl_xor_sync(FULL, tracks, d);
+    if (lane_id() == 0 && tracks) atomicAdd(&C->n_tracks, (unsigned long long)tracks);
 }
 
-// collide stage: Simulator::collision (general.cpp:121-163) + weight_roulette (population_control.cpp:9-15)
-__global__ void __launch_bounds__(256)
-k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, Counters* C, uint32_t* next, HistoryAcc H,
+// collide stage
+__global__ void __launch_bounds__(BLOCK)
+k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, Counters* C, uint32_t* next, HistoryAcc H,
           TallyAcc T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = q < C->q_collide;
-    uint32_t i = 0;
-    int h = 0, cell = 0, m = -1, u = -1, N_fission = -1;
-    double E = 0, wgt = 0, x = 0, y = 0, z = 0, t = 0;
-    uint64_t rng = 0;
-    MacroXS X = {0, 0, 0, 0, 0};
-    unsigned bank_nu = 0, n_sites = 0, n_second = 0;
-    bool alive = false, in_material = false;
-    if (valid) {
-        i = evq[q];
-        cell = B.cell[i];
-        m = P.cells[cell].material;
-        in_material = m >= 0;
-        h = B.hist[i];
-        if (!in_material) { B.wgt[i] = 0.0; }  // vacuum: kill (general.cpp:124-128)
-        else {
-            E = B.E[i]; wgt = B.wgt[i]; rng = B.rng[i]; u = B.uidx[i];
-            X.t = B.St[i]; X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; X.nf = B.nSf[i];
-            if (T.on && has_attached(P, MCB_ATTACH_CELL_C, cell)) {
-                ScoreState s;
-                s.w = wgt; s.E = E; s.speed = B.speed[i]; s.cell = cell; s.surface_old = -1; s.material = m; s.u = u; s.X = X;
-                score_attached(P, T, MCB_ATTACH_CELL_C, cell, s, 0.0, h);
+    __shared__ BlockScratch<2> scratchA[2];
+    __shared__ BlockScratch<1> scratchB[2];
+    const unsigned long long n = C->q_collide;
+    unsigned long long* const next_len = &C->n_active[(cur + 1) % 3];
+    unsigned collisions = 0;
+    int it = 0;
+    for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x, it++) {
+        const unsigned long long q = tile * BLOCK + threadIdx.x;
+        const bool valid = q < n;
+        uint32_t i = 0;
+        Particle p;
+        MacroXS X = {0, 0, 0, 0, 0};
+        CollideCtx c = {-1, -1, 0, 0};
+        int uidx = -1;
+        bool in_material = false;
+        if (valid) {
+            i = evq[q];
+            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
+            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+            X.t = B.St[i]; X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; X.nf = B.nSf[i]; uidx = B.uidx[i];
+            in_material = ev_collide_pre(P, p, X, uidx, nullptr, T, k_eff, c);
+            if (in_material) collisions++;
+        }
+        const unsigned cntA[2] = {c.n_sites, c.n_second};
+        unsigned long long* const curA[2] = {&C->site_cursor, &C->slot_cursor};
+        unsigned long long posA[2];
+        block_reserve<2>(scratchA[it & 1], cntA, curA, posA);
+        bool alive = false;
+        unsigned n_second_ok = 0;
+        if (valid) {
+            if (in_material) alive = ev_collide_post(P, B, p, X, uidx, nullptr, c, H, C, tmp_sites, tmp_hist, site_cap, n_slots, posA[0], posA[1], n_second_ok);
+            B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.rng[i] = p.rng;
+        }
+        // survivors and their secondaries go to the next iteration's queue
+        const unsigned cntB[1] = {(alive ? 1u : 0u) + n_second_ok};
+        unsigned long long* const curB[1] = {next_len};
+        unsigned long long posB[1];
+        block_reserve<1>(scratchB[it & 1], cntB, curB, posB);
+        unsigned long long o = posB[0];
+        if (alive) next[o++] = i;
+        for (unsigned b = 0; b < n_second_ok; b++) next[o++] = (uint32_t)(posA[1] + b);
+    }
+    for (int d = 16; d; d >>= 1) collisions += __shfl_xor_sync(FULL, collisions, d);
+    if (lane_id() == 0 && collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
+}
+
+// cross stage
+__global__ void __launch_bounds__(BLOCK)
+k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, Counters* C, uint32_t* next, TallyAcc T,
+        uint32_t n_slots)
+{
+    __shared__ BlockScratch<1> scratchA[2];
+    __shared__ BlockScratch<1> scratchB[2];
+    const unsigned long long n = C->q_cross;
+    const unsigned long long n_active = C->n_active[cur];
+    unsigned long long* const next_len = &C->n_active[(cur + 1) % 3];
+    unsigned crossings = 0;
+    int it = 0;
+    for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x, it++) {
+        const unsigned long long q = tile * BLOCK + threadIdx.x;
+        const bool valid = q < n;
+        uint32_t i = 0;
+        Particle p;
+        bool alive = false;
+        unsigned n_copy = 0;
+        if (valid) {
+            i = evq[n_active - 1 - q];
+            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
+            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+            alive = ev_cross_pre(P, p, B.surf[i], T, C, n_copy);
+            crossings++;
+        }
+        unsigned long long slot0 = 0;
+        if (P.shared_histories) {  // uniform: only problems with splitting reserve slots here
+            const unsigned cntA[1] = {n_copy};
+            unsigned long long* const curA[1] = {&C->slot_cursor};
+            unsigned long long posA[1];
+            block_reserve<1>(scratchA[it & 1], cntA, curA, posA);
+            slot0 = posA[0];
+        }
+        unsigned n_copy_ok = 0;
+        if (valid) {
+            alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_copy_ok);
+            if (alive) {
+                B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.t[i] = p.t;
+                B.wgt[i] = p.wgt; B.rng[i] = p.rng; B.cell[i] = p.cell;
             }
-            // floor( w/k * nuSigmaF / SigmaT + xi ) (general.cpp:135-136)
-            const double a = wgt / k_eff * X.nf / X.t;
-            const double bn = floor(a + mcb_urand(rng));
-            bank_nu = bn > 0.0 ? (unsigned)bn : 0u;
-            N_fission = select_nuclide(P, P.materials[m], u, E, 1, X.nf, mcb_urand(rng), nullptr);  // Material.cpp:116-125
-            if (N_fission >= 0) {
-                // prompt or delayed (ksearch.cpp:24-38, fixed_source.cpp:12,41-52)
-                const DevMaterial& M = P.materials[m];
-                int ln = 0;
-                for (int n = 0; n < M.n_nuc; n++) if (P.mat_nuclide[M.nuc_begin + n] == N_fission) { ln = n; break; }
-                const double beta = micro_col(P.nuclides[N_fission], nuclide_index(M, u, ln), E, 1);
-                const bool prompt = mcb_urand(rng) > beta;
-                if (P.ksearch) {
-                    if (!prompt) (void)mcb_urand(rng);  // precursor group pick, result unused
-                    n_sites = bank_nu;
-                } else if (prompt) {
-                    n_second = bank_nu;
-                } else {
-                    // delayed, non-TDMC branch: draws are consumed, no neutron is banked (fixed_source.cpp:41-63)
-                    (void)mcb_urand(rng);
-                    for (unsigned b = 0; b < bank_nu; b++) { (void)mcb_urand(rng); (void)mcb_urand(rng); }
-                }
+        }
+        const unsigned cntB[1] = {(alive ? 1u : 0u) + n_copy_ok};
+        unsigned long long* const curB[1] = {next_len};
+        unsigned long long posB[1];
+        block_reserve<1>(scratchB[it & 1], cntB, curB, posB);
+        unsigned long long o = posB[0];
+        if (alive) next[o++] = i;
+        for (unsigned b = 0; b < n_copy_ok; b++) next[o++] = (uint32_t)(slot0 + b);
+    }
+    for (int d = 16; d; d >>= 1) crossings += __shfl_xor_sync(FULL, crossings, d);
+    if (lane_id() == 0 && crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
+}
+
+// fused step: up to `max_events` events (lookup -> flight -> collide | cross) of every queued particle, chained in
+// registers, the whole block advancing in lockstep so that banking can use block-level reservations.  Survivors are
+// compacted into the next queue with their state written back once.  Per track this moves a fraction of the bytes
+// of the split stage kernels and pays the DRAM latency of the queue/bank indirection once per launch instead of
+// once per stage.  Queue lengths rotate over three counters: read [cur], fill [nxt], clear [(nxt+1)%3].
+#ifndef MCB_STEP_MINB
+#define MCB_STEP_MINB 2
+#endif
+__global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
+k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, int max_events, Counters* C, uint32_t* next,
+       HistoryAcc H, TallyAcc T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots, double k_eff)
+{
+    __shared__ BlockScratch<2> scratchA[2];
+    __shared__ BlockScratch<1> scratchB[2];
+    const int nxt = cur == 2 ? 0 : cur + 1;
+    const unsigned long long n = C->n_active[cur];
+    unsigned long long* const next_len = &C->n_active[nxt];
+    if (blockIdx.x == 0 && threadIdx.x == 0) C->n_active[nxt == 2 ? 0 : nxt + 1] = 0;
+    unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
+    int ss = 0, it = 0;
+    for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x, it++) {
+        const unsigned long long q = tile * BLOCK + threadIdx.x;
+        bool alive = q < n;
+        uint32_t i = 0;
+        Particle p;
+        if (alive) {
+            i = active[q];
+            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
+            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+        }
+        for (int step = 0; step < max_events; step++) {
+            if (!__syncthreads_or(alive)) break;
+            MacroXS X = {0, 0, 0, 0, 0};
+            XSDetail D;
+            CollideCtx c = {-1, -1, 0, 0};
+            int uidx = -1;
+            unsigned n_copy = 0;
+            bool to_cross = false, in_material = false;
+            if (alive) {
+                int S;
+                if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
+                to_cross = ev_flight(P, p, X, uidx, H, T, S);
+                tracks++;
+                if (to_cross) { alive = ev_cross_pre(P, p, S, T, C, n_copy); crossings++; }
+                else { in_material = ev_collide_pre(P, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
             }
-            x = B.x[i]; y = B.y[i]; z = B.z[i]; t = B.t[i];
+            const unsigned cnt[2] = {c.n_sites, c.n_second + n_copy};
+            unsigned long long* const cursor[2] = {&C->site_cursor, &C->slot_cursor};
+            unsigned long long pos[2];
+            block_reserve<2>(scratchA[ss & 1], cnt, cursor, pos);
+            ss++;
+            unsigned n_new = 0;
+            if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, pos[1], n_slots, C, n_new);
+            else if (in_material) alive = ev_collide_post(P, B, p, X, uidx, &D, c, H, C, tmp_sites, tmp_hist, site_cap, n_slots, pos[0], pos[1], n_new);
+            if (n_new) {  // secondaries (fixed-source fission, splitting) join the next queue; rare, so per thread
+                const unsigned long long o = atomicAdd(next_len, (unsigned long long)n_new);
+                for (unsigned b = 0; b < n_new; b++) next[o + b] = (uint32_t)(pos[1] + b);
+            }
+        }
+        const unsigned cntB[1] = {alive ? 1u : 0u};
+        unsigned long long* const curB[1] = {next_len};
+        unsigned long long posB[1];
+        block_reserve<1>(scratchB[it & 1], cntB, curB, posB);
+        if (alive) {
+            B.cell[i] = p.cell;
+            B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w;
+            B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.t[i] = p.t; B.rng[i] = p.rng;
+            next[posB[0]] = i;
         }
     }
-    count_add(&C->n_collisions, valid && in_material);
-    // reserve space for everything this warp banks: one atomic per warp
-    const unsigned long long site0 = warp_reserve<unsigned long long>(&C->site_cursor, n_sites);
-    const unsigned slot0 = warp_reserve<unsigned int>(&C->slot_cursor, n_second);
-    if (valid && in_material) {
-        if (n_sites) {
-            // implicit_fission_ksearch (ksearch.cpp:39-46): bank_nu sites, Watt energy then isotropic direction, w = 1
-            int seq0;
-            if (P.shared_histories) seq0 = atomicAdd(&H.nsite[h], (int)n_sites);
-            else { seq0 = H.nsite[h]; H.nsite[h] = seq0 + (int)n_sites; }
-            const DevNuclide& N = P.nuclides[N_fission];
-            for (unsigned b = 0; b < n_sites; b++) {
-                Site s;
-                s.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, E, rng);
-                isotropic_direction(rng, s.u, s.v, s.w);
-                s.x = x; s.y = y; s.z = z; s.t = t; s.cell = cell; s.seq = seq0 + (int)b;
-                if (site0 + b < site_cap) { tmp_sites[site0 + b] = s; tmp_hist[site0 + b] = h; }
-                else C->overflow_sites = 1;
-            }
-        }
-        if (n_second) {
-            // implicit_fission_fixed_source, prompt branch (fixed_source.cpp:12-22): same-history secondaries
-            const DevNuclide& N = P.nuclides[N_fission];
-            for (unsigned b = 0; b < n_second; b++) {
-                const double Es = watt_sample(N.watt_a, N.watt_b, N.watt_g, E, rng);
-                double du, dv, dw;
-                isotropic_direction(rng, du, dv, dw);
-                const unsigned j = slot0 + b;
-                if (j < n_slots) {
-                    B.x[j] = x; B.y[j] = y; B.z[j] = z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
-                    B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = t;
-                    B.rng[j] = mcb_rn_child_seed(rng, b); B.cell[j] = cell; B.hist[j] = h;
-                } else C->overflow_slots = 1;
-            }
-        }
-        if (P.ksearch && N_fission >= 0) hist_add(&H.kC[h], X.nf * wgt / X.t, P.shared_histories);  // estimate_C (Estimator.cpp:503-507)
-        // implicit absorption (general.cpp:154-156)
-        const double implicit = X.c + X.f;
-        wgt = wgt * (X.t - implicit) / X.t;
-        alive = true;
-        const int N_scatter = select_nuclide(P, P.materials[m], u, E, 0, X.s, mcb_urand(rng), nullptr);  // Material.cpp:106-115
-        if (N_scatter >= 0) {
-            double du = B.u[i], dv = B.v[i], dw = B.w[i], speed = B.speed[i];
-            scatter_sample(P.nuclides[N_scatter].A, du, dv, dw, E, speed, rng);
-            B.u[i] = du; B.v[i] = dv; B.w[i] = dw; B.E[i] = E; B.speed[i] = speed;
-        }
-        // weight_roulette (population_control.cpp:9-15)
-        if (wgt < P.wr) {
-            if (mcb_urand(rng) < wgt / P.ws) wgt = P.ws;
-            else { wgt = 0.0; alive = false; }
-        }
-        B.wgt[i] = wgt; B.rng[i] = rng;
+    for (int d = 16; d; d >>= 1) {
+        tracks += __shfl_xor_sync(FULL, tracks, d); collisions += __shfl_xor_sync(FULL, collisions, d);
+        crossings += __shfl_xor_sync(FULL, crossings, d); lookups += __shfl_xor_sync(FULL, lookups, d);
     }
-    // survivors and their secondaries go to the next iteration's queue
-    const unsigned pn = warp_append(&C->q_next, alive);
-    if (alive) next[pn] = i;
-    if (__any_sync(FULL, n_second > 0)) {
-        unsigned ok = 0;
-        for (unsigned b = 0; b < n_second; b++) if (slot0 + b < n_slots) ok++;
-        const unsigned p0 = warp_reserve<unsigned int>(&C->q_next, ok);
-        for (unsigned b = 0; b < ok; b++) next[p0 + b] = slot0 + b;
+    if (lane_id() == 0) {
+        if (tracks) atomicAdd(&C->n_tracks, (unsigned long long)tracks);
+        if (collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
+        if (crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
+        if (lookups) atomicAdd(&C->n_lookups, (unsigned long long)lookups);
     }
 }
 
-// cross stage: surface_hit (general.cpp:89-115) + cell_importance + weight_roulette (population_control.cpp:9-49)
-__global__ void __launch_bounds__(256)
-k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, uint32_t n_active, Counters* C, uint32_t* next,
-        TallyAcc T, uint32_t n_slots)
+// tail of a batch: every queued particle is followed to the end of its history in registers (the same events,
+// chained).  Secondaries born here are queued for another pass.  Cursors are bumped per thread: with a few
+// thousand particles left there is no contention to aggregate away.
+__global__ void __launch_bounds__(BLOCK)
+k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, Counters* C, uint32_t* next, HistoryAcc H,
+         TallyAcc T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = q < C->q_cross;
-    uint32_t i = 0;
-    bool alive = false;
-    unsigned n_copy = 0;
-    double x = 0, y = 0, z = 0, u = 0, v = 0, w = 0, t = 0, wgt = 0, E = 0, speed = 0;
-    uint64_t rng = 0;
-    int cell = 0, h = 0;
-    if (valid) {
-        i = evq[n_active - 1 - q];
-        const int S = B.surf[i];
-        const mcb_surface& Sf = P.surfaces[S];
-        x = B.x[i]; y = B.y[i]; z = B.z[i]; u = B.u[i]; v = B.v[i]; w = B.w[i]; t = B.t[i];
-        wgt = B.wgt[i]; rng = B.rng[i]; speed = B.speed[i]; E = B.E[i];
-        cell = B.cell[i]; h = B.hist[i];
-        int cell_old = cell;
-        alive = true;
-        if (Sf.bc == MCB_BC_TRANSMISSION) {
-            x += u * MCB_EPSILON_FLOAT; y += v * MCB_EPSILON_FLOAT; z += w * MCB_EPSILON_FLOAT;
-            t += MCB_EPSILON_FLOAT / speed;
-            const int cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, x, y, z);
-            if (cn < 0) {  // "[WARNING] A particle is lost" (general.cpp:31-33)
-                if (atomicExch(&C->lost, 1) == 0) { C->lost_pos[0] = x; C->lost_pos[1] = y; C->lost_pos[2] = z; }
-                alive = false; wgt = 0.0;
-            } else cell = cn;
-        } else if (Sf.bc == MCB_BC_VACUUM) {
-            alive = false; wgt = 0.0;
-        } else {
-            mcb_surf_reflect(Sf, u, v, w);
-            x += u * MCB_EPSILON_FLOAT; y += v * MCB_EPSILON_FLOAT; z += w * MCB_EPSILON_FLOAT;
-            t += MCB_EPSILON_FLOAT / speed;
-        }
-        if (T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
-            ScoreState s;
-            s.w = wgt; s.E = E; s.speed = speed; s.cell = cell; s.surface_old = S; s.material = P.cells[cell].material;
-            s.u = -1; s.X = MacroXS{0, 0, 0, 0, 0};
-            if (s.material >= 0) { s.u = union_index(P.materials[s.material], E); macro_xs(P, P.materials[s.material], s.u, E, s.X); }
-            score_attached(P, T, MCB_ATTACH_SURFACE, S, s, 0.0, h);
-        }
-        // cell_importance (population_control.cpp:21-49)
-        const double Iold = P.cells[cell_old].importance, Inew = P.cells[cell].importance;
-        if (Inew != Iold) {
-            const double rat = Inew / Iold;
-            if (rat < 1.0) {
-                if (mcb_urand(rng) < rat) wgt = wgt / rat;
-                else { alive = false; wgt = 0.0; }
+    const unsigned long long n = C->n_active[cur];
+    unsigned long long* const next_len = &C->n_active[(cur + 1) % 3];
+    unsigned long long tracks = 0, collisions = 0, crossings = 0, lookups = 0;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * BLOCK) {
+        const uint32_t i = active[q];
+        Particle p;
+        p.cell = B.cell[i]; p.hist = B.hist[i];
+        p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
+        p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+        bool alive = true;
+        while (alive) {
+            MacroXS X = {0, 0, 0, 0, 0};
+            XSDetail D;
+            int uidx = -1, S;
+            if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
+            const bool to_cross = ev_flight(P, p, X, uidx, H, T, S);
+            tracks++;
+            unsigned n_new = 0;
+            unsigned long long slot0 = 0;
+            if (to_cross) {
+                unsigned n_copy;
+                alive = ev_cross_pre(P, p, S, T, C, n_copy);
+                crossings++;
+                if (n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)n_copy);
+                alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
             } else {
-                const int ns = (int)floor(rat + mcb_urand(rng));
-                wgt = wgt / (double)ns;
-                n_copy = ns > 1 ? (unsigned)(ns - 1) : 0u;
+                CollideCtx c;
+                alive = ev_collide_pre(P, p, X, uidx, &D, T, k_eff, c);
+                if (alive) {
+                    collisions++;
+                    unsigned long long site0 = 0;
+                    if (c.n_sites) site0 = atomicAdd(&C->site_cursor, (unsigned long long)c.n_sites);
+                    if (c.n_second) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)c.n_second);
+                    alive = ev_collide_post(P, B, p, X, uidx, &D, c, H, C, tmp_sites, tmp_hist, site_cap, n_slots, site0, slot0, n_new);
+                }
+            }
+            if (n_new) {
+                const unsigned long long o = atomicAdd(next_len, (unsigned long long)n_new);
+                for (unsigned b = 0; b < n_new; b++) next[o + b] = (uint32_t)(slot0 + b);
             }
         }
     }
-    count_add(&C->n_crossings, valid);
-    const unsigned slot0 = warp_reserve<unsigned int>(&C->slot_cursor, n_copy);
-    unsigned ok = 0;
-    if (valid) {
-        // split copies carry the state after the importance draw; stream j = (j+1)*2^40 draws ahead
-        for (unsigned b = 0; b < n_copy; b++) {
-            const unsigned j = slot0 + b;
-            if (j < n_slots) {
-                B.x[j] = x; B.y[j] = y; B.z[j] = z; B.u[j] = u; B.v[j] = v; B.w[j] = w;
-                B.E[j] = E; B.speed[j] = speed; B.wgt[j] = wgt; B.t[j] = t;
-                B.rng[j] = mcb_rn_child_seed(rng, b); B.cell[j] = cell; B.hist[j] = h;
-                ok++;
-            } else C->overflow_slots = 1;
-        }
-        // weight_roulette: also draws for a particle that was just killed (w = 0 < wr), like the reference
-        if (wgt < P.wr) {
-            if (mcb_urand(rng) < wgt / P.ws) wgt = P.ws;
-            else { wgt = 0.0; alive = false; }
-        }
-        B.x[i] = x; B.y[i] = y; B.z[i] = z; B.u[i] = u; B.v[i] = v; B.w[i] = w; B.t[i] = t;
-        B.wgt[i] = wgt; B.rng[i] = rng; B.cell[i] = cell;
-    }
-    const unsigned pn = warp_append(&C->q_next, alive);
-    if (alive) next[pn] = i;
-    if (__any_sync(FULL, n_copy > 0)) {
-        const unsigned p0 = warp_reserve<unsigned int>(&C->q_next, ok);
-        for (unsigned b = 0; b < ok; b++) next[p0 + b] = slot0 + b;
-    }
+    if (tracks) atomicAdd(&C->n_tracks, tracks);
+    if (collisions) atomicAdd(&C->n_collisions, collisions);
+    if (crossings) atomicAdd(&C->n_crossings, crossings);
+    if (lookups) atomicAdd(&C->n_lookups, lookups);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -596,6 +866,29 @@ __global__ void k_tally_final(const double* partial, int n_chunks, int64_t n_tal
     squared[t] += q;
 }
 
+// host-facing bank layout (n x 8 doubles + n cells) <-> Site records
+__global__ void __launch_bounds__(256)
+k_pack_sites(const double* __restrict__ s8, const int32_t* __restrict__ cells, uint64_t n, Site* out)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double* s = s8 + 8 * q;
+    Site d;
+    d.x = s[0]; d.y = s[1]; d.z = s[2]; d.u = s[3]; d.v = s[4]; d.w = s[5]; d.E = s[6]; d.t = s[7];
+    d.cell = cells[q]; d.seq = 0;
+    out[q] = d;
+}
+__global__ void __launch_bounds__(256)
+k_unpack_sites(const Site* __restrict__ in, uint64_t n, double* s8, int32_t* cells)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const Site d = in[q];
+    double* s = s8 + 8 * q;
+    s[0] = d.x; s[1] = d.y; s[2] = d.z; s[3] = d.u; s[4] = d.v; s[5] = d.w; s[6] = d.E; s[7] = d.t;
+    cells[q] = d.cell;
+}
+
 __global__ void k_iota(uint32_t* a, uint32_t n)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,34 +994,63 @@ inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n
 // ---------------------------------------------------------------------------------------------
 namespace mcbk {
 
+static thread_local uint64_t g_launches = 0;
+uint64_t launch_count() { return g_launches; }
+#define MCB_LAUNCHED(k) (g_launches += (k))
+
+static unsigned grid_for(uint64_t n_hint)
+{
+    // persistent tile loops: enough blocks to fill the machine a few times over, never more than the work
+    const uint64_t need = (n_hint + BLOCK - 1) / BLOCK;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 16ull));
+}
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
-            uint64_t nps0, const Site* sbank, uint64_t n_sbank)
+            uint64_t nps0, const Site* sbank, uint64_t n_sbank, Counters* C)
 {
-    if (count) k_source<<<blocks_for(count), 256, 0, st>>>(P, B, active, first_hist, count, nps0, sbank, n_sbank);
+    k_source<<<std::max(1u, blocks_for(count)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, sbank, n_sbank, C);
+    MCB_LAUNCHED(1);
 }
-void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, uint32_t n, Counters* C)
+void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C)
 {
-    if (n) k_xs_stage<<<blocks_for(n), 256, 0, st>>>(P, B, active, n, C);
+    k_xs_stage<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, C);
+    MCB_LAUNCHED(1);
 }
-void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, uint32_t n, uint32_t* evq,
-            Counters* C, const HistoryAcc& H, const TallyAcc& T)
+void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint,
+            uint32_t* evq, Counters* C, const HistoryAcc& H, const TallyAcc& T)
 {
-    if (n) k_flight<<<blocks_for(n), 256, 0, st>>>(P, B, active, n, evq, C, H, T);
+    k_flight<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, evq, C, H, T);
+    MCB_LAUNCHED(1);
 }
-void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, uint32_t n_upper, Counters* C,
+void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
              uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
              uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
-    if (n_upper) k_collide<<<blocks_for(n_upper), 256, 0, st>>>(P, B, evq, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    k_collide<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    MCB_LAUNCHED(1);
 }
-void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, uint32_t n_active,
-           uint32_t n_upper, Counters* C, uint32_t* next, const TallyAcc& T, uint32_t n_slots)
+void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
+           uint32_t* next, const TallyAcc& T, uint32_t n_slots)
 {
-    if (n_upper) k_cross<<<blocks_for(n_upper), 256, 0, st>>>(P, B, evq, n_active, C, next, T, n_slots);
+    k_cross<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, T, n_slots);
+    MCB_LAUNCHED(1);
+}
+void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, int max_events, uint64_t n_hint,
+          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+          uint64_t site_cap, uint32_t n_slots, double k_eff)
+{
+    k_step<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, max_events, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    MCB_LAUNCHED(1);
+}
+void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
+            uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap,
+            uint32_t n_slots, double k_eff)
+{
+    k_finish<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    MCB_LAUNCHED(1);
 }
 void bank_order(cudaStream_t st, const Site* tmp, const int32_t* tmp_hist, uint64_t n, const uint32_t* offset, Site* out)
 {
-    if (n) k_bank_order<<<blocks_for(n), 256, 0, st>>>(tmp, tmp_hist, n, offset, out);
+    if (n) { k_bank_order<<<blocks_for(n), 256, 0, st>>>(tmp, tmp_hist, n, offset, out); MCB_LAUNCHED(1); }
 }
 size_t scan_temp_bytes(uint32_t n)
 {
@@ -738,20 +1060,20 @@ size_t scan_temp_bytes(uint32_t n)
 }
 void scan_sites(cudaStream_t st, void* temp, size_t temp_bytes, const int32_t* nsite, uint32_t* offset, uint32_t n)
 {
-    if (n) cub::DeviceScan::ExclusiveSum(temp, temp_bytes, nsite, offset, (int)n, st);
+    if (n) { cub::DeviceScan::ExclusiveSum(temp, temp_bytes, nsite, offset, (int)n, st); MCB_LAUNCHED(2); }  // init + scan kernels
 }
 void reduce_k(cudaStream_t st, const double* kC, const double* kTL, uint32_t n, Counters* C)
 {
-    if (n) k_reduce_k<<<min(blocks_for(n), 148u * 8u), 256, 0, st>>>(kC, kTL, n, C);
+    if (n) { k_reduce_k<<<min(blocks_for(n), 148u * 8u), 256, 0, st>>>(kC, kTL, n, C); MCB_LAUNCHED(1); }
 }
 void entropy_history(cudaStream_t st, const DevProblem& P, const Site* bank, const uint32_t* offset,
                      const int32_t* nsite, uint32_t n_hist, Counters* C)
 {
-    if (n_hist) k_entropy_history<<<min(blocks_for(n_hist), 148u * 8u), 256, 0, st>>>(P, bank, offset, nsite, n_hist, C);
+    if (n_hist) { k_entropy_history<<<min(blocks_for(n_hist), 148u * 8u), 256, 0, st>>>(P, bank, offset, nsite, n_hist, C); MCB_LAUNCHED(1); }
 }
 void entropy_histogram(cudaStream_t st, const DevProblem& P, const Site* bank, uint64_t n, unsigned long long* bins)
 {
-    if (n) k_entropy_histogram<<<min(blocks_for(n), 148u * 8u), 256, 0, st>>>(P, bank, n, bins);
+    if (n) { k_entropy_histogram<<<min(blocks_for(n), 148u * 8u), 256, 0, st>>>(P, bank, n, bins); MCB_LAUNCHED(1); }
 }
 int tally_chunks(uint32_t n_hist) { return (int)((n_hist + TALLY_CHUNK - 1) / TALLY_CHUNK); }
 void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist, int64_t n_tallies, double* partial,
@@ -761,45 +1083,54 @@ void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist,
     const int nc = tally_chunks(n_hist);
     k_tally_partial<<<dim3(nc, (unsigned)n_tallies), 256, 0, st>>>(acc, stride, n_hist, partial, nc);
     k_tally_final<<<blocks_for(n_tallies, 128), 128, 0, st>>>(partial, nc, n_tallies, sum, squared);
+    MCB_LAUNCHED(2);
+}
+void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out)
+{
+    if (n) { k_pack_sites<<<blocks_for(n), 256, 0, st>>>(s8, cells, n, out); MCB_LAUNCHED(1); }
+}
+void unpack_sites(cudaStream_t st, const Site* in, uint64_t n, double* s8, int32_t* cells)
+{
+    if (n) { k_unpack_sites<<<blocks_for(n), 256, 0, st>>>(in, n, s8, cells); MCB_LAUNCHED(1); }
 }
 void iota(cudaStream_t st, uint32_t* a, uint32_t n)
 {
-    if (n) k_iota<<<blocks_for(n), 256, 0, st>>>(a, n);
+    if (n) { k_iota<<<blocks_for(n), 256, 0, st>>>(a, n); MCB_LAUNCHED(1); }
 }
 
 void xs_lookup(cudaStream_t st, const DevProblem& P, int material, const double* E, int64_t n, double* out5)
 {
-    if (n) k_xs_lookup<<<blocks_for(n), 256, 0, st>>>(P, material, E, n, out5);
+    if (n) { k_xs_lookup<<<blocks_for(n), 256, 0, st>>>(P, material, E, n, out5); MCB_LAUNCHED(1); }
 }
 void select_channel(cudaStream_t st, const DevProblem& P, int material, int kind, const double* E, const double* xi,
                     int64_t n, int32_t* out)
 {
-    if (n) k_select_channel<<<blocks_for(n), 256, 0, st>>>(P, material, kind, E, xi, n, out);
+    if (n) { k_select_channel<<<blocks_for(n), 256, 0, st>>>(P, material, kind, E, xi, n, out); MCB_LAUNCHED(1); }
 }
 void beta(cudaStream_t st, const DevProblem& P, int material, int local_n, const double* E, int64_t n, double* out)
 {
-    if (n) k_beta<<<blocks_for(n), 256, 0, st>>>(P, material, local_n, E, n, out);
+    if (n) { k_beta<<<blocks_for(n), 256, 0, st>>>(P, material, local_n, E, n, out); MCB_LAUNCHED(1); }
 }
 void rng(cudaStream_t st, uint64_t seed0, const uint64_t* nps, int64_t n, int ndraw, uint64_t* out)
 {
-    if (n) k_rng<<<blocks_for(n), 256, 0, st>>>(seed0, nps, n, ndraw, out);
+    if (n) { k_rng<<<blocks_for(n), 256, 0, st>>>(seed0, nps, n, ndraw, out); MCB_LAUNCHED(1); }
 }
 void geometry(cudaStream_t st, const DevProblem& P, const int32_t* cell, const double* pos, const double* dir,
               int64_t n, double* out3)
 {
-    if (n) k_geometry<<<blocks_for(n), 256, 0, st>>>(P, cell, pos, dir, n, out3);
+    if (n) { k_geometry<<<blocks_for(n), 256, 0, st>>>(P, cell, pos, dir, n, out3); MCB_LAUNCHED(1); }
 }
 void search_cell(cudaStream_t st, const DevProblem& P, const double* pos, int64_t n, int32_t* out)
 {
-    if (n) k_search_cell<<<blocks_for(n), 256, 0, st>>>(P, pos, n, out);
+    if (n) { k_search_cell<<<blocks_for(n), 256, 0, st>>>(P, pos, n, out); MCB_LAUNCHED(1); }
 }
 void scatter(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, int64_t n, double* io5)
 {
-    if (n) k_scatter<<<blocks_for(n), 256, 0, st>>>(P, nuclide, nps, n, io5);
+    if (n) { k_scatter<<<blocks_for(n), 256, 0, st>>>(P, nuclide, nps, n, io5); MCB_LAUNCHED(1); }
 }
 void watt(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, const double* E, int64_t n, double* out)
 {
-    if (n) k_watt<<<blocks_for(n), 256, 0, st>>>(P, nuclide, nps, E, n, out);
+    if (n) { k_watt<<<blocks_for(n), 256, 0, st>>>(P, nuclide, nps, E, n, out); MCB_LAUNCHED(1); }
 }
 
 }  // namespace mcbk

@@ -6,17 +6,28 @@
 
 namespace mcbk {
 
-// stages of one generation
+uint64_t launch_count();  // kernels launched by this thread through the launchers below
+
+// stages of one generation.  `cur` = iteration % 3 selects the queue-length counter the iteration reads
+// (Counters::n_active[cur]); it fills [(cur+1)%3] and clears [(cur+2)%3].  n_hint (an upper bound of the queue
+// length known to the host) only sizes the grid.
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
-            uint64_t nps0, const Site* sbank, uint64_t n_sbank);
-void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, uint32_t n, Counters* C);
-void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, uint32_t n, uint32_t* evq,
-            Counters* C, const HistoryAcc& H, const TallyAcc& T);
-void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, uint32_t n_upper, Counters* C,
+            uint64_t nps0, const Site* sbank, uint64_t n_sbank, Counters* C);
+void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C);
+void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint,
+            uint32_t* evq, Counters* C, const HistoryAcc& H, const TallyAcc& T);
+void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
              uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
              uint64_t site_cap, uint32_t n_slots, double k_eff);
-void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, uint32_t n_active,
-           uint32_t n_upper, Counters* C, uint32_t* next, const TallyAcc& T, uint32_t n_slots);
+void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
+           uint32_t* next, const TallyAcc& T, uint32_t n_slots);
+// fused: up to max_events events per queued particle in one launch
+void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, int max_events, uint64_t n_hint,
+          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+          uint64_t site_cap, uint32_t n_slots, double k_eff);
+void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
+            uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap,
+            uint32_t n_slots, double k_eff);
 
 // generation close-out
 void bank_order(cudaStream_t st, const Site* tmp, const int32_t* tmp_hist, uint64_t n, const uint32_t* offset, Site* out);
@@ -30,6 +41,8 @@ int tally_chunks(uint32_t n_hist);
 void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist, int64_t n_tallies, double* partial,
                   double* sum, double* squared);
 void iota(cudaStream_t st, uint32_t* a, uint32_t n);
+void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out);
+void unpack_sites(cudaStream_t st, const Site* in, uint64_t n, double* s8, int32_t* cells);
 
 // parity / bench kernels on plain device arrays
 void xs_lookup(cudaStream_t st, const DevProblem& P, int material, const double* E, int64_t n, double* out5);
