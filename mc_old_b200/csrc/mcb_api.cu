@@ -163,8 +163,8 @@ struct mcb_ctx {
     HistoryAcc H{};
     // fission bank
     uint64_t site_cap = 0, global_cap = 0;
-    DevBuf<Site> d_tmp_sites, d_local_bank, d_global_bank;
-    DevBuf<int32_t> d_tmp_hist;
+    DevBuf<SiteReq> d_site_reqs;
+    DevBuf<Site> d_local_bank, d_global_bank;
     DevBuf<double> d_io_sites;       // staging for host-facing bank I/O (n x 8 doubles)
     DevBuf<int32_t> d_io_cells;
     uint64_t n_local_sites = 0, n_source_sites = 0;  // local bank of the last cycle; global source bank for the next
@@ -408,8 +408,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         // the first generations of a badly converged source bank up to ~3 sites per history (k_cycle of a 14 MeV
         // point source in HEU is 2.7); leave room for 4
         ctx->site_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity : 4 * ctx->shard_count + 4096;
-        CK(ctx->d_tmp_sites.alloc(ctx->site_cap));
-        CK(ctx->d_tmp_hist.alloc(ctx->site_cap));
+        CK(ctx->d_site_reqs.alloc(ctx->site_cap));
         CK(ctx->d_local_bank.alloc(ctx->site_cap));
         if (ctx->world > 1) {
             ctx->global_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity * ctx->world : 4 * p->n_sample + 4096ull * ctx->world;
@@ -550,7 +549,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
             mcbk::flight(st, P, ctx->B, q_in, cur, known_n, ctx->q_ev, C, ctx->H, T);
             ctx->timer.end(st);
             ctx->timer.begin(st, ST_COLLIDE);
-            mcbk::collide(st, P, ctx->B, ctx->q_ev, cur, known_n, C, q_out, ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+            mcbk::collide(st, P, ctx->B, ctx->q_ev, cur, known_n, C, q_out, ctx->H, T, ctx->d_site_reqs.p,
                           ctx->site_cap, ctx->n_slots, ctx->k);
             ctx->timer.end(st);
             ctx->timer.begin(st, ST_CROSS);
@@ -558,7 +557,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
             ctx->timer.end(st);
         } else {
             ctx->timer.begin(st, ST_STEP);
-            mcbk::step(st, P, ctx->B, q_in, cur, ctx->step_events, known_n, C, q_out, ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+            mcbk::step(st, P, ctx->B, q_in, cur, ctx->step_events, known_n, C, q_out, ctx->H, T, ctx->d_site_reqs.p,
                        ctx->site_cap, ctx->n_slots, ctx->k);
             ctx->timer.end(st);
         }
@@ -586,7 +585,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
         const int cur = it % 3, nxt = (it + 1) % 3;
         CK(cudaMemsetAsync(&C->n_active[nxt], 0, sizeof(unsigned long long), st));
         ctx->timer.begin(st, ST_FINISH);
-        mcbk::finish(st, P, ctx->B, queue[it & 1], cur, n_left, C, queue[(it + 1) & 1], ctx->H, T, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p,
+        mcbk::finish(st, P, ctx->B, queue[it & 1], cur, n_left, C, queue[(it + 1) & 1], ctx->H, T, ctx->d_site_reqs.p,
                      ctx->site_cap, ctx->n_slots, ctx->k);
         ctx->timer.end(st);
         CK(cudaMemcpyAsync(&ctx->h_ring[0], &C->n_active[nxt], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -640,7 +639,7 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     if (ctx->ksearch) {
         ctx->timer.begin(st, ST_BANK);
         mcbk::scan_sites(st, ctx->d_scan_temp.p, ctx->d_scan_temp.n, ctx->H.nsite, ctx->d_site_offset.p, (uint32_t)ctx->shard_count);
-        mcbk::bank_order(st, ctx->d_tmp_sites.p, ctx->d_tmp_hist.p, n_local, ctx->d_site_offset.p, ctx->d_local_bank.p);
+        mcbk::bank_sample_order(st, ctx->P, ctx->d_site_reqs.p, n_local, ctx->d_site_offset.p, ctx->d_local_bank.p);
         ctx->timer.end(st);
         if (ctx->entropy_on) {
             ctx->timer.begin(st, ST_CLOSEOUT);

@@ -72,6 +72,14 @@ struct Site {
     int32_t cell, seq;                    // seq = order of banking within the parent history
 };
 
+// a fission site as the collision leaves it: where, from what, and the stream it will be sampled from.  The
+// outgoing energy and direction are drawn later, in one dense pass over the whole generation's requests.
+struct SiteReq {
+    double x, y, z, t, E_in;
+    uint64_t seed;
+    int32_t cell, seq, hist, nuclide;
+};
+
 struct Counters {
     unsigned long long n_tracks, n_collisions, n_lookups, n_crossings, n_histories;
     unsigned long long site_cursor;       // unordered fission sites banked this cycle
@@ -195,9 +203,12 @@ __device__ __forceinline__ int select_from_detail(const DevProblem& P, const Dev
                                                   double xi, int* local_n)
 {
     const double thr = total * xi;
-    for (int n = 0; n < M.n_nuc; n++)
-        if (cum[n] > thr) { *local_n = n; return __ldg(&P.mat_nuclide[M.nuc_begin + n]); }
-    return -1;
+    int sel = -1;
+    for (int n = M.n_nuc - 1; n >= 0; n--)   // single exit; the last hit is the first nuclide with cum > thr
+        if (cum[n] > thr) sel = n;
+    if (sel < 0) return -1;
+    *local_n = sel;
+    return __ldg(&P.mat_nuclide[M.nuc_begin + sel]);
 }
 // Material::SigmaA (Material.cpp:34-41)
 __device__ __forceinline__ double macro_sigma_a(const DevProblem& P, const DevMaterial& M, int u, double E)
@@ -211,19 +222,24 @@ __device__ __forceinline__ double macro_sigma_a(const DevProblem& P, const DevMa
 }
 // Material::nuclide_scatter (kind 0) / nuclide_nufission (kind 1) (Material.cpp:106-125): global nuclide index or -1.
 // `total` is the macroscopic xs the partial sums are compared against (SigmaS or nuSigmaF at the same E).
+// The loop has a single exit (no early return): lanes that pick different nuclides must leave it together, or the
+// warp runs everything that follows once per picked nuclide.
 __device__ __forceinline__ int select_nuclide(const DevProblem& P, const DevMaterial& M, int u, double E, int kind,
                                               double total, double xi, int* local_n)
 {
     const double thr = total * xi;
     double s = 0.0;
+    int sel = -1;
     for (int n = 0; n < M.n_nuc; n++) {
         const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
         MicroXS m;
         micro_xs(P.nuclides[gn], nuclide_index(M, u, n), E, m);
         s += (kind == 0 ? m.s : m.f * m.nu) * __ldg(&P.mat_density[M.nuc_begin + n]);
-        if (s > thr) { if (local_n) *local_n = n; return gn; }
+        if (sel < 0 && s > thr) sel = n;
     }
-    return -1;
+    if (sel < 0) return -1;
+    if (local_n) *local_n = sel;
+    return __ldg(&P.mat_nuclide[M.nuc_begin + sel]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -239,43 +239,52 @@ __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p,
     }
     return true;
 }
-// collide event, second half: bank the fission neutrons at [site0, ..) / [slot0, ..), k_C, implicit capture,
-// scatter, weight_roulette (general.cpp:139-163, ksearch.cpp:39-46, fixed_source.cpp:12-22, population_control.cpp:9-15).
-// Returns whether the particle survives; n_second_ok = secondaries that found a slot.
-__device__ __forceinline__ bool ev_collide_post(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx,
-                                                const XSDetail* D, const CollideCtx& c, const HistoryAcc& H, Counters* C, Site* tmp_sites,
-                                                int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots,
-                                                unsigned long long site0, unsigned long long slot0, unsigned& n_second_ok)
+// collide event, banking part.  k-eigenvalue (ksearch.cpp:39-46): one request per fission site goes to
+// [site0, ..) of the request buffer; its Watt energy and isotropic direction are sampled by k_bank_sample_order
+// from the request's own stream.  Fixed source (fixed_source.cpp:12-22): same-history secondaries are written to
+// bank slots [slot0, ..), each sampled from, and continuing on, its own stream.  The parent's stream does not
+// advance.  Only lanes that bank anything call this; callers reconverge the warp afterwards.
+__device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank& B, const Particle& p, const CollideCtx& c,
+                                                const HistoryAcc& H, Counters* C, SiteReq* reqs, uint64_t site_cap,
+                                                uint32_t n_slots, unsigned long long site0, unsigned long long slot0,
+                                                unsigned& n_second_ok)
 {
     n_second_ok = 0;
-    const double E_in = p.E;
+    uint64_t seed = p.rng;
     if (c.n_sites) {
         const int seq0 = atomicAdd(&H.nsite[p.hist], (int)c.n_sites);
-        const DevNuclide& N = P.nuclides[c.N_fission];
         for (unsigned b = 0; b < c.n_sites; b++) {
-            Site s;
-            s.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, E_in, p.rng);   // energy first, then direction (App. D-4)
-            isotropic_direction(p.rng, s.u, s.v, s.w);
-            s.x = p.x; s.y = p.y; s.z = p.z; s.t = p.t; s.cell = p.cell; s.seq = seq0 + (int)b;
-            if (site0 + b < site_cap) { tmp_sites[site0 + b] = s; tmp_hist[site0 + b] = p.hist; }
+            seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
+            SiteReq r;
+            r.x = p.x; r.y = p.y; r.z = p.z; r.t = p.t; r.E_in = p.E; r.seed = seed;
+            r.cell = p.cell; r.seq = seq0 + (int)b; r.hist = p.hist; r.nuclide = c.N_fission;
+            if (site0 + b < site_cap) reqs[site0 + b] = r;
             else C->overflow_sites = 1;
         }
     }
     if (c.n_second) {
         const DevNuclide& N = P.nuclides[c.N_fission];
         for (unsigned b = 0; b < c.n_second; b++) {
-            const double Es = watt_sample(N.watt_a, N.watt_b, N.watt_g, E_in, p.rng);
+            seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
+            uint64_t rs = seed;
+            const double Es = watt_sample(N.watt_a, N.watt_b, N.watt_g, p.E, rs);   // energy first, then direction (App. D-4)
             double du, dv, dw;
-            isotropic_direction(p.rng, du, dv, dw);
+            isotropic_direction(rs, du, dv, dw);
             const unsigned long long j = slot0 + b;
             if (j < n_slots) {
                 B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
                 B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = p.t;
-                B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
+                B.rng[j] = rs; B.cell[j] = p.cell; B.hist[j] = p.hist;
                 n_second_ok++;
             } else C->overflow_slots = 1;
         }
     }
+}
+// collide event, last part: k_C, implicit capture, scatter, weight_roulette (general.cpp:146-163,
+// population_control.cpp:9-15).  Returns whether the particle survives.
+__device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
+                                                   const CollideCtx& c, const HistoryAcc& H)
+{
     if (P.ksearch && c.N_fission >= 0) hist_add(&H.kC[p.hist], X.nf * p.wgt / X.t);  // estimate_C (Estimator.cpp:503-507)
     // implicit absorption (general.cpp:154-156)
     const double implicit = X.c + X.f;
@@ -480,7 +489,7 @@ k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
 // collide stage
 __global__ void __launch_bounds__(BLOCK)
 k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, Counters* C, uint32_t* next, HistoryAcc H,
-          TallyAcc T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots, double k_eff)
+          TallyAcc T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     __shared__ BlockScratch<2> scratchA[2];
     __shared__ BlockScratch<1> scratchB[2];
@@ -512,8 +521,11 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
         block_reserve<2>(scratchA[it & 1], cntA, curA, posA);
         bool alive = false;
         unsigned n_second_ok = 0;
+        if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, posA[0], posA[1], n_second_ok);
+        __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
+        if (in_material) alive = ev_collide_scatter(P, p, X, uidx, nullptr, c, H);
+        __syncwarp();
         if (valid) {
-            if (in_material) alive = ev_collide_post(P, B, p, X, uidx, nullptr, c, H, C, tmp_sites, tmp_hist, site_cap, n_slots, posA[0], posA[1], n_second_ok);
             B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.rng[i] = p.rng;
         }
         // survivors and their secondaries go to the next iteration's queue
@@ -594,7 +606,7 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
 #endif
 __global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
 k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, int max_events, Counters* C, uint32_t* next,
-       HistoryAcc H, TallyAcc T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots, double k_eff)
+       HistoryAcc H, TallyAcc T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     __shared__ BlockScratch<2> scratchA[2];
     __shared__ BlockScratch<1> scratchB[2];
@@ -637,8 +649,12 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
             block_reserve<2>(scratchA[ss & 1], cnt, cursor, pos);
             ss++;
             unsigned n_new = 0;
+            if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, pos[0], pos[1], n_new);
+            __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
             if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, pos[1], n_slots, C, n_new);
-            else if (in_material) alive = ev_collide_post(P, B, p, X, uidx, &D, c, H, C, tmp_sites, tmp_hist, site_cap, n_slots, pos[0], pos[1], n_new);
+            __syncwarp();
+            if (in_material) alive = ev_collide_scatter(P, p, X, uidx, &D, c, H);
+            __syncwarp();
             if (n_new) {  // secondaries (fixed-source fission, splitting) join the next queue; rare, so per thread
                 const unsigned long long o = atomicAdd(next_len, (unsigned long long)n_new);
                 for (unsigned b = 0; b < n_new; b++) next[o + b] = (uint32_t)(pos[1] + b);
@@ -672,7 +688,7 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
 // thousand particles left there is no contention to aggregate away.
 __global__ void __launch_bounds__(BLOCK)
 k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, Counters* C, uint32_t* next, HistoryAcc H,
-         TallyAcc T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap, uint32_t n_slots, double k_eff)
+         TallyAcc T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     const unsigned long long n = C->n_active[cur];
     unsigned long long* const next_len = &C->n_active[(cur + 1) % 3];
@@ -707,7 +723,8 @@ k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
                     unsigned long long site0 = 0;
                     if (c.n_sites) site0 = atomicAdd(&C->site_cursor, (unsigned long long)c.n_sites);
                     if (c.n_second) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)c.n_second);
-                    alive = ev_collide_post(P, B, p, X, uidx, &D, c, H, C, tmp_sites, tmp_hist, site_cap, n_slots, site0, slot0, n_new);
+                    if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new);
+                    alive = ev_collide_scatter(P, p, X, uidx, &D, c, H);
                 }
             }
             if (n_new) {
@@ -725,15 +742,22 @@ k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
 // ---------------------------------------------------------------------------------------------
 // generation close-out
 // ---------------------------------------------------------------------------------------------
-// fission bank in canonical order (parent history, banking order): position = offset[hist] + seq
+// fission bank in canonical order (parent history, banking order): position = offset[hist] + seq.  The site's
+// energy (Watt spectrum of the fissioning nuclide at the incident energy) and isotropic direction are sampled
+// here, one thread per site from the site's own stream (ksearch.cpp:41-46: energy first, then direction).
 __global__ void __launch_bounds__(256)
-k_bank_order(const Site* __restrict__ tmp, const int32_t* __restrict__ tmp_hist, uint64_t n,
-             const uint32_t* __restrict__ offset, Site* out)
+k_bank_sample_order(const DevProblem P, const SiteReq* __restrict__ reqs, uint64_t n, const uint32_t* __restrict__ offset, Site* out)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const Site s = tmp[q];
-    out[(uint64_t)offset[tmp_hist[q]] + (uint64_t)s.seq] = s;
+    const SiteReq r = reqs[q];
+    const DevNuclide& N = P.nuclides[r.nuclide];
+    uint64_t rng = r.seed;
+    Site s;
+    s.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, r.E_in, rng);
+    isotropic_direction(rng, s.u, s.v, s.w);
+    s.x = r.x; s.y = r.y; s.z = r.z; s.t = r.t; s.cell = r.cell; s.seq = r.seq;
+    out[(uint64_t)offset[r.hist] + (uint64_t)r.seq] = s;
 }
 
 __device__ __forceinline__ int entropy_bin(const DevProblem& P, double x, double y, double z)  // Entropy.cpp:27-35
@@ -1022,10 +1046,10 @@ void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t*
     MCB_LAUNCHED(1);
 }
 void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
-             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs,
              uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
-    k_collide<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    k_collide<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, H, T, reqs, site_cap, n_slots, k_eff);
     MCB_LAUNCHED(1);
 }
 void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
@@ -1035,22 +1059,22 @@ void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* 
     MCB_LAUNCHED(1);
 }
 void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, int max_events, uint64_t n_hint,
-          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs,
           uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
-    k_step<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, max_events, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    k_step<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, max_events, C, next, H, T, reqs, site_cap, n_slots, k_eff);
     MCB_LAUNCHED(1);
 }
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
-            uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap,
+            uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff)
 {
-    k_finish<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, C, next, H, T, tmp_sites, tmp_hist, site_cap, n_slots, k_eff);
+    k_finish<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, C, next, H, T, reqs, site_cap, n_slots, k_eff);
     MCB_LAUNCHED(1);
 }
-void bank_order(cudaStream_t st, const Site* tmp, const int32_t* tmp_hist, uint64_t n, const uint32_t* offset, Site* out)
+void bank_sample_order(cudaStream_t st, const DevProblem& P, const SiteReq* reqs, uint64_t n, const uint32_t* offset, Site* out)
 {
-    if (n) { k_bank_order<<<blocks_for(n), 256, 0, st>>>(tmp, tmp_hist, n, offset, out); MCB_LAUNCHED(1); }
+    if (n) { k_bank_sample_order<<<blocks_for(n), 256, 0, st>>>(P, reqs, n, offset, out); MCB_LAUNCHED(1); }
 }
 size_t scan_temp_bytes(uint32_t n)
 {

@@ -17,20 +17,20 @@ void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_
 void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint,
             uint32_t* evq, Counters* C, const HistoryAcc& H, const TallyAcc& T);
 void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
-             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs,
              uint64_t site_cap, uint32_t n_slots, double k_eff);
 void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
            uint32_t* next, const TallyAcc& T, uint32_t n_slots);
 // fused: up to max_events events per queued particle in one launch
 void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, int max_events, uint64_t n_hint,
-          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist,
+          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs,
           uint64_t site_cap, uint32_t n_slots, double k_eff);
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
-            uint32_t* next, const HistoryAcc& H, const TallyAcc& T, Site* tmp_sites, int32_t* tmp_hist, uint64_t site_cap,
+            uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff);
 
 // generation close-out
-void bank_order(cudaStream_t st, const Site* tmp, const int32_t* tmp_hist, uint64_t n, const uint32_t* offset, Site* out);
+void bank_sample_order(cudaStream_t st, const DevProblem& P, const SiteReq* reqs, uint64_t n, const uint32_t* offset, Site* out);
 size_t scan_temp_bytes(uint32_t n);
 void scan_sites(cudaStream_t st, void* temp, size_t temp_bytes, const int32_t* nsite, uint32_t* offset, uint32_t n);
 void reduce_k(cudaStream_t st, const double* kC, const double* kTL, uint32_t n, Counters* C);

@@ -744,14 +744,30 @@ static int surface_hit(mco_ctx* c, particle* P, int S) /* general.cpp:89-115 */
 }
 /* fission-site particle: Particle(P.pos(), isotropic.sample(), Chi(E), P.time(), 1.0, ..) — g++ evaluates the
  * arguments right to left: Watt energy first, then the direction (ksearch.cpp:41-46, fixed_source.cpp:16-21) */
-static particle fission_neutron(mco_ctx* c, particle* P, int nuc)
+/* MCO_RNG_HISTORY: the b-th neutron banked by a collision is sampled from its own stream, the parent's state at the
+ * banking point jumped (b+1)*2^40 draws ahead; the parent's stream does not advance.  (With one global stream, as in
+ * the reference, the neutrons are simply sampled from it in order.)  This lets the GPU sample all fission sites of
+ * a generation in one dense pass instead of inside the divergent collision branch. */
+static particle fission_neutron(mco_ctx* c, particle* P, int nuc, int b)
 {
     const mcb_nuclide* N = &c->p->nuclides[nuc];
-    rng_ref r = {c, P, 0};
     double dir[3];
-    const double E = watt_sample(N->watt_a, N->watt_b, N->watt_g, P->E, &r);
-    isotropic_direction(&r, dir);
-    return p_make(P->pos, dir, E, P->t, 1.0, P->cell);
+    if (c->rng_mode == MCO_RNG_HISTORY) {
+        uint64_t s = mco_lcg_skip(P->rng, ((uint64_t)(b + 1)) << 40);
+        rng_ref r = {0, 0, &s};
+        particle Q;
+        const double E = watt_sample(N->watt_a, N->watt_b, N->watt_g, P->E, &r);
+        isotropic_direction(&r, dir);
+        Q = p_make(P->pos, dir, E, P->t, 1.0, P->cell);
+        Q.rng = s;
+        c->n_draws += 0;
+        return Q;
+    } else {
+        rng_ref r = {c, P, 0};
+        const double E = watt_sample(N->watt_a, N->watt_b, N->watt_g, P->E, &r);
+        isotropic_direction(&r, dir);
+        return p_make(P->pos, dir, E, P->t, 1.0, P->cell);
+    }
 }
 static void collision(mco_ctx* c, particle* P) /* general.cpp:121-163 */
 {
@@ -777,7 +793,7 @@ static void collision(mco_ctx* c, particle* P) /* general.cpp:121-163 */
             (void)urand(c, P); /* precursor group pick; the result is never used */
         }
         for (i = 0; i < bank_nu; i++) {
-            particle Q = fission_neutron(c, P, N_fission);
+            particle Q = fission_neutron(c, P, N_fission, i);
             push(&c->Fbank, &c->Fn, &c->Fcap, &Q);
         }
         /* EstimatorK::estimate_C (Estimator.cpp:503-507) */
@@ -787,8 +803,7 @@ static void collision(mco_ctx* c, particle* P) /* general.cpp:121-163 */
         /* implicit_fission_fixed_source, prompt branch (fixed_source.cpp:12-22) */
         if (urand(c, P) > micro(p, N_fission, X_BETA, P->E)) {
             for (i = 0; i < bank_nu; i++) {
-                particle Q = fission_neutron(c, P, N_fission);
-                give_child_stream(c, P, &Q);
+                particle Q = fission_neutron(c, P, N_fission, i); /* HISTORY mode: Q continues on its own stream */
                 push(&c->Pbank, &c->Pn, &c->Pcap, &Q);
             }
         } else {
