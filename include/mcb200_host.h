@@ -36,8 +36,14 @@ void mcbh_set_run(mcbh_deck* d, uint64_t n_sample, uint64_t n_cycle, uint64_t n_
  * n_surfaces, n_cells, n_estimators, n_tallies, n_sources, entropy_on, n_xs_rows, n_scores, n_filters, trmm_present */
 void mcbh_info(mcbh_deck* d, int64_t out[16]);
 
-/* names for reporting (Estimator::report): kind 0 nuclide, 1 material, 2 surface, 3 cell; NULL when out of range */
+/* names for reporting (Estimator::report): kind 0 nuclide, 1 material, 2 surface, 3 cell, 4 estimator, 5 score
+ * (global score index); NULL when out of range */
 const char* mcbh_name(const mcbh_deck* d, int kind, int index);
+/* tally layout for reporting (Estimator.cpp:280-295,368-422): out = attach, score_begin, n_scores, filter_begin,
+ * n_filters, tally_begin, n_tallies, simulate / out = type, grid_begin, grid_n, size; -1 when out of range */
+int mcbh_estimator_info(const mcbh_deck* d, int estimator, int64_t out[8]);
+int mcbh_filter_info(const mcbh_deck* d, int filter, int64_t out[4]);
+const double* mcbh_filter_grid(const mcbh_deck* d);
 const char* mcbh_mode(const mcbh_deck* d);            /* "fixed source" | "k-eigenvalue" */
 const char* mcbh_simulation_name(const mcbh_deck* d);
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z); /* general.cpp:26-34; -1 = lost */

@@ -91,6 +91,12 @@ def host_lib():
         L.mcbh_mode.restype = C.c_char_p
         L.mcbh_mode.argtypes = [C.c_void_p]
         L.mcbh_search_cell.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.mcbh_estimator_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.mcbh_filter_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.mcbh_filter_grid.restype = C.POINTER(C.c_double)
+        L.mcbh_filter_grid.argtypes = [C.c_void_p]
+        L.mcbh_simulation_name.restype = C.c_char_p
+        L.mcbh_simulation_name.argtypes = [C.c_void_p]
         _host = L
     return _host
 
@@ -192,6 +198,29 @@ class Deck:
     def name(self, kind: int, index: int) -> Optional[str]:
         s = host_lib().mcbh_name(self._h, kind, index)
         return s.decode() if s is not None else None
+
+    def estimators(self) -> list:
+        """Tally layout for reporting (Estimator.cpp:280-295,368-422): one dict per estimator with its scores and
+        filters; tally t of score k lives at tally_begin + k*prod(filter sizes) + row-major filter index."""
+        L = host_lib()
+        grid = L.mcbh_filter_grid(self._h)
+        out = []
+        for e in range(self.info["n_estimators"]):
+            v = (C.c_int64 * 8)()
+            L.mcbh_estimator_info(self._h, e, v)
+            filters = []
+            for f in range(v[3], v[3] + v[4]):
+                w = (C.c_int64 * 4)()
+                L.mcbh_filter_info(self._h, f, w)
+                filters.append({"type": int(w[0]), "grid": [grid[i] for i in range(w[1], w[1] + w[2])], "size": int(w[3])})
+            out.append({"name": self.name(4, e), "attach": int(v[0]),
+                        "scores": [self.name(5, k) for k in range(v[1], v[1] + v[2])], "filters": filters,
+                        "tally_begin": int(v[5]), "n_tallies": int(v[6]), "simulate": int(v[7])})
+        return out
+
+    @property
+    def simulation_name(self) -> str:
+        return host_lib().mcbh_simulation_name(self._h).decode()
 
     @property
     def mode(self) -> str:

@@ -53,10 +53,28 @@ const char* mcbh_name(const mcbh_deck* d, int kind, int index)
     case 1: v = &d->deck.material_names; break;
     case 2: v = &d->deck.surface_names; break;
     case 3: v = &d->deck.cell_names; break;
+    case 4: return index < (int)d->deck.estimators.size() ? d->deck.estimators[index].name : nullptr;
+    case 5: return index < (int)d->deck.scores.size() ? d->deck.scores[index].name : nullptr;
     default: return nullptr;
     }
     return index < (int)v->size() ? (*v)[index].c_str() : nullptr;
 }
+int mcbh_estimator_info(const mcbh_deck* d, int e, int64_t out[8])
+{
+    if (!d || e < 0 || e >= (int)d->deck.estimators.size()) return -1;
+    const mcb_estimator& E = d->deck.estimators[e];
+    const int64_t v[8] = {E.attach, E.score_begin, E.n_scores, E.filter_begin, E.n_filters, E.tally_begin, E.n_tallies, E.simulate};
+    for (int i = 0; i < 8; i++) out[i] = v[i];
+    return 0;
+}
+int mcbh_filter_info(const mcbh_deck* d, int f, int64_t out[4])
+{
+    if (!d || f < 0 || f >= (int)d->deck.filters.size()) return -1;
+    const mcb_filter& F = d->deck.filters[f];
+    out[0] = F.type; out[1] = F.grid_begin; out[2] = F.grid_n; out[3] = F.size;
+    return 0;
+}
+const double* mcbh_filter_grid(const mcbh_deck* d) { return d ? d->deck.filter_grid.data() : nullptr; }
 const char* mcbh_mode(const mcbh_deck* d) { return d ? d->deck.mode.c_str() : nullptr; }
 const char* mcbh_simulation_name(const mcbh_deck* d) { return d ? d->deck.simulation_name.c_str() : nullptr; }
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z) { return d ? d->deck.search_cell(x, y, z) : -1; }

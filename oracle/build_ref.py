@@ -34,7 +34,7 @@ REF = os.environ.get("MCB_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 OBJ = os.path.join(OUT, "obj")
 STUB = os.path.join(HERE, "h5stub")
-CXX = os.environ.get("CXX", "g++")
+CXX = os.environ.get("MCB_CXX", "g++")  # not $CXX: a toolchain wrapper that links libstdc++ statically breaks in-process loading
 # x86-64 SSE2 double arithmetic, no FMA contraction: this is what bit-exactness is defined against.
 CXXFLAGS = ["-std=c++11", "-O3", "-w", "-fPIC", "-ffp-contract=off", "-I" + STUB, "-I" + os.path.join(REF, "include")]
 
