@@ -80,6 +80,7 @@ struct mco_ctx {
     /* ShannonEntropy (include/Entropy.h:19-36) */
     double* ent_p; int ent_I;
     uint32_t child_counter; /* secondaries spawned by the current event (stream derivation) */
+    double *hist_kC, *hist_kTL; size_t hist_n; /* per-history k scores of the last cycle (shard-local order) */
 };
 
 /* Urand (Random.cpp:121-126) — global stream or the particle's own */
@@ -911,7 +912,8 @@ mco_ctx* mco_create(const mcb_problem* p, int rng_mode, int pick_mode)
 void mco_destroy(mco_ctx* c)
 {
     if (!c) return;
-    free(c->Pbank); free(c->Fbank); free(c->Sbank); free(c->cdf); free(c->tallies); free(c->ent_p); free(c);
+    free(c->Pbank); free(c->Fbank); free(c->Sbank); free(c->cdf); free(c->tallies); free(c->ent_p);
+    free(c->hist_kC); free(c->hist_kTL); free(c);
 }
 void mco_set_shard(mco_ctx* c, uint64_t begin, uint64_t count) { c->shard_begin = begin; c->shard_count = count; }
 
@@ -927,6 +929,11 @@ int mco_transport_cycle(mco_ctx* c)
     bank_set_up(c, nsrc);
     c->Fn = 0;
     c->cyc_tracks0 = c->Ntrack; c->cyc_coll0 = c->Ncollision; c->cyc_hist = 0;
+    if (p->ksearch && c->hist_n != (size_t)c->shard_count) {
+        c->hist_n = (size_t)c->shard_count;
+        c->hist_kC = (double*)realloc(c->hist_kC, (c->hist_n ? c->hist_n : 1) * sizeof(double));
+        c->hist_kTL = (double*)realloc(c->hist_kTL, (c->hist_n ? c->hist_n : 1) * sizeof(double));
+    }
     for (h = c->shard_begin; h < c->shard_begin + c->shard_count; h++) {
         particle src, stream;
         size_t j;
@@ -951,6 +958,7 @@ int mco_transport_cycle(mco_ctx* c)
         }
         if (p->ksearch) {                                  /* EstimatorK::end_history (Estimator.cpp:514-525) */
             c->H_sum += entropy_H(c);
+            c->hist_kC[h - c->shard_begin] = c->k_C; c->hist_kTL[h - c->shard_begin] = c->k_TL;
             c->k_sum_C += c->k_C; c->k_sum_TL += c->k_TL;
             c->k_sq_C += c->k_C * c->k_C; c->k_sq_TL += c->k_TL * c->k_TL;
             c->k_C = 0; c->k_TL = 0;
@@ -963,6 +971,12 @@ void mco_get_partials(const mco_ctx* c, double* s, uint64_t* n)
 {
     s[0] = c->k_sum_C; s[1] = c->k_sum_TL; s[2] = c->k_sq_C; s[3] = c->k_sq_TL; s[4] = c->H_sum;
     n[0] = c->Fn; n[1] = c->Ntrack - c->cyc_tracks0; n[2] = c->Ncollision - c->cyc_coll0; n[3] = c->cyc_hist;
+}
+int64_t mco_get_history_k(const mco_ctx* c, double* kC, double* kTL)
+{
+    if (!c->hist_kC) return 0;
+    memcpy(kC, c->hist_kC, c->hist_n * sizeof(double)); memcpy(kTL, c->hist_kTL, c->hist_n * sizeof(double));
+    return (int64_t)c->hist_n;
 }
 int64_t mco_bank_size(const mco_ctx* c) { return (int64_t)c->Fn; }
 void mco_get_bank(const mco_ctx* c, double* s, int32_t* cells)

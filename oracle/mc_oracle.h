@@ -8,7 +8,7 @@
  * Parity status: PINNED.  In rng_mode 0 the oracle reproduces the compiled
  * reference (oracle/_ref/MC_ref, built from /root/reference by
  * oracle/build_ref.py) bit for bit — k per cycle, entropy, tallies, Ntrack — on
- * the decks tests/test_oracle_vs_ref.py runs; golden outputs of the reference
+ * the decks tests/test_oracle_golden.py runs; golden outputs of the reference
  * are committed under tests/golden/.
  */
 #ifndef MC_ORACLE_H
@@ -50,6 +50,8 @@ int mco_run_cycle(mco_ctx* c, mco_cycle_result* out);
 /* split phases for sharded runs: transport the owned histories, exchange, close the cycle with global sums */
 int mco_transport_cycle(mco_ctx* c);
 void mco_get_partials(const mco_ctx* c, double* sums5, uint64_t* counts4); /* {kC,kTL,kC2,kTL2,H}, {sites,tracks,coll,hist} */
+/* EstimatorK::k_C / k_TL of every owned history of the last cycle at end_history (Estimator.cpp:514-525) */
+int64_t mco_get_history_k(const mco_ctx* c, double* kC, double* kTL);
 int64_t mco_bank_size(const mco_ctx* c);
 void mco_get_bank(const mco_ctx* c, double* sites8, int32_t* cells);       /* x,y,z,u,v,w,E,t per site, banking order */
 void mco_set_source_bank(mco_ctx* c, const double* sites8, const int32_t* cells, int64_t n);

@@ -53,6 +53,8 @@ def oracle():
         L.mco_run_cycle.argtypes = [vp, C.POINTER(OracleCycle)]
         L.mco_transport_cycle.argtypes = [vp]
         L.mco_get_partials.argtypes = [vp, vp, vp]
+        L.mco_get_history_k.restype = i64
+        L.mco_get_history_k.argtypes = [vp, vp, vp]
         L.mco_bank_size.restype = i64
         L.mco_bank_size.argtypes = [vp]
         L.mco_get_bank.argtypes = [vp, vp, vp]
@@ -125,6 +127,17 @@ class Oracle:
             raise RuntimeError("oracle: particle lost / empty source bank")
         return r
 
+    def run_cycle_keep_bank(self):
+        """run_cycle through the split phases, returning (result, fission sites, cells) of the generation"""
+        self.transport_cycle()
+        sums, counts = self.partials()
+        sites, cells = self.bank()
+        ts, tq = self.tally_partials()
+        r = self.close_cycle(sums, counts, ts, tq)
+        if self.deck.info["ksearch"]:
+            self.set_source_bank(sites, cells)
+        return r, sites, cells
+
     def run(self):
         info = self.deck.info
         res = [self.run_cycle() for _ in range(info["n_cycle"])]
@@ -140,6 +153,11 @@ class Oracle:
         s = np.zeros(5); n = np.zeros(4, dtype=np.uint64)
         self.L.mco_get_partials(self.h, _p(s), _p(n))
         return s, n
+
+    def history_k(self, n):
+        kC = np.zeros(max(n, 1)); kTL = np.zeros(max(n, 1))
+        got = self.L.mco_get_history_k(self.h, _p(kC), _p(kTL))
+        return kC[:got], kTL[:got]
 
     def bank(self):
         n = self.L.mco_bank_size(self.h)

@@ -1,0 +1,316 @@
+"""Run-level parity of the CUDA transport loop (mcb_run_cycle through the C-ABI) against the oracle.
+
+Two kinds of comparison:
+
+* TRAJECTORY parity against the oracle in MCO_RNG_HISTORY / MCO_PICK_FLOOR mode, which restates the GPU's stream
+  layout (per-history streams RN_init_particle-style, per-site child streams) on top of the reference's physics:
+  every history draws the same xi on both sides, so per-history k scores, the fission bank and the tallies agree
+  to rounding of CUDA's libm vs glibc (log, sin, cos) — tolerance 1e-9 relative for >= 99.5 % of the histories
+  (an ulp can flip a rejection test or a floor(), which changes that one history).
+* STATISTICAL parity against the oracle in MCO_RNG_GLOBAL mode, which is bit-identical to the compiled reference
+  (tests/test_oracle_golden.py): k-eff within 3 sigma combined, chi-square over tally bins (north_star).
+"""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import oracle_lib as ol
+import mc_old_b200 as mcb
+from mc_old_b200 import decks
+
+pytestmark = pytest.mark.gpu
+
+
+def _close_frac(a, b, rtol=1e-9, atol=0.0):
+    a = np.asarray(a); b = np.asarray(b)
+    return float(np.mean(np.abs(a - b) <= atol + rtol * np.abs(b)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trajectory parity
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fused", "split"])
+def test_heu_history_parity(mode):
+    """HEU sphere, 3 generations of 20000 histories: per-history k_C / k_TL (EstimatorK::end_history,
+    Estimator.cpp:514-525), fission-bank size and sites, track / collision counts.  Generations are kept in lock
+    step by handing the GPU's bank and the oracle's k to the other side."""
+    n = 20000
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=2, passive=1))
+    ctx = mcb.Context(deck, device=0, split_stages=(mode == "split"))
+    orc = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
+    for cyc in range(3):
+        g = ctx.run_cycle()
+        o, os_, ocell = orc.run_cycle_keep_bank()
+        gC, gT = ctx.history_k(n)
+        oC, oT = orc.history_k(n)
+        assert g.n_histories == n == o.n_histories
+        fc, ft = _close_frac(gC, oC, atol=1e-15), _close_frac(gT, oT, atol=1e-15)
+        assert fc >= 0.995 and ft >= 0.995, (cyc, fc, ft)
+        assert abs(int(g.n_sites) - int(o.n_sites)) <= 0.005 * o.n_sites
+        assert abs(int(g.n_tracks) - int(o.n_tracks)) <= 0.005 * o.n_tracks
+        assert abs(int(g.n_collisions) - int(o.n_collisions)) <= 0.005 * o.n_collisions
+        assert abs(g.k_cycle - o.k_cycle) <= 2e-3 * o.k_cycle
+        # the cycle's sums are the exact sums of the per-history scores
+        assert g.k_sum_C == pytest.approx(float(np.sum(gC)), rel=1e-12)
+        assert g.k_sq_TL == pytest.approx(float(np.sum(gT * gT)), rel=1e-12)
+        # fission bank in canonical order: sites of histories that agree are the same sites
+        gs, gcell = ctx.fission_bank(int(g.n_sites))
+        if gs.shape[0] == os_.shape[0]:
+            same = np.all(np.abs(gs[:, :3] - os_[:, :3]) < 1e-9, axis=1)
+            assert same.mean() >= 0.98
+            assert _close_frac(gs[same, 6], os_[same, 6]) >= 0.995        # Watt energy from the site's own stream
+            assert np.mean(np.all(np.abs(gs[same, 3:6] - os_[same, 3:6]) < 1e-9, axis=1)) >= 0.995
+        # lock step: same source bank and the same k on both sides for the next generation
+        orc.set_source_bank(gs, gcell)
+        ctx.k = orc.k
+    ctx.close()
+
+
+def test_heu_entropy_history_parity():
+    """per-history Shannon entropy averaged over the cycle (Estimator.cpp:514-528, Entropy.cpp:43-62)"""
+    n = 20000
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=1, passive=1, entropy=True))
+    ctx = mcb.Context(deck, device=0)
+    orc = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
+    for cyc in range(2):
+        g = ctx.run_cycle(); o = orc.run_cycle()
+        assert g.H == pytest.approx(o.H, rel=5e-3), cyc
+        assert g.H_cycle_conventional > g.H
+        gs, gcell = ctx.fission_bank(int(g.n_sites))
+        orc.set_source_bank(gs, gcell); ctx.k = orc.k
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("heu_tallies", 10000)])
+def test_tallies_history_parity(name, n):
+    """Estimator::score / end_history / end_cycle / end_simulation (Estimator.cpp:298-367) on every deck family:
+    surface, cell-TL and cell-C estimators, energy filters, splitting (cell_importance, population_control.cpp:21-49)
+    and same-history fission secondaries (fixed_source.cpp:12-22).  Same per-history streams on both sides, so the
+    per-bin means agree far inside their statistical error: |gpu - oracle| <= 0.2 sigma + 1e-9 relative."""
+    xml = {"slab": lambda: decks.slab(samples=n), "shield": lambda: decks.shielding(samples=n),
+           "shield_split": lambda: decks.shielding(samples=n, split=True), "fsf": lambda: decks.fixed_source_fissile(samples=n),
+           "heu_tallies": lambda: decks.heu_sphere(samples=n, active=1, passive=0, estimators=True)}[name]()
+    deck = mcb.Deck(xml=xml)
+    ctx = mcb.Context(deck, device=0)
+    orc = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
+    g = ctx.run_cycle(); o = orc.run_cycle()
+    orc.end_simulation()
+    gm, gu = ctx.tallies(); om, ou = orc.tallies()
+    assert abs(int(g.n_tracks) - int(o.n_tracks)) <= 0.01 * o.n_tracks
+    scored = ou > 0
+    assert scored.any()
+    assert np.all(np.abs(gm - om) <= 0.2 * ou + 1e-9 * np.abs(om)), (name, gm, om, ou)
+    assert np.all(np.abs(gu[scored] - ou[scored]) <= 0.05 * ou[scored])
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# statistical parity with the reference's own stream layout
+# ---------------------------------------------------------------------------------------------------------------
+def test_heu_keff_3sigma():
+    """k-eff within 3 sigma combined of the reference (north_star).  Reference side: the oracle in GLOBAL mode,
+    bit-identical to MC_ref, 1e4 x (10 + 30) generations; GPU side: 1e5 x (10 + 30).  Also anchored on the k the
+    survey measured with the reference binary (0.926044 +- 0.000352 at 1e4 x 200)."""
+    deck_o = mcb.Deck(xml=decks.heu_sphere(samples=10000, active=30, passive=10))
+    res = ol.Oracle(deck_o, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF).run()
+    k_o, s_o = res[-1].k_avg, res[-1].k_uncer
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=100000, active=30, passive=10))
+    ctx = mcb.Context(deck, device=0)
+    r = [ctx.run_cycle() for _ in range(40)][-1]
+    ctx.close()
+    assert abs(r.k_avg - k_o) <= 3 * np.hypot(r.k_uncer, s_o), (r.k_avg, r.k_uncer, k_o, s_o)
+    assert abs(r.k_avg - 0.926044) <= 3 * np.hypot(r.k_uncer, 0.000352)
+    assert r.k_uncer < s_o
+
+
+def test_ucube_keff_and_entropy_3sigma():
+    """examples/UCube (the one deck with an <entropy> mesh): k and the per-history-averaged H against the
+    reference-identical oracle"""
+    deck_o = mcb.Deck(xml=decks.ucube(samples=5000, active=10, passive=5))
+    res = ol.Oracle(deck_o, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF).run()
+    k_o, s_o = res[-1].k_avg, res[-1].k_uncer
+    H_o = np.array([r.H for r in res[5:]])
+    deck = mcb.Deck(xml=decks.ucube(samples=50000, active=10, passive=5))
+    ctx = mcb.Context(deck, device=0)
+    rs = [ctx.run_cycle() for _ in range(15)]
+    ctx.close()
+    assert abs(rs[-1].k_avg - k_o) <= 3 * np.hypot(rs[-1].k_uncer, s_o)
+    H_g = np.array([r.H for r in rs[5:]])
+    sd = np.hypot(H_o.std(ddof=1) / np.sqrt(H_o.size), H_g.std(ddof=1) / np.sqrt(H_g.size))
+    assert abs(H_g.mean() - H_o.mean()) <= 3 * sd + 1e-3 * H_o.mean()
+
+
+@pytest.mark.parametrize("name", ["shield", "fsf", "heu_tallies"])
+def test_tallies_chi_square(name):
+    """chi-square over tally bins against the reference-identical oracle run (independent streams): below the
+    99.9 % quantile of chi2_N"""
+    from scipy.stats import chi2
+    mk = {"shield": lambda n: decks.shielding(samples=n), "fsf": lambda n: decks.fixed_source_fissile(samples=n),
+          "heu_tallies": lambda n: decks.heu_sphere(samples=n, active=4, passive=4, estimators=True)}[name]
+    n_o, n_g = (20000, 400000) if name != "heu_tallies" else (5000, 50000)
+    deck_o = mcb.Deck(xml=mk(n_o))
+    orc = ol.Oracle(deck_o, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF)
+    orc.run()
+    om, ou = orc.tallies()
+    deck = mcb.Deck(xml=mk(n_g))
+    ctx = mcb.Context(deck, device=0)
+    for _ in range(deck.info["n_cycle"]):
+        ctx.run_cycle()
+    gm, gu = ctx.tallies()
+    ctx.close()
+    ok = (ou > 0) & (gu > 0)
+    x2 = float(np.sum((gm[ok] - om[ok]) ** 2 / (gu[ok] ** 2 + ou[ok] ** 2)))
+    assert x2 < chi2.ppf(0.999, int(ok.sum())), (name, x2, int(ok.sum()))
+
+
+def test_slab_analytic_1e7():
+    """test/test_integral_Simulator.cpp:20-29: leakage = exp(-(1.2*1 + 0.75*4)); 3 sigma at 1e7 histories"""
+    deck = mcb.Deck(xml=decks.slab(samples=10_000_000))
+    ctx = mcb.Context(deck, device=0)
+    r = ctx.run_cycle()
+    m, u = ctx.tallies()
+    ctx.close()
+    assert r.n_histories == 10_000_000
+    assert abs(m[0] - np.exp(-4.2)) <= 3 * u[0], (m[0], u[0])
+    assert 3.0e-5 < u[0] < 4.5e-5   # sqrt(p(1-p)/N) = 3.84e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full size, determinism, host-buffer round trips, errors
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_generation_properties():
+    """HEU sphere at 1e7 histories per generation (BASELINE.json configs[2]): conservation identities of the event
+    loop and physical invariants of the fission bank"""
+    n = 10_000_000
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=1, passive=1))
+    ctx = mcb.Context(deck, device=0)
+    for cyc in range(2):
+        r = ctx.run_cycle()
+        assert r.n_histories == n
+        assert r.n_tracks == r.n_collisions + r.n_crossings      # every flight ends in exactly one event
+        assert r.n_lookups == r.n_tracks                          # one lookup per flight in a material
+        assert 0.8 < r.k_cycle < 3.0
+        kC, kT = ctx.history_k(n)
+        assert r.k_sum_C == pytest.approx(float(np.sum(kC)), rel=1e-11)
+        assert r.k_sum_TL == pytest.approx(float(np.sum(kT)), rel=1e-11)
+        assert r.k_cycle == (r.k_sum_C / n + r.k_sum_TL / n) / 2
+        sites, cells = ctx.fission_bank(int(r.n_sites))
+        assert sites.shape[0] == r.n_sites
+        assert np.all(np.sum(sites[:, :3] ** 2, axis=1) <= 7.68 ** 2 * (1 + 1e-12))
+        assert np.allclose(np.sum(sites[:, 3:6] ** 2, axis=1), 1.0, atol=1e-12)
+        assert np.all(sites[:, 6] > 0) and np.all(cells == 0)
+        # E[sites per history] = k_C estimator / k_prev : the implicit-fission banking is unbiased
+        assert r.n_sites == pytest.approx(r.k_sum_C / (1.0 if cyc == 0 else k_prev), rel=5e-3)
+        k_prev = r.k_cycle
+    ctx.close()
+
+
+def test_batching_does_not_change_results():
+    """a generation processed in several bank batches (small bank_capacity) gives bit-identical k sums (exact
+    fixed-point accumulation) and an identical fission bank (canonical order)"""
+    n = 50000
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=1, passive=1))
+    out = []
+    for cap in (0, 12000, 7001):
+        ctx = mcb.Context(deck, device=0, bank_capacity=cap)
+        rs = [ctx.run_cycle() for _ in range(2)]
+        bank = ctx.fission_bank(int(rs[-1].n_sites))
+        out.append((rs, bank))
+        ctx.close()
+    for rs, bank in out[1:]:
+        for a, b in zip(out[0][0], rs):
+            assert (a.k_sum_C, a.k_sum_TL, a.k_sq_C, a.k_sq_TL, a.n_sites, a.n_tracks) == \
+                   (b.k_sum_C, b.k_sum_TL, b.k_sq_C, b.k_sq_TL, b.n_sites, b.n_tracks)
+        assert np.array_equal(out[0][1][0], bank[0]) and np.array_equal(out[0][1][1], bank[1])
+
+
+def test_split_and_fused_kernels_agree():
+    """the one-kernel-per-event-type mode and the fused multi-event kernel are the same computation"""
+    n = 30000
+    deck = mcb.Deck(xml=decks.ucube(samples=n, active=1, passive=1))
+    res = []
+    for split in (False, True):
+        ctx = mcb.Context(deck, device=0, split_stages=split)
+        rs = [ctx.run_cycle() for _ in range(2)]
+        res.append((rs, ctx.fission_bank(int(rs[-1].n_sites))))
+        ctx.close()
+    for a, b in zip(res[0][0], res[1][0]):
+        assert (a.k_sum_C, a.k_sum_TL, a.H, a.n_sites, a.n_tracks, a.n_collisions) == \
+               (b.k_sum_C, b.k_sum_TL, b.H, b.n_sites, b.n_tracks, b.n_collisions)
+    assert np.array_equal(res[0][1][0], res[1][1][0])
+
+
+def test_source_bank_host_round_trip():
+    """mcb_get_source_bank -> mcb_set_source_bank (the host-buffer form of Sbank = Fbank, handler.cpp:16) is the
+    identity, and an empty bank is the reference's "[ERROR] Source bank is empty..." (Source.cpp:33-39)"""
+    n = 20000
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=2, passive=1))
+    a = mcb.Context(deck, device=0); b = mcb.Context(deck, device=0)
+    ra = a.run_cycle(); rb = b.run_cycle()
+    sites, cells = a.source_bank(int(ra.n_sites))
+    assert sites.shape[0] == ra.n_sites
+    b.set_source_bank(sites, cells)
+    s2, c2 = b.source_bank(int(ra.n_sites))
+    assert np.array_equal(sites, s2) and np.array_equal(cells, c2)
+    ra = a.run_cycle(); rb = b.run_cycle()
+    assert (ra.k_sum_C, ra.k_sum_TL, ra.n_sites) == (rb.k_sum_C, rb.k_sum_TL, rb.n_sites)
+    b.set_source_bank(np.zeros((0, 8)), np.zeros(0, dtype=np.int32))
+    with pytest.raises(RuntimeError, match="Source bank is empty"):
+        b.run_cycle()
+    a.close(); b.close()
+
+
+def test_capacity_and_lost_particle_errors():
+    """a fission bank that overflows is an error, not a truncation; a particle that leaves every cell is the
+    reference's "[WARNING] A particle is lost" (general.cpp:31-33) as a status code"""
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=20000, active=1, passive=1))
+    ctx = mcb.Context(deck, device=0, site_capacity=1000)
+    with pytest.raises(RuntimeError, match="fission bank overflow"):
+        ctx.run_cycle()
+    ctx.close()
+    # a slab whose right-hand outside cell is missing: particles crossing x = 5 find no cell
+    xml = decks.slab(samples=1000).replace('<cell name="right outside" importance="0.0">\n        <surface name="px3" sense="+1"/>\n    </cell>', "")
+    assert "right outside" not in xml
+    deck = mcb.Deck(xml=xml)
+    ctx = mcb.Context(deck, device=0)
+    with pytest.raises(RuntimeError, match="particle is lost"):
+        ctx.run_cycle()
+    ctx.close()
+
+
+def test_reproducible_across_contexts():
+    """same deck, same seed -> bit-identical generations (per-history streams, exact sums, canonical bank order)"""
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=30000, active=2, passive=1))
+    runs = []
+    for _ in range(2):
+        ctx = mcb.Context(deck, device=0)
+        rs = [ctx.run_cycle() for _ in range(3)]
+        runs.append(([(r.k_cycle, r.k_sq_C, r.n_sites, r.n_tracks) for r in rs], ctx.fission_bank(int(rs[-1].n_sites))[0]))
+        ctx.close()
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1], runs[1][1])
+
+
+def test_multi_gpu_matches_single_gpu():
+    """2 ranks over NCCL (one process per GPU): k per generation is bit-identical to the 1-GPU run (exact integer
+    all-reduce), the global fission bank is the rank-ordered concatenation"""
+    import json
+    import os
+    import subprocess
+    import sys
+    if mcb.cuda_lib().mcb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", worker, "--samples", "40000", "--cycles", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    multi = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=40000, active=2, passive=1))
+    ctx = mcb.Context(deck, device=0)
+    rs = [ctx.run_cycle() for _ in range(3)]
+    sites, _ = ctx.source_bank(int(rs[-1].n_sites))
+    ctx.close()
+    assert [r.k_cycle.hex() for r in rs] == multi["k_cycle_hex"]
+    assert [int(r.n_sites) for r in rs] == multi["n_sites"]
+    assert float(np.sum(sites[:, 6])).hex() == multi["bank_energy_sum_hex"]

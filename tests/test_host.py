@@ -1,0 +1,211 @@
+"""Host-side logic, CPU only: the C-ABI libraries load and export every symbol include/*.h declares, the deck
+loader (replacement of the reference's Simulator constructor, setup.cpp:30-1069) keeps the grammar, defaults and
+error messages, the history sharding rule, and the N > 1 data flow (shard -> transport -> all-reduce of the sums +
+all-gather of the fission bank -> identical close-out on every rank) over gloo with world_size 2.
+No compute call touches a GPU here.
+"""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import mc_old_b200 as mcb
+from mc_old_b200 import decks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, prefix):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(%s_[a-z0-9_]+)\s*\(" % prefix, text)))
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    """include/mcb200.h is the drop-in boundary: every entry point it declares must be in libmcb200.so"""
+    names = _declared("mcb200.h", "mcb")
+    assert len(names) >= 25
+    L = C.CDLL(mcb.CUDA_LIB)
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_host_library_exports_every_declared_symbol():
+    names = _declared("mcb200_host.h", "mcbh")
+    assert len(names) >= 12
+    L = C.CDLL(mcb.HOST_LIB)
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_no_cpu_fallback():
+    """without a device the product refuses to compute (no CPU fallback)"""
+    if mcb.cuda_lib().mcb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    deck = mcb.Deck(xml=decks.slab(samples=10))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        mcb.Context(deck)
+
+
+def test_product_does_not_touch_the_oracle():
+    """nothing under mc_old_b200/ or bench.py's own arm links, imports or opens oracle code"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mc_old_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "mc_oracle" not in text and "oracle_lib" not in text and "libref_harness" not in text, f
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (7, 8), (10 ** 9, 8), (2 ** 40 + 3, 7), (0, 4)])
+def test_shard_range_partitions_the_histories(n, world):
+    """contiguous rank-ordered slices that cover [0, n) exactly"""
+    end = 0
+    sizes = []
+    for r in range(world):
+        b, c = mcb.shard_range(n, r, world)
+        assert b == end
+        end = b + c
+        sizes.append(c)
+    assert end == n
+    assert max(sizes) - min(sizes) <= 1
+
+
+# ---- deck loader -------------------------------------------------------------------------------------------------
+def test_deck_facts_of_the_baseline_configs():
+    """sizes of BASELINE.json's decks as SURVEY §8 lists them"""
+    d = mcb.Deck(xml=decks.slab(samples=1e6)).info
+    assert (d["n_sample"], d["ksearch"], d["n_nuclides"], d["n_materials"], d["n_surfaces"], d["n_cells"], d["n_tallies"]) == \
+           (10 ** 6, 0, 3, 2, 3, 4, 1)
+    d = mcb.Deck(xml=decks.heu_sphere(samples=1e7, active=150, passive=50)).info
+    assert (d["n_sample"], d["n_cycle"], d["n_passive"], d["ksearch"], d["n_nuclides"], d["n_surfaces"], d["n_cells"]) == \
+           (10 ** 7, 200, 50, 1, 2, 1, 2)
+    assert d["n_xs_rows"] == 41010 + 162680
+    d = mcb.Deck(xml=decks.shielding(samples=1e8)).info
+    assert (d["n_nuclides"], d["n_materials"], d["n_surfaces"], d["n_cells"], d["n_estimators"], d["n_tallies"]) == (6, 3, 8, 10, 1, 2)
+    d = mcb.Deck(xml=decks.gcr(samples=400, active=100, passive=10)).info
+    assert (d["n_nuclides"], d["n_materials"], d["n_surfaces"], d["n_cells"]) == (4, 1, 2, 1)
+    assert d["n_xs_rows"] == 41010 + 162680 + 2714 + 1021
+    d = mcb.Deck(xml=decks.ucube(samples=1e4)).info
+    assert d["entropy_on"] == 1
+
+
+def test_deck_source_forms():
+    """<point x y z .../> (setup.cpp:1051-1063) and the HEU example's own <source position= .../> form, which the
+    reference rejects and this loader accepts as a superset"""
+    a = mcb.Deck(xml=decks.heu_sphere(samples=100, source_tag="point"))
+    b = mcb.Deck(xml=decks.heu_sphere(samples=100, source_tag="source"))
+    assert a.info["n_sources"] == b.info["n_sources"] == 1
+    o1 = ol.Oracle(a, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF).run_cycle()
+    o2 = ol.Oracle(b, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF).run_cycle()
+    assert o1.k_cycle == o2.k_cycle
+
+
+def test_deck_error_messages():
+    """the reference's messages where it has one (it prints and exits; the loader returns them)"""
+    with pytest.raises(ValueError, match="Unknown source type"):
+        mcb.Deck(xml=decks.slab(samples=10).replace("<point ", "<disk_z ").replace("/>\n</sources>", "/>\n</sources>"))
+    with pytest.raises(ValueError, match="Unknown nuclide"):
+        mcb.Deck(xml=decks.slab(samples=10).replace('<nuclide name="nuc3" density="0.1"/>', '<nuclide name="nope" density="0.1"/>'))
+    with pytest.raises(ValueError, match="tdmc"):
+        mcb.Deck(xml=decks.slab(samples=10).replace("</simulation>", '<tdmc time="1.0 2.0"/></simulation>'))
+    with pytest.raises(ValueError, match="TRMM|trmm"):
+        mcb.Deck(xml=decks.gcr(samples=10, trmm=True))
+    assert mcb.Deck(xml=decks.gcr(samples=10, trmm=True), flags=mcb.IGNORE_TRMM).info["trmm_present"] == 1
+    with pytest.raises(ValueError):
+        mcb.Deck(io_dir="/nonexistent/dir")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree not present")
+@pytest.mark.parametrize("example", ["slab_analytic", "HEU_sphere_criticality", "shielding_vReduction", "UCube", "infinite_GCR_TRMM"])
+def test_reference_example_decks_load_unchanged(example):
+    """the reference's own input.xml files parse as they are"""
+    deck = mcb.Deck(io_dir="/root/reference/examples/" + example, flags=mcb.IGNORE_TRMM)
+    i = deck.info
+    assert i["n_sample"] > 0 and i["n_cells"] > 0 and i["n_sources"] > 0
+    assert deck.mode == ("k-eigenvalue" if i["ksearch"] else "fixed source")
+
+
+def test_estimator_layout_matches_reference_order():
+    """[score][filter1][filter2] row-major (Estimator.cpp:280-295)"""
+    deck = mcb.Deck(xml=decks.fixed_source_fissile(samples=10))
+    est = {e["name"]: e for e in deck.estimators()}
+    tl = est["core_tl"]
+    assert tl["scores"] == ["flux", "fission", "nu-fission", "capture", "scatter", "total", "absorption"]
+    assert [f["size"] for f in tl["filters"]] == [2, 6]
+    assert tl["n_tallies"] == 7 * 2 * 6
+    assert est["interface"]["scores"] == ["cross", "flux"] and est["interface"]["n_tallies"] == 4
+    assert sum(e["n_tallies"] for e in est.values()) == deck.info["n_tallies"]
+
+
+# ---- N > 1 data flow over gloo ----------------------------------------------------------------------------------
+def _gloo_worker(rank, world, port, xml, cycles, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    deck = mcb.Deck(xml=xml)
+    n = deck.info["n_sample"]
+    b, c = mcb.shard_range(n, rank, world)
+    orc = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
+    orc.set_shard(b, c)
+    out = []
+    for _ in range(cycles):
+        orc.transport_cycle()
+        sums, counts = orc.partials()
+        ts, tq = orc.tally_partials()
+        sites, cells = orc.bank()
+        # all-reduce of the sums (the library does this in exact integer arithmetic; doubles here)
+        t = torch.from_numpy(np.concatenate([sums, counts.astype(np.float64), ts, tq]))
+        dist.all_reduce(t)
+        t = t.numpy()
+        nt = ts.size
+        # all-gather of the bank: counts first, then the padded slices, concatenated in rank order
+        cnt = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(cnt, torch.tensor([sites.shape[0]], dtype=torch.int64))
+        m = max(int(x) for x in cnt)
+        pad = torch.zeros((m, 9), dtype=torch.float64)
+        pad[:sites.shape[0], :8] = torch.from_numpy(sites)
+        pad[:sites.shape[0], 8] = torch.from_numpy(cells.astype(np.float64))
+        parts = [torch.zeros((m, 9), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        g = torch.cat([p[:int(k)] for p, k in zip(parts, cnt)]).numpy()
+        r = orc.close_cycle(t[:5], t[5:9].astype(np.uint64), t[9:9 + nt], t[9 + nt:])
+        orc.set_source_bank(np.ascontiguousarray(g[:, :8]), g[:, 8].astype(np.int32))
+        out.append((r.k_cycle, int(r.n_sites), int(r.n_tracks), float(np.sum(g[:, 6]))))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_generations_match_one_rank():
+    """two ranks, each transporting its shard of every generation, combined the way the library combines GPUs
+    (SURVEY §8e): same fission bank (rank-ordered concatenation = canonical order) and same k as one rank"""
+    import torch.multiprocessing as mp
+    xml = decks.heu_sphere(samples=3001, active=2, passive=1)
+    cycles = 3
+    deck = mcb.Deck(xml=xml)
+    one = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
+    want = []
+    for _ in range(cycles):
+        r, sites, cells = one.run_cycle_keep_bank()
+        want.append((r.k_cycle, int(r.n_sites), int(r.n_tracks), float(np.sum(sites[:, 6]))))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 400
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, xml, cycles, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1]                       # the close-out is identical on every rank
+    for (k, ns, nt, es), (k1, ns1, nt1, es1) in zip(got[0], want):
+        assert ns == ns1 and nt == nt1             # integer results do not depend on the number of ranks
+        assert es == pytest.approx(es1, rel=1e-13)  # same sites, same order (summation order is the same too)
+        assert k == pytest.approx(k1, rel=1e-12)   # double sums of two partials vs one running sum
