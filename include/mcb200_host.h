@@ -48,6 +48,12 @@ const char* mcbh_mode(const mcbh_deck* d);            /* "fixed source" | "k-eig
 const char* mcbh_simulation_name(const mcbh_deck* d);
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z); /* general.cpp:26-34; -1 = lost */
 
+/* self-check of the device lookup structure (union grid + map + hash, built by the same code mcb_create uses):
+ * idx_out[i*Nn + k] = row index the device lookup uses for nuclide k of `material` at E[i]; must equal the
+ * reference's binary_search(E, n_E) = #{n_E < E} - 1 (Algorithm.cpp:46-64).  Returns Nn; stats = nU, n_hash,
+ * shift, largest hash bin. */
+int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, int32_t* idx_out, int64_t stats[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,8 +120,10 @@ __device__ __forceinline__ double2 ld_row2(const double* p)
 
 // XSTable::xs for all tables of one nuclide at E (XSec.cpp:9-40, Algorithm.cpp:103-105); idx = #{n_E < E} - 1.
 // sigma_t / sigma_a are interpolated from their per-grid-point values (setup.cpp:371-372), not summed afterwards.
+static __device__ __noinline__ int row_bisect_cold(const double* rows, int n, double E) { return mcb_row_bisect(rows, n, E); }
 __device__ __forceinline__ void micro_xs(const DevNuclide& N, int idx, double E, MicroXS& m)
 {
+    if (idx == MCB_MAP_BISECT) idx = row_bisect_cold(N.rows, N.n_rows, E);
     if (idx < 0 || idx >= N.n_rows - 1) {
         const double* r = N.rows + (size_t)(idx < 0 ? 0 : N.n_rows - 1) * MCB_XS_ROW;
         const double2 a = ld_row2(r), b = ld_row2(r + 2), c = ld_row2(r + 4);
@@ -145,6 +147,7 @@ __device__ __forceinline__ void micro_xs(const DevNuclide& N, int idx, double E,
 // one derived column: 0 sigma_a (= sigma_c + sigma_f per grid point), 1 beta
 __device__ __forceinline__ double micro_col(const DevNuclide& N, int idx, double E, int col)
 {
+    if (idx == MCB_MAP_BISECT) idx = row_bisect_cold(N.rows, N.n_rows, E);
     if (idx < 0 || idx >= N.n_rows - 1) {
         const double* r = N.rows + (size_t)(idx < 0 ? 0 : N.n_rows - 1) * MCB_XS_ROW;
         return col == 0 ? r[2] + r[3] : r[5];

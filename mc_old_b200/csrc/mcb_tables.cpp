@@ -25,11 +25,20 @@ void build_material_tables(const mcb_problem* p, int material, int max_mant_bits
     std::sort(T.U.begin(), T.U.end());
     T.U.erase(std::unique(T.U.begin(), T.U.end()), T.U.end());
     const int nU = (int)T.U.size();
-    // map[u][n] = #{n_E <= U[u]} - 1 : one merge pass per nuclide
+    // map[u][n] = #{n_E <= U[u]} - 1 : one merge pass per nuclide.  A grid that is not ascending (xs_library/005011.txt
+    // has two descents) has no such count: the reference's bisection (Algorithm.cpp:46-64) then returns whatever its
+    // probe sequence leads to, so the column is marked MCB_MAP_BISECT and the device repeats that bisection.
     T.map.assign((size_t)nU * T.n_nuc, -1);
     for (int i = nb; i < ne; i++) {
         const mcb_nuclide& N = p->nuclides[p->mat_nuclide[i]];
         const double* rows = p->xs_rows + (size_t)N.row_begin * MCB_XS_ROW;
+        bool ascending = true;
+        for (int r = 1; r < N.n_rows; r++) if (rows[(size_t)r * MCB_XS_ROW] < rows[(size_t)(r - 1) * MCB_XS_ROW]) ascending = false;
+        if (!ascending) {
+            for (int u = 0; u < nU; u++) T.map[(size_t)u * T.n_nuc + (i - nb)] = MCB_MAP_BISECT;
+            T.n_bisect++;
+            continue;
+        }
         int r = 0;
         for (int u = 0; u < nU; u++) {
             while (r < N.n_rows && rows[(size_t)r * MCB_XS_ROW] <= T.U[u]) r++;

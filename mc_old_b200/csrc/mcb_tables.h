@@ -20,6 +20,8 @@
 
 #include "mcb200.h"
 
+#define MCB_MAP_BISECT (-2) /* map entry of a nuclide whose grid is not ascending: bisect its rows like the reference */
+
 #if defined(__CUDACC__)
 #define MCB_THD __host__ __device__ __forceinline__
 #else
@@ -47,6 +49,18 @@ MCB_THD int mcb_union_count_less(const double* U, const int32_t* hash, int64_t k
     return lo;
 }
 
+// binary_search (Algorithm.cpp:46-64) over column 0 of n rows of MCB_XS_ROW doubles: the probe sequence of the
+// reference, whatever the order of the grid
+MCB_THD int mcb_row_bisect(const double* rows, int n, double E)
+{
+    int left = 0, right = n - 1;
+    while (left <= right) {
+        const int mid = (left + right) / 2;
+        if (rows[(size_t)mid * MCB_XS_ROW] < E) left = mid + 1; else right = mid - 1;
+    }
+    return right;
+}
+
 #ifdef __cplusplus
 #include <vector>
 namespace mcb {
@@ -57,6 +71,7 @@ struct MaterialTables {
     std::vector<int32_t> hash;   // n_hash + 1
     int64_t key_min = 0;
     int32_t n_hash = 0, shift = 0, n_nuc = 0;
+    int32_t n_bisect = 0;        // nuclides whose grid is not ascending
     int32_t max_bin = 0;         // largest number of grid points in one hash bin (search depth statistics)
 };
 

@@ -3,6 +3,7 @@
 
 #include "deck.h"
 #include "mcb200_host.h"
+#include "mcb_tables.h"
 
 struct mcbh_deck { mcb::Deck deck; };
 
@@ -78,5 +79,27 @@ const double* mcbh_filter_grid(const mcbh_deck* d) { return d ? d->deck.filter_g
 const char* mcbh_mode(const mcbh_deck* d) { return d ? d->deck.mode.c_str() : nullptr; }
 const char* mcbh_simulation_name(const mcbh_deck* d) { return d ? d->deck.simulation_name.c_str() : nullptr; }
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z) { return d ? d->deck.search_cell(x, y, z) : -1; }
+
+int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, int32_t* idx_out, int64_t stats[4])
+{
+    if (!d) return -1;
+    const mcb_problem* p = d->deck.view();
+    if (material < 0 || material >= p->n_materials) return -1;
+    mcb::MaterialTables T;
+    mcb::build_material_tables(p, material, 12, T);
+    for (int64_t i = 0; i < n; i++) {
+        const int u = mcb_union_count_less(T.U.data(), T.hash.data(), T.key_min, T.n_hash, T.shift, (int32_t)T.U.size(), E[i]) - 1;
+        for (int k = 0; k < T.n_nuc; k++) {
+            int idx = u < 0 ? -1 : T.map[(size_t)u * T.n_nuc + k];
+            if (idx == MCB_MAP_BISECT) {
+                const mcb_nuclide& N = p->nuclides[p->mat_nuclide[p->mat_begin[material] + k]];
+                idx = mcb_row_bisect(p->xs_rows + (size_t)N.row_begin * MCB_XS_ROW, N.n_rows, E[i]);
+            }
+            idx_out[i * T.n_nuc + k] = idx;
+        }
+    }
+    if (stats) { stats[0] = (int64_t)T.U.size(); stats[1] = T.n_hash; stats[2] = T.shift; stats[3] = T.max_bin; }
+    return T.n_nuc;
+}
 
 }  // extern "C"

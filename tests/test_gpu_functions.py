@@ -66,12 +66,15 @@ def test_xs_lookup_vs_oracle_1e6(name, ctxs):
         assert got.tobytes() == want.tobytes(), "material %d of %s" % (m, name)
 
 
-def test_xs_lookup_every_grid_point(ctxs):
-    """every grid energy of U-235 and U-238 and its +-1 ulp neighbours in the HEU material (union-grid / hash edges)"""
-    deck, ctx = ctxs("heu")
-    g = np.concatenate([gc.grid_energies("092235"), gc.grid_energies("092238")])
-    E = np.concatenate([g, np.nextafter(g, 0.0), np.nextafter(g, np.inf)])
-    assert ctx.xs_lookup(0, E).tobytes() == ol.xs_lookup(deck, 0, E).tobytes()
+@pytest.mark.parametrize("name", sorted(FN_DECKS))
+def test_xs_lookup_every_grid_point(name, ctxs):
+    """every grid energy of every nuclide of every material and its +-1 ulp neighbours (union-grid / hash edges,
+    duplicate energies, and the two descents of the B-11 grid that the reference bisects as they are)"""
+    deck, ctx = ctxs(name)
+    for m, zaids in enumerate(gc._MAT_ZAIDS[name]):
+        g = np.concatenate([gc.grid_energies(z) for z in zaids])
+        E = np.concatenate([g, np.nextafter(g, 0.0), np.nextafter(g, np.inf)])
+        assert ctx.xs_lookup(m, E).tobytes() == ol.xs_lookup(deck, m, E).tobytes(), "material %d of %s" % (m, name)
 
 
 def test_xs_lookup_edge_inputs(ctxs):

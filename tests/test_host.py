@@ -12,6 +12,7 @@ import sys
 import numpy as np
 import pytest
 
+import golden_cases as gc
 import oracle_lib as ol
 import mc_old_b200 as mcb
 from mc_old_b200 import decks
@@ -139,6 +140,45 @@ def test_estimator_layout_matches_reference_order():
     assert tl["n_tallies"] == 7 * 2 * 6
     assert est["interface"]["scores"] == ["cross", "flux"] and est["interface"]["n_tallies"] == 4
     assert sum(e["n_tallies"] for e in est.values()) == deck.info["n_tallies"]
+
+
+def _reference_bisect(grid, E):
+    """binary_search of the reference (Algorithm.cpp:46-64), probe by probe, vectorised over E; valid for grids that
+    are not ascending too (xs_library/005011.txt has two descents)"""
+    left = np.zeros(E.shape, dtype=np.int64)
+    right = np.full(E.shape, len(grid) - 1, dtype=np.int64)
+    while True:
+        live = left <= right
+        if not live.any():
+            return right
+        mid = (left + right) // 2
+        less = np.zeros(E.shape, dtype=bool)
+        less[live] = grid[mid[live]] < E[live]
+        left = np.where(live & less, mid + 1, left)
+        right = np.where(live & ~less, mid - 1, right)
+
+
+@pytest.mark.parametrize("name", sorted(gc.function_decks()))
+def test_union_grid_indices_equal_reference_bisection(name):
+    """the device lookup structure (union grid + map + hash, mcb_tables) yields, for every nuclide of every material,
+    the row index the reference's per-nuclide bisection yields: every grid point and its +-1 ulp neighbours,
+    duplicates, out-of-range energies, and the non-ascending B-11 grid"""
+    deck = mcb.Deck(xml=gc.function_decks()[name])
+    L = mcb.host_lib()
+    L.mcbh_union_indices.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    for m, zaids in enumerate(gc._MAT_ZAIDS[name]):
+        grids = [gc.grid_energies(z) for z in zaids]
+        allg = np.concatenate(grids)
+        E = np.concatenate([gc.energies(name, m), allg, np.nextafter(allg, 0.0), np.nextafter(allg, np.inf),
+                            np.array([0.0, -1.0, 1e-300, 1e300])])
+        idx = np.zeros((E.size, len(zaids)), dtype=np.int32)
+        stats = np.zeros(4, dtype=np.int64)
+        nn = L.mcbh_union_indices(deck._h, m, E.ctypes.data, E.size, idx.ctypes.data, stats.ctypes.data)
+        assert nn == len(zaids)
+        for k, g in enumerate(grids):
+            want = _reference_bisect(g, E)
+            assert np.array_equal(idx[:, k], want), "material %d nuclide %s of %s" % (m, zaids[k], name)
+        assert stats[0] <= allg.size and stats[3] >= 1
 
 
 # ---- N > 1 data flow over gloo ----------------------------------------------------------------------------------
