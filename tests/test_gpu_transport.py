@@ -107,20 +107,31 @@ def test_tallies_history_parity(name, n):
 # ---------------------------------------------------------------------------------------------------------------
 # statistical parity with the reference's own stream layout
 # ---------------------------------------------------------------------------------------------------------------
+def _k_sigma(res, n_passive):
+    """standard error of k_avg.  The reference's own k_uncer = sqrt(sum(var_C + var_TL))/Navg/2 (Estimator.cpp:539-549)
+    treats the collision and track-length estimators as independent; they are almost fully correlated, so it
+    understates the spread of k_avg by ~sqrt(2) (measured here: 8 reference-identical oracle runs of 1e4 x 190 give a
+    spread of the cycle means / sqrt(n) of 0.00052 against a reported 0.00034).  Use the larger of the two."""
+    k = np.array([r.k_cycle for r in res[n_passive:]])
+    return max(res[-1].k_uncer, float(k.std(ddof=1) / np.sqrt(k.size)))
+
+
 def test_heu_keff_3sigma():
     """k-eff within 3 sigma combined of the reference (north_star).  Reference side: the oracle in GLOBAL mode,
     bit-identical to MC_ref, 1e4 x (10 + 30) generations; GPU side: 1e5 x (10 + 30).  Also anchored on the k the
-    survey measured with the reference binary (0.926044 +- 0.000352 at 1e4 x 200)."""
+    survey measured with the reference binary (0.926044 +- 0.000352 reported at 1e4 x 200; x1.5 for the
+    correlation the reported figure leaves out, see _k_sigma)."""
     deck_o = mcb.Deck(xml=decks.heu_sphere(samples=10000, active=30, passive=10))
     res = ol.Oracle(deck_o, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF).run()
-    k_o, s_o = res[-1].k_avg, res[-1].k_uncer
+    k_o, s_o = res[-1].k_avg, _k_sigma(res, 10)
     deck = mcb.Deck(xml=decks.heu_sphere(samples=100000, active=30, passive=10))
     ctx = mcb.Context(deck, device=0)
-    r = [ctx.run_cycle() for _ in range(40)][-1]
+    rs = [ctx.run_cycle() for _ in range(40)]
     ctx.close()
-    assert abs(r.k_avg - k_o) <= 3 * np.hypot(r.k_uncer, s_o), (r.k_avg, r.k_uncer, k_o, s_o)
-    assert abs(r.k_avg - 0.926044) <= 3 * np.hypot(r.k_uncer, 0.000352)
-    assert r.k_uncer < s_o
+    r, s_g = rs[-1], _k_sigma(rs, 10)
+    assert abs(r.k_avg - k_o) <= 3 * np.hypot(s_g, s_o), (r.k_avg, s_g, k_o, s_o)
+    assert abs(r.k_avg - 0.926044) <= 3 * np.hypot(s_g, 1.5 * 0.000352), (r.k_avg, s_g)
+    assert r.k_uncer < res[-1].k_uncer
 
 
 def test_ucube_keff_and_entropy_3sigma():
@@ -140,14 +151,14 @@ def test_ucube_keff_and_entropy_3sigma():
     assert abs(H_g.mean() - H_o.mean()) <= 3 * sd + 1e-3 * H_o.mean()
 
 
-@pytest.mark.parametrize("name", ["shield", "fsf", "heu_tallies"])
+@pytest.mark.parametrize("name", ["shield", "fsf"])
 def test_tallies_chi_square(name):
     """chi-square over tally bins against the reference-identical oracle run (independent streams): below the
-    99.9 % quantile of chi2_N"""
+    99.9 % quantile of chi2_N.  Fixed-source decks: histories are independent, so the reported
+    uncertainties are the true standard errors."""
     from scipy.stats import chi2
-    mk = {"shield": lambda n: decks.shielding(samples=n), "fsf": lambda n: decks.fixed_source_fissile(samples=n),
-          "heu_tallies": lambda n: decks.heu_sphere(samples=n, active=4, passive=4, estimators=True)}[name]
-    n_o, n_g = (20000, 400000) if name != "heu_tallies" else (5000, 50000)
+    mk = {"shield": lambda n: decks.shielding(samples=n), "fsf": lambda n: decks.fixed_source_fissile(samples=n)}[name]
+    n_o, n_g = 20000, 400000
     deck_o = mcb.Deck(xml=mk(n_o))
     orc = ol.Oracle(deck_o, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF)
     orc.run()
@@ -161,6 +172,52 @@ def test_tallies_chi_square(name):
     ok = (ou > 0) & (gu > 0)
     x2 = float(np.sum((gm[ok] - om[ok]) ** 2 / (gu[ok] ** 2 + ou[ok] ** 2)))
     assert x2 < chi2.ppf(0.999, int(ok.sum())), (name, x2, int(ok.sum()))
+
+
+def test_tallies_chi_square_k_mode():
+    """k-eigenvalue tallies (HEU sphere with cell / energy / surface estimators).  Generations are correlated and
+    the scores of one estimator are functions of the same tracks, so neither the reported uncertainties nor a
+    chi-square over all 31 tallies are calibrated.  Instead: 16 independent replicas (seeds) per side give the
+    standard error of every tally empirically; the chi-square runs over the bins of ONE score per estimator (flux in
+    7 energy bins, collision flux, leakage); threshold = 99.9 % quantile of chi2_N x 1.25 for the variance being
+    estimated from 16 + 16 replicas."""
+    from scipy.stats import chi2
+    R = 16
+
+    def replicas(n, run):
+        out = []
+        for seed in range(1, R + 1):
+            deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=4, passive=4, estimators=True))
+            deck.set_run(seed=2 * seed + 1)
+            out.append(run(deck))
+        return np.array(out)
+
+    def run_oracle(deck):
+        orc = ol.Oracle(deck, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF)
+        orc.run()
+        return orc.tallies()[0]
+
+    def run_gpu(deck):
+        ctx = mcb.Context(deck, device=0)
+        for _ in range(deck.info["n_cycle"]):
+            ctx.run_cycle()
+        m = ctx.tallies()[0]
+        ctx.close()
+        return m
+
+    o = replicas(5000, run_oracle)
+    g = replicas(50000, run_gpu)
+    bins = list(range(0, 7)) + [28, 30]  # sphere_rates flux x 7 energy bins, sphere_coll flux, leak cross
+    om, gm = o.mean(axis=0), g.mean(axis=0)
+    ov, gv = o.var(axis=0, ddof=1) / R, g.var(axis=0, ddof=1) / R
+    ok = [b for b in bins if ov[b] > 0 and gv[b] > 0]
+    assert len(ok) >= 6
+    x2 = float(sum((gm[b] - om[b]) ** 2 / (gv[b] + ov[b]) for b in ok))
+    assert x2 < 1.25 * chi2.ppf(0.999, len(ok)), (x2, len(ok))
+    # every tally, one by one: within 5 empirical standard errors
+    nz = (ov > 0) & (gv > 0)
+    z = np.abs(gm[nz] - om[nz]) / np.sqrt(gv[nz] + ov[nz])
+    assert z.max() < 5.0, z
 
 
 def test_slab_analytic_1e7():
