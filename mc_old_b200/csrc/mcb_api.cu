@@ -154,6 +154,7 @@ struct mcb_ctx {
     cudaEvent_t ev_ring[MCB_RING] = {};
     uint64_t finish_below = 0;       // queue length under which the tail kernel takes over
     bool split_stages = false;       // one kernel per event type (profiling mode) instead of the fused step kernel
+    bool walk_mode = true;           // history walk (one launch per pass over the bank) instead of the event-queue loop
     int step_events = 2;             // events chained per particle and launch by the fused step kernel
     // per-history accumulators
     DevBuf<double> d_hist_k;         // kC, kTL
@@ -397,6 +398,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     for (int i = 0; i < MCB_RING; i++) CK(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
     ctx->finish_below = getenv("MCB_FINISH_BELOW") ? strtoull(getenv("MCB_FINISH_BELOW"), nullptr, 10) : 148ull * 256ull;
     ctx->split_stages = (cfg && (cfg->reserved & 2)) || (getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "split"));
+    ctx->walk_mode = !ctx->split_stages && !(getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "step"));
     if (getenv("MCB_STEP_EVENTS")) ctx->step_events = std::max(1, atoi(getenv("MCB_STEP_EVENTS")));
     const size_t nh = std::max<uint64_t>(ctx->shard_count, 1);
     CK(ctx->d_hist_k.alloc(2 * nh));
@@ -529,6 +531,38 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     ctx->timer.begin(st, ST_SOURCE);
     mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, sbank, ctx->n_source_sites, C);
     ctx->timer.end(st);
+
+    if (ctx->walk_mode) {
+        // History walk: pass 0 follows the primaries in slots [0, nb) to the end of their chains; secondaries born on
+        // the way (fixed-source fission, splitting) land in slots >= nb and are walked by the next pass.
+        uint32_t begin = 0, end = nb;
+        int passes = 0;
+        while (begin < end) {
+            CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
+            ctx->timer.begin(st, ST_STEP);
+            mcbk::walk(st, P, ctx->B, begin, end, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->n_slots, ctx->k);
+            ctx->timer.end(st);
+            passes++;
+            if (!P.shared_histories) break;  // one particle per history: nothing can be born
+            CK(cudaMemcpyAsync(&ctx->h_ring[0], &C->slot_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            begin = end;
+            end = (uint32_t)std::min<unsigned long long>(ctx->h_ring[0], ctx->n_slots);
+        }
+        *n_iterations += passes;
+        CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const Counters& hc = *ctx->h_counters;
+        if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
+        if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
+        if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
+        if (T.on) {
+            ctx->timer.begin(st, ST_CLOSEOUT);
+            mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
+            ctx->timer.end(st);
+        }
+        return MCB_OK;
+    }
 
     // Event loop.  Queue lengths live on the device; the host launches iterations ahead of what it knows and
     // learns the lengths from asynchronous copies into a pinned ring (an iteration on an empty queue is a no-op).

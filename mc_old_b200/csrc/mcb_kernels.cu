@@ -19,7 +19,10 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int BLOCK = 256;
+#ifndef MCB_BLOCK
+#define MCB_BLOCK 256
+#endif
+constexpr int BLOCK = MCB_BLOCK;
 constexpr int WARPS = BLOCK / 32;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
@@ -172,8 +175,13 @@ __device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p
 
 // flight event: surface_intersect + collision_distance + move_particle (general.cpp:40-83,177-207).
 // Returns true when the flight ends on a surface (S_hit), false when it ends in a collision.
+// A history whose particles never share it with others in flight (k-eigenvalue without splitting) can keep its
+// EstimatorK scores and its site count in registers (HistLocal) and store them once when it ends; otherwise they
+// are bumped in memory with reductions.
+struct HistLocal { double kC, kTL; int nsite; };
+
 __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
-                                          const TallyAcc& T, int& S_hit)
+                                          const TallyAcc& T, int& S_hit, HistLocal* L = nullptr)
 {
     const int m = P.cells[p.cell].material;
     double dsurf;
@@ -186,7 +194,10 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, cons
     // Particle::move (Particle.cpp:66-76)
     p.x += p.u * l; p.y += p.v * l; p.z += p.w * l;
     p.t += l / p.speed;
-    if (P.ksearch && m >= 0) hist_add(&H.kTL[p.hist], X.nf * p.wgt * l);  // estimate_TL (Estimator.cpp:509-512)
+    if (P.ksearch && m >= 0) {  // estimate_TL (Estimator.cpp:509-512)
+        if (L) L->kTL += X.nf * p.wgt * l;
+        else hist_add(&H.kTL[p.hist], X.nf * p.wgt * l);
+    }
     if (T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
         ScoreState s;
         s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = -1; s.material = m; s.u = uidx; s.X = X;
@@ -247,12 +258,14 @@ __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p,
 __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank& B, const Particle& p, const CollideCtx& c,
                                                 const HistoryAcc& H, Counters* C, SiteReq* reqs, uint64_t site_cap,
                                                 uint32_t n_slots, unsigned long long site0, unsigned long long slot0,
-                                                unsigned& n_second_ok)
+                                                unsigned& n_second_ok, HistLocal* L = nullptr)
 {
     n_second_ok = 0;
     uint64_t seed = p.rng;
     if (c.n_sites) {
-        const int seq0 = atomicAdd(&H.nsite[p.hist], (int)c.n_sites);
+        int seq0;
+        if (L) { seq0 = L->nsite; L->nsite += (int)c.n_sites; }
+        else seq0 = atomicAdd(&H.nsite[p.hist], (int)c.n_sites);
         for (unsigned b = 0; b < c.n_sites; b++) {
             seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
             SiteReq r;
@@ -283,9 +296,12 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank&
 // collide event, last part: k_C, implicit capture, scatter, weight_roulette (general.cpp:146-163,
 // population_control.cpp:9-15).  Returns whether the particle survives.
 __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
-                                                   const CollideCtx& c, const HistoryAcc& H)
+                                                   const CollideCtx& c, const HistoryAcc& H, HistLocal* L = nullptr)
 {
-    if (P.ksearch && c.N_fission >= 0) hist_add(&H.kC[p.hist], X.nf * p.wgt / X.t);  // estimate_C (Estimator.cpp:503-507)
+    if (P.ksearch && c.N_fission >= 0) {  // estimate_C (Estimator.cpp:503-507)
+        if (L) L->kC += X.nf * p.wgt / X.t;
+        else hist_add(&H.kC[p.hist], X.nf * p.wgt / X.t);
+    }
     // implicit absorption (general.cpp:154-156)
     const double implicit = X.c + X.f;
     p.wgt = p.wgt * (X.t - implicit) / X.t;
@@ -683,6 +699,108 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
     }
 }
 
+// history walk: the whole event chain of a particle in registers, one launch per pass over bank slots
+// [begin, end).  Every warp is autonomous (no block barriers): it draws slot indices in private chunks from a
+// global head counter and, at every iteration, refills the lanes whose particle has just ended with the next slots,
+// so lanes stay busy until the pass runs dry; fission-site requests are reserved with one cursor atomic per warp and
+// iteration.  Nothing but the site requests (and the rare secondaries, which go to slots >= end and are walked by
+// the next pass) is written back: the particle record is read once.  With one particle per history the EstimatorK
+// scores live in registers and are stored once when the history ends.
+__global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
+k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk, Counters* C, HistoryAcc H, TallyAcc T,
+       SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
+{
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool local_acc = !P.shared_histories;
+    unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
+    bool alive = false, exhausted = false;
+    Particle p;
+    HistLocal L = {0.0, 0.0, 0};
+    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of slots
+    for (;;) {
+        // ---- refill the idle lanes
+        unsigned idle = __ballot_sync(FULL, !alive);
+        while (idle && !exhausted) {
+            if (chunk_next == chunk_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&C->walk_head, (unsigned long long)chunk);
+                base = __shfl_sync(FULL, base, 0);
+                const unsigned long long b = (unsigned long long)begin + base;
+                chunk_next = (uint32_t)(b < end ? b : end);
+                chunk_end = (uint32_t)(b + chunk < end ? b + chunk : end);
+                if (chunk_next == chunk_end) { exhausted = true; break; }
+            }
+            const unsigned take = min((unsigned)__popc(idle), chunk_end - chunk_next);
+            const unsigned rank = __popc(idle & lt_mask);
+            if (!alive && rank < take) {
+                const uint32_t j = chunk_next + rank;
+                p.cell = B.cell[j]; p.hist = B.hist[j];
+                p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
+                p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
+                L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
+                alive = true;
+            }
+            chunk_next += take;
+            idle = __ballot_sync(FULL, !alive);
+        }
+        if (idle == FULL) break;  // nothing in flight and nothing left to draw
+        // ---- one event per live lane
+        MacroXS X = {0, 0, 0, 0, 0};
+        XSDetail D;
+        CollideCtx c = {-1, -1, 0, 0};
+        int uidx = -1;
+        unsigned n_copy = 0;
+        bool to_cross = false, in_material = false;
+        const bool was_alive = alive;
+        if (alive) {
+            int S;
+            if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
+            to_cross = ev_flight(P, p, X, uidx, H, T, S, local_acc ? &L : nullptr);
+            tracks++;
+            if (to_cross) { alive = ev_cross_pre(P, p, S, T, C, n_copy); crossings++; }
+            else { in_material = ev_collide_pre(P, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
+        }
+        __syncwarp();
+        // fission-site requests: one reservation per warp
+        unsigned long long site0 = 0;
+        {
+            unsigned v = c.n_sites;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(FULL, v, d); if (lane >= (unsigned)d) v += t; }
+            const unsigned total = __shfl_sync(FULL, v, 31);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 31) base = atomicAdd(&C->site_cursor, (unsigned long long)total);
+                site0 = __shfl_sync(FULL, base, 31) + (v - c.n_sites);
+            }
+        }
+        // secondaries (fixed-source fission neutrons, split copies) are rare: one slot reservation per lane
+        unsigned long long slot0 = 0;
+        if (c.n_second + n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)(c.n_second + n_copy));
+        unsigned n_new = 0;
+        if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr);
+        __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
+        if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
+        __syncwarp();
+        if (in_material) alive = ev_collide_scatter(P, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
+        __syncwarp();
+        if (local_acc && was_alive && !alive) {  // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525)
+            H.kC[p.hist] = L.kC; H.kTL[p.hist] = L.kTL; H.nsite[p.hist] = L.nsite;
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        tracks += __shfl_xor_sync(FULL, tracks, d); collisions += __shfl_xor_sync(FULL, collisions, d);
+        crossings += __shfl_xor_sync(FULL, crossings, d); lookups += __shfl_xor_sync(FULL, lookups, d);
+    }
+    if (lane == 0) {
+        if (tracks) atomicAdd(&C->n_tracks, (unsigned long long)tracks);
+        if (collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
+        if (crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
+        if (lookups) atomicAdd(&C->n_lookups, (unsigned long long)lookups);
+    }
+}
+
 // tail of a batch: every queued particle is followed to the end of its history in registers (the same events,
 // chained).  Secondaries born here are queued for another pass.  Cursors are bumped per thread: with a few
 // thousand particles left there is no contention to aggregate away.
@@ -1026,12 +1144,12 @@ static unsigned grid_for(uint64_t n_hint)
 {
     // persistent tile loops: enough blocks to fill the machine a few times over, never more than the work
     const uint64_t need = (n_hint + BLOCK - 1) / BLOCK;
-    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 16ull));
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 16ull * (256 / BLOCK)));
 }
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
             uint64_t nps0, const Site* sbank, uint64_t n_sbank, Counters* C)
 {
-    k_source<<<std::max(1u, blocks_for(count)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, sbank, n_sbank, C);
+    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, sbank, n_sbank, C);
     MCB_LAUNCHED(1);
 }
 void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C)
@@ -1063,6 +1181,19 @@ void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* a
           uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     k_step<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, max_events, C, next, H, T, reqs, site_cap, n_slots, k_eff);
+    MCB_LAUNCHED(1);
+}
+void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, uint32_t end, Counters* C, const HistoryAcc& H,
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
+{
+    if (end <= begin) return;
+    // persistent: every resident warp draws chunks of slots until the pass runs dry
+    const uint32_t n = end - begin;
+    const unsigned resident = 148u * MCB_STEP_MINB;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + BLOCK - 1) / BLOCK, resident));
+    const uint64_t warps = (uint64_t)grid * WARPS;
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
+    k_walk<<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff);
     MCB_LAUNCHED(1);
 }
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
