@@ -121,55 +121,82 @@ def reference_arm(args):
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every few milliseconds from a
+    thread (a generation is ~9 ms, `nvidia-smi -lms` cannot see it); nvidia-smi is the fallback."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, device):
-        self.path = tempfile.mktemp(prefix="mcb_clocks_", suffix=".csv")
-        self.f = open(self.path, "w")
+        import threading
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = False
+        self.smi = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
         except Exception:
-            self.p = None
+            self.nv = None
+            self.path = tempfile.mktemp(prefix="mcb_clocks_", suffix=".csv")
+            self.f = open(self.path, "w")
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self.smi = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                             "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.smi = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.BAD.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 7:
-                continue
+        if self.nv is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+        elif self.smi is not None:
+            self.smi.terminate()
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        try:
+                self.smi.wait(timeout=5)
+            except Exception:
+                self.smi.kill()
+            self.f.close()
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                try:
+                    self.sm.append(float(c[0])); self.max_mhz = float(c[1])
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
             os.unlink(self.path)
-        except OSError:
-            pass
-        return out
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=float, default=1e7, help="histories per generation per GPU")
@@ -201,7 +228,7 @@ def main():
         dist.barrier()  # creates torch's NCCL communicator, so libnccl is loaded before ours binds it
     per_gpu = int(args.samples)
     n_sample = per_gpu * world
-    total_cycles = args.warmup + 3 * args.steps + 8
+    total_cycles = args.warmup + 3 * args.steps + 8  # all passive but the warm-up: the HEU deck has no user tallies
     deck = mcb.Deck(xml=decks.heu_sphere(samples=n_sample, active=total_cycles, passive=args.warmup))
     stream = torch.cuda.current_stream()
     ctx = mcb.Context(deck, device=local_rank, rank=rank, world=world, stream=stream.cuda_stream)
@@ -292,11 +319,11 @@ def main():
                     "step": BYTES_STEP(nn)}
         total_bytes = 2.0 * per_gen[dominant] * per_unit[dominant]
         achieved = total_bytes / (stages[dominant]["ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else dominant), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
+        roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" and os.environ.get("MCB_MODE") != "step" else dominant)), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
                     "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "bytes_per_unit": per_unit[dominant], "units_per_launch": 2.0 * per_gen[dominant] / max(stages[dominant]["launches"], 1),
                     "avg_launch_ms": stages[dominant]["ms"] / max(stages[dominant]["launches"], 1),
-                    "note": "units of the tail kernel (k_finish) are counted with the dominant kernel's: its time is listed under stages"}
+                    "note": "bytes_per_unit is SURVEY 8(d)'s fixed per-track figure (record in+out 224, lookup 72+100*Nn, sites 20); the walk kernel keeps the record in registers and the tables in L2, so its DRAM traffic is below it (DESIGN.md 4)"}
     ctx.close()
 
     cpu = None
@@ -312,7 +339,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "histories_per_generation": n_sample, "histories_per_gpu": per_gpu,
                        "parallelism": "histories sharded over %d GPU(s); NCCL all-reduce of k sums + all-gather of the fission bank per generation" % world,
-                       "l2": "inputs larger than L2 (particle bank %.1f GB per GPU streams through HBM every stage)" % (per_gpu * 188 / 1e9)},
+                       "l2": "inputs larger than L2: per GPU and generation the source bank (%.2f GB), particle bank (%.2f GB) and site requests (%.2f GB) stream through HBM" % (per_gpu * 72 / 1e9, per_gpu * 100 / 1e9, per_gpu * 64 / 1e9)},
             "collisions_per_second": coll / (ms * 1e-3), "tracks_per_second": tracks / (ms * 1e-3),
             "xs_lookups_per_second": lookups / (ms * 1e-3),
             "k_cycle_last": res[-1].k_cycle, "event_loop_iterations_per_step": sum(r.n_iterations for r in res) / args.steps,

@@ -165,10 +165,16 @@ struct mcb_ctx {
     // fission bank
     uint64_t site_cap = 0, global_cap = 0;
     DevBuf<SiteReq> d_site_reqs;
-    DevBuf<Site> d_local_bank, d_global_bank;
+    DevBuf<Site> d_local_bank[2];    // this rank's canonical bank; two of them with world > 1 (peers may still read the last one)
+    DevBuf<Site> d_global_bank;      // the whole bank in one array: only for banks set / read through the host API, or without P2P
+    int bank_w = 0;                  // d_local_bank[bank_w] is the one the running cycle writes
+    Site* peer_bank[2][MCB_MAX_WORLD] = {};  // peer_bank[b][r] = rank r's d_local_bank[b] mapped here (CUDA IPC); [rank] = own
+    bool p2p = false;                // the peers' banks are mapped: source sites are read in place over NVLink
+    SourceBankView view{};           // the bank the next cycle samples (n = 0: the deck's sources)
     DevBuf<double> d_io_sites;       // staging for host-facing bank I/O (n x 8 doubles)
     DevBuf<int32_t> d_io_cells;
-    uint64_t n_local_sites = 0, n_source_sites = 0;  // local bank of the last cycle; global source bank for the next
+    uint64_t n_local_sites = 0;      // local bank of the last cycle
+    int bank_last = 0;               // d_local_bank[bank_last] holds it
     bool source_is_bank = false;
     // tallies
     DevBuf<double> d_tally_acc, d_tally_partial, d_tally_sum, d_tally_sq;
@@ -181,8 +187,9 @@ struct mcb_ctx {
     double k = 1.0, mean_accumulator = 0.0, uncer_sq_accumulator = 0.0;
     // comm
     ncclComm_t comm = nullptr;
-    DevBuf<unsigned long long> d_comm;               // reduction buffer
-    DevBuf<unsigned long long> d_counts;             // all-gather of per-rank site counts
+    DevBuf<unsigned long long> d_send, d_recv;       // per-rank close-out vector and its all-gather
+    unsigned long long *h_send = nullptr, *h_recv = nullptr;  // pinned
+    size_t vec_len = 0;
     // timing
     StageTimer timer;
     mcb_stage_times stage{};
@@ -275,7 +282,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     std::vector<mcb::MaterialTables> tabs(p->n_materials);
     size_t nU = 0, nmap = 0, nhash = 0;
     for (int m = 0; m < p->n_materials; m++) {
-        mcb::build_material_tables(p, m, 12, tabs[m]);
+        mcb::build_material_tables(p, m, getenv("MCB_HASH_BITS") ? atoi(getenv("MCB_HASH_BITS")) : 14, tabs[m]);
         nU += tabs[m].U.size(); nmap += tabs[m].map.size(); nhash += tabs[m].hash.size();
         ctx->mat_n_nuc.push_back(tabs[m].n_nuc);
     }
@@ -411,10 +418,11 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         // point source in HEU is 2.7); leave room for 4
         ctx->site_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity : 4 * ctx->shard_count + 4096;
         CK(ctx->d_site_reqs.alloc(ctx->site_cap));
-        CK(ctx->d_local_bank.alloc(ctx->site_cap));
+        CK(ctx->d_local_bank[0].alloc(ctx->site_cap));
+        ctx->global_cap = ctx->site_cap;
         if (ctx->world > 1) {
+            CK(ctx->d_local_bank[1].alloc(ctx->site_cap));
             ctx->global_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity * ctx->world : 4 * p->n_sample + 4096ull * ctx->world;
-            CK(ctx->d_global_bank.alloc(ctx->global_cap));
         }
     }
     if (p->n_tallies > 0) {
@@ -428,8 +436,12 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         ctx->tally_mean.assign(p->n_tallies, 0.0);
         ctx->tally_uncer.assign(p->n_tallies, 0.0);
     }
-    CK(ctx->d_comm.alloc(32 + 2 * (size_t)std::max<int64_t>(p->n_tallies, 0)));
-    CK(ctx->d_counts.alloc(ctx->world));
+    if (ctx->world > MCB_MAX_WORLD) return ctx->fail(MCB_ERR_ARG, "world %d > %d", ctx->world, MCB_MAX_WORLD);
+    ctx->vec_len = 16 + (size_t)entropy_bins + 2 * (size_t)std::max<int64_t>(p->n_tallies, 0);
+    CK(ctx->d_send.alloc(ctx->vec_len));
+    CK(ctx->d_recv.alloc(ctx->vec_len * ctx->world));
+    CK(cudaMallocHost((void**)&ctx->h_send, ctx->vec_len * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void**)&ctx->h_recv, ctx->vec_len * ctx->world * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1)); CK(cudaEventCreate(&ctx->ev2));
     // the cross-section tables are read by every lookup and fit in L2 many times over: ask for them to persist
     {
@@ -475,6 +487,11 @@ void mcb_destroy(mcb_ctx* ctx)
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    if (ctx->h_send) cudaFreeHost(ctx->h_send);
+    if (ctx->h_recv) cudaFreeHost(ctx->h_recv);
+    for (int b = 0; b < 2; b++)
+        for (int r = 0; r < ctx->world && r < MCB_MAX_WORLD; r++)
+            if (r != ctx->rank && ctx->peer_bank[b][r]) cudaIpcCloseMemHandle(ctx->peer_bank[b][r]);
     for (int i = 0; i < MCB_RING; i++) if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -504,6 +521,45 @@ int mcb_comm_init(mcb_ctx* ctx, const char id[128])
     ncclUniqueId uid;
     memcpy(&uid, id, 128);
     NK(g_nccl.CommInitRank(&ctx->comm, ctx->world, uid, ctx->rank));
+    // Map every peer's fission banks into this process (CUDA IPC over NVLink / NVSwitch): the source kernel then reads
+    // the sites it draws straight from the HBM of the rank that banked them and the bank is never gathered.
+    if (ctx->ksearch && !getenv("MCB_NO_P2P")) {
+        const int W = ctx->world;
+        cudaIpcMemHandle_t mine[2];
+        bool ok = cudaIpcGetMemHandle(&mine[0], ctx->d_local_bank[0].p) == cudaSuccess &&
+                  cudaIpcGetMemHandle(&mine[1], ctx->d_local_bank[1].p) == cudaSuccess;
+        cudaGetLastError();
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        const size_t rec = 2 * sizeof(cudaIpcMemHandle_t) + 8;  // two handles + "I could export" flag
+        DevBuf<unsigned char> d_mine, d_all;
+        std::vector<unsigned char> h_mine(rec, 0), h_all(rec * W, 0);
+        memcpy(h_mine.data(), mine, 2 * sizeof(cudaIpcMemHandle_t));
+        h_mine[2 * sizeof(cudaIpcMemHandle_t)] = ok ? 1 : 0;
+        CK(d_mine.upload(h_mine.data(), rec));
+        CK(d_all.alloc(rec * W));
+        NK(g_nccl.AllGather(d_mine.p, d_all.p, rec, ncclChar, ctx->comm, ctx->stream));
+        CK(cudaMemcpyAsync(h_all.data(), d_all.p, rec * W, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < W; r++) ok = ok && h_all[r * rec + 2 * sizeof(cudaIpcMemHandle_t)] == 1;
+        for (int r = 0; r < W && ok; r++) {
+            for (int b = 0; b < 2; b++) {
+                if (r == ctx->rank) { ctx->peer_bank[b][r] = ctx->d_local_bank[b].p; continue; }
+                cudaIpcMemHandle_t h;
+                memcpy(&h, h_all.data() + r * rec + b * sizeof(cudaIpcMemHandle_t), sizeof(h));
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+                ctx->peer_bank[b][r] = (Site*)ptr;
+            }
+        }
+        // every rank must take the same path: agree on the outcome
+        unsigned long long flag = ok ? 1 : 0;
+        DevBuf<unsigned long long> d_flag;
+        CK(d_flag.upload(&flag, 1));
+        NK(g_nccl.AllReduce(d_flag.p, d_flag.p, 1, ncclUint64, ncclMin, ctx->comm, ctx->stream));
+        CK(cudaMemcpyAsync(&flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->p2p = flag == 1;
+    }
     return MCB_OK;
 }
 
@@ -524,12 +580,12 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     TallyAcc T;
     T.acc = ctx->d_tally_acc.p; T.stride = ctx->batch_hist; T.first_hist = (int32_t)h0; T.on = tally_on && ctx->n_tallies > 0;
     const uint64_t nps0 = ctx->icycle * ctx->n_sample + ctx->shard_begin;
-    const Site* sbank = nullptr;
-    if (ctx->source_is_bank) sbank = ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p;
+    SourceBankView V = ctx->view;
+    if (!ctx->source_is_bank) { memset(&V, 0, sizeof(V)); }
     Counters* C = ctx->d_counters.p;
     uint32_t* queue[2] = {ctx->q_active, ctx->q_next};
     ctx->timer.begin(st, ST_SOURCE);
-    mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, sbank, ctx->n_source_sites, C);
+    mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, V, C);
     ctx->timer.end(st);
 
     if (ctx->walk_mode) {
@@ -649,7 +705,7 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     cudaStream_t st = ctx->stream;
     const bool tally_on = ctx->icycle >= ctx->n_passive;  // handler.cpp:15
     const uint64_t launches0 = mcbk::launch_count();
-    if (ctx->source_is_bank && ctx->n_source_sites == 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
+    if (ctx->source_is_bank && ctx->view.n == 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
     if (ctx->world > 1 && !ctx->comm) return ctx->fail(MCB_ERR_COMM, "world > 1 but mcb_comm_init was not called");
     Counters* C = ctx->d_counters.p;
     CK(cudaEventRecord(ctx->ev0, st));
@@ -670,20 +726,24 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint64_t n_local = ctx->h_counters->site_cursor;
+    // with world > 1 the banks alternate: peers may still be drawing their sources from the one written last cycle
+    const int bw = ctx->world > 1 ? ctx->bank_w : 0;
+    Site* const wbank = ctx->d_local_bank[bw].p;
     if (ctx->ksearch) {
         ctx->timer.begin(st, ST_BANK);
         mcbk::scan_sites(st, ctx->d_scan_temp.p, ctx->d_scan_temp.n, ctx->H.nsite, ctx->d_site_offset.p, (uint32_t)ctx->shard_count);
-        mcbk::bank_sample_order(st, ctx->P, ctx->d_site_reqs.p, n_local, ctx->d_site_offset.p, ctx->d_local_bank.p);
+        mcbk::bank_sample_order(st, ctx->P, ctx->d_site_reqs.p, n_local, ctx->d_site_offset.p, wbank);
         ctx->timer.end(st);
         if (ctx->entropy_on) {
             ctx->timer.begin(st, ST_CLOSEOUT);
-            mcbk::entropy_history(st, ctx->P, ctx->d_local_bank.p, ctx->d_site_offset.p, ctx->H.nsite, (uint32_t)ctx->shard_count, C);
+            mcbk::entropy_history(st, ctx->P, wbank, ctx->d_site_offset.p, ctx->H.nsite, (uint32_t)ctx->shard_count, C);
             CK(cudaMemsetAsync(ctx->d_entropy_bins.p, 0, ctx->d_entropy_bins.n * sizeof(unsigned long long), st));
-            mcbk::entropy_histogram(st, ctx->P, ctx->d_local_bank.p, n_local, ctx->d_entropy_bins.p);
+            mcbk::entropy_histogram(st, ctx->P, wbank, n_local, ctx->d_entropy_bins.p);
             ctx->timer.end(st);
         }
     }
     ctx->n_local_sites = n_local;
+    ctx->bank_last = bw;
     CK(cudaEventRecord(ctx->ev1, st));
 
     // ---- gather the sums: [0..9] fixed-point limbs, [10..15] counters, then tally sum / squared (as doubles) ----
@@ -708,44 +768,60 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
         }
         CK(cudaStreamSynchronize(st));
     }
+    SourceBankView next_view;
+    memset(&next_view, 0, sizeof(next_view));
+    next_view.flat = wbank; next_view.n = n_local;
     if (ctx->world > 1) {
-        // integer sums are exact, so k does not depend on the number of GPUs; tally sums are doubles
-        DevBuf<unsigned long long> d_red;
-        DevBuf<double> d_t;
-        CK(d_red.upload(red.data(), red.size()));
-        NK(g_nccl.AllReduce(d_red.p, d_red.p, red.size(), ncclUint64, ncclSum, ctx->comm, st));
-        if (nt && tally_on) {
-            std::vector<double> both(2 * nt);
-            memcpy(both.data(), tsum.data(), nt * sizeof(double)); memcpy(both.data() + nt, tsq.data(), nt * sizeof(double));
-            CK(d_t.upload(both.data(), both.size()));
-            NK(g_nccl.AllReduce(d_t.p, d_t.p, both.size(), ncclDouble, ncclSum, ctx->comm, st));
-            CK(cudaMemcpyAsync(both.data(), d_t.p, both.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            memcpy(tsum.data(), both.data(), nt * sizeof(double)); memcpy(tsq.data(), both.data() + nt, nt * sizeof(double));
+        // One all-gather of every rank's close-out vector: [0..9] fixed-point limbs, [10] sites, [11..15] counters,
+        // entropy histogram, tally sum / squared (double bit patterns).  Every rank adds the vectors in rank order:
+        // integer sums are exact, double sums have a fixed order, so all ranks hold identical results, and the site
+        // counts give the global index range of every rank's bank slice.
+        const int W = ctx->world;
+        const size_t VL = ctx->vec_len, nb = ctx->d_entropy_bins.n;
+        unsigned long long* hs = ctx->h_send;
+        memcpy(hs, red.data(), (16 + nb) * sizeof(unsigned long long));
+        if (nt) { memcpy(hs + 16 + nb, tsum.data(), nt * sizeof(double)); memcpy(hs + 16 + nb + nt, tsq.data(), nt * sizeof(double)); }
+        CK(cudaMemcpyAsync(ctx->d_send.p, hs, VL * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        NK(g_nccl.AllGather(ctx->d_send.p, ctx->d_recv.p, VL, ncclUint64, ctx->comm, st));
+        CK(cudaMemcpyAsync(ctx->h_recv, ctx->d_recv.p, VL * W * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<unsigned long long> counts(W);
+        std::fill(red.begin(), red.end(), 0ull);
+        std::fill(tsum.begin(), tsum.end(), 0.0); std::fill(tsq.begin(), tsq.end(), 0.0);
+        for (int r = 0; r < W; r++) {
+            const unsigned long long* v = ctx->h_recv + (size_t)r * VL;
+            counts[r] = v[10];
+            for (size_t i = 0; i < 16 + nb; i++) red[i] += v[i];
+            if (nt && tally_on) {
+                const double* ts = reinterpret_cast<const double*>(v + 16 + nb);
+                for (size_t t = 0; t < nt; t++) { tsum[t] += ts[t]; tsq[t] += ts[nt + t]; }
+            }
         }
-        // fission bank: all ranks learn every rank's count, then each rank's slice is broadcast into place
         if (ctx->ksearch) {
-            unsigned long long mine = n_local;
-            DevBuf<unsigned long long> d_mine;
-            CK(d_mine.upload(&mine, 1));
-            NK(g_nccl.AllGather(d_mine.p, ctx->d_counts.p, 1, ncclUint64, ctx->comm, st));
-            std::vector<unsigned long long> counts(ctx->world);
-            CK(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, ctx->world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
             uint64_t total = 0;
             for (auto c : counts) total += c;
-            if (total > ctx->global_cap) return ctx->fail(MCB_ERR_CAPACITY, "global fission bank overflow: %llu sites", (unsigned long long)total);
-            NK(g_nccl.GroupStart());
-            uint64_t off = 0;
-            for (int r = 0; r < ctx->world; r++) {
-                if (counts[r]) NK(g_nccl.Broadcast(ctx->d_local_bank.p, ctx->d_global_bank.p + off, counts[r] * sizeof(Site), ncclChar, r, ctx->comm, st));
-                off += counts[r];
-            }
-            NK(g_nccl.GroupEnd());
             n_global_sites = total;
+            if (ctx->p2p) {
+                // nothing moves: next cycle's source kernel reads each drawn site from the HBM of the rank that banked it
+                next_view.flat = nullptr; next_view.n_seg = W; next_view.n = total;
+                uint64_t off = 0;
+                for (int r = 0; r < W; r++) { next_view.seg[r] = ctx->peer_bank[bw][r]; next_view.prefix[r] = off; off += counts[r]; }
+                next_view.prefix[W] = off;
+                ctx->bank_w ^= 1;
+            } else {
+                // no peer access: each rank's slice is broadcast into place (all-gather-v)
+                if (total > ctx->global_cap) return ctx->fail(MCB_ERR_CAPACITY, "global fission bank overflow: %llu sites", (unsigned long long)total);
+                if (ctx->d_global_bank.n < ctx->global_cap) CK(ctx->d_global_bank.alloc(ctx->global_cap));
+                NK(g_nccl.GroupStart());
+                uint64_t off = 0;
+                for (int r = 0; r < W; r++) {
+                    if (counts[r]) NK(g_nccl.Broadcast(wbank, ctx->d_global_bank.p + off, counts[r] * sizeof(Site), ncclChar, r, ctx->comm, st));
+                    off += counts[r];
+                }
+                NK(g_nccl.GroupEnd());
+                next_view.flat = ctx->d_global_bank.p; next_view.n = total;
+            }
         }
-        CK(cudaMemcpyAsync(red.data(), d_red.p, red.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
     }
     CK(cudaEventRecord(ctx->ev2, st));
     CK(cudaEventSynchronize(ctx->ev2));
@@ -797,7 +873,7 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
             for (size_t b = 0; b < ctx->d_entropy_bins.n; b++) if (red[16 + b]) { const double pb = (double)red[16 + b] / (double)tot; Hc -= pb * std::log2(pb); }
             r.H_cycle_conventional = Hc;
         }
-        ctx->n_source_sites = n_global_sites;
+        ctx->view = next_view;
         ctx->source_is_bank = true;
     }
     r.n_sites = ctx->ksearch ? n_global_sites : 0;
@@ -866,14 +942,22 @@ static int64_t read_bank(mcb_ctx* ctx, const Site* bank, uint64_t have, double* 
 int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
 {
     if (!ctx) return MCB_ERR_ARG;
-    return read_bank(ctx, ctx->d_local_bank.p, ctx->n_local_sites, out, cells, max_n);
+    return read_bank(ctx, ctx->d_local_bank[ctx->bank_last].p, ctx->n_local_sites, out, cells, max_n);
 }
 
 int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
 {
     if (!ctx) return MCB_ERR_ARG;
     if (!ctx->source_is_bank) return 0;
-    return read_bank(ctx, ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p, ctx->n_source_sites, out, cells, max_n);
+    if (ctx->view.flat) return read_bank(ctx, ctx->view.flat, ctx->view.n, out, cells, max_n);
+    // segmented bank (peer slices): materialise the part asked for
+    const int64_t n = std::min<int64_t>((int64_t)ctx->view.n, max_n);
+    if (n <= 0) return 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
+    if (ctx->d_global_bank.n < (size_t)n && ctx->d_global_bank.alloc((size_t)n) != cudaSuccess)
+        return ctx->fail(MCB_ERR_CUDA, "out of device memory for the gathered bank");
+    mcbk::gather_sites(ctx->stream, ctx->view, (uint64_t)n, ctx->d_global_bank.p);
+    return read_bank(ctx, ctx->d_global_bank.p, (uint64_t)n, out, cells, max_n);
 }
 
 int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells, int64_t n)
@@ -881,9 +965,13 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
     if (!ctx || n < 0) return MCB_ERR_ARG;
     if (!ctx->ksearch) return ctx->fail(MCB_ERR_ARG, "mcb_set_source_bank: not a k-eigenvalue problem");
     CK(cudaSetDevice(ctx->device));
-    Site* dst = ctx->world > 1 ? ctx->d_global_bank.p : ctx->d_local_bank.p;
     const uint64_t cap = ctx->world > 1 ? ctx->global_cap : ctx->site_cap;
     if ((uint64_t)n > cap) return ctx->fail(MCB_ERR_CAPACITY, "source bank of %lld sites exceeds the capacity %llu", (long long)n, (unsigned long long)cap);
+    Site* dst = ctx->d_local_bank[0].p;
+    if (ctx->world > 1) {
+        if (ctx->d_global_bank.n < (size_t)std::max<int64_t>(n, 1)) CK(ctx->d_global_bank.alloc((size_t)std::max<int64_t>(n, 1)));
+        dst = ctx->d_global_bank.p;
+    }
     if (ctx->d_io_sites.n < (size_t)n * 8) { CK(ctx->d_io_sites.alloc((size_t)n * 8)); CK(ctx->d_io_cells.alloc((size_t)n)); }
     if (n) {
         CK(cudaMemcpyAsync(ctx->d_io_sites.p, sites8, (size_t)n * 8 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -891,7 +979,8 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
         mcbk::pack_sites(ctx->stream, ctx->d_io_sites.p, ctx->d_io_cells.p, (uint64_t)n, dst);
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_source_sites = (uint64_t)n;
+    memset(&ctx->view, 0, sizeof(ctx->view));
+    ctx->view.flat = dst; ctx->view.n = (uint64_t)n;
     ctx->source_is_bank = true;
     return MCB_OK;
 }

@@ -72,6 +72,26 @@ struct Site {
     int32_t cell, seq;                    // seq = order of banking within the parent history
 };
 
+// The source bank a generation samples from.  Single GPU / a bank handed in from the host: one flat array.
+// Multi-GPU: the global bank is the rank-order concatenation of every rank's canonical slice; the slices stay where
+// they were written and are read in place over NVLink through peer pointers (CUDA IPC), so the bank is never
+// gathered: seg[r] = rank r's slice, prefix[r] = global index of its first site.
+#define MCB_MAX_WORLD 16
+struct SourceBankView {
+    const Site* flat;
+    const Site* seg[MCB_MAX_WORLD];
+    unsigned long long prefix[MCB_MAX_WORLD + 1];
+    int32_t n_seg, pad;
+    unsigned long long n;                 // total sites; 0 with flat == nullptr and n_seg == 0 -> sample the deck's sources
+};
+__device__ __forceinline__ Site source_bank_site(const SourceBankView& V, unsigned long long j)
+{
+    if (V.flat) return V.flat[j];
+    int r = 0;
+    while (r + 1 < V.n_seg && j >= V.prefix[r + 1]) r++;
+    return V.seg[r][j - V.prefix[r]];
+}
+
 // a fission site as the collision leaves it: where, from what, and the stream it will be sampled from.  The
 // outgoing energy and direction are drawn later, in one dense pass over the whole generation's requests.
 struct SiteReq {
@@ -277,10 +297,14 @@ __device__ __forceinline__ double watt_sample(const double* va, const double* vb
 __device__ __forceinline__ void isotropic_direction(uint64_t& rng, double& dx, double& dy, double& dz)
 {
     const double mu = 2.0 * mcb_urand(rng) - 1.0;
-    const double azi = MCB_PI_2 * mcb_urand(rng);
     const double c = sqrt(1.0 - mu * mu);
     double sa, ca;
+#ifdef MCB_FAST_TRIG
+    sincospi(2.0 * mcb_urand(rng), &sa, &ca);
+#else
+    const double azi = MCB_PI_2 * mcb_urand(rng);
     sincos(azi, &sa, &ca);
+#endif
     dy = ca * c;
     dz = sa * c;
     dx = mu;
@@ -310,7 +334,11 @@ __device__ __forceinline__ void scatter_sample(double A, double& dx, double& dy,
             const double r1 = mcb_urand(rng), r2 = mcb_urand(rng);
             x = sqrt(-log(r1 * r2));
         } else {
+#ifdef MCB_FAST_TRIG
+            const double cos_val = cospi(0.5 * mcb_urand(rng));
+#else
             const double cos_val = cos(MCB_PI_HALF * mcb_urand(rng));
+#endif
             const double l1 = log(mcb_urand(rng));
             const double l2 = log(mcb_urand(rng));
             x = sqrt(-l1 - l2 * cos_val * cos_val);

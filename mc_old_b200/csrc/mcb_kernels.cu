@@ -393,7 +393,7 @@ __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B
 // (RN_init_particle, Random.cpp:196-204).
 __global__ void __launch_bounds__(BLOCK)
 k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint32_t count, uint64_t nps0,
-         const Site* sbank, uint64_t n_sbank, Counters* C)
+         const SourceBankView V, Counters* C)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q == 0) {  // queue state of the batch: `count` primaries in queue 0, slots behind them are free
@@ -405,10 +405,10 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     const double xi = mcb_urand(rng);
     double x, y, z, u, v, w, E, t;
     int cell;
-    if (sbank) {
-        uint64_t j = (uint64_t)(xi * (double)n_sbank);
-        if (j >= n_sbank) j = n_sbank - 1;
-        const Site s = sbank[j];
+    if (V.n) {
+        uint64_t j = (uint64_t)(xi * (double)V.n);
+        if (j >= V.n) j = V.n - 1;
+        const Site s = source_bank_site(V, j);  // local HBM, or a peer's HBM over NVLink
         x = s.x; y = s.y; z = s.z; u = s.u; v = s.v; w = s.w; E = s.E; t = s.t; cell = s.cell;
     } else {
         int j = (int)(xi * (double)P.n_sources);
@@ -744,7 +744,13 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
             chunk_next += take;
             idle = __ballot_sync(FULL, !alive);
         }
+#ifdef MCB_WALK_SYNC
+        // keep the warps of a block in phase: they then run the same stretch of this (large) loop body and share
+        // its instruction-cache lines instead of evicting each other's
+        if (!__syncthreads_or(idle != FULL)) break;
+#else
         if (idle == FULL) break;  // nothing in flight and nothing left to draw
+#endif
         // ---- one event per live lane
         MacroXS X = {0, 0, 0, 0, 0};
         XSDetail D;
@@ -1031,6 +1037,14 @@ k_unpack_sites(const Site* __restrict__ in, uint64_t n, double* s8, int32_t* cel
     cells[q] = d.cell;
 }
 
+// the global bank of a multi-GPU run, materialised on demand (host read-back): out[q] = site q of the view
+__global__ void __launch_bounds__(256)
+k_gather_sites(const SourceBankView V, uint64_t n, Site* out)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = source_bank_site(V, q);
+}
+
 __global__ void k_iota(uint32_t* a, uint32_t n)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1147,9 +1161,9 @@ static unsigned grid_for(uint64_t n_hint)
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 16ull * (256 / BLOCK)));
 }
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
-            uint64_t nps0, const Site* sbank, uint64_t n_sbank, Counters* C)
+            uint64_t nps0, const SourceBankView& V, Counters* C)
 {
-    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, sbank, n_sbank, C);
+    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C);
     MCB_LAUNCHED(1);
 }
 void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C)
@@ -1247,6 +1261,10 @@ void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_
 void unpack_sites(cudaStream_t st, const Site* in, uint64_t n, double* s8, int32_t* cells)
 {
     if (n) { k_unpack_sites<<<blocks_for(n), 256, 0, st>>>(in, n, s8, cells); MCB_LAUNCHED(1); }
+}
+void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t n, Site* out)
+{
+    if (n) { k_gather_sites<<<blocks_for(n), 256, 0, st>>>(V, n, out); MCB_LAUNCHED(1); }
 }
 void iota(cudaStream_t st, uint32_t* a, uint32_t n)
 {

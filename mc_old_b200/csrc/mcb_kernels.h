@@ -12,7 +12,7 @@ uint64_t launch_count();  // kernels launched by this thread through the launche
 // (Counters::n_active[cur]); it fills [(cur+1)%3] and clears [(cur+2)%3].  n_hint (an upper bound of the queue
 // length known to the host) only sizes the grid.
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
-            uint64_t nps0, const Site* sbank, uint64_t n_sbank, Counters* C);
+            uint64_t nps0, const SourceBankView& V, Counters* C);
 void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C);
 void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint,
             uint32_t* evq, Counters* C, const HistoryAcc& H, const TallyAcc& T);
@@ -44,6 +44,7 @@ void entropy_histogram(cudaStream_t st, const DevProblem& P, const Site* bank, u
 int tally_chunks(uint32_t n_hist);
 void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist, int64_t n_tallies, double* partial,
                   double* sum, double* squared);
+void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t n, Site* out);
 void iota(cudaStream_t st, uint32_t* a, uint32_t n);
 void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out);
 void unpack_sites(cudaStream_t st, const Site* in, uint64_t n, double* s8, int32_t* cells);

@@ -22,9 +22,9 @@ if [ "$STEP" = all ] || [ "$STEP" = ncu ]; then
       python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
   python tools/ncu_summary.py launches gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1
   cat gpurun_out/launches_summary.txt
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_step -c 1 \
-      -f -o gpurun_out/k_step python tools/prof_driver.py --samples 1e7 --cycles 3 --profile-cycle 2 > gpurun_out/ncu_full.log 2>&1
-  ncu -i gpurun_out/k_step.ncu-rep --page raw --csv > gpurun_out/k_step_raw.csv 2>/dev/null
-  python tools/ncu_summary.py raw gpurun_out/k_step_raw.csv > gpurun_out/k_step_summary.txt 2>&1
-  cat gpurun_out/k_step_summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${KERNEL:-k_walk} -c 1 \
+      -f -o gpurun_out/${KERNEL:-k_walk} python tools/prof_driver.py --samples 1e7 --cycles 3 --profile-cycle 2 > gpurun_out/ncu_full.log 2>&1
+  ncu -i gpurun_out/${KERNEL:-k_walk}.ncu-rep --page raw --csv > gpurun_out/${KERNEL:-k_walk}_raw.csv 2>/dev/null
+  python tools/ncu_summary.py raw gpurun_out/${KERNEL:-k_walk}_raw.csv > gpurun_out/${KERNEL:-k_walk}_summary.txt 2>&1
+  cat gpurun_out/${KERNEL:-k_walk}_summary.txt
 fi

@@ -1,36 +1,44 @@
 #!/usr/bin/env python3
-"""Instruction and stall-sample shares per code region of k_step from
-`ncu -i X.ncu-rep --page source --csv --print-source cuda,sass`."""
+"""Instruction and stall-sample shares per source FUNCTION of a kernel, from
+`ncu -i X.ncu-rep --page source --csv --print-source cuda,sass > src.csv`:   ncu_regions.py src.csv
+Lines are attributed to the function whose definition encloses them in the repository's sources."""
 import collections
 import csv
+import os
+import re
 import sys
 
-
-def region(f, l):
-    l = int(l)
-    if f == 'mcb_tables.h':
-        return 'lookup: union-grid search'
-    if f == 'mcb_device.cuh':
-        for hi, name in ((170, 'lookup: micro_xs rows'), (200, 'lookup: macro sums'), (245, 'select nuclide'), (275, 'watt'),
-                         (295, 'isotropic / dist1'), (340, 'scatter_sample'), (10**9, 'surface_intersect')):
-            if l <= hi:
-                return name
-    if f == 'mcb_physics.h':
-        for hi, name in ((62, 'rng'), (100, 'algorithm (quad, interp)'), (195, 'surface eval/distance'), (213, 'search_cell'),
-                         (240, 'scatter_direction'), (10**9, 'physics other')):
-            if l <= hi:
-                return name
-    if f == 'mcb_kernels.cu':
-        for hi, name in ((71, 'block_reserve'), (150, 'tally score'), (196, 'ev_flight'), (241, 'ev_collide_pre'),
-                         (282, 'ev_collide_bank'), (303, 'ev_collide_scatter (self)'), (370, 'ev_cross'), (10**9, 'k_step body')):
-            if l <= hi:
-                return name
-    return f
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = {f: os.path.join(ROOT, d, f) for d, f in (("mc_old_b200/csrc", "mcb_kernels.cu"), ("mc_old_b200/csrc", "mcb_device.cuh"),
+                                                ("mc_old_b200/csrc", "mcb_physics.h"), ("mc_old_b200/csrc", "mcb_tables.h"))}
+DEF = re.compile(r'^(?:static\s+)?(?:template\s*<[^>]*>\s*)?(?:__global__|__device__|MCB_HD|MCB_THD)[^;(]*?\b(\w+)\s*\(')
 
 
+def function_map(path):
+    """line number -> name of the last function definition that started at or before it"""
+    out, cur = {}, "?"
+    pending = ""
+    for i, line in enumerate(open(path), 1):
+        text = line.strip()
+        if text.startswith("template") and "(" not in text:
+            pending = text + " "
+            out[i] = cur
+            continue
+        m = DEF.match(re.sub(r'__launch_bounds__\([^)]*\)', '', pending + text))
+        if m is None and (pending + text).startswith("__global__"):
+            pending = pending + text + " "
+            out[i] = cur
+            continue
+        pending = ""
+        if m:
+            cur = m.group(1)
+        out[i] = cur
+    return out
+
+
+MAPS = {f: function_map(p) for f, p in SRC.items() if os.path.exists(p)}
 rows = list(csv.reader(open(sys.argv[1])))
-cur = None
-hdr = None
+cur, hdr = None, None
 agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
 for r in rows:
     if not r:
@@ -50,12 +58,15 @@ for r in rows:
             return float(d.get(k, '0').replace(',', ''))
         except ValueError:
             return 0.0
-    a = agg[region(cur, r[0])]
+    name = MAPS.get(cur, {}).get(int(r[0]), cur)
+    a = agg[name if cur in MAPS else "(" + str(cur) + ")"]
     a[0] += f('Instructions Executed')
     a[1] += f('Thread Instructions Executed')
     a[2] += f('Warp Stall Sampling (All Samples)')
 ti = sum(a[0] for a in agg.values())
 ts = sum(a[2] for a in agg.values())
-print("%-28s %7s %7s %6s" % ("region", "instr%", "stall%", "lanes"))
+print("total warp-instr %.3e  thread-instr %.3e  lanes/instr %.2f  stall samples %d" % (ti, sum(a[1] for a in agg.values()), sum(a[1] for a in agg.values()) / max(ti, 1), ts))
+print("%-28s %7s %7s %6s" % ("function", "instr%", "stall%", "lanes"))
 for k, a in sorted(agg.items(), key=lambda x: -x[1][2]):
-    print("%-28s %6.1f%% %6.1f%% %6.1f" % (k, 100 * a[0] / ti, 100 * a[2] / ts, a[1] / max(a[0], 1)))
+    if a[0] or a[2]:
+        print("%-28s %6.1f%% %6.1f%% %6.1f" % (k, 100 * a[0] / ti, 100 * a[2] / max(ts, 1), a[1] / max(a[0], 1)))
