@@ -48,6 +48,15 @@ const char* mcbh_mode(const mcbh_deck* d);            /* "fixed source" | "k-eig
 const char* mcbh_simulation_name(const mcbh_deck* d);
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z); /* general.cpp:26-34; -1 = lost */
 
+/* Simulator::report (src/simulator/report.cpp:9-52), Estimator::report (src/Estimator.cpp:368-422) and
+ * EstimatorK::report (:562-594): writes the reference's output.h5 tree to `path` with the library's own
+ * HDF5 writer (host/h5lite.cpp; there is no libhdf5 in the image).  k_cycle / H_cycle: n_cycle values; k_avg / k_uncer:
+ * n_active running values (ksearch decks only; pass NULL / 0 otherwise); tallies in the flat order of mcb_get_tallies.
+ * Returns 0, or -1 with mcbh_last_error(). */
+int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const double* k_cycle, const double* H_cycle,
+                      int32_t n_cycle, const double* k_avg, const double* k_uncer, int32_t n_active,
+                      const double* tally_mean, const double* tally_uncer, int64_t n_tallies);
+
 /* self-check of the device lookup structure (union grid + map + hash, built by the same code mcb_create uses):
  * idx_out[i*Nn + k] = row index the device lookup uses for nuclide k of `material` at E[i]; must equal the
  * reference's binary_search(E, n_E) = #{n_E < E} - 1 (Algorithm.cpp:46-64).  Returns Nn; stats = nU, n_hash,

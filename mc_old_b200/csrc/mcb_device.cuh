@@ -67,10 +67,30 @@ struct Bank {
 };
 
 // fission site / source site (AoS: sites are written and read by random index)
-struct Site {
+// 80 bytes, 16-byte aligned: a site is fetched with five 128-bit loads (it is drawn by random index, from local HBM or
+// from a peer's HBM over NVLink, where every request costs a round trip)
+struct alignas(16) Site {
     double x, y, z, u, v, w, E, t;
     int32_t cell, seq;                    // seq = order of banking within the parent history
+    int32_t pad[2];
 };
+static_assert(sizeof(Site) == 80, "Site is five 16-byte words");
+__device__ __forceinline__ Site load_site(const Site* p)
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+    const int4 e = *reinterpret_cast<const int4*>(q + 4);
+    Site s;
+    s.x = a.x; s.y = a.y; s.z = b.x; s.u = b.y; s.v = c.x; s.w = c.y; s.E = d.x; s.t = d.y;
+    s.cell = e.x; s.seq = e.y; s.pad[0] = 0; s.pad[1] = 0;
+    return s;
+}
+__device__ __forceinline__ void store_site(Site* p, const Site& s)
+{
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(s.x, s.y); q[1] = make_double2(s.z, s.u); q[2] = make_double2(s.v, s.w); q[3] = make_double2(s.E, s.t);
+    *reinterpret_cast<int4*>(q + 4) = make_int4(s.cell, s.seq, 0, 0);
+}
 
 // The source bank a generation samples from.  Single GPU / a bank handed in from the host: one flat array.
 // Multi-GPU: the global bank is the rank-order concatenation of every rank's canonical slice; the slices stay where
@@ -86,10 +106,10 @@ struct SourceBankView {
 };
 __device__ __forceinline__ Site source_bank_site(const SourceBankView& V, unsigned long long j)
 {
-    if (V.flat) return V.flat[j];
+    if (V.flat) return load_site(V.flat + j);
     int r = 0;
     while (r + 1 < V.n_seg && j >= V.prefix[r + 1]) r++;
-    return V.seg[r][j - V.prefix[r]];
+    return load_site(V.seg[r] + (j - V.prefix[r]));
 }
 
 // a fission site as the collision leaves it: where, from what, and the stream it will be sampled from.  The

@@ -881,7 +881,7 @@ k_bank_sample_order(const DevProblem P, const SiteReq* __restrict__ reqs, uint64
     s.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, r.E_in, rng);
     isotropic_direction(rng, s.u, s.v, s.w);
     s.x = r.x; s.y = r.y; s.z = r.z; s.t = r.t; s.cell = r.cell; s.seq = r.seq;
-    out[(uint64_t)offset[r.hist] + (uint64_t)r.seq] = s;
+    store_site(out + ((uint64_t)offset[r.hist] + (uint64_t)r.seq), s);
 }
 
 __device__ __forceinline__ int entropy_bin(const DevProblem& P, double x, double y, double z)  // Entropy.cpp:27-35
@@ -1024,14 +1024,14 @@ k_pack_sites(const double* __restrict__ s8, const int32_t* __restrict__ cells, u
     Site d;
     d.x = s[0]; d.y = s[1]; d.z = s[2]; d.u = s[3]; d.v = s[4]; d.w = s[5]; d.E = s[6]; d.t = s[7];
     d.cell = cells[q]; d.seq = 0;
-    out[q] = d;
+    store_site(out + q, d);
 }
 __global__ void __launch_bounds__(256)
 k_unpack_sites(const Site* __restrict__ in, uint64_t n, double* s8, int32_t* cells)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const Site d = in[q];
+    const Site d = load_site(in + q);
     double* s = s8 + 8 * q;
     s[0] = d.x; s[1] = d.y; s[2] = d.z; s[3] = d.u; s[4] = d.v; s[5] = d.w; s[6] = d.E; s[7] = d.t;
     cells[q] = d.cell;
@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(256)
 k_gather_sites(const SourceBankView V, uint64_t n, Site* out)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) out[q] = source_bank_site(V, q);
+    if (q < n) store_site(out + q, source_bank_site(V, q));
 }
 
 __global__ void k_iota(uint32_t* a, uint32_t n)

@@ -4,6 +4,7 @@
 #include "deck.h"
 #include "mcb200_host.h"
 #include "mcb_tables.h"
+#include "h5lite.h"
 
 struct mcbh_deck { mcb::Deck deck; };
 
@@ -79,6 +80,61 @@ const double* mcbh_filter_grid(const mcbh_deck* d) { return d ? d->deck.filter_g
 const char* mcbh_mode(const mcbh_deck* d) { return d ? d->deck.mode.c_str() : nullptr; }
 const char* mcbh_simulation_name(const mcbh_deck* d) { return d ? d->deck.simulation_name.c_str() : nullptr; }
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z) { return d ? d->deck.search_cell(x, y, z) : -1; }
+
+// Simulator::report (report.cpp:9-52) + Estimator::report (Estimator.cpp:368-422) + EstimatorK::report (:562-594)
+int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const double* k_cycle, const double* H_cycle,
+                      int32_t n_cycle, const double* k_avg, const double* k_uncer, int32_t n_active,
+                      const double* tally_mean, const double* tally_uncer, int64_t n_tallies)
+{
+    if (!d || !path) return -1;
+    const mcb_problem* p = d->deck.view();
+    if (n_tallies != p->n_tallies) { g_error = "mcbh_write_output: tally count does not match the deck"; return -1; }
+    h5lite::File f;
+    h5lite::Group& summary = f.root.group("summary");
+    summary.dataset_u64("Ncycle", p->n_cycle);
+    summary.dataset_u64("Nsample", p->n_sample);
+    summary.dataset_u64("Npassive", p->n_passive);
+    summary.dataset_u64("Ntrack", n_track);
+    summary.dataset_string("mode", d->deck.mode);
+    h5lite::Group& roulette = summary.group("survival_roulette");
+    roulette.dataset_f64("wr", p->wr);
+    roulette.dataset_f64("ws", p->ws);
+    static const char* const f_name[] = {"surface", "cell", "energy", "energy_initial", "time"};  // Estimator.h:307-369
+    static const char* const f_unit[] = {"id#", "id#", "eV", "eV", "s"};
+    for (size_t e = 0; e < d->deck.estimators.size(); e++) {
+        const mcb_estimator& E = d->deck.estimators[e];
+        h5lite::Group& g = f.root.group(E.name);
+        std::string indexing;
+        std::vector<uint64_t> dims;
+        uint64_t per_score = 1;
+        for (int i = 0; i < E.n_filters; i++) {
+            const mcb_filter& F = d->deck.filters[E.filter_begin + i];
+            indexing += std::string("[") + f_name[F.type] + "]";
+            h5lite::Dataset& ds = g.dataset_f64(f_name[F.type], {(uint64_t)F.grid_n}, d->deck.filter_grid.data() + F.grid_begin);
+            ds.attr_string("unit", f_unit[F.type]);
+            dims.push_back((uint64_t)F.size);
+            per_score *= (uint64_t)F.size;
+        }
+        g.attr_string("indexing", indexing);
+        for (int k = 0; k < E.n_scores; k++) {
+            h5lite::Group& sg = g.group(d->deck.scores[E.score_begin + k].name);
+            const int64_t t0 = E.tally_begin + (int64_t)k * (int64_t)per_score;
+            sg.dataset_f64("mean", dims, tally_mean + t0);
+            sg.dataset_f64("uncertainty", dims, tally_uncer + t0);
+        }
+    }
+    if (p->ksearch) {
+        h5lite::Group& ks = f.root.group("ksearch");
+        ks.dataset_f64("k_cycle", {(uint64_t)n_cycle}, k_cycle);
+        ks.dataset_f64("H_cycle", {(uint64_t)n_cycle}, H_cycle);
+        ks.dataset_f64("mean", n_active > 0 ? k_avg[n_active - 1] : 0.0);
+        ks.dataset_f64("uncertainty", n_active > 0 ? k_uncer[n_active - 1] : 0.0);
+        h5lite::Group& ka = ks.group("k_active");
+        ka.dataset_f64("mean", {(uint64_t)n_active}, k_avg);
+        ka.dataset_f64("uncertainty", {(uint64_t)n_active}, k_uncer);
+    }
+    return f.write(path, g_error) ? 0 : -1;
+}
 
 int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, int32_t* idx_out, int64_t stats[4])
 {
