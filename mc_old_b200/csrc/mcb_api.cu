@@ -523,7 +523,11 @@ int mcb_comm_init(mcb_ctx* ctx, const char id[128])
     NK(g_nccl.CommInitRank(&ctx->comm, ctx->world, uid, ctx->rank));
     // Map every peer's fission banks into this process (CUDA IPC over NVLink / NVSwitch): the source kernel then reads
     // the sites it draws straight from the HBM of the rank that banked them and the bank is never gathered.
-    if (ctx->ksearch && !getenv("MCB_NO_P2P")) {
+    // Measured on 8xB200 (NV18 all-to-all): with one peer the in-place reads cost 1.1 ms per 1e7 histories and beat the
+    // gather (9.4 vs 11.9 ms per generation); with 3 or 7 peers the same fine-grained reads collapse (63 / 134 ms), so
+    // from 4 ranks on the slices are gathered with NCCL instead unless MCB_P2P=1 forces the in-place path.
+    const bool want_p2p = getenv("MCB_P2P") ? atoi(getenv("MCB_P2P")) != 0 : ctx->world <= 2;
+    if (ctx->ksearch && want_p2p && !getenv("MCB_NO_P2P")) {
         const int W = ctx->world;
         cudaIpcMemHandle_t mine[2];
         bool ok = cudaIpcGetMemHandle(&mine[0], ctx->d_local_bank[0].p) == cudaSuccess &&

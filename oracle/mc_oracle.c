@@ -356,15 +356,51 @@ static double macro_nuSigmaF(const mcb_problem* p, int m, double E)
     for (i = p->mat_begin[m]; i < p->mat_begin[m + 1]; i++) sum += micro_nusigmaF(p, p->mat_nuclide[i], E) * p->mat_density[i];
     return sum;
 }
-/* Material::nuclide_scatter / nuclide_nufission (Material.cpp:106-125); -1 = nullptr */
+/* Nuclide::nusigmaF_prompt / nusigmaF_delayed (Nuclide.cpp:62-73): (1-beta)*sf*nu and beta*fraction_i*sf*nu, left to right */
+static double micro_nusigmaF_prompt(const mcb_problem* p, int n, double E)
+{
+    return (1.0 - micro(p, n, X_BETA, E)) * micro(p, n, X_F, E) * micro(p, n, X_NU, E);
+}
+static double micro_nusigmaF_delayed(const mcb_problem* p, int n, double E, int g)
+{
+    return micro(p, n, X_BETA, E) * p->nuclides[n].fraction[g] * micro(p, n, X_F, E) * micro(p, n, X_NU, E);
+}
+/* channel kinds: 0 scatter, 1 nu-fission, 2 prompt nu-fission, 3+g delayed nu-fission of group g */
+static double micro_kind(const mcb_problem* p, int n, int kind, double E)
+{
+    if (kind == 0) return micro(p, n, X_S, E);
+    if (kind == 1) return micro_nusigmaF(p, n, E);
+    if (kind == 2) return micro_nusigmaF_prompt(p, n, E);
+    return micro_nusigmaF_delayed(p, n, E, kind - 3);
+}
+/* Material::SigmaS / nuSigmaF / nuSigmaF_prompt / nuSigmaF_delayed (Material.cpp:26-82) */
+static double macro_kind(const mcb_problem* p, int m, int kind, double E)
+{
+    double sum = 0.0;
+    int i;
+    for (i = p->mat_begin[m]; i < p->mat_begin[m + 1]; i++) sum += micro_kind(p, p->mat_nuclide[i], kind, E) * p->mat_density[i];
+    return sum;
+}
+/* Material::nuSigmaF_delayed_decay (Material.cpp:83-91) */
+static double macro_delayed_decay(const mcb_problem* p, int m, double E, int g)
+{
+    double sum = 0.0;
+    int i;
+    for (i = p->mat_begin[m]; i < p->mat_begin[m + 1]; i++) {
+        const int n = p->mat_nuclide[i];
+        sum += micro_nusigmaF_delayed(p, n, E, g) / p->nuclides[n].lambda[g] * p->mat_density[i];
+    }
+    return sum;
+}
+/* Material::nuclide_scatter / nuclide_nufission / _prompt / _delayed (Material.cpp:106-146); -1 = nullptr */
 static int select_nuclide(const mcb_problem* p, int m, int kind, double E, double xi)
 {
-    const double u = (kind == 0 ? macro_(p, m, X_S, E) : macro_nuSigmaF(p, m, E)) * xi;
+    const double u = macro_kind(p, m, kind, E) * xi;
     double s = 0.0;
     int i;
     for (i = p->mat_begin[m]; i < p->mat_begin[m + 1]; i++) {
         const int n = p->mat_nuclide[i];
-        s += (kind == 0 ? micro(p, n, X_S, E) : micro_nusigmaF(p, n, E)) * p->mat_density[i];
+        s += micro_kind(p, n, kind, E) * p->mat_density[i];
         if (s > u) return n;
     }
     return -1;
@@ -530,6 +566,9 @@ static double score_value(const mco_ctx* c, const mcb_score* S, const particle* 
     case MCB_SCORE_TOTAL: return macro_(p, m, X_T, P->E) * kv;
     case MCB_SCORE_SCATTER_OLD: return macro_(p, m, X_S, P->E_old) * kv;
     case MCB_SCORE_NU_FISSION_OLD: return macro_nuSigmaF(p, m, P->E_old) * kv;
+    case MCB_SCORE_NU_FISSION_PROMPT_OLD: return macro_kind(p, m, 2, P->E_old) * kv;
+    case MCB_SCORE_NU_FISSION_DELAYED_OLD: return macro_kind(p, m, 3 + S->group, P->E_old) * kv;
+    case MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD: return macro_delayed_decay(p, m, P->E_old, S->group) * kv;
     default: return 0.0;
     }
 }
@@ -574,7 +613,44 @@ static void filter_idx_l(const mco_ctx* c, const mcb_filter* F, const particle* 
     }
 }
 /* Estimator::score (Estimator.cpp:298-336) */
-static void estimator_score(mco_ctx* c, int e, const particle* P, double l_in)
+static void estimator_score_plain(mco_ctx* c, int e, const particle* P, double l_in);
+static double chid_sample(const mcb_problem* p, int nuc, int g, rng_ref* r);
+/* EstimatorScatter / EstimatorFissionPrompt / EstimatorFissionDelayed ::score (Estimator.cpp:441-482): a copy of the
+ * particle undergoes the event, drawn from the same stream as the transport, and is scored with the generic
+ * estimator: energy_old = incident energy, energy = outgoing energy */
+static void estimator_score(mco_ctx* c, int e, particle* P, double l_in)
+{
+    const mcb_problem* p = c->p;
+    const mcb_estimator* E = &p->estimators[e];
+    if (E->simulate == MCB_SIM_NONE) { estimator_score_plain(c, e, P, l_in); return; }
+    {
+        particle Q = *P;
+        rng_ref r;
+        const int m = p->cells[P->cell].material;
+        int n;
+        r.c = c; r.P = P; r.raw = 0;
+        if (m < 0) return;
+        if (E->simulate == MCB_SIM_SCATTER) {
+            n = select_nuclide(p, m, 0, P->E, urand(c, P));
+            if (n < 0) return; /* the reference dereferences a null nuclide here */
+            scatter_sample(p->nuclides[n].A, &Q, &r);
+        } else if (E->simulate == MCB_SIM_FISSION || E->simulate == MCB_SIM_FISSION_PROMPT) {
+            const mcb_nuclide* N;
+            n = select_nuclide(p, m, E->simulate == MCB_SIM_FISSION ? 1 : 2, P->E, urand(c, P));
+            if (n < 0) return;
+            N = &p->nuclides[n];
+            p_set_energy(&Q, watt_sample(N->watt_a, N->watt_b, N->watt_g, P->E, &r));
+        } else {
+            const int g = E->simulate - MCB_SIM_FISSION_DELAYED;
+            n = select_nuclide(p, m, 3 + g, P->E, urand(c, P));
+            if (n < 0) return;
+            p_set_energy(&Q, chid_sample(p, n, g, &r));
+        }
+        Q.rng = P->rng;
+        estimator_score_plain(c, e, &Q, l_in);
+    }
+}
+static void estimator_score_plain(mco_ctx* c, int e, const particle* P, double l_in)
 {
     const mcb_problem* p = c->p;
     const mcb_estimator* E = &p->estimators[e];
@@ -610,7 +686,7 @@ static void estimator_score(mco_ctx* c, int e, const particle* P, double l_in)
     }
 }
 /* estimators attached to a cell (TL or C) or to a surface, in deck order */
-static void score_attached(mco_ctx* c, int attach, int id, const particle* P, double l)
+static void score_attached(mco_ctx* c, int attach, int id, particle* P, double l)
 {
     const mcb_problem* p = c->p;
     int e, i;
