@@ -102,6 +102,9 @@ enum { MCB_SCORE_FLUX = 0, MCB_SCORE_ABSORPTION, MCB_SCORE_SCATTER, MCB_SCORE_CA
        MCB_SCORE_NU_FISSION_DELAYED_OLD, MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD };
 enum { MCB_FILTER_SURFACE = 0, MCB_FILTER_CELL, MCB_FILTER_ENERGY, MCB_FILTER_ENERGY_OLD, MCB_FILTER_TIME };
 enum { MCB_ATTACH_SURFACE = 0, MCB_ATTACH_CELL_TL = 1, MCB_ATTACH_CELL_C = 2 };
+/* simulate-then-score estimators of the TRMM tally set (Estimator.cpp:441-482): a copy of the particle scatters /
+ * fissions before the generic scoring.  MCB_SIM_FISSION_DELAYED + g = delayed group g (0..5) */
+enum { MCB_SIM_NONE = 0, MCB_SIM_SCATTER = 1, MCB_SIM_FISSION = 2, MCB_SIM_FISSION_PROMPT = 3, MCB_SIM_FISSION_DELAYED = 4 };
 
 typedef struct mcb_score {
     int32_t score, kernel, group, reserved;
@@ -117,7 +120,7 @@ typedef struct mcb_estimator {
     int32_t score_begin, n_scores;
     int32_t filter_begin, n_filters; /* filter 0 is the surface/cell id filter */
     int32_t tally_begin, n_tallies;  /* range in the global tally vector; layout [score][f1][f2].. row-major */
-    int32_t simulate;                /* 0 plain; TRMM simulate-then-score kinds are reserved */
+    int32_t simulate;                /* MCB_SIM_* */
     char name[64];
 } mcb_estimator;
 

@@ -486,8 +486,85 @@ bool Deck::load_string(const std::string& xml_text, const std::string& xs_dir, i
         trmm_present = true;
         if (!p.ksearch) { error = "[ERROR] TRMM should be run in ksearch mode"; return false; }
         if (!(flags & DECK_IGNORE_TRMM)) {
-            error = "unsupported: <trmm> tally set (SURVEY.md §8f-2); load with DECK_IGNORE_TRMM for transport + k only";
-            return false;
+            const XmlNode& T = *doc.child("trmm");
+            // nine estimators in this order (setup.cpp:828-842,1004-1012): simple, scatter, fission_prompt, delayed 1..6
+            struct Spec { std::string name; int simulate; std::vector<mcb_score> sc; };
+            auto mk = [](const std::string& n, int score, int kernel, int group) {
+                mcb_score S;
+                std::memset(&S, 0, sizeof(S));
+                copy_name(S.name, sizeof(S.name), n);
+                S.score = score; S.kernel = kernel; S.group = group;
+                return S;
+            };
+            std::vector<Spec> specs;
+            Spec simple{"TRM_simple", MCB_SIM_NONE, {}};
+            simple.sc.push_back(mk("collision", MCB_SCORE_TOTAL, MCB_KERNEL_TRACK_VELOCITY, 0));                  // setup.cpp:848-851
+            simple.sc.push_back(mk("flux", MCB_SCORE_FLUX, MCB_KERNEL_TRACK, 0));                                 // :853-856
+            for (int i = 0; i < 6; i++)                                                                            // :858-864
+                simple.sc.push_back(mk("NuFissionDelayed_" + std::to_string(i + 1), MCB_SCORE_NU_FISSION_DELAYED_OLD, MCB_KERNEL_TRACK, i));
+            for (int i = 0; i < 6; i++)                                                                            // :866-873
+                simple.sc.push_back(mk("NuFissionDelayedLambda_" + std::to_string(i + 1), MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD, MCB_KERNEL_TRACK, i));
+            simple.sc.push_back(mk("inverse_speed", MCB_SCORE_INVERSE_VELOCITY, MCB_KERNEL_TRACK, 0));            // :875-878
+            specs.push_back(simple);
+            specs.push_back({"TRM_matrix_scatter", MCB_SIM_SCATTER, {mk("InScatter", MCB_SCORE_SCATTER_OLD, MCB_KERNEL_TRACK_VELOCITY, 0)}});  // :890-892
+            specs.push_back({"TRM_matrix_fission_prompt", MCB_SIM_FISSION_PROMPT,
+                             {mk("NuFissionPrompt", MCB_SCORE_NU_FISSION_PROMPT_OLD, MCB_KERNEL_TRACK_VELOCITY, 0)}});                         // :894-897
+            for (int i = 0; i < 6; i++)                                                                                                            // :880-888
+                specs.push_back({"TRMM_matrix_fission_delayed_" + std::to_string(i + 1), MCB_SIM_FISSION_DELAYED + i,
+                                 {mk("NuFissionDelayedEmission_" + std::to_string(i + 1), MCB_SCORE_NU_FISSION_DELAYED_OLD, MCB_KERNEL_TRACK_VELOCITY, i)}});
+            // filters: the cell filter, then per <filter>: energy -> [energy_initial][energy] for the matrix estimators
+            std::vector<double> cell_grid;
+            for (const XmlNode* c : T.children("cell")) {
+                const int id = find_name(cell_names, c->attribute("name").value());
+                if (id < 0) { error = "[ERROR] Unknown cell label " + c->attribute("name").value() + " in trmm"; return false; }
+                cell_grid.push_back(id);
+            }
+            struct FSpec { int type; std::vector<double> grid; };
+            std::vector<FSpec> extra;
+            for (const XmlNode* f : T.children("filter")) {
+                std::vector<double> grid;
+                if (!parse_filter_grid(*f, grid, "trmm", error)) return false;
+                if (!f->attribute("type")) { error = "[ERROR] Need filter type for trmm"; return false; }
+                const std::string f_name = f->attribute("type").value();
+                if (f_name == "energy") extra.push_back({MCB_FILTER_ENERGY, grid});
+                else if (f_name == "time") extra.push_back({MCB_FILTER_TIME, grid});
+                else { error = "[ERROR] Unknown filter type for trmm"; return false; }
+                if (grid.size() < 2) { error = "[ERROR] filter grid of trmm needs two points"; return false; }
+            }
+            for (const Spec& sp : specs) {
+                mcb_estimator E;
+                std::memset(&E, 0, sizeof(E));
+                copy_name(E.name, sizeof(E.name), sp.name);
+                E.attach = MCB_ATTACH_CELL_TL;
+                E.simulate = sp.simulate;
+                E.score_begin = (int32_t)scores.size();
+                scores.insert(scores.end(), sp.sc.begin(), sp.sc.end());
+                E.n_scores = (int32_t)sp.sc.size();
+                E.filter_begin = (int32_t)filters.size();
+                auto add_filter = [&](int type, const std::vector<double>& grid) {
+                    mcb_filter F;
+                    std::memset(&F, 0, sizeof(F));
+                    F.type = type;
+                    F.grid_begin = (int32_t)filter_grid.size(); F.grid_n = (int32_t)grid.size();
+                    F.size = (type == MCB_FILTER_CELL || type == MCB_FILTER_SURFACE) ? F.grid_n : F.grid_n - 1;
+                    filter_grid.insert(filter_grid.end(), grid.begin(), grid.end());
+                    filters.push_back(F);
+                };
+                add_filter(MCB_FILTER_CELL, cell_grid);
+                for (const FSpec& fs : extra) {
+                    if (fs.type == MCB_FILTER_ENERGY && sp.simulate != MCB_SIM_NONE) add_filter(MCB_FILTER_ENERGY_OLD, fs.grid);
+                    add_filter(fs.type, fs.grid);
+                }
+                E.n_filters = (int32_t)filters.size() - E.filter_begin;
+                int64_t nt = E.n_scores;
+                for (int i = 0; i < E.n_filters; i++) nt *= filters[E.filter_begin + i].size;
+                E.tally_begin = (int32_t)n_tallies;
+                E.n_tallies = (int32_t)nt;
+                n_tallies += nt;
+                estimators.push_back(E);
+            }
+            p.n_tallies = n_tallies;
+            trmm_built = true;
         }
     }
 

@@ -25,7 +25,8 @@ struct Deck {
     std::string simulation_name;
     std::string mode = "fixed source";
     std::vector<std::string> nuclide_names, material_names, surface_names, cell_names;
-    bool trmm_present = false;
+    bool trmm_present = false;   // the deck has a <trmm> block
+    bool trmm_built = false;     // ... and its nine estimators were created (not DECK_IGNORE_TRMM)
 
     // flattened storage
     std::vector<mcb_nuclide> nuclides;

@@ -650,6 +650,16 @@ static void estimator_score(mco_ctx* c, int e, particle* P, double l_in)
         estimator_score_plain(c, e, &Q, l_in);
     }
 }
+/* ReactionFission::ChiD -> DistributionDelayedNeutron::sample (Distribution.cpp:97-102): tabulated CDF, lin-lin */
+static double chid_sample(const mcb_problem* p, int nuc, int g, rng_ref* r)
+{
+    const mcb_nuclide* N = &p->nuclides[nuc];
+    const double* cdf = p->delayed_data + N->chid_cdf_begin[g];
+    const double* v = p->delayed_data + N->chid_E_begin;
+    const double xi = draw(r);
+    const int idx = mco_binary_search(xi, cdf, N->chid_cdf_n[g]);
+    return mco_interpolate(xi, cdf[idx], cdf[idx + 1], v[idx], v[idx + 1]);
+}
 static void estimator_score_plain(mco_ctx* c, int e, const particle* P, double l_in)
 {
     const mcb_problem* p = c->p;

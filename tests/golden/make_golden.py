@@ -31,8 +31,27 @@ from mc_old_b200 import decks  # noqa: E402
 import golden_cases as gc  # noqa: E402
 
 
+def runs_only(names):
+    """regenerate only the named whole-run records of runs.json (python make_golden.py --runs name ...)"""
+    path = os.path.join(HERE, "runs.json")
+    runs = json.load(open(path))
+    for name in names:
+        xml, patched = gc.run_decks()[name]
+        d = decks.write(tempfile.mkdtemp(prefix="gold_"), xml)
+        stdout, parsed = ol.run_ref(d, patched=patched)
+        rec = {"patched": patched, "stdout_cycle_lines": [ln for ln in stdout.splitlines() if ln[:1].isdigit()]}
+        for k, v in parsed.items():
+            rec[k] = v if isinstance(v, str) else ([int(x) for x in v] if v.dtype == np.uint64 else [float(x).hex() for x in v])
+        runs[name] = rec
+    with open(path, "w") as f:
+        json.dump(runs, f, indent=0, sort_keys=True)
+    print("updated", names)
+
+
 def main():
     assert ol.have_ref(), "oracle/_ref is not built"
+    if len(sys.argv) > 2 and sys.argv[1] == "--runs":
+        return runs_only(sys.argv[2:])
     fn = {}
     for name, xml in gc.function_decks().items():
         d = decks.write(tempfile.mkdtemp(prefix="gold_"), xml)

@@ -30,6 +30,7 @@ def run_decks():
         "heu_entropy": (decks.heu_sphere(samples=1000, active=2, passive=2, entropy=True), False),
         "ucube": (decks.ucube(samples=1000, active=3, passive=2), False),
         "gcr": (decks.gcr(samples=100, active=2, passive=2), False),
+        "gcr_trmm": (decks.gcr(samples=60, active=2, passive=1, trmm=True), False),
         "slab": (decks.slab(samples=20000), True),
         "shield": (decks.shielding(samples=4000), True),
         "shield_split": (decks.shielding(samples=3000, split=True), True),

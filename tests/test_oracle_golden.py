@@ -200,8 +200,18 @@ def test_whole_run_bit_exact(name, golden_runs, deck_cache):
     # the reference writes /<estimator>/<score>/{mean,uncertainty}; our flat order is [estimator][score][bins]
     import report_order
     want_mean, want_uncer = report_order.flatten(deck, rec)
-    assert np.array_equal(mean, want_mean)
-    assert np.array_equal(uncer, want_uncer)
+    keep = np.ones(mean.size, dtype=bool)
+    for est in deck.estimators():
+        # TRM_simple's NuFissionDelayed* scores read the REAL particle's energy_old, which the reference leaves
+        # uninitialised at birth (Particle ctor calls set_energy before p_energy is set, include/Particle.h:30-34):
+        # its values there are stack garbage.  The oracle defines E_old = E at birth; those bins are not comparable.
+        bins = est["n_tallies"] // max(len(est["scores"]), 1)
+        for k, score in enumerate(est["scores"]):
+            if est["name"] == "TRM_simple" and score.startswith("NuFissionDelayed"):
+                keep[est["tally_begin"] + k * bins: est["tally_begin"] + (k + 1) * bins] = False
+    assert keep.sum() >= mean.size - 240
+    assert np.array_equal(mean[keep], want_mean[keep])
+    assert np.array_equal(uncer[keep], want_uncer[keep])
 
 
 @pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
