@@ -57,6 +57,11 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
                       int32_t n_cycle, const double* k_avg, const double* k_uncer, int32_t n_active,
                       const double* tally_mean, const double* tally_uncer, int64_t n_tallies);
 
+/* TRM assembly of the TRMM tally set (report.cpp:53-157) from the flat tally means: TRM (G+6)^2 row-major,
+ * inverse_speed G, C_initial 6, psi_initial G.  Returns G, or -1 when the deck has no TRMM set. */
+int mcbh_trm_assemble(mcbh_deck* d, const double* tally_mean, double* TRM, double* inverse_speed, double* C_initial,
+                      double* psi_initial);
+
 /* self-check of the device lookup structure (union grid + map + hash, built by the same code mcb_create uses):
  * idx_out[i*Nn + k] = row index the device lookup uses for nuclide k of `material` at E[i]; must equal the
  * reference's binary_search(E, n_E) = #{n_E < E} - 1 (Algorithm.cpp:46-64).  Returns Nn; stats = nU, n_hash,

@@ -81,6 +81,70 @@ const char* mcbh_mode(const mcbh_deck* d) { return d ? d->deck.mode.c_str() : nu
 const char* mcbh_simulation_name(const mcbh_deck* d) { return d ? d->deck.simulation_name.c_str() : nullptr; }
 int mcbh_search_cell(const mcbh_deck* d, double x, double y, double z) { return d ? d->deck.search_cell(x, y, z) : -1; }
 
+// TRM assembly (report.cpp:53-157) from the means of the TRMM tally set (the deck's last nine estimators):
+// TRM (G+6)^2 row-major, inverse_speed G, C_initial 6, psi_initial G.  Returns G, or -1 without a TRMM set.
+int mcbh_trm_assemble(mcbh_deck* d, const double* tally_mean, double* TRM, double* inverse_speed, double* C_initial,
+                      double* psi_initial)
+{
+    if (!d || !d->deck.trmm_built || d->deck.estimators.size() < 9) return -1;
+    const size_t e0 = d->deck.estimators.size() - 9;
+    const mcb_estimator& Es = d->deck.estimators[e0];
+    const double* simple = tally_mean + Es.tally_begin;
+    const double* scatter = tally_mean + d->deck.estimators[e0 + 1].tally_begin;
+    const double* prompt = tally_mean + d->deck.estimators[e0 + 2].tally_begin;
+    const double* delayed[6];
+    for (int j = 0; j < 6; j++) delayed[j] = tally_mean + d->deck.estimators[e0 + 3 + j].tally_begin;
+    const int score_N = Es.n_scores;
+    const int G = Es.n_tallies / score_N, J = 6, N = G + J;
+    for (int i = 0; i < N * N; i++) TRM[i] = 0.0;
+    int idx = 0;
+    for (int f = 0; f < G; f++) {  // M (report.cpp:62-78)
+        for (int i = 0; i < G; i++) {
+            if (i == f) {
+                TRM[idx] = -simple[i];
+                TRM[idx] += scatter[i + i * G];
+                TRM[idx] += prompt[i + i * G];
+                TRM[idx] /= simple[i + G];
+            } else {
+                TRM[idx] = scatter[f + i * G];
+                TRM[idx] += prompt[f + i * G];
+                TRM[idx] /= simple[i + G];
+            }
+            idx++;
+        }
+        idx += J;
+    }
+    for (int j = 0; j < J; j++) {  // D (:80-88)
+        for (int g = 0; g < G; g++) {
+            TRM[idx] = simple[2 * G + j * G + g];
+            TRM[idx] /= simple[G + g];
+            idx++;
+        }
+        idx += J;
+    }
+    double lambda[6];
+    for (int j = 0; j < J; j++) {  // L (:90-102)
+        double num = 0.0, denom = 0.0;
+        for (int g = 0; g < G; g++) { num += simple[2 * G + j * G + g]; denom += simple[2 * G + J * G + j * G + g]; }
+        lambda[j] = num / denom;
+        TRM[N * (G + j) + G + j] = -lambda[j];
+    }
+    for (int g = 0; g < G; g++) {  // P (:104-116)
+        for (int j = 0; j < J; j++) {
+            double num = 0.0, denom = 0.0;
+            for (int gp = 0; gp < G; gp++) { num += delayed[j][g + gp * G]; denom += simple[2 * G + j * G + gp]; }
+            TRM[N * g + G + j] = num / denom * lambda[j];
+        }
+    }
+    for (int i = 0; i < G; i++) inverse_speed[i] = simple[i + (score_N - 1) * G] / simple[i + G];  // :125-135
+    for (int j = 0; j < J; j++) {  // :137-147
+        C_initial[j] = 0.0;
+        for (int g = 0; g < G; g++) C_initial[j] += simple[2 * G + J * G + j * G + g];
+    }
+    for (int g = 0; g < G; g++) psi_initial[g] = simple[g + G];  // :149-157
+    return G;
+}
+
 // Simulator::report (report.cpp:9-52) + Estimator::report (Estimator.cpp:368-422) + EstimatorK::report (:562-594)
 int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const double* k_cycle, const double* H_cycle,
                       int32_t n_cycle, const double* k_avg, const double* k_uncer, int32_t n_active,
@@ -132,6 +196,16 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
         h5lite::Group& ka = ks.group("k_active");
         ka.dataset_f64("mean", {(uint64_t)n_active}, k_avg);
         ka.dataset_f64("uncertainty", {(uint64_t)n_active}, k_uncer);
+    }
+    if (d->deck.trmm_built) {  // report.cpp:53-157
+        const mcb_estimator& Es = d->deck.estimators[d->deck.estimators.size() - 9];
+        const int G = Es.n_tallies / Es.n_scores, N = G + 6;
+        std::vector<double> TRM((size_t)N * N), inv(G), Ci(6), psi(G);
+        mcbh_trm_assemble(d, tally_mean, TRM.data(), inv.data(), Ci.data(), psi.data());
+        f.root.dataset_f64("TRM", {(uint64_t)N, (uint64_t)N}, TRM.data());
+        f.root.dataset_f64("inverse_speed", {(uint64_t)G}, inv.data());
+        f.root.dataset_f64("C_initial", {6}, Ci.data());
+        f.root.dataset_f64("psi_initial", {(uint64_t)G}, psi.data());
     }
     return f.write(path, g_error) ? 0 : -1;
 }

@@ -113,9 +113,11 @@ def test_deck_error_messages():
         mcb.Deck(xml=decks.slab(samples=10).replace('<nuclide name="nuc3" density="0.1"/>', '<nuclide name="nope" density="0.1"/>'))
     with pytest.raises(ValueError, match="tdmc"):
         mcb.Deck(xml=decks.slab(samples=10).replace("</simulation>", '<tdmc time="1.0 2.0"/></simulation>'))
-    with pytest.raises(ValueError, match="TRMM|trmm"):
-        mcb.Deck(xml=decks.gcr(samples=10, trmm=True))
-    assert mcb.Deck(xml=decks.gcr(samples=10, trmm=True), flags=mcb.IGNORE_TRMM).info["trmm_present"] == 1
+    with pytest.raises(ValueError, match="TRMM should be run in ksearch mode"):
+        mcb.Deck(xml=decks.slab(samples=10) + '<trmm><cell name="slab 1"/><filter type="energy" grid="1 2"/></trmm>')
+    assert mcb.Deck(xml=decks.gcr(samples=10, trmm=True), flags=mcb.IGNORE_TRMM).info["n_estimators"] == 0
+    t = mcb.Deck(xml=decks.gcr(samples=10, trmm=True))
+    assert t.info["trmm_present"] == 1 and t.info["n_estimators"] == 9 and t.info["n_tallies"] == 3500
     with pytest.raises(ValueError):
         mcb.Deck(io_dir="/nonexistent/dir")
 

@@ -41,7 +41,7 @@ def _write(deck, path, n_track=12345):
 def test_output_tree_matches_the_reference_run(name, tmp_path):
     """same dataset paths and element counts as the reference wrote for the deck"""
     xml, _patched = gc.run_decks()[name]
-    deck = mcb.Deck(xml=xml, flags=mcb.IGNORE_TRMM)
+    deck = mcb.Deck(xml=xml)
     path = str(tmp_path / "output.h5")
     w = _write(deck, path)
     f = h5mini.File(path)
@@ -65,6 +65,27 @@ def test_output_tree_matches_the_reference_run(name, tmp_path):
         assert np.array_equal(f.root["ksearch/H_cycle"].value, w["H_cycle"])
         assert np.array_equal(f.root["ksearch/k_active/mean"].value, w["k_avg"])
         assert f.root["ksearch/mean"].value == w["k_avg"][-1] and f.root["ksearch/uncertainty"].value == w["k_uncer"][-1]
+
+
+def test_trm_assembly_matches_the_reference(tmp_path):
+    """report.cpp:53-157: TRM, inverse_speed, C_initial, psi_initial computed from the reference's own tally means
+    equal what the reference wrote, bit for bit"""
+    import report_order
+    rec = {k: (np.array([float.fromhex(x) for x in v]) if k.startswith("/") and isinstance(v, list) and v and isinstance(v[0], str) else v)
+           for k, v in GOLDEN["gcr_trmm"].items()}
+    deck = mcb.Deck(xml=gc.run_decks()["gcr_trmm"][0])
+    mean, _ = report_order.flatten(deck, rec)
+    L = mcb.host_lib()
+    L.mcbh_trm_assemble.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    G = 20
+    TRM = np.zeros((G + 6) ** 2); inv = np.zeros(G); Ci = np.zeros(6); psi = np.zeros(G)
+    assert L.mcbh_trm_assemble(deck._h, mean.ctypes.data, TRM.ctypes.data, inv.ctypes.data, Ci.ctypes.data, psi.ctypes.data) == G
+    for got, key in ((TRM, "/TRM"), (inv, "/inverse_speed"), (Ci, "/C_initial"), (psi, "/psi_initial")):
+        want = rec[key]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), key
+        assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), key
+    heu = mcb.Deck(xml=decks.heu_sphere(samples=10))
+    assert L.mcbh_trm_assemble(heu._h, mean.ctypes.data, TRM.ctypes.data, inv.ctypes.data, Ci.ctypes.data, psi.ctypes.data) == -1
 
 
 def test_estimator_groups_layout_and_attributes(tmp_path):
