@@ -130,7 +130,7 @@ struct mcb_ctx {
     DevProblem P{};
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevNuclide> d_nuclides;
-    DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid;
+    DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid, d_delayed, d_bank_eold;
     DevBuf<int32_t> d_map, d_hash, d_mat_nuclide, d_cell_surface, d_cell_sense, d_attach_begin[3], d_attach_list[3];
     DevBuf<mcb_surface> d_surfaces;
     DevBuf<mcb_cell> d_cells;
@@ -246,11 +246,21 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     if (p->abi_version != MCB_ABI_VERSION) return ctx->fail(MCB_ERR_ARG, "mcb_problem.abi_version %d != %d", p->abi_version, MCB_ABI_VERSION);
     if (p->n_sample == 0) return ctx->fail(MCB_ERR_ARG, "n_sample is zero");
     if (p->n_sources <= 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
-    for (int f = 0; f < p->n_filters; f++)
-        if (p->filters[f].type == MCB_FILTER_TIME || p->filters[f].type == MCB_FILTER_ENERGY_OLD)
-            return ctx->fail(MCB_ERR_ARG, "unsupported: time / energy_old filters (SURVEY §8f-3)");
-    for (int e = 0; e < p->n_estimators; e++)
-        if (p->estimators[e].simulate) return ctx->fail(MCB_ERR_ARG, "unsupported: TRMM simulate-then-score estimators (SURVEY §8f-2)");
+    bool track_old = false;
+    for (int f = 0; f < p->n_filters; f++) {
+        if (p->filters[f].type == MCB_FILTER_TIME) return ctx->fail(MCB_ERR_ARG, "unsupported: time filters (SURVEY §8f-3)");
+        if (p->filters[f].type == MCB_FILTER_ENERGY_OLD) track_old = true;
+    }
+    for (int e = 0; e < p->n_estimators; e++) {
+        const int sim = p->estimators[e].simulate;
+        if (sim < MCB_SIM_NONE || sim > MCB_SIM_FISSION_DELAYED + 5) return ctx->fail(MCB_ERR_ARG, "estimator %d: unknown simulate kind %d", e, sim);
+        if (sim != MCB_SIM_NONE) track_old = true;
+    }
+    for (int k = 0; k < p->n_scores; k++)
+        if (p->scores[k].score >= MCB_SCORE_SCATTER_OLD) {
+            track_old = true;
+            if (p->scores[k].group < 0 || p->scores[k].group > 5) return ctx->fail(MCB_ERR_ARG, "score %d: precursor group %d", k, p->scores[k].group);
+        }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ctx->fail(MCB_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     ctx->device = cfg ? cfg->device : 0;
@@ -270,6 +280,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
 
     // ---- nuclear data: rows + per-material union grid / map / hash ----
     CK(ctx->d_xs_rows.upload(p->xs_rows, (size_t)p->n_xs_rows * MCB_XS_ROW));
+    CK(ctx->d_delayed.upload(p->delayed_data, (size_t)std::max<int64_t>(p->n_delayed_data, 0)));
     std::vector<DevNuclide> nuc(p->n_nuclides);
     for (int n = 0; n < p->n_nuclides; n++) {
         const mcb_nuclide& N = p->nuclides[n];
@@ -277,6 +288,9 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         D.rows = ctx->d_xs_rows.p + (size_t)N.row_begin * MCB_XS_ROW;
         D.n_rows = N.n_rows; D.has_delayed = N.has_delayed; D.A = N.A;
         memcpy(D.watt_a, N.watt_a, sizeof(D.watt_a)); memcpy(D.watt_b, N.watt_b, sizeof(D.watt_b)); memcpy(D.watt_g, N.watt_g, sizeof(D.watt_g));
+        memcpy(D.lambda, N.lambda, sizeof(D.lambda)); memcpy(D.fraction, N.fraction, sizeof(D.fraction));
+        D.chid_E = ctx->d_delayed.p ? ctx->d_delayed.p + N.chid_E_begin : nullptr;
+        for (int g = 0; g < 6; g++) { D.chid_cdf[g] = ctx->d_delayed.p ? ctx->d_delayed.p + N.chid_cdf_begin[g] : nullptr; D.chid_cdf_n[g] = N.chid_cdf_n[g]; }
     }
     CK(ctx->d_nuclides.upload(nuc.data(), nuc.size()));
     std::vector<mcb::MaterialTables> tabs(p->n_materials);
@@ -358,6 +372,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     P.ksearch = p->ksearch; P.n_materials = p->n_materials; P.n_nuclides = p->n_nuclides; P.n_surfaces = p->n_surfaces;
     P.n_cells = p->n_cells; P.n_sources = p->n_sources; P.n_estimators = p->n_estimators; P.entropy_on = p->entropy_on;
     P.shared_histories = (!p->ksearch || splitting) ? 1 : 0;
+    P.track_old = track_old ? 1 : 0;
     P.wr = p->wr; P.ws = p->ws; P.seed0 = ctx->seed; P.n_sample = p->n_sample;
     P.materials = ctx->d_materials.p; P.nuclides = ctx->d_nuclides.p; P.mat_nuclide = ctx->d_mat_nuclide.p; P.mat_density = ctx->d_mat_density.p;
     P.surfaces = ctx->d_surfaces.p; P.cells = ctx->d_cells.p; P.cell_surface = ctx->d_cell_surface.p; P.cell_sense = ctx->d_cell_sense.p;
@@ -395,6 +410,8 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         B.rng = ctx->d_bank_rng.p;
         int32_t* i = ctx->d_bank_i32.p;
         B.cell = i; B.hist = i + ns; B.uidx = i + 2 * ns; B.surf = i + 3 * ns;
+        B.Eold = nullptr;
+        if (track_old) { CK(ctx->d_bank_eold.alloc(ns)); B.Eold = ctx->d_bank_eold.p; }
     }
     CK(ctx->d_queue.alloc(3 * ns));
     ctx->q_active = ctx->d_queue.p; ctx->q_next = ctx->d_queue.p + ns; ctx->q_ev = ctx->d_queue.p + 2 * ns;

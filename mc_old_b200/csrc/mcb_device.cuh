@@ -28,11 +28,16 @@ struct DevNuclide {
     int32_t n_rows, has_delayed;
     double A;
     double watt_a[3], watt_b[3], watt_g[3];
+    // delayed neutrons (setup.cpp:377-412): decay constants, group fractions, tabulated emission spectra
+    double lambda[6], fraction[6];
+    const double* chid_E;
+    const double* chid_cdf[6];
+    int32_t chid_cdf_n[6];
 };
 struct DevProblem {
     int32_t ksearch, n_materials, n_nuclides, n_surfaces, n_cells, n_sources, n_estimators, entropy_on;
     int32_t shared_histories;    // several particles of one history can be in flight (secondaries / splitting)
-    int32_t pad;
+    int32_t track_old;           // some estimator reads Particle::energy_old (TRMM tally set): Bank::Eold is maintained
     double wr, ws;
     uint64_t seed0, n_sample;
     const DevMaterial* materials;
@@ -61,6 +66,7 @@ struct Bank {
     double *x, *y, *z, *u, *v, *w, *E, *speed, *wgt, *t;
     uint64_t* rng;
     int32_t *cell, *hist;                 // hist = history index local to this rank's shard
+    double* Eold;                         // Particle::energy_old (Particle.cpp:42-56), only when DevProblem::track_old
     double *St, *Ss, *Sc, *Sf, *nSf;      // macroscopic xs of the cell's material at E (stage: xs_lookup)
     int32_t* uidx;                        // union-grid index of E in that material
     int32_t* surf;                        // surface hit by the last flight (stage: flight)
@@ -286,9 +292,59 @@ __device__ __forceinline__ int select_nuclide(const DevProblem& P, const DevMate
     return __ldg(&P.mat_nuclide[M.nuc_begin + sel]);
 }
 
+// Reaction channels of the TRMM tally set: 0 scatter, 1 nu-fission, 2 prompt nu-fission, 3+g delayed nu-fission of
+// precursor group g (Nuclide.cpp:57-73): sigma_s | sigma_f*nu | (1-beta)*sigma_f*nu | beta*fraction_g*sigma_f*nu
+__device__ __forceinline__ double micro_channel(const DevNuclide& N, const MicroXS& m, int kind)
+{
+    if (kind == 0) return m.s;
+    if (kind == 1) return m.f * m.nu;
+    if (kind == 2) return (1.0 - m.beta) * m.f * m.nu;
+    return m.beta * N.fraction[kind - 3] * m.f * m.nu;
+}
+// Material::SigmaS / nuSigmaF / nuSigmaF_prompt / nuSigmaF_delayed (Material.cpp:26-82) at any energy; with xi >= 0 also
+// Material::nuclide_scatter / _nufission / _nufission_prompt / _nufission_delayed (Material.cpp:106-146): *picked =
+// global nuclide index or -1.  decay = true: nuSigmaF_delayed_decay (Material.cpp:83-91), each term divided by lambda_g.
+static __device__ __noinline__ double macro_channel(const DevProblem& P, const DevMaterial& M, double E, int kind, bool decay, double xi,
+                                             int* picked)
+{
+    const int u = union_index(M, E);
+    double sum = 0.0;
+    for (int n = 0; n < M.n_nuc; n++) {
+        const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
+        const DevNuclide& N = P.nuclides[gn];
+        MicroXS m;
+        micro_xs(N, nuclide_index(M, u, n), E, m);
+        const double v = micro_channel(N, m, kind);
+        sum += (decay ? v / N.lambda[kind - 3] : v) * __ldg(&P.mat_density[M.nuc_begin + n]);
+    }
+    if (picked) {
+        const double thr = sum * xi;
+        double s = 0.0;
+        int sel = -1;
+        for (int n = 0; n < M.n_nuc; n++) {
+            const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
+            const DevNuclide& N = P.nuclides[gn];
+            MicroXS m;
+            micro_xs(N, nuclide_index(M, u, n), E, m);
+            s += micro_channel(N, m, kind) * __ldg(&P.mat_density[M.nuc_begin + n]);
+            if (sel < 0 && s > thr) sel = gn;
+        }
+        *picked = sel;
+    }
+    return sum;
+}
+
 // ---------------------------------------------------------------------------------------------
 // distributions / reactions
 // ---------------------------------------------------------------------------------------------
+// ReactionFission::ChiD -> DistributionDelayedNeutron::sample (Distribution.cpp:97-102): tabulated CDF, lin-lin
+__device__ __forceinline__ double chid_sample(const DevNuclide& N, int g, uint64_t& rng)
+{
+    const double xi = mcb_urand(rng);
+    const double* cdf = N.chid_cdf[g];
+    const int idx = mcb_binary_search(xi, cdf, N.chid_cdf_n[g]);
+    return mcb_interpolate(xi, cdf[idx], cdf[idx + 1], N.chid_E[idx], N.chid_E[idx + 1]);
+}
 // DistributionWatt::sample (Distribution.cpp:34-73); returns eV
 __device__ __forceinline__ double watt_sample(const double* va, const double* vb, const double* vg, double E,
                                               uint64_t& rng)

@@ -80,10 +80,11 @@ __device__ __forceinline__ void hist_add(double* p, double v) { atomicAdd(p, v);
 // ---------------------------------------------------------------------------------------------
 // tally scoring (Estimator::score, Estimator.cpp:298-336, for filters that yield one bin: surface, cell, energy)
 // ---------------------------------------------------------------------------------------------
-struct ScoreState {
-    double w, E, speed;
-    int cell, surface_old, material, u;
-    MacroXS X;  // macroscopic xs of `material` at E
+struct ScoreState {   // the particle as Score / Filter / the simulating estimators see it
+    double w, E, E_old, speed;
+    double u, v, wd;  // direction
+    int cell, surface_old, material, uidx;
+    MacroXS X;        // macroscopic xs of `material` at E
 };
 
 __device__ __forceinline__ double kernel_value(int kernel, const ScoreState& s, double l)  // Estimator.cpp:17-41
@@ -102,19 +103,27 @@ __device__ __forceinline__ double score_value(const DevProblem& P, const mcb_sco
     if (S.score == MCB_SCORE_FLUX) return kv;
     if (S.score == MCB_SCORE_INVERSE_VELOCITY) return kv / s.speed;
     if (s.material < 0) return 0.0;
+    const DevMaterial& M = P.materials[s.material];
     switch (S.score) {
-    case MCB_SCORE_ABSORPTION: return macro_sigma_a(P, P.materials[s.material], s.u, s.E) * kv;
+    case MCB_SCORE_ABSORPTION: return macro_sigma_a(P, M, s.uidx, s.E) * kv;
     case MCB_SCORE_SCATTER: return s.X.s * kv;
     case MCB_SCORE_CAPTURE: return s.X.c * kv;
     case MCB_SCORE_FISSION: return s.X.f * kv;
     case MCB_SCORE_NU_FISSION: return s.X.nf * kv;
     case MCB_SCORE_TOTAL: return s.X.t * kv;
+    // the "Old" scores of the TRMM tally set evaluate at Particle::energy_old (Estimator.cpp:96-118)
+    case MCB_SCORE_SCATTER_OLD: return macro_channel(P, M, s.E_old, 0, false, 0.0, nullptr) * kv;
+    case MCB_SCORE_NU_FISSION_OLD: return macro_channel(P, M, s.E_old, 1, false, 0.0, nullptr) * kv;
+    case MCB_SCORE_NU_FISSION_PROMPT_OLD: return macro_channel(P, M, s.E_old, 2, false, 0.0, nullptr) * kv;
+    case MCB_SCORE_NU_FISSION_DELAYED_OLD: return macro_channel(P, M, s.E_old, 3 + S.group, false, 0.0, nullptr) * kv;
+    case MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD: return macro_channel(P, M, s.E_old, 3 + S.group, true, 0.0, nullptr) * kv;
     default: return 0.0;
     }
 }
-__device__ __noinline__ void estimator_score(const DevProblem& P, const TallyAcc& T, int e, const ScoreState& s, double l, int hist)
+// Estimator::score (Estimator.cpp:298-336) for filters that yield one bin (surface, cell, energy, energy_old)
+__device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, const mcb_estimator& E, const ScoreState& s,
+                                                      double l, int hist)
 {
-    const mcb_estimator E = P.estimators[e];
     int64_t idx_1D = 0;
     int64_t factor_next = 1;  // idx_factor[i+1] (Estimator.cpp:288-295), built from the last filter backwards
     for (int i = E.n_filters - 1; i >= 0; i--) {
@@ -124,8 +133,8 @@ __device__ __noinline__ void estimator_score(const DevProblem& P, const TallyAcc
         switch (F.type) {
         case MCB_FILTER_SURFACE: idx = mcb_binary_search((double)s.surface_old, g, F.grid_n) + 1; break;  // Estimator.cpp:133-140
         case MCB_FILTER_CELL: idx = mcb_binary_search((double)s.cell, g, F.grid_n) + 1; break;            // :141-148
-        default: {                                                                                         // energy :149-163
-            idx = mcb_binary_search(s.E, g, F.grid_n);
+        default: {                                                                                         // energy :149-163, energy_old :165-179
+            idx = mcb_binary_search(F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, g, F.grid_n);
             if (idx < 0 || idx >= F.grid_n - 1) return;
         }
         }
@@ -140,11 +149,45 @@ __device__ __noinline__ void estimator_score(const DevProblem& P, const TallyAcc
         if (t >= E.tally_begin && t < E.tally_begin + E.n_tallies) atomicAdd(acc + t * T.stride, v);
     }
 }
+// One estimator scores one event.  The TRMM estimators first let a COPY of the particle scatter / fission, drawing
+// from the particle's own stream like the reference draws from its global one (EstimatorScatter / FissionPrompt /
+// FissionDelayed::score, Estimator.cpp:441-482): energy_old = incident energy, energy and speed = outgoing.
+__device__ __forceinline__ void estimator_score(const DevProblem& P, const TallyAcc& T, int e, const ScoreState& s, uint64_t& rng, double l,
+                                             int hist)
+{
+    const mcb_estimator E = P.estimators[e];
+    if (E.simulate == MCB_SIM_NONE) { estimator_score_plain(P, T, E, s, l, hist); return; }
+    if (s.material < 0) return;
+    const DevMaterial& M = P.materials[s.material];
+    ScoreState q = s;
+    int n = -1;
+    if (E.simulate == MCB_SIM_SCATTER) {
+        (void)macro_channel(P, M, s.E, 0, false, mcb_urand(rng), &n);
+        if (n < 0) return;  // the reference dereferences a null nuclide here
+        scatter_sample(P.nuclides[n].A, q.u, q.v, q.wd, q.E, q.speed, rng);
+    } else if (E.simulate == MCB_SIM_FISSION || E.simulate == MCB_SIM_FISSION_PROMPT) {
+        (void)macro_channel(P, M, s.E, E.simulate == MCB_SIM_FISSION ? 1 : 2, false, mcb_urand(rng), &n);
+        if (n < 0) return;
+        const DevNuclide& N = P.nuclides[n];
+        q.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, s.E, rng);
+        q.speed = mcb_speed_of_energy(q.E);
+    } else {
+        const int g = E.simulate - MCB_SIM_FISSION_DELAYED;
+        (void)macro_channel(P, M, s.E, 3 + g, false, mcb_urand(rng), &n);
+        if (n < 0) return;
+        q.E = chid_sample(P.nuclides[n], g, rng);
+        q.speed = mcb_speed_of_energy(q.E);
+    }
+    q.E_old = s.E;  // Particle::set_energy / set_speed (Particle.cpp:42-56)
+    q.uidx = union_index(M, q.E);
+    macro_xs(P, M, q.uidx, q.E, q.X);
+    estimator_score_plain(P, T, E, q, l, hist);
+}
 __device__ __forceinline__ void score_attached(const DevProblem& P, const TallyAcc& T, int kind, int id,
-                                               const ScoreState& s, double l, int hist)
+                                               const ScoreState& s, uint64_t& rng, double l, int hist)
 {
     const int b = P.attach_begin[kind][id], e = P.attach_begin[kind][id + 1];
-    for (int i = b; i < e; i++) estimator_score(P, T, P.attach_list[kind][i], s, l, hist);
+    for (int i = b; i < e; i++) estimator_score(P, T, P.attach_list[kind][i], s, rng, l, hist);
 }
 __device__ __forceinline__ bool has_attached(const DevProblem& P, int kind, int id)
 {
@@ -159,7 +202,26 @@ struct Particle {
     double x, y, z, u, v, w, E, speed, wgt, t;
     uint64_t rng;
     int cell, hist;
+    int slot;  // bank slot the particle was loaded from (addresses Bank::Eold)
 };
+// all estimators attached to surface / cell `id` score one event of particle p.  Cold: kept out of line so that the
+// transport kernels' registers are not shaped by it.  surface_old >= 0: surface estimators, the cross sections of the
+// cell the particle is now in are looked up here.
+__device__ __noinline__ void score_event(const DevProblem& P, const Bank& B, const TallyAcc& T, int kind, int id, Particle& p, int material,
+                                         int uidx, const MacroXS* X, int surface_old, double l)
+{
+    ScoreState s;
+    s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.u = p.u; s.v = p.v; s.wd = p.w;
+    s.E_old = P.track_old ? B.Eold[p.slot] : p.E;
+    s.cell = p.cell; s.surface_old = surface_old; s.material = material; s.uidx = uidx;
+    if (X) s.X = *X;
+    else {
+        s.X = MacroXS{0, 0, 0, 0, 0};
+        s.uidx = -1;
+        if (material >= 0) { s.uidx = union_index(P.materials[material], p.E); macro_xs(P, P.materials[material], s.uidx, p.E, s.X); }
+    }
+    score_attached(P, T, kind, id, s, p.rng, l, p.hist);
+}
 
 // xs_lookup event
 template <bool DETAIL>
@@ -180,7 +242,7 @@ __device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p
 // are bumped in memory with reductions.
 struct HistLocal { double kC, kTL; int nsite; };
 
-__device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
+__device__ __forceinline__ bool ev_flight(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
                                           const TallyAcc& T, int& S_hit, HistLocal* L = nullptr)
 {
     const int m = P.cells[p.cell].material;
@@ -199,9 +261,7 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, cons
         else hist_add(&H.kTL[p.hist], X.nf * p.wgt * l);
     }
     if (T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
-        ScoreState s;
-        s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = -1; s.material = m; s.u = uidx; s.X = X;
-        score_attached(P, T, MCB_ATTACH_CELL_TL, p.cell, s, l, p.hist);
+        score_event(P, B, T, MCB_ATTACH_CELL_TL, p.cell, p, m, uidx, &X, -1, l);
     }
     return to_cross;
 }
@@ -213,16 +273,14 @@ struct CollideCtx {
     int m, N_fission;
     unsigned n_sites, n_second;
 };
-__device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
+__device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
                                                const TallyAcc& T, double k_eff, CollideCtx& c)
 {
     c.m = P.cells[p.cell].material;
     c.N_fission = -1; c.n_sites = 0; c.n_second = 0;
     if (c.m < 0) { p.wgt = 0.0; return false; }  // vacuum: kill (general.cpp:124-128)
     if (T.on && has_attached(P, MCB_ATTACH_CELL_C, p.cell)) {
-        ScoreState s;
-        s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = -1; s.material = c.m; s.u = uidx; s.X = X;
-        score_attached(P, T, MCB_ATTACH_CELL_C, p.cell, s, 0.0, p.hist);
+        score_event(P, B, T, MCB_ATTACH_CELL_C, p.cell, p, c.m, uidx, &X, -1, 0.0);
     }
     // floor( w/k * nuSigmaF / SigmaT + xi ) (general.cpp:135-136)
     const double a = p.wgt / k_eff * X.nf / X.t;
@@ -288,6 +346,7 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank&
                 B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
                 B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = p.t;
                 B.rng[j] = rs; B.cell[j] = p.cell; B.hist[j] = p.hist;
+                if (P.track_old) B.Eold[j] = Es;
                 n_second_ok++;
             } else C->overflow_slots = 1;
         }
@@ -295,7 +354,7 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank&
 }
 // collide event, last part: k_C, implicit capture, scatter, weight_roulette (general.cpp:146-163,
 // population_control.cpp:9-15).  Returns whether the particle survives.
-__device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
+__device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
                                                    const CollideCtx& c, const HistoryAcc& H, HistLocal* L = nullptr)
 {
     if (P.ksearch && c.N_fission >= 0) {  // estimate_C (Estimator.cpp:503-507)
@@ -309,7 +368,10 @@ __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, Particle
     int ln_s = 0;
     const int N_scatter = D ? select_from_detail(P, P.materials[c.m], D->cum_s, X.s, xi_s, &ln_s)
                             : select_nuclide(P, P.materials[c.m], uidx, p.E, 0, X.s, xi_s, &ln_s);  // Material.cpp:106-115
-    if (N_scatter >= 0) scatter_sample(P.nuclides[N_scatter].A, p.u, p.v, p.w, p.E, p.speed, p.rng);
+    if (N_scatter >= 0) {
+        if (P.track_old) B.Eold[p.slot] = p.E;  // Particle::set_speed keeps the pre-collision energy (Particle.cpp:49-56)
+        scatter_sample(P.nuclides[N_scatter].A, p.u, p.v, p.w, p.E, p.speed, p.rng);
+    }
     // weight_roulette (population_control.cpp:9-15)
     if (p.wgt < P.wr) {
         if (mcb_urand(p.rng) < p.wgt / P.ws) p.wgt = P.ws;
@@ -320,7 +382,7 @@ __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, Particle
 
 // cross event, first half: surface_hit + cell_importance up to the split (general.cpp:89-115,
 // population_control.cpp:21-43).  n_copy = split copies the second half will write.
-__device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, int S, const TallyAcc& T, Counters* C, unsigned& n_copy)
+__device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B, Particle& p, int S, const TallyAcc& T, Counters* C, unsigned& n_copy)
 {
     n_copy = 0;
     if (S < 0) { p.wgt = 0.0; return false; }  // no surface ahead: cannot happen in a closed geometry
@@ -343,11 +405,7 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
         p.t += MCB_EPSILON_FLOAT / p.speed;
     }
     if (T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
-        ScoreState s;
-        s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.cell = p.cell; s.surface_old = S; s.material = P.cells[p.cell].material;
-        s.u = -1; s.X = MacroXS{0, 0, 0, 0, 0};
-        if (s.material >= 0) { s.u = union_index(P.materials[s.material], p.E); macro_xs(P, P.materials[s.material], s.u, p.E, s.X); }
-        score_attached(P, T, MCB_ATTACH_SURFACE, S, s, 0.0, p.hist);
+        score_event(P, B, T, MCB_ATTACH_SURFACE, S, p, P.cells[p.cell].material, -1, nullptr, S, 0.0);
     }
     const double Iold = P.cells[cell_old].importance, Inew = P.cells[p.cell].importance;
     if (Inew != Iold) {
@@ -375,6 +433,7 @@ __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B
             B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = p.u; B.v[j] = p.v; B.w[j] = p.w;
             B.E[j] = p.E; B.speed[j] = p.speed; B.wgt[j] = p.wgt; B.t[j] = p.t;
             B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
+            if (P.track_old) B.Eold[j] = B.Eold[p.slot];
             n_copy_ok++;
         } else C->overflow_slots = 1;
     }
@@ -424,6 +483,7 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     B.x[q] = x; B.y[q] = y; B.z[q] = z; B.u[q] = u; B.v[q] = v; B.w[q] = w;
     B.E[q] = E; B.speed[q] = mcb_speed_of_energy(E); B.wgt[q] = 1.0; B.t[q] = t;
     B.rng[q] = rng; B.cell[q] = cell; B.hist[q] = h;
+    if (P.track_old) B.Eold[q] = E;  // the reference leaves energy_old uninitialised at birth; defined as E here
     active[q] = q;
 }
 
@@ -479,7 +539,7 @@ k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
         if (valid) {
             i = active[q];
             Particle p;
-            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
             p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
             p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
             MacroXS X;
@@ -487,7 +547,7 @@ k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
             int uidx = 0;
             if (T.on) { X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; uidx = B.uidx[i]; }
             int S;
-            to_cross = ev_flight(P, p, X, uidx, H, T, S);
+            to_cross = ev_flight(P, B, p, X, uidx, H, T, S);
             B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.t[i] = p.t; B.rng[i] = p.rng; B.surf[i] = S;
             tracks++;
         }
@@ -524,11 +584,11 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
         bool in_material = false;
         if (valid) {
             i = evq[q];
-            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
             p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
             p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
             X.t = B.St[i]; X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; X.nf = B.nSf[i]; uidx = B.uidx[i];
-            in_material = ev_collide_pre(P, p, X, uidx, nullptr, T, k_eff, c);
+            in_material = ev_collide_pre(P, B, p, X, uidx, nullptr, T, k_eff, c);
             if (in_material) collisions++;
         }
         const unsigned cntA[2] = {c.n_sites, c.n_second};
@@ -539,7 +599,7 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
         unsigned n_second_ok = 0;
         if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, posA[0], posA[1], n_second_ok);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (in_material) alive = ev_collide_scatter(P, p, X, uidx, nullptr, c, H);
+        if (in_material) alive = ev_collide_scatter(P, B, p, X, uidx, nullptr, c, H);
         __syncwarp();
         if (valid) {
             B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.rng[i] = p.rng;
@@ -578,10 +638,10 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
         unsigned n_copy = 0;
         if (valid) {
             i = evq[n_active - 1 - q];
-            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
             p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
             p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
-            alive = ev_cross_pre(P, p, B.surf[i], T, C, n_copy);
+            alive = ev_cross_pre(P, B, p, B.surf[i], T, C, n_copy);
             crossings++;
         }
         unsigned long long slot0 = 0;
@@ -639,7 +699,7 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
         Particle p;
         if (alive) {
             i = active[q];
-            p.cell = B.cell[i]; p.hist = B.hist[i];
+            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
             p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
             p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
         }
@@ -654,10 +714,10 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
             if (alive) {
                 int S;
                 if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-                to_cross = ev_flight(P, p, X, uidx, H, T, S);
+                to_cross = ev_flight(P, B, p, X, uidx, H, T, S);
                 tracks++;
-                if (to_cross) { alive = ev_cross_pre(P, p, S, T, C, n_copy); crossings++; }
-                else { in_material = ev_collide_pre(P, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
+                if (to_cross) { alive = ev_cross_pre(P, B, p, S, T, C, n_copy); crossings++; }
+                else { in_material = ev_collide_pre(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
             }
             const unsigned cnt[2] = {c.n_sites, c.n_second + n_copy};
             unsigned long long* const cursor[2] = {&C->site_cursor, &C->slot_cursor};
@@ -669,7 +729,7 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
             __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
             if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, pos[1], n_slots, C, n_new);
             __syncwarp();
-            if (in_material) alive = ev_collide_scatter(P, p, X, uidx, &D, c, H);
+            if (in_material) alive = ev_collide_scatter(P, B, p, X, uidx, &D, c, H);
             __syncwarp();
             if (n_new) {  // secondaries (fixed-source fission, splitting) join the next queue; rare, so per thread
                 const unsigned long long o = atomicAdd(next_len, (unsigned long long)n_new);
@@ -735,7 +795,7 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
             const unsigned rank = __popc(idle & lt_mask);
             if (!alive && rank < take) {
                 const uint32_t j = chunk_next + rank;
-                p.cell = B.cell[j]; p.hist = B.hist[j];
+                p.cell = B.cell[j]; p.hist = B.hist[j]; p.slot = (int)j;
                 p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
                 p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
                 L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
@@ -762,10 +822,10 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
         if (alive) {
             int S;
             if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-            to_cross = ev_flight(P, p, X, uidx, H, T, S, local_acc ? &L : nullptr);
+            to_cross = ev_flight(P, B, p, X, uidx, H, T, S, local_acc ? &L : nullptr);
             tracks++;
-            if (to_cross) { alive = ev_cross_pre(P, p, S, T, C, n_copy); crossings++; }
-            else { in_material = ev_collide_pre(P, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
+            if (to_cross) { alive = ev_cross_pre(P, B, p, S, T, C, n_copy); crossings++; }
+            else { in_material = ev_collide_pre(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
         }
         __syncwarp();
         // fission-site requests: one reservation per warp
@@ -789,7 +849,7 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
         if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
         __syncwarp();
-        if (in_material) alive = ev_collide_scatter(P, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
+        if (in_material) alive = ev_collide_scatter(P, B, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
         __syncwarp();
         if (local_acc && was_alive && !alive) {  // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525)
             H.kC[p.hist] = L.kC; H.kTL[p.hist] = L.kTL; H.nsite[p.hist] = L.nsite;
@@ -820,7 +880,7 @@ k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
     for (unsigned long long q = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * BLOCK) {
         const uint32_t i = active[q];
         Particle p;
-        p.cell = B.cell[i]; p.hist = B.hist[i];
+        p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
         p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
         p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
         bool alive = true;
@@ -829,26 +889,26 @@ k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
             XSDetail D;
             int uidx = -1, S;
             if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-            const bool to_cross = ev_flight(P, p, X, uidx, H, T, S);
+            const bool to_cross = ev_flight(P, B, p, X, uidx, H, T, S);
             tracks++;
             unsigned n_new = 0;
             unsigned long long slot0 = 0;
             if (to_cross) {
                 unsigned n_copy;
-                alive = ev_cross_pre(P, p, S, T, C, n_copy);
+                alive = ev_cross_pre(P, B, p, S, T, C, n_copy);
                 crossings++;
                 if (n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)n_copy);
                 alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
             } else {
                 CollideCtx c;
-                alive = ev_collide_pre(P, p, X, uidx, &D, T, k_eff, c);
+                alive = ev_collide_pre(P, B, p, X, uidx, &D, T, k_eff, c);
                 if (alive) {
                     collisions++;
                     unsigned long long site0 = 0;
                     if (c.n_sites) site0 = atomicAdd(&C->site_cursor, (unsigned long long)c.n_sites);
                     if (c.n_second) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)c.n_second);
                     if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new);
-                    alive = ev_collide_scatter(P, p, X, uidx, &D, c, H);
+                    alive = ev_collide_scatter(P, B, p, X, uidx, &D, c, H);
                 }
             }
             if (n_new) {
