@@ -204,24 +204,30 @@ struct Particle {
     int cell, hist;
     int slot;  // bank slot the particle was loaded from (addresses Bank::Eold)
 };
-// all estimators attached to surface / cell `id` score one event of particle p.  Cold: kept out of line so that the
-// transport kernels' registers are not shaped by it.  surface_old >= 0: surface estimators, the cross sections of the
-// cell the particle is now in are looked up here.
-__device__ __noinline__ void score_event(const DevProblem& P, const Bank& B, const TallyAcc& T, int kind, int id, Particle& p, int material,
-                                         int uidx, const MacroXS* X, int surface_old, double l)
+// all estimators attached to surface / cell `id` score one event of particle p.  Cold and out of line, with every
+// input BY VALUE (no address of a register-resident particle escapes), so that the transport kernels' register
+// allocation is not shaped by it; returns the particle's stream state (the simulating estimators draw from it).
+// have_X = false (surface estimators): the cross sections of the cell the particle is now in are looked up here.
+__device__ __noinline__ uint64_t score_event(const DevProblem& P, const Bank& B, const TallyAcc& T, int kind, int id, double w, double E,
+                                             double speed, double du, double dv, double dw, int cell, int hist, int slot, uint64_t rng,
+                                             int material, int uidx, bool have_X, double Xt, double Xs, double Xc, double Xf, double Xnf,
+                                             int surface_old, double l)
 {
     ScoreState s;
-    s.w = p.wgt; s.E = p.E; s.speed = p.speed; s.u = p.u; s.v = p.v; s.wd = p.w;
-    s.E_old = P.track_old ? B.Eold[p.slot] : p.E;
-    s.cell = p.cell; s.surface_old = surface_old; s.material = material; s.uidx = uidx;
-    if (X) s.X = *X;
-    else {
-        s.X = MacroXS{0, 0, 0, 0, 0};
+    s.w = w; s.E = E; s.speed = speed; s.u = du; s.v = dv; s.wd = dw;
+    s.E_old = P.track_old ? B.Eold[slot] : E;
+    s.cell = cell; s.surface_old = surface_old; s.material = material; s.uidx = uidx;
+    s.X = MacroXS{Xt, Xs, Xc, Xf, Xnf};
+    if (!have_X) {
         s.uidx = -1;
-        if (material >= 0) { s.uidx = union_index(P.materials[material], p.E); macro_xs(P, P.materials[material], s.uidx, p.E, s.X); }
+        if (material >= 0) { s.uidx = union_index(P.materials[material], E); macro_xs(P, P.materials[material], s.uidx, E, s.X); }
     }
-    score_attached(P, T, kind, id, s, p.rng, l, p.hist);
+    score_attached(P, T, kind, id, s, rng, l, hist);
+    return rng;
 }
+#define MCB_SCORE_EVENT(kind, id, p, material, uidx, have_X, X, surface_old, l)                                              \
+    (p).rng = score_event(P, B, T, kind, id, (p).wgt, (p).E, (p).speed, (p).u, (p).v, (p).w, (p).cell, (p).hist, (p).slot, \
+                          (p).rng, material, uidx, have_X, (X).t, (X).s, (X).c, (X).f, (X).nf, surface_old, l)
 
 // xs_lookup event
 template <bool DETAIL>
@@ -242,6 +248,7 @@ __device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p
 // are bumped in memory with reductions.
 struct HistLocal { double kC, kTL; int nsite; };
 
+template <bool TALLY>
 __device__ __forceinline__ bool ev_flight(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
                                           const TallyAcc& T, int& S_hit, HistLocal* L = nullptr)
 {
@@ -260,8 +267,8 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, const Bank& B, Pa
         if (L) L->kTL += X.nf * p.wgt * l;
         else hist_add(&H.kTL[p.hist], X.nf * p.wgt * l);
     }
-    if (T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
-        score_event(P, B, T, MCB_ATTACH_CELL_TL, p.cell, p, m, uidx, &X, -1, l);
+    if (TALLY && T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
+        MCB_SCORE_EVENT(MCB_ATTACH_CELL_TL, p.cell, p, m, uidx, true, X, -1, l);
     }
     return to_cross;
 }
@@ -273,14 +280,15 @@ struct CollideCtx {
     int m, N_fission;
     unsigned n_sites, n_second;
 };
+template <bool TALLY>
 __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
                                                const TallyAcc& T, double k_eff, CollideCtx& c)
 {
     c.m = P.cells[p.cell].material;
     c.N_fission = -1; c.n_sites = 0; c.n_second = 0;
     if (c.m < 0) { p.wgt = 0.0; return false; }  // vacuum: kill (general.cpp:124-128)
-    if (T.on && has_attached(P, MCB_ATTACH_CELL_C, p.cell)) {
-        score_event(P, B, T, MCB_ATTACH_CELL_C, p.cell, p, c.m, uidx, &X, -1, 0.0);
+    if (TALLY && T.on && has_attached(P, MCB_ATTACH_CELL_C, p.cell)) {
+        MCB_SCORE_EVENT(MCB_ATTACH_CELL_C, p.cell, p, c.m, uidx, true, X, -1, 0.0);
     }
     // floor( w/k * nuSigmaF / SigmaT + xi ) (general.cpp:135-136)
     const double a = p.wgt / k_eff * X.nf / X.t;
@@ -313,6 +321,7 @@ __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, const Bank& 
 // from the request's own stream.  Fixed source (fixed_source.cpp:12-22): same-history secondaries are written to
 // bank slots [slot0, ..), each sampled from, and continuing on, its own stream.  The parent's stream does not
 // advance.  Only lanes that bank anything call this; callers reconverge the warp afterwards.
+template <bool TALLY>
 __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank& B, const Particle& p, const CollideCtx& c,
                                                 const HistoryAcc& H, Counters* C, SiteReq* reqs, uint64_t site_cap,
                                                 uint32_t n_slots, unsigned long long site0, unsigned long long slot0,
@@ -346,7 +355,7 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank&
                 B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
                 B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = p.t;
                 B.rng[j] = rs; B.cell[j] = p.cell; B.hist[j] = p.hist;
-                if (P.track_old) B.Eold[j] = Es;
+                if (TALLY && P.track_old) B.Eold[j] = Es;
                 n_second_ok++;
             } else C->overflow_slots = 1;
         }
@@ -354,6 +363,7 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank&
 }
 // collide event, last part: k_C, implicit capture, scatter, weight_roulette (general.cpp:146-163,
 // population_control.cpp:9-15).  Returns whether the particle survives.
+template <bool TALLY>
 __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
                                                    const CollideCtx& c, const HistoryAcc& H, HistLocal* L = nullptr)
 {
@@ -369,7 +379,7 @@ __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, const Ba
     const int N_scatter = D ? select_from_detail(P, P.materials[c.m], D->cum_s, X.s, xi_s, &ln_s)
                             : select_nuclide(P, P.materials[c.m], uidx, p.E, 0, X.s, xi_s, &ln_s);  // Material.cpp:106-115
     if (N_scatter >= 0) {
-        if (P.track_old) B.Eold[p.slot] = p.E;  // Particle::set_speed keeps the pre-collision energy (Particle.cpp:49-56)
+        if (TALLY && P.track_old) B.Eold[p.slot] = p.E;  // Particle::set_speed keeps the pre-collision energy (Particle.cpp:49-56)
         scatter_sample(P.nuclides[N_scatter].A, p.u, p.v, p.w, p.E, p.speed, p.rng);
     }
     // weight_roulette (population_control.cpp:9-15)
@@ -382,6 +392,7 @@ __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, const Ba
 
 // cross event, first half: surface_hit + cell_importance up to the split (general.cpp:89-115,
 // population_control.cpp:21-43).  n_copy = split copies the second half will write.
+template <bool TALLY>
 __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B, Particle& p, int S, const TallyAcc& T, Counters* C, unsigned& n_copy)
 {
     n_copy = 0;
@@ -404,8 +415,9 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B,
         p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
         p.t += MCB_EPSILON_FLOAT / p.speed;
     }
-    if (T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
-        score_event(P, B, T, MCB_ATTACH_SURFACE, S, p, P.cells[p.cell].material, -1, nullptr, S, 0.0);
+    if (TALLY && T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
+        const MacroXS X0 = {0, 0, 0, 0, 0};
+        MCB_SCORE_EVENT(MCB_ATTACH_SURFACE, S, p, P.cells[p.cell].material, -1, false, X0, S, 0.0);
     }
     const double Iold = P.cells[cell_old].importance, Inew = P.cells[p.cell].importance;
     if (Inew != Iold) {
@@ -423,6 +435,7 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B,
 }
 // cross event, second half: the split copies (population_control.cpp:44-48) and weight_roulette, which also
 // draws for a particle that was just killed (w = 0 < wr), like the reference
+template <bool TALLY>
 __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B, Particle& p, bool alive, unsigned n_copy,
                                               unsigned long long slot0, uint32_t n_slots, Counters* C, unsigned& n_copy_ok)
 {
@@ -433,7 +446,7 @@ __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B
             B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = p.u; B.v[j] = p.v; B.w[j] = p.w;
             B.E[j] = p.E; B.speed[j] = p.speed; B.wgt[j] = p.wgt; B.t[j] = p.t;
             B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
-            if (P.track_old) B.Eold[j] = B.Eold[p.slot];
+            if (TALLY && P.track_old) B.Eold[j] = B.Eold[p.slot];
             n_copy_ok++;
         } else C->overflow_slots = 1;
     }
@@ -547,7 +560,7 @@ k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
             int uidx = 0;
             if (T.on) { X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; uidx = B.uidx[i]; }
             int S;
-            to_cross = ev_flight(P, B, p, X, uidx, H, T, S);
+            to_cross = ev_flight<true>(P, B, p, X, uidx, H, T, S);
             B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.t[i] = p.t; B.rng[i] = p.rng; B.surf[i] = S;
             tracks++;
         }
@@ -588,7 +601,7 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
             p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
             p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
             X.t = B.St[i]; X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; X.nf = B.nSf[i]; uidx = B.uidx[i];
-            in_material = ev_collide_pre(P, B, p, X, uidx, nullptr, T, k_eff, c);
+            in_material = ev_collide_pre<true>(P, B, p, X, uidx, nullptr, T, k_eff, c);
             if (in_material) collisions++;
         }
         const unsigned cntA[2] = {c.n_sites, c.n_second};
@@ -597,9 +610,9 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
         block_reserve<2>(scratchA[it & 1], cntA, curA, posA);
         bool alive = false;
         unsigned n_second_ok = 0;
-        if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, posA[0], posA[1], n_second_ok);
+        if (c.n_sites | c.n_second) ev_collide_bank<true>(P, B, p, c, H, C, reqs, site_cap, n_slots, posA[0], posA[1], n_second_ok);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (in_material) alive = ev_collide_scatter(P, B, p, X, uidx, nullptr, c, H);
+        if (in_material) alive = ev_collide_scatter<true>(P, B, p, X, uidx, nullptr, c, H);
         __syncwarp();
         if (valid) {
             B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.rng[i] = p.rng;
@@ -641,7 +654,7 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
             p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
             p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
             p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
-            alive = ev_cross_pre(P, B, p, B.surf[i], T, C, n_copy);
+            alive = ev_cross_pre<true>(P, B, p, B.surf[i], T, C, n_copy);
             crossings++;
         }
         unsigned long long slot0 = 0;
@@ -654,7 +667,7 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
         }
         unsigned n_copy_ok = 0;
         if (valid) {
-            alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_copy_ok);
+            alive = ev_cross_post<true>(P, B, p, alive, n_copy, slot0, n_slots, C, n_copy_ok);
             if (alive) {
                 B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.t[i] = p.t;
                 B.wgt[i] = p.wgt; B.rng[i] = p.rng; B.cell[i] = p.cell;
@@ -714,10 +727,10 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
             if (alive) {
                 int S;
                 if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-                to_cross = ev_flight(P, B, p, X, uidx, H, T, S);
+                to_cross = ev_flight<true>(P, B, p, X, uidx, H, T, S);
                 tracks++;
-                if (to_cross) { alive = ev_cross_pre(P, B, p, S, T, C, n_copy); crossings++; }
-                else { in_material = ev_collide_pre(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
+                if (to_cross) { alive = ev_cross_pre<true>(P, B, p, S, T, C, n_copy); crossings++; }
+                else { in_material = ev_collide_pre<true>(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
             }
             const unsigned cnt[2] = {c.n_sites, c.n_second + n_copy};
             unsigned long long* const cursor[2] = {&C->site_cursor, &C->slot_cursor};
@@ -725,11 +738,11 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
             block_reserve<2>(scratchA[ss & 1], cnt, cursor, pos);
             ss++;
             unsigned n_new = 0;
-            if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, pos[0], pos[1], n_new);
+            if (c.n_sites | c.n_second) ev_collide_bank<true>(P, B, p, c, H, C, reqs, site_cap, n_slots, pos[0], pos[1], n_new);
             __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-            if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, pos[1], n_slots, C, n_new);
+            if (to_cross) alive = ev_cross_post<true>(P, B, p, alive, n_copy, pos[1], n_slots, C, n_new);
             __syncwarp();
-            if (in_material) alive = ev_collide_scatter(P, B, p, X, uidx, &D, c, H);
+            if (in_material) alive = ev_collide_scatter<true>(P, B, p, X, uidx, &D, c, H);
             __syncwarp();
             if (n_new) {  // secondaries (fixed-source fission, splitting) join the next queue; rare, so per thread
                 const unsigned long long o = atomicAdd(next_len, (unsigned long long)n_new);
@@ -766,6 +779,7 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
 // iteration.  Nothing but the site requests (and the rare secondaries, which go to slots >= end and are walked by
 // the next pass) is written back: the particle record is read once.  With one particle per history the EstimatorK
 // scores live in registers and are stored once when the history ends.
+template <bool TALLY>
 __global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
 k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk, Counters* C, HistoryAcc H, TallyAcc T,
        SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
@@ -822,10 +836,10 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
         if (alive) {
             int S;
             if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-            to_cross = ev_flight(P, B, p, X, uidx, H, T, S, local_acc ? &L : nullptr);
+            to_cross = ev_flight<TALLY>(P, B, p, X, uidx, H, T, S, local_acc ? &L : nullptr);
             tracks++;
-            if (to_cross) { alive = ev_cross_pre(P, B, p, S, T, C, n_copy); crossings++; }
-            else { in_material = ev_collide_pre(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
+            if (to_cross) { alive = ev_cross_pre<TALLY>(P, B, p, S, T, C, n_copy); crossings++; }
+            else { in_material = ev_collide_pre<TALLY>(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
         }
         __syncwarp();
         // fission-site requests: one reservation per warp
@@ -845,11 +859,11 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
         unsigned long long slot0 = 0;
         if (c.n_second + n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)(c.n_second + n_copy));
         unsigned n_new = 0;
-        if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr);
+        if (c.n_sites | c.n_second) ev_collide_bank<TALLY>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (to_cross) alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
+        if (to_cross) alive = ev_cross_post<TALLY>(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
         __syncwarp();
-        if (in_material) alive = ev_collide_scatter(P, B, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
+        if (in_material) alive = ev_collide_scatter<TALLY>(P, B, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
         __syncwarp();
         if (local_acc && was_alive && !alive) {  // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525)
             H.kC[p.hist] = L.kC; H.kTL[p.hist] = L.kTL; H.nsite[p.hist] = L.nsite;
@@ -889,26 +903,26 @@ k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
             XSDetail D;
             int uidx = -1, S;
             if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-            const bool to_cross = ev_flight(P, B, p, X, uidx, H, T, S);
+            const bool to_cross = ev_flight<true>(P, B, p, X, uidx, H, T, S);
             tracks++;
             unsigned n_new = 0;
             unsigned long long slot0 = 0;
             if (to_cross) {
                 unsigned n_copy;
-                alive = ev_cross_pre(P, B, p, S, T, C, n_copy);
+                alive = ev_cross_pre<true>(P, B, p, S, T, C, n_copy);
                 crossings++;
                 if (n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)n_copy);
-                alive = ev_cross_post(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
+                alive = ev_cross_post<true>(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
             } else {
                 CollideCtx c;
-                alive = ev_collide_pre(P, B, p, X, uidx, &D, T, k_eff, c);
+                alive = ev_collide_pre<true>(P, B, p, X, uidx, &D, T, k_eff, c);
                 if (alive) {
                     collisions++;
                     unsigned long long site0 = 0;
                     if (c.n_sites) site0 = atomicAdd(&C->site_cursor, (unsigned long long)c.n_sites);
                     if (c.n_second) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)c.n_second);
-                    if (c.n_sites | c.n_second) ev_collide_bank(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new);
-                    alive = ev_collide_scatter(P, B, p, X, uidx, &D, c, H);
+                    if (c.n_sites | c.n_second) ev_collide_bank<true>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new);
+                    alive = ev_collide_scatter<true>(P, B, p, X, uidx, &D, c, H);
                 }
             }
             if (n_new) {
@@ -1267,7 +1281,9 @@ void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, u
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + BLOCK - 1) / BLOCK, resident));
     const uint64_t warps = (uint64_t)grid * WARPS;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
-    k_walk<<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff);
+    // two instances: the one for cycles that score nothing carries no estimator code (and no energy_old upkeep)
+    if (T.on) k_walk<true><<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff);
+    else k_walk<false><<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff);
     MCB_LAUNCHED(1);
 }
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
