@@ -37,7 +37,7 @@ BYTES_LOOKUP = lambda nn: 72 + 100 * nn   # E + mat 12, hash 4, bra
 BYTES_FLIGHT = 180                        # queue 4 + state in 112 + state out 44 + k_TL rmw 16 + event queue 4
 BYTES_COLLIDE = lambda nn: 220 + 2 * 96 * nn + 27  # state in 144 + out 76 + 2 selections x Nn x 2 rows + 0.35 sites x 76
 BYTES_CROSS = 140
-# fused step kernel: the whole-loop figure of SURVEY §8d per track = particle record in + out (224) + one xs lookup
+# walk kernel: the whole-loop figure of SURVEY §8d per track = particle record in + out (224) + one xs lookup
 # (72 + 100 Nn) + 76-byte fission sites (one per ~3.8 tracks in HEU)
 BYTES_STEP = lambda nn: 224 + 72 + 100 * nn + 20
 
@@ -319,7 +319,7 @@ def main():
                     "step": BYTES_STEP(nn)}
         total_bytes = 2.0 * per_gen[dominant] * per_unit[dominant]
         achieved = total_bytes / (stages[dominant]["ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" and os.environ.get("MCB_MODE") != "step" else dominant)), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
+        roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" else dominant)), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
                     "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "bytes_per_unit": per_unit[dominant], "units_per_launch": 2.0 * per_gen[dominant] / max(stages[dominant]["launches"], 1),
                     "avg_launch_ms": stages[dominant]["ms"] / max(stages[dominant]["launches"], 1),

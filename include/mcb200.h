@@ -172,7 +172,7 @@ typedef struct mcb_ctx mcb_ctx;
 typedef struct mcb_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t rank, world;       /* history sharding: this process owns histories [n*rank/world, n*(rank+1)/world) */
-    int32_t reserved;          /* flags: 1 = time every stage launch with CUDA events; 2 = one kernel per event type */
+    int32_t reserved;          /* flags: 1 = time every stage launch with CUDA events; 2 = event-queue mode, one kernel per event type */
     int64_t bank_capacity;     /* particle slots in flight on this GPU (0 = choose) */
     int64_t site_capacity;     /* fission sites this GPU can bank per cycle (0 = choose) */
     void* stream;              /* cudaStream_t to launch on (NULL = library-owned stream) */
@@ -198,7 +198,7 @@ typedef struct mcb_stage_times { /* accumulated CUDA-event time per kernel class
     uint64_t units_lookup;     /* particles looked up (for the xs roofline) */
     double ms_finish;          /* tail kernel: the last few particles of a batch followed to the end in registers */
     uint64_t n_finish;
-    double ms_step;            /* fused step kernel: several events per particle and launch */
+    double ms_step;            /* history-walk kernel (k_walk): all events of a particle chained in registers */
     uint64_t n_step;
 } mcb_stage_times;
 

@@ -153,9 +153,8 @@ struct mcb_ctx {
     unsigned long long* h_ring = nullptr;  // pinned: queue lengths of the last MCB_RING iterations
     cudaEvent_t ev_ring[MCB_RING] = {};
     uint64_t finish_below = 0;       // queue length under which the tail kernel takes over
-    bool split_stages = false;       // one kernel per event type (profiling mode) instead of the fused step kernel
+    bool split_stages = false;       // event-queue mode: one kernel per event type (cross-check / profiling) instead of the walk kernel
     bool walk_mode = true;           // history walk (one launch per pass over the bank) instead of the event-queue loop
-    int step_events = 2;             // events chained per particle and launch by the fused step kernel
     // per-history accumulators
     DevBuf<double> d_hist_k;         // kC, kTL
     DevBuf<int32_t> d_nsite;
@@ -422,8 +421,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     for (int i = 0; i < MCB_RING; i++) CK(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
     ctx->finish_below = getenv("MCB_FINISH_BELOW") ? strtoull(getenv("MCB_FINISH_BELOW"), nullptr, 10) : 148ull * 256ull;
     ctx->split_stages = (cfg && (cfg->reserved & 2)) || (getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "split"));
-    ctx->walk_mode = !ctx->split_stages && !(getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "step"));
-    if (getenv("MCB_STEP_EVENTS")) ctx->step_events = std::max(1, atoi(getenv("MCB_STEP_EVENTS")));
+    ctx->walk_mode = !ctx->split_stages;
     const size_t nh = std::max<uint64_t>(ctx->shard_count, 1);
     CK(ctx->d_hist_k.alloc(2 * nh));
     CK(ctx->d_nsite.alloc(nh));
@@ -652,7 +650,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
         const int cur = it % 3, nxt = (it + 1) % 3;
         uint32_t* q_in = queue[it & 1];
         uint32_t* q_out = queue[(it + 1) & 1];
-        if (ctx->split_stages) {
+        {
             ctx->timer.begin(st, ST_LOOKUP);
             mcbk::xs_stage(st, P, ctx->B, q_in, cur, known_n, C);
             ctx->timer.end(st);
@@ -665,11 +663,6 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
             ctx->timer.end(st);
             ctx->timer.begin(st, ST_CROSS);
             mcbk::cross(st, P, ctx->B, ctx->q_ev, cur, known_n, C, q_out, T, ctx->n_slots);
-            ctx->timer.end(st);
-        } else {
-            ctx->timer.begin(st, ST_STEP);
-            mcbk::step(st, P, ctx->B, q_in, cur, ctx->step_events, known_n, C, q_out, ctx->H, T, ctx->d_site_reqs.p,
-                       ctx->site_cap, ctx->n_slots, ctx->k);
             ctx->timer.end(st);
         }
         CK(cudaMemcpyAsync(&ctx->h_ring[it % R], &C->n_active[nxt], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

@@ -1,12 +1,16 @@
-// mcb_kernels.cu — sm_100a kernels of the event-based particle-history transport loop.
+// mcb_kernels.cu — sm_100a kernels of the particle-history transport loop.
 //
 // One generation (reference: one pass of the cycle body of Simulator::start(), handler.cpp:14-44) is
-//   source  -> { xs_lookup -> flight -> collide | cross } until the bank is empty -> close-out kernels.
-// Particles live in an SoA bank (Bank); each stage runs over an index queue of the particles whose next event it
-// is; the queues are rebuilt every iteration by stream compaction (warp prefix sums, ONE cursor atomic per block).
-// Queue lengths stay on the device: every stage kernel is a persistent tile loop that reads its length from
-// Counters, so the host never has to wait for an iteration before launching the next one.  When only a few
-// particles are left, k_finish runs each of them to the end of its history in registers.
+//   k_source -> k_walk (one launch per pass over the bank) -> close-out kernels.
+// k_source fills an SoA bank (Bank) with the generation's source particles.  k_walk follows every particle through
+// its whole chain of events { xs_lookup -> flight -> collide | cross } in registers; warps are autonomous, draw bank
+// slots in chunks from a device-side head counter and refill a lane as soon as its particle has ended, so the lanes
+// stay busy until the bank runs dry.  Fission sites leave the kernel as requests (one warp-aggregated cursor
+// reservation per iteration) and are sampled and put into canonical order by k_bank_sample_order.
+//
+// The event-queue formulation of the same loop (k_xs_stage / k_flight / k_collide / k_cross over index queues
+// rebuilt by block-level stream compaction, k_finish for the tail) is kept as a cross-check (MCB_MODE=split): both
+// must produce bit-identical generations (tests/test_gpu_transport.py).
 //
 // Nothing here is GEMM-shaped: the loop is FP64 scalar work, L2-resident table gathers and HBM streams of the
 // bank, so tensor cores are unused on purpose.
@@ -20,7 +24,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef MCB_BLOCK
-#define MCB_BLOCK 256
+#define MCB_BLOCK 128  // measured (tools/sweep.sh): 128 x 5 blocks per SM beats 256 x 2, 192 x 3 and 96 x 7 for the walk kernel
 #endif
 constexpr int BLOCK = MCB_BLOCK;
 constexpr int WARPS = BLOCK / 32;
@@ -685,92 +689,9 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
     if (lane_id() == 0 && crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
 }
 
-// fused step: up to `max_events` events (lookup -> flight -> collide | cross) of every queued particle, chained in
-// registers, the whole block advancing in lockstep so that banking can use block-level reservations.  Survivors are
-// compacted into the next queue with their state written back once.  Per track this moves a fraction of the bytes
-// of the split stage kernels and pays the DRAM latency of the queue/bank indirection once per launch instead of
-// once per stage.  Queue lengths rotate over three counters: read [cur], fill [nxt], clear [(nxt+1)%3].
 #ifndef MCB_STEP_MINB
-#define MCB_STEP_MINB 2
+#define MCB_STEP_MINB 5
 #endif
-__global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
-k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, int max_events, Counters* C, uint32_t* next,
-       HistoryAcc H, TallyAcc T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
-{
-    __shared__ BlockScratch<2> scratchA[2];
-    __shared__ BlockScratch<1> scratchB[2];
-    const int nxt = cur == 2 ? 0 : cur + 1;
-    const unsigned long long n = C->n_active[cur];
-    unsigned long long* const next_len = &C->n_active[nxt];
-    if (blockIdx.x == 0 && threadIdx.x == 0) C->n_active[nxt == 2 ? 0 : nxt + 1] = 0;
-    unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
-    int ss = 0, it = 0;
-    for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x, it++) {
-        const unsigned long long q = tile * BLOCK + threadIdx.x;
-        bool alive = q < n;
-        uint32_t i = 0;
-        Particle p;
-        if (alive) {
-            i = active[q];
-            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
-            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
-            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
-        }
-        for (int step = 0; step < max_events; step++) {
-            if (!__syncthreads_or(alive)) break;
-            MacroXS X = {0, 0, 0, 0, 0};
-            XSDetail D;
-            CollideCtx c = {-1, -1, 0, 0};
-            int uidx = -1;
-            unsigned n_copy = 0;
-            bool to_cross = false, in_material = false;
-            if (alive) {
-                int S;
-                if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-                to_cross = ev_flight<true>(P, B, p, X, uidx, H, T, S);
-                tracks++;
-                if (to_cross) { alive = ev_cross_pre<true>(P, B, p, S, T, C, n_copy); crossings++; }
-                else { in_material = ev_collide_pre<true>(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
-            }
-            const unsigned cnt[2] = {c.n_sites, c.n_second + n_copy};
-            unsigned long long* const cursor[2] = {&C->site_cursor, &C->slot_cursor};
-            unsigned long long pos[2];
-            block_reserve<2>(scratchA[ss & 1], cnt, cursor, pos);
-            ss++;
-            unsigned n_new = 0;
-            if (c.n_sites | c.n_second) ev_collide_bank<true>(P, B, p, c, H, C, reqs, site_cap, n_slots, pos[0], pos[1], n_new);
-            __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-            if (to_cross) alive = ev_cross_post<true>(P, B, p, alive, n_copy, pos[1], n_slots, C, n_new);
-            __syncwarp();
-            if (in_material) alive = ev_collide_scatter<true>(P, B, p, X, uidx, &D, c, H);
-            __syncwarp();
-            if (n_new) {  // secondaries (fixed-source fission, splitting) join the next queue; rare, so per thread
-                const unsigned long long o = atomicAdd(next_len, (unsigned long long)n_new);
-                for (unsigned b = 0; b < n_new; b++) next[o + b] = (uint32_t)(pos[1] + b);
-            }
-        }
-        const unsigned cntB[1] = {alive ? 1u : 0u};
-        unsigned long long* const curB[1] = {next_len};
-        unsigned long long posB[1];
-        block_reserve<1>(scratchB[it & 1], cntB, curB, posB);
-        if (alive) {
-            B.cell[i] = p.cell;
-            B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w;
-            B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.t[i] = p.t; B.rng[i] = p.rng;
-            next[posB[0]] = i;
-        }
-    }
-    for (int d = 16; d; d >>= 1) {
-        tracks += __shfl_xor_sync(FULL, tracks, d); collisions += __shfl_xor_sync(FULL, collisions, d);
-        crossings += __shfl_xor_sync(FULL, crossings, d); lookups += __shfl_xor_sync(FULL, lookups, d);
-    }
-    if (lane_id() == 0) {
-        if (tracks) atomicAdd(&C->n_tracks, (unsigned long long)tracks);
-        if (collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
-        if (crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
-        if (lookups) atomicAdd(&C->n_lookups, (unsigned long long)lookups);
-    }
-}
 
 // history walk: the whole event chain of a particle in registers, one launch per pass over bank slots
 // [begin, end).  Every warp is autonomous (no block barriers): it draws slot indices in private chunks from a
@@ -779,14 +700,14 @@ k_step(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur,
 // iteration.  Nothing but the site requests (and the rare secondaries, which go to slots >= end and are walked by
 // the next pass) is written back: the particle record is read once.  With one particle per history the EstimatorK
 // scores live in registers and are stored once when the history ends.
-template <bool TALLY>
+template <bool TALLY, bool SHARED>
 __global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
 k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk, Counters* C, HistoryAcc H, TallyAcc T,
        SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
-    const bool local_acc = !P.shared_histories;
+    constexpr bool local_acc = !SHARED;  // SHARED = DevProblem::shared_histories: secondaries / split copies can exist
     unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
     bool alive = false, exhausted = false;
     Particle p;
@@ -857,7 +778,8 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
         }
         // secondaries (fixed-source fission neutrons, split copies) are rare: one slot reservation per lane
         unsigned long long slot0 = 0;
-        if (c.n_second + n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)(c.n_second + n_copy));
+        if (!SHARED) { c.n_second = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
+        else if (c.n_second + n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)(c.n_second + n_copy));
         unsigned n_new = 0;
         if (c.n_sites | c.n_second) ev_collide_bank<TALLY>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
@@ -1264,13 +1186,6 @@ void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* 
     k_cross<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, T, n_slots);
     MCB_LAUNCHED(1);
 }
-void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, int max_events, uint64_t n_hint,
-          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs,
-          uint64_t site_cap, uint32_t n_slots, double k_eff)
-{
-    k_step<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, active, cur, max_events, C, next, H, T, reqs, site_cap, n_slots, k_eff);
-    MCB_LAUNCHED(1);
-}
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, uint32_t end, Counters* C, const HistoryAcc& H,
           const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
@@ -1282,8 +1197,11 @@ void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, u
     const uint64_t warps = (uint64_t)grid * WARPS;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
     // two instances: the one for cycles that score nothing carries no estimator code (and no energy_old upkeep)
-    if (T.on) k_walk<true><<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff);
-    else k_walk<false><<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff);
+    // and one pair for problems where nothing is born in flight (k-eigenvalue without splitting)
+#define MCB_WALK(TALLY, SHARED) k_walk<TALLY, SHARED><<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff)
+    if (T.on) { if (P.shared_histories) MCB_WALK(true, true); else MCB_WALK(true, false); }
+    else { if (P.shared_histories) MCB_WALK(false, true); else MCB_WALK(false, false); }
+#undef MCB_WALK
     MCB_LAUNCHED(1);
 }
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,

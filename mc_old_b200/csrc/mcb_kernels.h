@@ -21,10 +21,6 @@ void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t
              uint64_t site_cap, uint32_t n_slots, double k_eff);
 void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
            uint32_t* next, const TallyAcc& T, uint32_t n_slots);
-// fused: up to max_events events per queued particle in one launch
-void step(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, int max_events, uint64_t n_hint,
-          Counters* C, uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs,
-          uint64_t site_cap, uint32_t n_slots, double k_eff);
 // history walk: every particle in bank slots [begin, end) followed to the end of its chain in registers, lanes refilled
 // as particles end; secondaries born on the way land in slots >= end (Counters::slot_cursor) for the next pass
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, uint32_t end, Counters* C, const HistoryAcc& H,
