@@ -170,6 +170,11 @@ struct mcb_ctx {
     Site* peer_bank[2][MCB_MAX_WORLD] = {};  // peer_bank[b][r] = rank r's d_local_bank[b] mapped here (CUDA IPC); [rank] = own
     bool p2p = false;                // the peers' banks are mapped: source sites are read in place over NVLink
     SourceBankView view{};           // the bank the next cycle samples (n = 0: the deck's sources)
+    DevBuf<unsigned long long> d_sort_key;   // sorted sourcing (segmented bank): 2 x batch keys
+    DevBuf<uint32_t> d_sort_val;             // 2 x batch values
+    DevBuf<uint64_t> d_sort_rng;
+    DevBuf<unsigned char> d_sort_temp;
+    mcbk::SortScratch sort{};
     DevBuf<double> d_io_sites;       // staging for host-facing bank I/O (n x 8 doubles)
     DevBuf<int32_t> d_io_cells;
     uint64_t n_local_sites = 0;      // local bank of the last cycle
@@ -541,7 +546,7 @@ int mcb_comm_init(mcb_ctx* ctx, const char id[128])
     // Measured on 8xB200 (NV18 all-to-all): with one peer the in-place reads cost 1.1 ms per 1e7 histories and beat the
     // gather (9.4 vs 11.9 ms per generation); with 3 or 7 peers the same fine-grained reads collapse (63 / 134 ms), so
     // from 4 ranks on the slices are gathered with NCCL instead unless MCB_P2P=1 forces the in-place path.
-    const bool want_p2p = getenv("MCB_P2P") ? atoi(getenv("MCB_P2P")) != 0 : ctx->world <= 2;
+    const bool want_p2p = getenv("MCB_P2P") ? atoi(getenv("MCB_P2P")) != 0 : true;
     if (ctx->ksearch && want_p2p && !getenv("MCB_NO_P2P")) {
         const int W = ctx->world;
         cudaIpcMemHandle_t mine[2];
@@ -604,7 +609,20 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     Counters* C = ctx->d_counters.p;
     uint32_t* queue[2] = {ctx->q_active, ctx->q_next};
     ctx->timer.begin(st, ST_SOURCE);
-    mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, V, C);
+    const mcbk::SortScratch* sort = nullptr;
+    if (V.n && !V.flat) {  // bank spread over the ranks: read it in ascending order
+        if (!ctx->d_sort_key.p) {
+            const size_t nbh = ctx->batch_hist;
+            CK(ctx->d_sort_key.alloc(2 * nbh)); CK(ctx->d_sort_val.alloc(2 * nbh)); CK(ctx->d_sort_rng.alloc(nbh));
+            CK(ctx->d_sort_temp.alloc(mcbk::sort_temp_bytes((uint32_t)nbh) + 256));
+            ctx->sort.key_in = ctx->d_sort_key.p; ctx->sort.key_out = ctx->d_sort_key.p + nbh;
+            ctx->sort.val_in = ctx->d_sort_val.p; ctx->sort.val_out = ctx->d_sort_val.p + nbh;
+            ctx->sort.rng_after = ctx->d_sort_rng.p; ctx->sort.temp = ctx->d_sort_temp.p; ctx->sort.temp_bytes = ctx->d_sort_temp.n;
+        }
+        ctx->sort.rot = V.prefix[std::min(ctx->rank, V.n_seg - 1)];
+        sort = &ctx->sort;
+    }
+    mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, V, C, sort);
     ctx->timer.end(st);
 
     if (ctx->walk_mode) {

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 namespace {
@@ -467,23 +468,47 @@ __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B
 // source: SourceBank::get_source (Source.cpp:42-46) with j = floor(xi*N), SourcePoint / SourceDelta (Source.cpp:16-24)
 // History h (shard-local) of this cycle gets the stream of nps = cycle*Nsample + (shard_begin + h)
 // (RN_init_particle, Random.cpp:196-204).
+// Sorted sourcing (a bank spread over several GPUs): drawing sites by random index from peers' HBM thrashes the
+// address translation of the peer mappings once the banks exceed ~1 GB (measured: 188 ms instead of 7 ms for 4e7
+// draws from a 3.2 GB peer bank).  So the draws are made first (k_pick), sorted by site index (cub radix sort), and
+// k_source then walks the bank in ascending order: slot q gets the history whose draw is the q-th smallest, every
+// peer page is visited once, neighbouring threads read neighbouring (or the same) sites.
+__global__ void __launch_bounds__(BLOCK)
+k_pick(uint64_t seed0, uint64_t nps0, int32_t first_hist, uint32_t count, unsigned long long n_bank, unsigned long long rot,
+       unsigned long long* key, uint32_t* val, uint64_t* rng_after)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    uint64_t rng = mcb_rn_history_seed(seed0, nps0 + (uint64_t)(first_hist + (int32_t)q));
+    const double xi = mcb_urand(rng);
+    unsigned long long j = (unsigned long long)(xi * (double)n_bank);
+    if (j >= n_bank) j = n_bank - 1;
+    // the sweep of rank r starts at its own slice (rot = global index of its first site) and wraps around: at any
+    // moment the ranks read from different peers instead of all queueing at rank 0's HBM
+    key[q] = j >= rot ? j - rot : j + n_bank - rot; val[q] = q; rng_after[q] = rng;
+}
+
 __global__ void __launch_bounds__(BLOCK)
 k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint32_t count, uint64_t nps0,
-         const SourceBankView V, Counters* C)
+         const SourceBankView V, Counters* C, const unsigned long long* __restrict__ sorted_key,
+         const uint32_t* __restrict__ sorted_val, const uint64_t* __restrict__ rng_after, unsigned long long rot)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q == 0) {  // queue state of the batch: `count` primaries in queue 0, slots behind them are free
         C->n_active[0] = count; C->n_active[1] = 0; C->n_active[2] = 0; C->q_collide = 0; C->q_cross = 0; C->slot_cursor = count;
     }
     if (q >= count) return;
-    const int32_t h = first_hist + (int32_t)q;
-    uint64_t rng = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)h);
-    const double xi = mcb_urand(rng);
+    int32_t h;
+    uint64_t rng;
+    double xi = 0.0;
+    if (sorted_key) { h = first_hist + (int32_t)sorted_val[q]; rng = rng_after[sorted_val[q]]; }
+    else { h = first_hist + (int32_t)q; rng = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)h); xi = mcb_urand(rng); }
     double x, y, z, u, v, w, E, t;
     int cell;
     if (V.n) {
-        uint64_t j = (uint64_t)(xi * (double)V.n);
-        if (j >= V.n) j = V.n - 1;
+        uint64_t j;
+        if (sorted_key) { j = sorted_key[q] + rot; if (j >= V.n) j -= V.n; }
+        else { j = (uint64_t)(xi * (double)V.n); if (j >= V.n) j = V.n - 1; }
         const Site s = source_bank_site(V, j);  // local HBM, or a peer's HBM over NVLink
         x = s.x; y = s.y; z = s.z; u = s.u; v = s.v; w = s.w; E = s.E; t = s.t; cell = s.cell;
     } else {
@@ -1157,10 +1182,29 @@ static unsigned grid_for(uint64_t n_hint)
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 16ull * (256 / BLOCK)));
 }
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
-            uint64_t nps0, const SourceBankView& V, Counters* C)
+            uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort)
 {
-    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C);
+    if (sort && V.n) {
+        // draws -> sorted by site index -> the bank is read in ascending order
+        k_pick<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P.seed0, nps0, first_hist, count, V.n, sort->rot, sort->key_in, sort->val_in, sort->rng_after);
+        int bits = 1;
+        while (bits < 64 && (V.n >> bits)) bits++;
+        size_t tb = sort->temp_bytes;
+        cub::DeviceRadixSort::SortPairs(sort->temp, tb, sort->key_in, sort->key_out, sort->val_in, sort->val_out, (int)count, 0, bits, st);
+        k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, sort->key_out,
+                                                                          sort->val_out, sort->rng_after, sort->rot);
+        MCB_LAUNCHED(2 + (bits + 7) / 8 + 2);  // pick, source, the sort's histogram / onesweep passes
+        return;
+    }
+    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, nullptr, nullptr, nullptr, 0ull);
     MCB_LAUNCHED(1);
+}
+size_t sort_temp_bytes(uint32_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 64, (cudaStream_t)0);
+    return bytes;
 }
 void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C)
 {

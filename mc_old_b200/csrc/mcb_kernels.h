@@ -11,8 +11,19 @@ uint64_t launch_count();  // kernels launched by this thread through the launche
 // stages of one generation.  `cur` = iteration % 3 selects the queue-length counter the iteration reads
 // (Counters::n_active[cur]); it fills [(cur+1)%3] and clears [(cur+2)%3].  n_hint (an upper bound of the queue
 // length known to the host) only sizes the grid.
+// scratch of the sorted sourcing path (bank spread over several GPUs): draws, their sorted order, stream states
+struct SortScratch {
+    unsigned long long *key_in, *key_out;
+    uint32_t *val_in, *val_out;
+    uint64_t* rng_after;
+    void* temp;
+    size_t temp_bytes;
+    unsigned long long rot;  // global index at which this rank's sweep over the bank starts
+};
+size_t sort_temp_bytes(uint32_t n);
+// sort != nullptr: the draws are sorted by site index first and the bank is read in ascending order
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
-            uint64_t nps0, const SourceBankView& V, Counters* C);
+            uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort);
 void xs_stage(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C);
 void flight(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint,
             uint32_t* evq, Counters* C, const HistoryAcc& H, const TallyAcc& T);
