@@ -130,7 +130,7 @@ struct mcb_ctx {
     DevProblem P{};
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevNuclide> d_nuclides;
-    DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid, d_delayed, d_bank_eold;
+    DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid, d_delayed, d_bank_eold, d_bank_told;
     DevBuf<int32_t> d_map, d_hash, d_mat_nuclide, d_cell_surface, d_cell_sense, d_attach_begin[3], d_attach_list[3];
     DevBuf<mcb_surface> d_surfaces;
     DevBuf<mcb_cell> d_cells;
@@ -250,9 +250,11 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     if (p->abi_version != MCB_ABI_VERSION) return ctx->fail(MCB_ERR_ARG, "mcb_problem.abi_version %d != %d", p->abi_version, MCB_ABI_VERSION);
     if (p->n_sample == 0) return ctx->fail(MCB_ERR_ARG, "n_sample is zero");
     if (p->n_sources <= 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
-    bool track_old = false;
+    bool track_old = false, track_time = false;
+    for (int e = 0; e < p->n_estimators; e++)
+        if (p->estimators[e].n_filters > 4) return ctx->fail(MCB_ERR_ARG, "estimator %d has more than 4 filters", e);
     for (int f = 0; f < p->n_filters; f++) {
-        if (p->filters[f].type == MCB_FILTER_TIME) return ctx->fail(MCB_ERR_ARG, "unsupported: time filters (SURVEY §8f-3)");
+        if (p->filters[f].type == MCB_FILTER_TIME) track_time = true;
         if (p->filters[f].type == MCB_FILTER_ENERGY_OLD) track_old = true;
     }
     for (int e = 0; e < p->n_estimators; e++) {
@@ -377,6 +379,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     P.n_cells = p->n_cells; P.n_sources = p->n_sources; P.n_estimators = p->n_estimators; P.entropy_on = p->entropy_on;
     P.shared_histories = (!p->ksearch || splitting) ? 1 : 0;
     P.track_old = track_old ? 1 : 0;
+    P.track_time = track_time ? 1 : 0; P.pad = 0;
     P.wr = p->wr; P.ws = p->ws; P.seed0 = ctx->seed; P.n_sample = p->n_sample;
     P.materials = ctx->d_materials.p; P.nuclides = ctx->d_nuclides.p; P.mat_nuclide = ctx->d_mat_nuclide.p; P.mat_density = ctx->d_mat_density.p;
     P.surfaces = ctx->d_surfaces.p; P.cells = ctx->d_cells.p; P.cell_surface = ctx->d_cell_surface.p; P.cell_sense = ctx->d_cell_sense.p;
@@ -390,7 +393,8 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     mcb_shard_range(p->n_sample, ctx->rank, ctx->world, &ctx->shard_begin, &ctx->shard_count);
     if (ctx->shard_count >= (1ull << 31)) return ctx->fail(MCB_ERR_ARG, "more than 2^31 histories per GPU per generation");
     // secondaries (same-history fission neutrons, splitting) need free slots behind the primaries of a batch
-    const uint64_t per_hist = P.shared_histories ? 4 : 1;
+    // (the walk kernel reuses the slots behind the running pass, so this bounds two consecutive passes, not a history)
+    const uint64_t per_hist = P.shared_histories ? 6 : 1;
     uint64_t cap = cfg && cfg->bank_capacity > 0 ? (uint64_t)cfg->bank_capacity : (1ull << 26);
     cap = std::min<uint64_t>(cap, (1ull << 31) - 1);
     uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(ctx->shard_count, cap / per_hist));
@@ -416,6 +420,8 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         B.cell = i; B.hist = i + ns; B.uidx = i + 2 * ns; B.surf = i + 3 * ns;
         B.Eold = nullptr;
         if (track_old) { CK(ctx->d_bank_eold.alloc(ns)); B.Eold = ctx->d_bank_eold.p; }
+        B.told = nullptr;
+        if (track_time) { CK(ctx->d_bank_told.alloc(ns)); CK(cudaMemset(ctx->d_bank_told.p, 0, ns * sizeof(double))); B.told = ctx->d_bank_told.p; }
     }
     CK(ctx->d_queue.alloc(3 * ns));
     ctx->q_active = ctx->d_queue.p; ctx->q_next = ctx->d_queue.p + ns; ctx->q_ev = ctx->d_queue.p + 2 * ns;
@@ -628,7 +634,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     if (ctx->walk_mode) {
         // History walk: pass 0 follows the primaries in slots [0, nb) to the end of their chains; secondaries born on
         // the way (fixed-source fission, splitting) land in slots >= nb and are walked by the next pass.
-        uint32_t begin = 0, end = nb;
+        uint64_t begin = 0, end = nb;
         int passes = 0;
         while (begin < end) {
             CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
@@ -640,7 +646,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
             CK(cudaMemcpyAsync(&ctx->h_ring[0], &C->slot_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             begin = end;
-            end = (uint32_t)std::min<unsigned long long>(ctx->h_ring[0], ctx->n_slots);
+            end = ctx->h_ring[0];
         }
         *n_iterations += passes;
         CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));

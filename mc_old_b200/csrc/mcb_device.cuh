@@ -38,6 +38,7 @@ struct DevProblem {
     int32_t ksearch, n_materials, n_nuclides, n_surfaces, n_cells, n_sources, n_estimators, entropy_on;
     int32_t shared_histories;    // several particles of one history can be in flight (secondaries / splitting)
     int32_t track_old;           // some estimator reads Particle::energy_old (TRMM tally set): Bank::Eold is maintained
+    int32_t track_time, pad;     // some estimator has a time filter: Bank::told (Particle::time_old) is maintained
     double wr, ws;
     uint64_t seed0, n_sample;
     const DevMaterial* materials;
@@ -67,6 +68,7 @@ struct Bank {
     uint64_t* rng;
     int32_t *cell, *hist;                 // hist = history index local to this rank's shard
     double* Eold;                         // Particle::energy_old (Particle.cpp:42-56), only when DevProblem::track_old
+    double* told;                         // Particle::time_old (Particle.cpp:66-76), only when DevProblem::track_time
     double *St, *Ss, *Sc, *Sf, *nSf;      // macroscopic xs of the cell's material at E (stage: xs_lookup)
     int32_t* uidx;                        // union-grid index of E in that material
     int32_t* surf;                        // surface hit by the last flight (stage: flight)

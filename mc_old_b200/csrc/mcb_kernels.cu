@@ -86,7 +86,7 @@ __device__ __forceinline__ void hist_add(double* p, double v) { atomicAdd(p, v);
 // tally scoring (Estimator::score, Estimator.cpp:298-336, for filters that yield one bin: surface, cell, energy)
 // ---------------------------------------------------------------------------------------------
 struct ScoreState {   // the particle as Score / Filter / the simulating estimators see it
-    double w, E, E_old, speed;
+    double w, E, E_old, speed, t, t_old;
     double u, v, wd;  // direction
     int cell, surface_old, material, uidx;
     MacroXS X;        // macroscopic xs of `material` at E
@@ -125,33 +125,89 @@ __device__ __forceinline__ double score_value(const DevProblem& P, const mcb_sco
     default: return 0.0;
     }
 }
-// Estimator::score (Estimator.cpp:298-336) for filters that yield one bin (surface, cell, energy, energy_old)
-__device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, const mcb_estimator& E, const ScoreState& s,
-                                                      double l, int hist)
+// Estimator::score (Estimator.cpp:298-336).  Surface / cell / energy / energy_old filters yield one bin; a time
+// filter (Estimator.cpp:199-246) splits the track [t_old, t] over the bins it spans, piece by piece; the loop scores
+// the shortest remaining piece of all filters, subtracts it everywhere and advances the exhausted ones, like the
+// reference's.  The time pieces are generated on demand.
+struct FilterCursor {
+    int idx;         // current bin
+    double l;        // remaining length of the current piece
+    int k, n;        // piece number, pieces in all
+    int loc1, loc2;  // time filter: bins of t_old and t
+    bool first;      // time filter: the piece of t_old's bin exists (loc1 >= 0)
+};
+__device__ __forceinline__ void time_piece(const mcb_filter& F, const double* g, const ScoreState& s, FilterCursor& c)
 {
-    int64_t idx_1D = 0;
-    int64_t factor_next = 1;  // idx_factor[i+1] (Estimator.cpp:288-295), built from the last filter backwards
-    for (int i = E.n_filters - 1; i >= 0; i--) {
+    const int Nbin = F.grid_n - 1;
+    int i = c.k;  // 0 = the piece in loc1 (when it exists), then the full bins, then the piece in loc2
+    if (c.first) {
+        if (i == 0) { c.idx = c.loc1; c.l = (g[c.loc1 + 1] - s.t_old) * s.speed; return; }
+        i--;
+    }
+    const int num_bin = c.loc2 - c.loc1 - 1;
+    if (i < num_bin) { c.idx = c.loc1 + i + 1; c.l = (g[c.loc1 + i + 2] - g[c.loc1 + i + 1]) * s.speed; return; }
+    (void)Nbin;
+    c.idx = c.loc2; c.l = (s.t - g[c.loc2]) * s.speed;
+}
+__device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, const mcb_estimator& E, const ScoreState& s,
+                                                      double l_in, int hist)
+{
+    constexpr int MAXF = 4;
+    FilterCursor cur[MAXF];
+    int64_t factor[MAXF + 1];  // idx_factor (Estimator.cpp:288-295)
+    const int nf = E.n_filters < MAXF ? E.n_filters : MAXF;
+    factor[nf] = 1;
+    for (int i = nf - 1; i >= 0; i--) factor[i] = factor[i + 1] * P.filters[E.filter_begin + i].size;
+    for (int i = 0; i < nf; i++) {
         const mcb_filter F = P.filters[E.filter_begin + i];
         const double* g = P.filter_grid + F.grid_begin;
-        int idx;
+        FilterCursor& c = cur[i];
+        c.k = 0; c.n = 1; c.l = l_in; c.first = false; c.loc1 = c.loc2 = 0;
         switch (F.type) {
-        case MCB_FILTER_SURFACE: idx = mcb_binary_search((double)s.surface_old, g, F.grid_n) + 1; break;  // Estimator.cpp:133-140
-        case MCB_FILTER_CELL: idx = mcb_binary_search((double)s.cell, g, F.grid_n) + 1; break;            // :141-148
-        default: {                                                                                         // energy :149-163, energy_old :165-179
-            idx = mcb_binary_search(F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, g, F.grid_n);
-            if (idx < 0 || idx >= F.grid_n - 1) return;
+        case MCB_FILTER_SURFACE: c.idx = mcb_binary_search((double)s.surface_old, g, F.grid_n) + 1; break;  // Estimator.cpp:133-140
+        case MCB_FILTER_CELL: c.idx = mcb_binary_search((double)s.cell, g, F.grid_n) + 1; break;            // :141-148
+        case MCB_FILTER_ENERGY:
+        case MCB_FILTER_ENERGY_OLD:                                                                          // :149-179
+            c.idx = mcb_binary_search(F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, g, F.grid_n);
+            if (c.idx < 0 || c.idx >= F.grid_n - 1) return;
+            break;
+        default: {                                                                                           // time :199-246
+            const int Nbin = F.grid_n - 1;
+            c.loc1 = mcb_binary_search(s.t_old, g, F.grid_n);
+            c.loc2 = mcb_binary_search(s.t, g, F.grid_n);
+            if (c.loc1 == c.loc2) {
+                if (c.loc1 < 0 || c.loc1 >= Nbin) return;
+                c.idx = c.loc1;
+            } else {
+                c.first = c.loc1 >= 0;
+                c.n = (c.first ? 1 : 0) + (c.loc2 - c.loc1 - 1) + (c.loc2 < Nbin ? 1 : 0);
+                if (c.n == 0) return;
+                time_piece(F, g, s, c);
+            }
         }
         }
-        idx_1D += (int64_t)idx * factor_next;
-        factor_next *= F.size;
     }
-    // factor_next is now idx_factor[0], the stride between scores
     double* acc = T.acc + (int64_t)(hist - T.first_hist);
-    for (int k = 0; k < E.n_scores; k++) {
-        const double v = score_value(P, P.scores[E.score_begin + k], s, l);
-        const int64_t t = E.tally_begin + idx_1D + (int64_t)k * factor_next;
-        if (t >= E.tally_begin && t < E.tally_begin + E.n_tallies) atomicAdd(acc + t * T.stride, v);
+    for (;;) {
+        double l = MCB_MAX_FLOAT;
+        int64_t idx_1D = 0;
+        for (int i = 0; i < nf; i++) { l = fmin(l, cur[i].l); idx_1D += (int64_t)cur[i].idx * factor[i + 1]; }
+        for (int k = 0; k < E.n_scores; k++) {
+            const double v = score_value(P, P.scores[E.score_begin + k], s, l);
+            const int64_t t = E.tally_begin + idx_1D + (int64_t)k * factor[0];
+            if (t >= E.tally_begin && t < E.tally_begin + E.n_tallies) atomicAdd(acc + t * T.stride, v);
+        }
+        for (int i = 0; i < nf; i++) {
+            FilterCursor& c = cur[i];
+            c.l -= l;
+            if (c.l < MCB_EPSILON_FLOAT) {
+                if (c.k == c.n - 1) return;
+                c.k++;
+                const mcb_filter F = P.filters[E.filter_begin + i];
+                time_piece(F, P.filter_grid + F.grid_begin, s, c);
+            }
+        }
+        if (nf == 0) return;
     }
 }
 // One estimator scores one event.  The TRMM estimators first let a COPY of the particle scatter / fission, drawing
@@ -214,13 +270,14 @@ struct Particle {
 // allocation is not shaped by it; returns the particle's stream state (the simulating estimators draw from it).
 // have_X = false (surface estimators): the cross sections of the cell the particle is now in are looked up here.
 __device__ __noinline__ uint64_t score_event(const DevProblem& P, const Bank& B, const TallyAcc& T, int kind, int id, double w, double E,
-                                             double speed, double du, double dv, double dw, int cell, int hist, int slot, uint64_t rng,
+                                             double speed, double t, double du, double dv, double dw, int cell, int hist, int slot, uint64_t rng,
                                              int material, int uidx, bool have_X, double Xt, double Xs, double Xc, double Xf, double Xnf,
                                              int surface_old, double l)
 {
     ScoreState s;
     s.w = w; s.E = E; s.speed = speed; s.u = du; s.v = dv; s.wd = dw;
     s.E_old = P.track_old ? B.Eold[slot] : E;
+    s.t = t; s.t_old = P.track_time ? B.told[slot] : t;
     s.cell = cell; s.surface_old = surface_old; s.material = material; s.uidx = uidx;
     s.X = MacroXS{Xt, Xs, Xc, Xf, Xnf};
     if (!have_X) {
@@ -231,7 +288,7 @@ __device__ __noinline__ uint64_t score_event(const DevProblem& P, const Bank& B,
     return rng;
 }
 #define MCB_SCORE_EVENT(kind, id, p, material, uidx, have_X, X, surface_old, l)                                              \
-    (p).rng = score_event(P, B, T, kind, id, (p).wgt, (p).E, (p).speed, (p).u, (p).v, (p).w, (p).cell, (p).hist, (p).slot, \
+    (p).rng = score_event(P, B, T, kind, id, (p).wgt, (p).E, (p).speed, (p).t, (p).u, (p).v, (p).w, (p).cell, (p).hist, (p).slot, \
                           (p).rng, material, uidx, have_X, (X).t, (X).s, (X).c, (X).f, (X).nf, surface_old, l)
 
 // xs_lookup event
@@ -267,6 +324,7 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, const Bank& B, Pa
     const double l = to_cross ? dsurf : dcol;
     // Particle::move (Particle.cpp:66-76)
     p.x += p.u * l; p.y += p.v * l; p.z += p.w * l;
+    if (TALLY && P.track_time) B.told[p.slot] = p.t;
     p.t += l / p.speed;
     if (P.ksearch && m >= 0) {  // estimate_TL (Estimator.cpp:509-512)
         if (L) L->kTL += X.nf * p.wgt * l;
@@ -330,7 +388,7 @@ template <bool TALLY>
 __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank& B, const Particle& p, const CollideCtx& c,
                                                 const HistoryAcc& H, Counters* C, SiteReq* reqs, uint64_t site_cap,
                                                 uint32_t n_slots, unsigned long long site0, unsigned long long slot0,
-                                                unsigned& n_second_ok, HistLocal* L = nullptr)
+                                                unsigned& n_second_ok, HistLocal* L = nullptr, unsigned long long ring_begin = 0)
 {
     n_second_ok = 0;
     uint64_t seed = p.rng;
@@ -355,8 +413,10 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank&
             const double Es = watt_sample(N.watt_a, N.watt_b, N.watt_g, p.E, rs);   // energy first, then direction (App. D-4)
             double du, dv, dw;
             isotropic_direction(rs, du, dv, dw);
-            const unsigned long long j = slot0 + b;
-            if (j < n_slots) {
+            // the bank is a ring: positions grow without bound, slots behind the running pass (ring_begin) are reused
+            const unsigned long long pos = slot0 + b;
+            if (pos - ring_begin < n_slots) {
+                const uint32_t j = (uint32_t)(pos % n_slots);
                 B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
                 B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = p.t;
                 B.rng[j] = rs; B.cell[j] = p.cell; B.hist[j] = p.hist;
@@ -407,6 +467,7 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B,
     bool alive = true;
     if (Sf.bc == MCB_BC_TRANSMISSION) {
         p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
+        if (TALLY && P.track_time) B.told[p.slot] = p.t;
         p.t += MCB_EPSILON_FLOAT / p.speed;
         const int cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, p.x, p.y, p.z);
         if (cn < 0) {  // "[WARNING] A particle is lost" (general.cpp:31-33)
@@ -418,6 +479,7 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B,
     } else {
         mcb_surf_reflect(Sf, p.u, p.v, p.w);
         p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
+        if (TALLY && P.track_time) B.told[p.slot] = p.t;
         p.t += MCB_EPSILON_FLOAT / p.speed;
     }
     if (TALLY && T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
@@ -442,12 +504,14 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B,
 // draws for a particle that was just killed (w = 0 < wr), like the reference
 template <bool TALLY>
 __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B, Particle& p, bool alive, unsigned n_copy,
-                                              unsigned long long slot0, uint32_t n_slots, Counters* C, unsigned& n_copy_ok)
+                                              unsigned long long slot0, uint32_t n_slots, Counters* C, unsigned& n_copy_ok,
+                                              unsigned long long ring_begin = 0)
 {
     n_copy_ok = 0;
     for (unsigned b = 0; b < n_copy; b++) {
-        const unsigned long long j = slot0 + b;
-        if (j < n_slots) {
+        const unsigned long long pos = slot0 + b;
+        if (pos - ring_begin < n_slots) {
+            const uint32_t j = (uint32_t)(pos % n_slots);
             B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = p.u; B.v[j] = p.v; B.w[j] = p.w;
             B.E[j] = p.E; B.speed[j] = p.speed; B.wgt[j] = p.wgt; B.t[j] = p.t;
             B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
@@ -727,7 +791,7 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
 // scores live in registers and are stored once when the history ends.
 template <bool TALLY, bool SHARED>
 __global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
-k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk, Counters* C, HistoryAcc H, TallyAcc T,
+k_walk(const DevProblem P, Bank B, unsigned long long begin, unsigned long long end, uint32_t chunk, Counters* C, HistoryAcc H, TallyAcc T,
        SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     const unsigned lane = lane_id();
@@ -737,7 +801,7 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
     bool alive = false, exhausted = false;
     Particle p;
     HistLocal L = {0.0, 0.0, 0};
-    uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of slots
+    unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of bank positions
     for (;;) {
         // ---- refill the idle lanes
         unsigned idle = __ballot_sync(FULL, !alive);
@@ -746,15 +810,16 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&C->walk_head, (unsigned long long)chunk);
                 base = __shfl_sync(FULL, base, 0);
-                const unsigned long long b = (unsigned long long)begin + base;
-                chunk_next = (uint32_t)(b < end ? b : end);
-                chunk_end = (uint32_t)(b + chunk < end ? b + chunk : end);
+                const unsigned long long b = begin + base;
+                chunk_next = b < end ? b : end;
+                chunk_end = b + chunk < end ? b + chunk : end;
                 if (chunk_next == chunk_end) { exhausted = true; break; }
             }
-            const unsigned take = min((unsigned)__popc(idle), chunk_end - chunk_next);
+            const unsigned take = min((unsigned)__popc(idle), (unsigned)(chunk_end - chunk_next));
             const unsigned rank = __popc(idle & lt_mask);
             if (!alive && rank < take) {
-                const uint32_t j = chunk_next + rank;
+                // ring: position -> slot (without secondaries positions never leave [0, n_slots))
+                const uint32_t j = SHARED ? (uint32_t)((chunk_next + rank) % n_slots) : (uint32_t)(chunk_next + rank);
                 p.cell = B.cell[j]; p.hist = B.hist[j]; p.slot = (int)j;
                 p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
                 p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
@@ -806,9 +871,9 @@ k_walk(const DevProblem P, Bank B, uint32_t begin, uint32_t end, uint32_t chunk,
         if (!SHARED) { c.n_second = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
         else if (c.n_second + n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)(c.n_second + n_copy));
         unsigned n_new = 0;
-        if (c.n_sites | c.n_second) ev_collide_bank<TALLY>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr);
+        if (c.n_sites | c.n_second) ev_collide_bank<TALLY>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr, begin);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (to_cross) alive = ev_cross_post<TALLY>(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
+        if (to_cross) alive = ev_cross_post<TALLY>(P, B, p, alive, n_copy, slot0, n_slots, C, n_new, begin);
         __syncwarp();
         if (in_material) alive = ev_collide_scatter<TALLY>(P, B, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
         __syncwarp();
@@ -1230,19 +1295,19 @@ void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* 
     k_cross<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, T, n_slots);
     MCB_LAUNCHED(1);
 }
-void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, uint32_t end, Counters* C, const HistoryAcc& H,
+void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
           const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
     if (end <= begin) return;
     // persistent: every resident warp draws chunks of slots until the pass runs dry
-    const uint32_t n = end - begin;
+    const uint64_t n = end - begin;
     const unsigned resident = 148u * MCB_STEP_MINB;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + BLOCK - 1) / BLOCK, resident));
     const uint64_t warps = (uint64_t)grid * WARPS;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
     // two instances: the one for cycles that score nothing carries no estimator code (and no energy_old upkeep)
     // and one pair for problems where nothing is born in flight (k-eigenvalue without splitting)
-#define MCB_WALK(TALLY, SHARED) k_walk<TALLY, SHARED><<<grid, BLOCK, 0, st>>>(P, B, begin, end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff)
+#define MCB_WALK(TALLY, SHARED) k_walk<TALLY, SHARED><<<grid, BLOCK, 0, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff)
     if (T.on) { if (P.shared_histories) MCB_WALK(true, true); else MCB_WALK(true, false); }
     else { if (P.shared_histories) MCB_WALK(false, true); else MCB_WALK(false, false); }
 #undef MCB_WALK

@@ -33,8 +33,9 @@ void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t
 void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
            uint32_t* next, const TallyAcc& T, uint32_t n_slots);
 // history walk: every particle in bank slots [begin, end) followed to the end of its chain in registers, lanes refilled
-// as particles end; secondaries born on the way land in slots >= end (Counters::slot_cursor) for the next pass
-void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t begin, uint32_t end, Counters* C, const HistoryAcc& H,
+// as particles end; secondaries born on the way land at positions >= end (Counters::slot_cursor) for the next pass.
+// The bank is a ring over positions: slot = position % n_slots, slots behind `begin` are reused
+void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
           const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff);
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,

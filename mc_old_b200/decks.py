@@ -365,6 +365,60 @@ def fixed_source_fissile(samples=2000):
 """
 
 
+def heu_leakage(samples=2000):
+    """examples/HEU_sphere_leakage/input.xml: fixed 14 MeV point source in the bare HEU sphere, time-binned leakage
+    (surface estimator with a time filter, Estimator.cpp:199-246); plus a track-length estimator with time x energy
+    filters (tracks split over several time bins) and a collision estimator with a time filter."""
+    return HEAD + f"""
+<simulation>
+    <description name="Fission Sphere" samples="{samples:g}"/>
+</simulation>
+<distributions>
+    <isotropic name="dir" datatype="point" />
+    <delta name="enrg" datatype="double" val="14.0e6"/>
+</distributions>
+<nuclides>
+    <nuclide name="U-235" ZAID="092235"/>
+    <nuclide name="U-238" ZAID="092238"/>
+</nuclides>
+<materials>
+    <material name="HEU">
+        <nuclide name="U-235" density="0.0455112"/>
+        <nuclide name="U-238" density="0.0033823"/>
+    </material>
+</materials>
+<surfaces>
+    <sphere name="suspicious_sphere"  x="0.0" y="0.0" z="0.0" r="7.68"/>
+</surfaces>
+<cells>
+    <cell name="sphere" material="HEU">
+        <surface name="suspicious_sphere" sense="-1" />
+    </cell>
+    <cell name="graveyard" importance="0.0">
+        <surface name="suspicious_sphere" sense="+1" />
+    </cell>
+</cells>
+<estimators>
+    <estimator name="sphere_leakage" scores="cross">
+        <surface name="suspicious_sphere"/>
+        <filter type="time" grid_linear="0.0 1e-10 1e-8"/>
+    </estimator>
+    <estimator name="sphere_flux_t" scores="flux fission">
+        <cell name="sphere"/>
+        <filter type="time" grid_linear="0.0 2e-10 6e-9"/>
+        <filter type="energy" grid="1e-5 1e5 1e6 5e6 2e7"/>
+    </estimator>
+    <estimator name="sphere_coll_t" type="C" scores="flux">
+        <cell name="sphere"/>
+        <filter type="time" grid="0.0 1e-9 3e-9 1e-8"/>
+    </estimator>
+</estimators>
+<sources>
+    <point x="0.0" y="0.0" z="0.0" direction="dir" energy="enrg"/>
+</sources>
+"""
+
+
 def write(dirpath, text):
     os.makedirs(dirpath, exist_ok=True)
     with open(os.path.join(dirpath, "input.xml"), "w") as f:

@@ -82,18 +82,20 @@ def test_heu_entropy_history_parity():
 
 
 @pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("heu_tallies", 10000),
-                                    ("gcr_trmm", 400)])
+                                    ("gcr_trmm", 400), ("leak_time", 20000)])
 def test_tallies_history_parity(name, n):
     """Estimator::score / end_history / end_cycle / end_simulation (Estimator.cpp:298-367) on every deck family:
     surface, cell-TL and cell-C estimators, energy filters, splitting (cell_importance, population_control.cpp:21-49)
     and same-history fission secondaries (fixed_source.cpp:12-22); the TRMM tally set of infinite_GCR_TRMM (3500 bins:
     energy_initial x energy matrices filled by simulate-then-score estimators, Estimator.cpp:441-482, delayed-neutron
-    scores at energy_old).  Same per-history streams on both sides, so the
+    scores at energy_old); time filters that split a track over the bins it spans (examples/HEU_sphere_leakage,
+    Estimator.cpp:199-246).  Same per-history streams on both sides, so the
     per-bin means agree far inside their statistical error: |gpu - oracle| <= 0.2 sigma + 1e-9 relative."""
     xml = {"slab": lambda: decks.slab(samples=n), "shield": lambda: decks.shielding(samples=n),
            "shield_split": lambda: decks.shielding(samples=n, split=True), "fsf": lambda: decks.fixed_source_fissile(samples=n),
            "heu_tallies": lambda: decks.heu_sphere(samples=n, active=1, passive=0, estimators=True),
-           "gcr_trmm": lambda: decks.gcr(samples=n, active=1, passive=0, trmm=True)}[name]()
+           "gcr_trmm": lambda: decks.gcr(samples=n, active=1, passive=0, trmm=True),
+           "leak_time": lambda: decks.heu_leakage(samples=n)}[name]()
     deck = mcb.Deck(xml=xml)
     ctx = mcb.Context(deck, device=0)
     orc = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
