@@ -50,6 +50,24 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the newest committed
+    `ncu --set full` summary under profiles/ (same workload: 1e7 histories per generation); None when absent."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_ncu_full_summary.txt" % kernel))):
+        tot, seen = 0.0, 0
+        for line in open(path):
+            m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m:
+                tot += float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 0.0)
+                seen += 1
+        if seen == 2:
+            best = (tot, os.path.relpath(path, ROOT))
+    return best
+
+
 # ---------------------------------------------------------------------------------------------
 # the reference on the host CPU (test infrastructure under oracle/ is executed here, and only here)
 # ---------------------------------------------------------------------------------------------
@@ -319,8 +337,12 @@ def main():
                     "step": BYTES_STEP(nn)}
         total_bytes = 2.0 * per_gen[dominant] * per_unit[dominant]
         achieved = total_bytes / (stages[dominant]["ms"] * 1e-3) / 1e9
+        kname = "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" else dominant))
+        tr = ncu_traffic(kname) if int(args.samples) == 10000000 else None
         roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" else dominant)), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
-                    "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None,
+                    "algorithmic_bytes_per_launch": total_bytes / max(stages[dominant]["launches"], 1),
                     "bytes_per_unit": per_unit[dominant], "units_per_launch": 2.0 * per_gen[dominant] / max(stages[dominant]["launches"], 1),
                     "avg_launch_ms": stages[dominant]["ms"] / max(stages[dominant]["launches"], 1),
                     "note": "bytes_per_unit is SURVEY 8(d)'s fixed per-track figure (record in+out 224, lookup 72+100*Nn, sites 20); the walk kernel keeps the record in registers and the tables in L2, so its DRAM traffic is below it (DESIGN.md 4)"}
