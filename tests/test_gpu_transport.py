@@ -354,9 +354,12 @@ def test_reproducible_across_contexts():
     assert np.array_equal(runs[0][1], runs[1][1])
 
 
-def test_multi_gpu_matches_single_gpu():
-    """2 ranks over NCCL (one process per GPU): k per generation is bit-identical to the 1-GPU run (exact integer
-    all-reduce), the global fission bank is the rank-ordered concatenation"""
+@pytest.mark.parametrize("bank", ["peer_reads", "nccl_gather"])
+def test_multi_gpu_matches_single_gpu(bank):
+    """2 ranks over NCCL (one process per GPU), with the bank read in place from the peer (CUDA IPC, sorted draws) or
+    gathered with NCCL: k, H, track counts and the bank per generation are bit-identical to the 1-GPU run (exact
+    integer sums, canonical bank order, per-history streams); tallies (double sums in rank order) agree
+    to rounding"""
     import json
     import os
     import subprocess
@@ -366,14 +369,19 @@ def test_multi_gpu_matches_single_gpu():
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgpu_worker.py")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29611", worker, "--samples", "40000", "--cycles", "3"],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, **({"MCB_NO_P2P": "1"} if bank == "nccl_gather" else {})))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     multi = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    deck = mcb.Deck(xml=decks.heu_sphere(samples=40000, active=2, passive=1))
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=40000, active=2, passive=1, entropy=True, estimators=True))
     ctx = mcb.Context(deck, device=0)
     rs = [ctx.run_cycle() for _ in range(3)]
     sites, _ = ctx.source_bank(int(rs[-1].n_sites))
+    mean, uncer = ctx.tallies()
     ctx.close()
+    assert [r.H.hex() for r in rs] == multi["H_hex"]
+    assert [int(r.n_tracks) for r in rs] == multi["n_tracks"]
+    assert np.allclose(mean, multi["tally_mean"], rtol=1e-12, atol=0) and np.allclose(uncer, multi["tally_uncer"], rtol=1e-9, atol=0)
     assert [r.k_cycle.hex() for r in rs] == multi["k_cycle_hex"]
     assert [int(r.n_sites) for r in rs] == multi["n_sites"]
     assert float(np.sum(sites[:, 6])).hex() == multi["bank_energy_sum_hex"]
