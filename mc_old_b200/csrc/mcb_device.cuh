@@ -303,20 +303,40 @@ __device__ __forceinline__ double micro_channel(const DevNuclide& N, const Micro
     if (kind == 2) return (1.0 - m.beta) * m.f * m.nu;
     return m.beta * N.fraction[kind - 3] * m.f * m.nu;
 }
-// Material::SigmaS / nuSigmaF / nuSigmaF_prompt / nuSigmaF_delayed (Material.cpp:26-82) at any energy; with xi >= 0 also
-// Material::nuclide_scatter / _nufission / _nufission_prompt / _nufission_delayed (Material.cpp:106-146): *picked =
-// global nuclide index or -1.  decay = true: nuSigmaF_delayed_decay (Material.cpp:83-91), each term divided by lambda_g.
-static __device__ __noinline__ double macro_channel(const DevProblem& P, const DevMaterial& M, double E, int kind, bool decay, double xi,
-                                             int* picked)
+// The per-nuclide microscopic data of one material at one energy, kept while one event is scored: the TRMM tally set
+// asks for a dozen different channel sums at the same two energies (the particle's energy and its energy_old).
+struct ChannelCache {
+    double E[2];
+    int32_t mat[2], used;
+    MicroXS m[2][MCB_MAX_MAT_NUCLIDES];
+};
+__device__ __forceinline__ void channel_cache_reset(ChannelCache& C) { C.mat[0] = C.mat[1] = -1; C.used = 0; }
+__device__ __noinline__ static int channel_cache_get(const DevProblem& P, int material, double E, ChannelCache& C)
 {
+    for (int i = 0; i < 2; i++) if (C.mat[i] == material && C.E[i] == E) return i;
+    const int i = C.used & 1;
+    C.used++;
+    const DevMaterial& M = P.materials[material];
     const int u = union_index(M, E);
-    double sum = 0.0;
     for (int n = 0; n < M.n_nuc; n++) {
         const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
-        const DevNuclide& N = P.nuclides[gn];
-        MicroXS m;
-        micro_xs(N, nuclide_index(M, u, n), E, m);
-        const double v = micro_channel(N, m, kind);
+        micro_xs(P.nuclides[gn], nuclide_index(M, u, n), E, C.m[i][n]);
+    }
+    C.E[i] = E; C.mat[i] = material;
+    return i;
+}
+// Material::SigmaS / nuSigmaF / nuSigmaF_prompt / nuSigmaF_delayed (Material.cpp:26-82) at any energy; with `picked`
+// also Material::nuclide_scatter / _nufission / _nufission_prompt / _nufission_delayed (Material.cpp:106-146): *picked =
+// global nuclide index or -1.  decay = true: nuSigmaF_delayed_decay (Material.cpp:83-91), each term divided by lambda_g.
+__device__ __noinline__ static double macro_channel(const DevProblem& P, int material, double E, int kind, bool decay, double xi,
+                                                    int* picked, ChannelCache& C)
+{
+    const DevMaterial& M = P.materials[material];
+    const MicroXS* m = C.m[channel_cache_get(P, material, E, C)];
+    double sum = 0.0;
+    for (int n = 0; n < M.n_nuc; n++) {
+        const DevNuclide& N = P.nuclides[__ldg(&P.mat_nuclide[M.nuc_begin + n])];
+        const double v = micro_channel(N, m[n], kind);
         sum += (decay ? v / N.lambda[kind - 3] : v) * __ldg(&P.mat_density[M.nuc_begin + n]);
     }
     if (picked) {
@@ -325,10 +345,7 @@ static __device__ __noinline__ double macro_channel(const DevProblem& P, const D
         int sel = -1;
         for (int n = 0; n < M.n_nuc; n++) {
             const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
-            const DevNuclide& N = P.nuclides[gn];
-            MicroXS m;
-            micro_xs(N, nuclide_index(M, u, n), E, m);
-            s += micro_channel(N, m, kind) * __ldg(&P.mat_density[M.nuc_begin + n]);
+            s += micro_channel(P.nuclides[gn], m[n], kind) * __ldg(&P.mat_density[M.nuc_begin + n]);
             if (sel < 0 && s > thr) sel = gn;
         }
         *picked = sel;

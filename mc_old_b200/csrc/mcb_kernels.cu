@@ -102,7 +102,7 @@ __device__ __forceinline__ double kernel_value(int kernel, const ScoreState& s, 
     default: return s.w * l * s.speed;
     }
 }
-__device__ __forceinline__ double score_value(const DevProblem& P, const mcb_score& S, const ScoreState& s, double l)
+__device__ __forceinline__ double score_value(const DevProblem& P, const mcb_score& S, const ScoreState& s, double l, ChannelCache& CC)
 {  // Estimator.cpp:48-124
     const double kv = kernel_value(S.kernel, s, l);
     if (S.score == MCB_SCORE_FLUX) return kv;
@@ -117,11 +117,11 @@ __device__ __forceinline__ double score_value(const DevProblem& P, const mcb_sco
     case MCB_SCORE_NU_FISSION: return s.X.nf * kv;
     case MCB_SCORE_TOTAL: return s.X.t * kv;
     // the "Old" scores of the TRMM tally set evaluate at Particle::energy_old (Estimator.cpp:96-118)
-    case MCB_SCORE_SCATTER_OLD: return macro_channel(P, M, s.E_old, 0, false, 0.0, nullptr) * kv;
-    case MCB_SCORE_NU_FISSION_OLD: return macro_channel(P, M, s.E_old, 1, false, 0.0, nullptr) * kv;
-    case MCB_SCORE_NU_FISSION_PROMPT_OLD: return macro_channel(P, M, s.E_old, 2, false, 0.0, nullptr) * kv;
-    case MCB_SCORE_NU_FISSION_DELAYED_OLD: return macro_channel(P, M, s.E_old, 3 + S.group, false, 0.0, nullptr) * kv;
-    case MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD: return macro_channel(P, M, s.E_old, 3 + S.group, true, 0.0, nullptr) * kv;
+    case MCB_SCORE_SCATTER_OLD: return macro_channel(P, s.material, s.E_old, 0, false, 0.0, nullptr, CC) * kv;
+    case MCB_SCORE_NU_FISSION_OLD: return macro_channel(P, s.material, s.E_old, 1, false, 0.0, nullptr, CC) * kv;
+    case MCB_SCORE_NU_FISSION_PROMPT_OLD: return macro_channel(P, s.material, s.E_old, 2, false, 0.0, nullptr, CC) * kv;
+    case MCB_SCORE_NU_FISSION_DELAYED_OLD: return macro_channel(P, s.material, s.E_old, 3 + S.group, false, 0.0, nullptr, CC) * kv;
+    case MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD: return macro_channel(P, s.material, s.E_old, 3 + S.group, true, 0.0, nullptr, CC) * kv;
     default: return 0.0;
     }
 }
@@ -150,7 +150,7 @@ __device__ __forceinline__ void time_piece(const mcb_filter& F, const double* g,
     c.idx = c.loc2; c.l = (s.t - g[c.loc2]) * s.speed;
 }
 __device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, const mcb_estimator& E, const ScoreState& s,
-                                                      double l_in, int hist)
+                                                      double l_in, int hist, ChannelCache& CC)
 {
     constexpr int MAXF = 4;
     FilterCursor cur[MAXF];
@@ -193,7 +193,7 @@ __device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const
         int64_t idx_1D = 0;
         for (int i = 0; i < nf; i++) { l = fmin(l, cur[i].l); idx_1D += (int64_t)cur[i].idx * factor[i + 1]; }
         for (int k = 0; k < E.n_scores; k++) {
-            const double v = score_value(P, P.scores[E.score_begin + k], s, l);
+            const double v = score_value(P, P.scores[E.score_begin + k], s, l, CC);
             const int64_t t = E.tally_begin + idx_1D + (int64_t)k * factor[0];
             if (t >= E.tally_begin && t < E.tally_begin + E.n_tallies) atomicAdd(acc + t * T.stride, v);
         }
@@ -214,41 +214,48 @@ __device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const
 // from the particle's own stream like the reference draws from its global one (EstimatorScatter / FissionPrompt /
 // FissionDelayed::score, Estimator.cpp:441-482): energy_old = incident energy, energy and speed = outgoing.
 __device__ __forceinline__ void estimator_score(const DevProblem& P, const TallyAcc& T, int e, const ScoreState& s, uint64_t& rng, double l,
-                                             int hist)
+                                             int hist, ChannelCache& CC)
 {
     const mcb_estimator E = P.estimators[e];
-    if (E.simulate == MCB_SIM_NONE) { estimator_score_plain(P, T, E, s, l, hist); return; }
+    if (E.simulate == MCB_SIM_NONE) { estimator_score_plain(P, T, E, s, l, hist, CC); return; }
     if (s.material < 0) return;
     const DevMaterial& M = P.materials[s.material];
     ScoreState q = s;
     int n = -1;
     if (E.simulate == MCB_SIM_SCATTER) {
-        (void)macro_channel(P, M, s.E, 0, false, mcb_urand(rng), &n);
+        (void)macro_channel(P, s.material, s.E, 0, false, mcb_urand(rng), &n, CC);
         if (n < 0) return;  // the reference dereferences a null nuclide here
         scatter_sample(P.nuclides[n].A, q.u, q.v, q.wd, q.E, q.speed, rng);
     } else if (E.simulate == MCB_SIM_FISSION || E.simulate == MCB_SIM_FISSION_PROMPT) {
-        (void)macro_channel(P, M, s.E, E.simulate == MCB_SIM_FISSION ? 1 : 2, false, mcb_urand(rng), &n);
+        (void)macro_channel(P, s.material, s.E, E.simulate == MCB_SIM_FISSION ? 1 : 2, false, mcb_urand(rng), &n, CC);
         if (n < 0) return;
         const DevNuclide& N = P.nuclides[n];
         q.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, s.E, rng);
         q.speed = mcb_speed_of_energy(q.E);
     } else {
         const int g = E.simulate - MCB_SIM_FISSION_DELAYED;
-        (void)macro_channel(P, M, s.E, 3 + g, false, mcb_urand(rng), &n);
+        (void)macro_channel(P, s.material, s.E, 3 + g, false, mcb_urand(rng), &n, CC);
         if (n < 0) return;
         q.E = chid_sample(P.nuclides[n], g, rng);
         q.speed = mcb_speed_of_energy(q.E);
     }
     q.E_old = s.E;  // Particle::set_energy / set_speed (Particle.cpp:42-56)
-    q.uidx = union_index(M, q.E);
-    macro_xs(P, M, q.uidx, q.E, q.X);
-    estimator_score_plain(P, T, E, q, l, hist);
+    // cross sections at the outgoing energy only when a score or kernel of this estimator reads them
+    bool needs_X = false;
+    for (int k = 0; k < E.n_scores; k++) {
+        const mcb_score& S = P.scores[E.score_begin + k];
+        if (S.kernel == MCB_KERNEL_COLLISION || (S.score >= MCB_SCORE_ABSORPTION && S.score <= MCB_SCORE_TOTAL)) needs_X = true;
+    }
+    if (needs_X) { q.uidx = union_index(M, q.E); macro_xs(P, M, q.uidx, q.E, q.X); }
+    estimator_score_plain(P, T, E, q, l, hist, CC);
 }
 __device__ __forceinline__ void score_attached(const DevProblem& P, const TallyAcc& T, int kind, int id,
                                                const ScoreState& s, uint64_t& rng, double l, int hist)
 {
     const int b = P.attach_begin[kind][id], e = P.attach_begin[kind][id + 1];
-    for (int i = b; i < e; i++) estimator_score(P, T, P.attach_list[kind][i], s, rng, l, hist);
+    ChannelCache CC;  // microscopic data at the (at most two) energies the estimators of this event ask about
+    channel_cache_reset(CC);
+    for (int i = b; i < e; i++) estimator_score(P, T, P.attach_list[kind][i], s, rng, l, hist, CC);
 }
 __device__ __forceinline__ bool has_attached(const DevProblem& P, int kind, int id)
 {
