@@ -361,7 +361,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "histories_per_generation": n_sample, "histories_per_gpu": per_gpu,
                        "parallelism": "histories sharded over %d GPU(s); NCCL all-reduce of k sums + all-gather of the fission bank per generation" % world,
-                       "l2": "inputs larger than L2: per GPU and generation the source bank (%.2f GB), particle bank (%.2f GB) and site requests (%.2f GB) stream through HBM" % (per_gpu * 72 / 1e9, per_gpu * 100 / 1e9, per_gpu * 64 / 1e9)},
+                       "l2": "inputs larger than L2: per GPU and generation the source bank (%.2f GB), particle bank (%.2f GB) and site requests (%.2f GB) stream through HBM" % (per_gpu * 64 / 1e9, per_gpu * 100 / 1e9, per_gpu * 64 / 1e9)},
             "collisions_per_second": coll / (ms * 1e-3), "tracks_per_second": tracks / (ms * 1e-3),
             "xs_lookups_per_second": lookups / (ms * 1e-3),
             "k_cycle_last": res[-1].k_cycle, "event_loop_iterations_per_step": sum(r.n_iterations for r in res) / args.steps,

@@ -166,6 +166,7 @@ struct mcb_ctx {
     DevBuf<SiteReq> d_site_reqs;
     DevBuf<Site> d_local_bank[2];    // this rank's canonical bank; two of them with world > 1 (peers may still read the last one)
     DevBuf<Site> d_global_bank;      // the whole bank in one array: only for banks set / read through the host API, or without P2P
+    DevBuf<double> d_host_dirs;      // explicit directions of a bank set through the host API (n x 3)
     int bank_w = 0;                  // d_local_bank[bank_w] is the one the running cycle writes
     Site* peer_bank[2][MCB_MAX_WORLD] = {};  // peer_bank[b][r] = rank r's d_local_bank[b] mapped here (CUDA IPC); [rank] = own
     bool p2p = false;                // the peers' banks are mapped: source sites are read in place over NVLink
@@ -616,7 +617,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     uint32_t* queue[2] = {ctx->q_active, ctx->q_next};
     ctx->timer.begin(st, ST_SOURCE);
     const mcbk::SortScratch* sort = nullptr;
-    if (V.n && !V.flat) {  // bank spread over the ranks: read it in ascending order
+    if (V.n && (!V.flat || getenv("MCB_FORCE_SORT"))) {  // bank spread over the ranks: read it in ascending order
         if (!ctx->d_sort_key.p) {
             const size_t nbh = ctx->batch_hist;
             CK(ctx->d_sort_key.alloc(2 * nbh)); CK(ctx->d_sort_val.alloc(2 * nbh)); CK(ctx->d_sort_rng.alloc(nbh));
@@ -625,7 +626,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
             ctx->sort.val_in = ctx->d_sort_val.p; ctx->sort.val_out = ctx->d_sort_val.p + nbh;
             ctx->sort.rng_after = ctx->d_sort_rng.p; ctx->sort.temp = ctx->d_sort_temp.p; ctx->sort.temp_bytes = ctx->d_sort_temp.n;
         }
-        ctx->sort.rot = V.prefix[std::min(ctx->rank, V.n_seg - 1)];
+        ctx->sort.rot = V.flat ? 0 : V.prefix[std::min(ctx->rank, V.n_seg - 1)];
         sort = &ctx->sort;
     }
     mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, V, C, sort);
@@ -958,7 +959,7 @@ void mcb_set_stage_timing(mcb_ctx* ctx, int on)
     if (ctx) ctx->timer.on = on != 0;
 }
 
-static int64_t read_bank(mcb_ctx* ctx, const Site* bank, uint64_t have, double* out, int32_t* cells, int64_t max_n)
+static int64_t read_bank(mcb_ctx* ctx, const Site* bank, const double* dir_x, uint64_t have, double* out, int32_t* cells, int64_t max_n)
 {
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
     const int64_t n = std::min<int64_t>((int64_t)have, max_n);
@@ -968,7 +969,7 @@ static int64_t read_bank(mcb_ctx* ctx, const Site* bank, uint64_t have, double* 
         if (ctx->d_io_sites.alloc((size_t)n * 8) != cudaSuccess || ctx->d_io_cells.alloc((size_t)n) != cudaSuccess)
             return ctx->fail(MCB_ERR_CUDA, "out of device memory for the bank staging buffers");
     }
-    mcbk::unpack_sites(ctx->stream, bank, (uint64_t)n, ctx->d_io_sites.p, ctx->d_io_cells.p);
+    mcbk::unpack_sites(ctx->stream, bank, dir_x, (uint64_t)n, ctx->d_io_sites.p, ctx->d_io_cells.p);
     cudaError_t e = cudaSuccess;
     if (out) e = cudaMemcpyAsync(out, ctx->d_io_sites.p, (size_t)n * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && cells) e = cudaMemcpyAsync(cells, ctx->d_io_cells.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
@@ -980,14 +981,14 @@ static int64_t read_bank(mcb_ctx* ctx, const Site* bank, uint64_t have, double* 
 int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
 {
     if (!ctx) return MCB_ERR_ARG;
-    return read_bank(ctx, ctx->d_local_bank[ctx->bank_last].p, ctx->n_local_sites, out, cells, max_n);
+    return read_bank(ctx, ctx->d_local_bank[ctx->bank_last].p, nullptr, ctx->n_local_sites, out, cells, max_n);
 }
 
 int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n)
 {
     if (!ctx) return MCB_ERR_ARG;
     if (!ctx->source_is_bank) return 0;
-    if (ctx->view.flat) return read_bank(ctx, ctx->view.flat, ctx->view.n, out, cells, max_n);
+    if (ctx->view.flat) return read_bank(ctx, ctx->view.flat, ctx->view.dir_x, ctx->view.n, out, cells, max_n);
     // segmented bank (peer slices): materialise the part asked for
     const int64_t n = std::min<int64_t>((int64_t)ctx->view.n, max_n);
     if (n <= 0) return 0;
@@ -995,7 +996,7 @@ int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t m
     if (ctx->d_global_bank.n < (size_t)n && ctx->d_global_bank.alloc((size_t)n) != cudaSuccess)
         return ctx->fail(MCB_ERR_CUDA, "out of device memory for the gathered bank");
     mcbk::gather_sites(ctx->stream, ctx->view, (uint64_t)n, ctx->d_global_bank.p);
-    return read_bank(ctx, ctx->d_global_bank.p, (uint64_t)n, out, cells, max_n);
+    return read_bank(ctx, ctx->d_global_bank.p, nullptr, (uint64_t)n, out, cells, max_n);
 }
 
 int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells, int64_t n)
@@ -1014,11 +1015,12 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
     if (n) {
         CK(cudaMemcpyAsync(ctx->d_io_sites.p, sites8, (size_t)n * 8 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_io_cells.p, cells, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        mcbk::pack_sites(ctx->stream, ctx->d_io_sites.p, ctx->d_io_cells.p, (uint64_t)n, dst);
+        if (ctx->d_host_dirs.n < (size_t)n * 3) CK(ctx->d_host_dirs.alloc((size_t)n * 3));
+        mcbk::pack_sites(ctx->stream, ctx->d_io_sites.p, ctx->d_io_cells.p, (uint64_t)n, dst, ctx->d_host_dirs.p);
     }
     CK(cudaStreamSynchronize(ctx->stream));
     memset(&ctx->view, 0, sizeof(ctx->view));
-    ctx->view.flat = dst; ctx->view.n = (uint64_t)n;
+    ctx->view.flat = dst; ctx->view.dir_x = n ? ctx->d_host_dirs.p : nullptr; ctx->view.n = (uint64_t)n;
     ctx->source_is_bank = true;
     return MCB_OK;
 }

@@ -74,30 +74,48 @@ struct Bank {
     int32_t* surf;                        // surface hit by the last flight (stage: flight)
 };
 
-// fission site / source site (AoS: sites are written and read by random index)
-// 80 bytes, 16-byte aligned: a site is fetched with five 128-bit loads (it is drawn by random index, from local HBM or
-// from a peer's HBM over NVLink, where every request costs a round trip)
+// fission site / source site (AoS: sites are written and read by random index).
+// 64 bytes = two 32-byte sectors, fetched with four 128-bit loads: it is drawn from local HBM or from a peer's HBM over
+// NVLink, where every sector is a request on the wire.  The isotropic emission direction is kept as the two numbers
+// it is made of (DistributionIsotropicDirection::sample, Distribution.cpp:78-92: mu = 2 xi1 - 1 and the azimuth draw
+// xi2) and rebuilt by site_direction() with the very expressions that sample it, so nothing is lost.  A bank handed
+// in from the host carries explicit directions instead, in a side array (SourceBankView::dir_x).
 struct alignas(16) Site {
-    double x, y, z, u, v, w, E, t;
-    int32_t cell, seq;                    // seq = order of banking within the parent history
-    int32_t pad[2];
+    double x, y, z, E, t;
+    double mu, xi;                        // direction = (mu, cos(2 pi xi) sqrt(1-mu^2), sin(2 pi xi) sqrt(1-mu^2))
+    int32_t cell, pad;
 };
-static_assert(sizeof(Site) == 80, "Site is five 16-byte words");
+static_assert(sizeof(Site) == 64, "Site is two 32-byte sectors");
 __device__ __forceinline__ Site load_site(const Site* p)
 {
     const double2* q = reinterpret_cast<const double2*>(p);
-    const double2 a = q[0], b = q[1], c = q[2], d = q[3];
-    const int4 e = *reinterpret_cast<const int4*>(q + 4);
+    const double2 a = q[0], b = q[1], c = q[2];
+    const int4 d = *reinterpret_cast<const int4*>(q + 3);
     Site s;
-    s.x = a.x; s.y = a.y; s.z = b.x; s.u = b.y; s.v = c.x; s.w = c.y; s.E = d.x; s.t = d.y;
-    s.cell = e.x; s.seq = e.y; s.pad[0] = 0; s.pad[1] = 0;
+    s.x = a.x; s.y = a.y; s.z = b.x; s.E = b.y; s.t = c.x; s.mu = c.y;
+    s.xi = __hiloint2double(d.y, d.x); s.cell = d.z; s.pad = 0;
     return s;
 }
 __device__ __forceinline__ void store_site(Site* p, const Site& s)
 {
     double2* q = reinterpret_cast<double2*>(p);
-    q[0] = make_double2(s.x, s.y); q[1] = make_double2(s.z, s.u); q[2] = make_double2(s.v, s.w); q[3] = make_double2(s.E, s.t);
-    *reinterpret_cast<int4*>(q + 4) = make_int4(s.cell, s.seq, 0, 0);
+    q[0] = make_double2(s.x, s.y); q[1] = make_double2(s.z, s.E); q[2] = make_double2(s.t, s.mu);
+    *reinterpret_cast<int4*>(q + 3) = make_int4(__double2loint(s.xi), __double2hiint(s.xi), s.cell, 0);
+}
+// direction of an isotropic emission from its two draws (Distribution.cpp:78-92: x is the polar axis)
+__device__ __forceinline__ void direction_from_draws(double mu, double xi, double& dx, double& dy, double& dz)
+{
+    const double c = sqrt(1.0 - mu * mu);
+    double sa, ca;
+#ifdef MCB_FAST_TRIG
+    sincospi(2.0 * xi, &sa, &ca);
+#else
+    const double azi = MCB_PI_2 * xi;
+    sincos(azi, &sa, &ca);
+#endif
+    dy = ca * c;
+    dz = sa * c;
+    dx = mu;
 }
 
 // The source bank a generation samples from.  Single GPU / a bank handed in from the host: one flat array.
@@ -107,6 +125,7 @@ __device__ __forceinline__ void store_site(Site* p, const Site& s)
 #define MCB_MAX_WORLD 16
 struct SourceBankView {
     const Site* flat;
+    const double* dir_x;                  // flat banks handed in from the host: n x 3 explicit directions (else nullptr)
     const Site* seg[MCB_MAX_WORLD];
     unsigned long long prefix[MCB_MAX_WORLD + 1];
     int32_t n_seg, pad;
@@ -118,6 +137,12 @@ __device__ __forceinline__ Site source_bank_site(const SourceBankView& V, unsign
     int r = 0;
     while (r + 1 < V.n_seg && j >= V.prefix[r + 1]) r++;
     return load_site(V.seg[r] + (j - V.prefix[r]));
+}
+__device__ __forceinline__ void source_bank_direction(const SourceBankView& V, unsigned long long j, const Site& s, double& u, double& v,
+                                                      double& w)
+{
+    if (V.dir_x) { u = V.dir_x[3 * j]; v = V.dir_x[3 * j + 1]; w = V.dir_x[3 * j + 2]; }
+    else direction_from_draws(s.mu, s.xi, u, v, w);
 }
 
 // a fission site as the collision leaves it: where, from what, and the stream it will be sampled from.  The
@@ -392,17 +417,8 @@ __device__ __forceinline__ double watt_sample(const double* va, const double* vb
 __device__ __forceinline__ void isotropic_direction(uint64_t& rng, double& dx, double& dy, double& dz)
 {
     const double mu = 2.0 * mcb_urand(rng) - 1.0;
-    const double c = sqrt(1.0 - mu * mu);
-    double sa, ca;
-#ifdef MCB_FAST_TRIG
-    sincospi(2.0 * mcb_urand(rng), &sa, &ca);
-#else
-    const double azi = MCB_PI_2 * mcb_urand(rng);
-    sincos(azi, &sa, &ca);
-#endif
-    dy = ca * c;
-    dz = sa * c;
-    dx = mu;
+    const double xi = mcb_urand(rng);
+    direction_from_draws(mu, xi, dx, dy, dz);
 }
 // Delta / Uniform (Distribution.cpp:30-33) / Watt at incident energy 0
 __device__ __forceinline__ double dist1_sample(const mcb_dist1& d, uint64_t& rng)

@@ -581,7 +581,8 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
         if (sorted_key) { j = sorted_key[q] + rot; if (j >= V.n) j -= V.n; }
         else { j = (uint64_t)(xi * (double)V.n); if (j >= V.n) j = V.n - 1; }
         const Site s = source_bank_site(V, j);  // local HBM, or a peer's HBM over NVLink
-        x = s.x; y = s.y; z = s.z; u = s.u; v = s.v; w = s.w; E = s.E; t = s.t; cell = s.cell;
+        x = s.x; y = s.y; z = s.z; E = s.E; t = s.t; cell = s.cell;
+        source_bank_direction(V, j, s, u, v, w);
     } else {
         int j = (int)(xi * (double)P.n_sources);
         if (j >= P.n_sources) j = P.n_sources - 1;
@@ -972,8 +973,9 @@ k_bank_sample_order(const DevProblem P, const SiteReq* __restrict__ reqs, uint64
     uint64_t rng = r.seed;
     Site s;
     s.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, r.E_in, rng);
-    isotropic_direction(rng, s.u, s.v, s.w);
-    s.x = r.x; s.y = r.y; s.z = r.z; s.t = r.t; s.cell = r.cell; s.seq = r.seq;
+    s.mu = 2.0 * mcb_urand(rng) - 1.0;  // the two draws of the isotropic direction (rebuilt when the site is used)
+    s.xi = mcb_urand(rng);
+    s.x = r.x; s.y = r.y; s.z = r.z; s.t = r.t; s.cell = r.cell; s.pad = 0;
     store_site(out + ((uint64_t)offset[r.hist] + (uint64_t)r.seq), s);
 }
 
@@ -1109,24 +1111,28 @@ __global__ void k_tally_final(const double* partial, int n_chunks, int64_t n_tal
 
 // host-facing bank layout (n x 8 doubles + n cells) <-> Site records
 __global__ void __launch_bounds__(256)
-k_pack_sites(const double* __restrict__ s8, const int32_t* __restrict__ cells, uint64_t n, Site* out)
+k_pack_sites(const double* __restrict__ s8, const int32_t* __restrict__ cells, uint64_t n, Site* out, double* dir_x)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const double* s = s8 + 8 * q;
     Site d;
-    d.x = s[0]; d.y = s[1]; d.z = s[2]; d.u = s[3]; d.v = s[4]; d.w = s[5]; d.E = s[6]; d.t = s[7];
-    d.cell = cells[q]; d.seq = 0;
+    d.x = s[0]; d.y = s[1]; d.z = s[2]; d.E = s[6]; d.t = s[7]; d.mu = 0.0; d.xi = 0.0;
+    d.cell = cells[q]; d.pad = 0;
+    dir_x[3 * q] = s[3]; dir_x[3 * q + 1] = s[4]; dir_x[3 * q + 2] = s[5];  // explicit directions ride beside the sites
     store_site(out + q, d);
 }
 __global__ void __launch_bounds__(256)
-k_unpack_sites(const Site* __restrict__ in, uint64_t n, double* s8, int32_t* cells)
+k_unpack_sites(const Site* __restrict__ in, const double* __restrict__ dir_x, uint64_t n, double* s8, int32_t* cells)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const Site d = load_site(in + q);
     double* s = s8 + 8 * q;
-    s[0] = d.x; s[1] = d.y; s[2] = d.z; s[3] = d.u; s[4] = d.v; s[5] = d.w; s[6] = d.E; s[7] = d.t;
+    double u, v, w;
+    if (dir_x) { u = dir_x[3 * q]; v = dir_x[3 * q + 1]; w = dir_x[3 * q + 2]; }
+    else direction_from_draws(d.mu, d.xi, u, v, w);
+    s[0] = d.x; s[1] = d.y; s[2] = d.z; s[3] = u; s[4] = v; s[5] = w; s[6] = d.E; s[7] = d.t;
     cells[q] = d.cell;
 }
 
@@ -1364,13 +1370,13 @@ void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist,
     k_tally_final<<<blocks_for(n_tallies, 128), 128, 0, st>>>(partial, nc, n_tallies, sum, squared);
     MCB_LAUNCHED(2);
 }
-void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out)
+void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out, double* dir_x)
 {
-    if (n) { k_pack_sites<<<blocks_for(n), 256, 0, st>>>(s8, cells, n, out); MCB_LAUNCHED(1); }
+    if (n) { k_pack_sites<<<blocks_for(n), 256, 0, st>>>(s8, cells, n, out, dir_x); MCB_LAUNCHED(1); }
 }
-void unpack_sites(cudaStream_t st, const Site* in, uint64_t n, double* s8, int32_t* cells)
+void unpack_sites(cudaStream_t st, const Site* in, const double* dir_x, uint64_t n, double* s8, int32_t* cells)
 {
-    if (n) { k_unpack_sites<<<blocks_for(n), 256, 0, st>>>(in, n, s8, cells); MCB_LAUNCHED(1); }
+    if (n) { k_unpack_sites<<<blocks_for(n), 256, 0, st>>>(in, dir_x, n, s8, cells); MCB_LAUNCHED(1); }
 }
 void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t n, Site* out)
 {

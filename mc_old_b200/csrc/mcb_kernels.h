@@ -54,8 +54,10 @@ void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist,
                   double* sum, double* squared);
 void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t n, Site* out);
 void iota(cudaStream_t st, uint32_t* a, uint32_t n);
-void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out);
-void unpack_sites(cudaStream_t st, const Site* in, uint64_t n, double* s8, int32_t* cells);
+// host-facing bank layout (n x 8 doubles + n cells) <-> Site records; dir_x = n x 3 explicit directions of a bank that
+// came from the host (nullptr for banks the device made: their directions are rebuilt from the stored draws)
+void pack_sites(cudaStream_t st, const double* s8, const int32_t* cells, uint64_t n, Site* out, double* dir_x);
+void unpack_sites(cudaStream_t st, const Site* in, const double* dir_x, uint64_t n, double* s8, int32_t* cells);
 
 // parity / bench kernels on plain device arrays
 void xs_lookup(cudaStream_t st, const DevProblem& P, int material, const double* E, int64_t n, double* out5);
