@@ -549,8 +549,11 @@ k_pick(uint64_t seed0, uint64_t nps0, int32_t first_hist, uint32_t count, unsign
        unsigned long long* key, uint32_t* val, uint64_t* rng_after)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint64_t s_base;  // stream of the block's first history; the others are a short skip away
+    if (threadIdx.x == 0) s_base = mcb_rn_history_seed(seed0, nps0 + (uint64_t)(first_hist + (int32_t)(blockIdx.x * blockDim.x)));
+    __syncthreads();
     if (q >= count) return;
-    uint64_t rng = mcb_rn_history_seed(seed0, nps0 + (uint64_t)(first_hist + (int32_t)q));
+    uint64_t rng = mcb_rn_history_seed_from(s_base, threadIdx.x);
     const double xi = mcb_urand(rng);
     unsigned long long j = (unsigned long long)(xi * (double)n_bank);
     if (j >= n_bank) j = n_bank - 1;
@@ -568,12 +571,17 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     if (q == 0) {  // queue state of the batch: `count` primaries in queue 0, slots behind them are free
         C->n_active[0] = count; C->n_active[1] = 0; C->n_active[2] = 0; C->q_collide = 0; C->q_cross = 0; C->slot_cursor = count;
     }
+    __shared__ uint64_t s_base;  // stream of the block's first history; the others are a short skip away
+    if (!sorted_key) {
+        if (threadIdx.x == 0) s_base = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)(first_hist + (int32_t)(blockIdx.x * blockDim.x)));
+        __syncthreads();
+    }
     if (q >= count) return;
     int32_t h;
     uint64_t rng;
     double xi = 0.0;
     if (sorted_key) { h = first_hist + (int32_t)sorted_val[q]; rng = rng_after[sorted_val[q]]; }
-    else { h = first_hist + (int32_t)q; rng = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)h); xi = mcb_urand(rng); }
+    else { h = first_hist + (int32_t)q; rng = mcb_rn_history_seed_from(s_base, threadIdx.x); xi = mcb_urand(rng); }
     double x, y, z, u, v, w, E, t;
     int cell;
     if (V.n) {
