@@ -965,8 +965,9 @@ static int64_t read_bank(mcb_ctx* ctx, const Site* bank, const double* dir_x, ui
     const int64_t n = std::min<int64_t>((int64_t)have, max_n);
     if (n <= 0) return 0;
     // Site records -> the host-facing layout on the device, then straight into the caller's buffers
-    if (ctx->d_io_sites.n < (size_t)n * 8) {
-        if (ctx->d_io_sites.alloc((size_t)n * 8) != cudaSuccess || ctx->d_io_cells.alloc((size_t)n) != cudaSuccess)
+    if (ctx->d_io_sites.n < (size_t)n * 8) {  // grow with headroom: the bank size wanders from generation to generation
+        const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        if (ctx->d_io_sites.alloc(cap * 8) != cudaSuccess || ctx->d_io_cells.alloc(cap) != cudaSuccess)
             return ctx->fail(MCB_ERR_CUDA, "out of device memory for the bank staging buffers");
     }
     mcbk::unpack_sites(ctx->stream, bank, dir_x, (uint64_t)n, ctx->d_io_sites.p, ctx->d_io_cells.p);
@@ -1011,11 +1012,14 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
         if (ctx->d_global_bank.n < (size_t)std::max<int64_t>(n, 1)) CK(ctx->d_global_bank.alloc((size_t)std::max<int64_t>(n, 1)));
         dst = ctx->d_global_bank.p;
     }
-    if (ctx->d_io_sites.n < (size_t)n * 8) { CK(ctx->d_io_sites.alloc((size_t)n * 8)); CK(ctx->d_io_cells.alloc((size_t)n)); }
+    if (ctx->d_io_sites.n < (size_t)n * 8) {
+        const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        CK(ctx->d_io_sites.alloc(cap * 8)); CK(ctx->d_io_cells.alloc(cap));
+    }
     if (n) {
         CK(cudaMemcpyAsync(ctx->d_io_sites.p, sites8, (size_t)n * 8 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_io_cells.p, cells, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        if (ctx->d_host_dirs.n < (size_t)n * 3) CK(ctx->d_host_dirs.alloc((size_t)n * 3));
+        if (ctx->d_host_dirs.n < (size_t)n * 3) CK(ctx->d_host_dirs.alloc(((size_t)n + (size_t)n / 4 + 1024) * 3));
         mcbk::pack_sites(ctx->stream, ctx->d_io_sites.p, ctx->d_io_cells.p, (uint64_t)n, dst, ctx->d_host_dirs.p);
     }
     CK(cudaStreamSynchronize(ctx->stream));
