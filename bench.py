@@ -221,6 +221,7 @@ def main():
     ap.add_argument("--ref-samples", type=float, default=2e5, help="histories per generation of the CPU reference runs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-xs", action="store_true", help="skip the xs_lookup microbench")
     args = ap.parse_args()
     args.ref_samples = int(args.ref_samples)
     if args.warmup < 3:
@@ -346,6 +347,28 @@ def main():
                     "bytes_per_unit": per_unit[dominant], "units_per_launch": 2.0 * per_gen[dominant] / max(stages[dominant]["launches"], 1),
                     "avg_launch_ms": stages[dominant]["ms"] / max(stages[dominant]["launches"], 1),
                     "note": "bytes_per_unit is SURVEY 8(d)'s fixed per-track figure (record in+out 224, lookup 72+100*Nn, sites 20); the walk kernel keeps the record in registers and the tables in L2, so its DRAM traffic is below it (DESIGN.md 4)"}
+    # ---- xs_lookup microbench (SURVEY 8d input 1): macroscopic cross sections of the HEU material at 2^26 energies,
+    # log-uniform on [1e-5, 2e7] eV and Watt-shaped (what the transport loop asks for); device-resident in and out ----
+    xs_micro = None
+    if rank == 0 and not args.no_xs:
+        n_e = 1 << 26
+        g = torch.Generator(device="cuda"); g.manual_seed(12345)
+        out5 = torch.empty((n_e, 5), dtype=torch.float64, device="cuda")
+        xs_micro = {}
+        for label in ("log_uniform", "watt_spectrum"):
+            u = torch.rand(n_e, dtype=torch.float64, device="cuda", generator=g)
+            if label == "log_uniform":
+                E = torch.exp(np.log(1e-5) + u * (np.log(2e7) - np.log(1e-5)))
+            else:  # Maxwellian-like fission spectrum, T = 1.3 MeV: E = -T (ln u1 + ln u2 cos^2(pi u3 / 2))
+                u2 = torch.rand(n_e, dtype=torch.float64, device="cuda", generator=g)
+                u3 = torch.rand(n_e, dtype=torch.float64, device="cuda", generator=g)
+                E = -1.3e6 * (torch.log(u) + torch.log(u2) * torch.cos(0.5 * np.pi * u3) ** 2)
+            torch.cuda.synchronize()
+            best = min(ctx.xs_lookup_device(0, E.data_ptr(), n_e, out5.data_ptr()) for _ in range(5))
+            bytes_alg = n_e * BYTES_LOOKUP(nn)
+            xs_micro[label] = {"lookups_per_second": n_e / (best * 1e-3), "ms": best, "algorithmic_GBps": bytes_alg / (best * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": bytes_alg / (best * 1e-3) / 1e9 / peak, "io_GBps": n_e * 48 / (best * 1e-3) / 1e9}
+        del out5
     ctx.close()
 
     cpu = None
@@ -364,6 +387,8 @@ def main():
                        "l2": "inputs larger than L2: per GPU and generation the source bank (%.2f GB), particle bank (%.2f GB) and site requests (%.2f GB) stream through HBM" % (per_gpu * 64 / 1e9, per_gpu * 100 / 1e9, per_gpu * 64 / 1e9)},
             "collisions_per_second": coll / (ms * 1e-3), "tracks_per_second": tracks / (ms * 1e-3),
             "xs_lookups_per_second": lookups / (ms * 1e-3),
+            "xs_lookup_algorithmic_GBps": lookups * BYTES_LOOKUP(2) / world / (ms * 1e-3) / 1e9,
+            "xs_lookup_microbench": xs_micro,
             "k_cycle_last": res[-1].k_cycle, "event_loop_iterations_per_step": sum(r.n_iterations for r in res) / args.steps,
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "stages_ms_2_generations": stages,
             "cpu_baseline": cpu,

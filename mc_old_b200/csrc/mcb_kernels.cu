@@ -611,7 +611,7 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
 
 // xs_lookup stage: macroscopic cross sections of every queued particle at its energy in its cell's material.
 // As the first kernel of an iteration it also clears the queue lengths the iteration is going to fill.
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_xs_stage(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, Counters* C)
 {
     const unsigned long long n = C->n_active[cur];
@@ -645,7 +645,7 @@ k_xs_stage(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int 
 }
 
 // flight stage.  The event queue is split in place: collisions from the front, surface hits from the back.
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, uint32_t* evq, Counters* C,
          HistoryAcc H, TallyAcc T)
 {
@@ -685,7 +685,7 @@ k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
 }
 
 // collide stage
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, Counters* C, uint32_t* next, HistoryAcc H,
           TallyAcc T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {
@@ -740,7 +740,7 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
 }
 
 // cross stage
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, Counters* C, uint32_t* next, TallyAcc T,
         uint32_t n_slots)
 {
@@ -912,7 +912,7 @@ k_walk(const DevProblem P, Bank B, unsigned long long begin, unsigned long long 
 // tail of a batch: every queued particle is followed to the end of its history in registers (the same events,
 // chained).  Secondaries born here are queued for another pass.  Cursors are bumped per thread: with a few
 // thousand particles left there is no contention to aggregate away.
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cur, Counters* C, uint32_t* next, HistoryAcc H,
          TallyAcc T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
 {

@@ -19,7 +19,7 @@ if [ "$STEP" = all ] || [ "$STEP" = bench ]; then
 fi
 if [ "$STEP" = all ] || [ "$STEP" = ncu ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
+      python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-xs > gpurun_out/bench_under_ncu.log 2>&1
   python tools/ncu_summary.py launches gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1
   cat gpurun_out/launches_summary.txt
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${KERNEL:-k_walk} -c 1 \
