@@ -8,7 +8,8 @@ Workload (BASELINE.json north_star target): examples/HEU_sphere_criticality phys
 U-235 + U-238, k-eigenvalue power iteration), scaled to --samples histories per generation PER GPU (weak scaling;
 default 1e7, i.e. 8e7 ~ the 1e8 target at 8 GPUs).  A "step" is one generation: source resampling from the fission
 bank, the event loop until every history is finished, fission-bank ordering, k close-out and, for N > 1, the NCCL
-all-reduce of the k sums and the all-gather of the fission bank.
+all-gather of the ranks' close-out sums; the fission bank stays where it was banked and the next generation
+reads the sites it draws in place over NVLink (CUDA IPC peer mappings, draws sorted by site index).
 
 `value`  histories/s with the source bank resident in HBM (device time, CUDA events on the launch stream, max over
          ranks).
@@ -284,7 +285,7 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
-    hist = sum(r.n_histories for r in res)          # global counts (all-reduced inside the library)
+    hist = sum(r.n_histories for r in res)          # global counts (summed over the ranks inside the library)
     coll = sum(r.n_collisions for r in res)
     tracks = sum(r.n_tracks for r in res)
     lookups = sum(r.n_lookups for r in res)
@@ -383,7 +384,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "histories_per_generation": n_sample, "histories_per_gpu": per_gpu,
-                       "parallelism": "histories sharded over %d GPU(s); NCCL all-reduce of k sums + all-gather of the fission bank per generation" % world,
+                       "parallelism": "histories sharded over %d GPU(s); per generation one NCCL all-gather of the close-out sums, fission bank read in place over NVLink" % world,
                        "l2": "inputs larger than L2: per GPU and generation the source bank (%.2f GB), particle bank (%.2f GB) and site requests (%.2f GB) stream through HBM" % (per_gpu * 64 / 1e9, per_gpu * 100 / 1e9, per_gpu * 64 / 1e9)},
             "collisions_per_second": coll / (ms * 1e-3), "tracks_per_second": tracks / (ms * 1e-3),
             "xs_lookups_per_second": lookups / (ms * 1e-3),

@@ -225,7 +225,8 @@ void mcb_set_stage_timing(mcb_ctx* ctx, int on);
 /* fission bank of the last cycle on this rank, canonical order: out = n x 8 doubles (x,y,z,u,v,w,E,t), cells = n */
 int64_t mcb_get_fission_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n);
 
-/* the global source bank the next cycle will sample (after the all-gather), same layout; identical on every rank */
+/* the global source bank the next cycle will sample (rank-order concatenation of the ranks' banks, gathered on
+ * demand), same layout; identical on every rank */
 int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t max_n);
 /* source bank of the next cycle from HOST memory (n x 8 doubles x,y,z,u,v,w,E,t + n cells), replacing the bank the
  * last cycle produced: the host-buffer form of `Sbank = Fbank` (handler.cpp:16).  With world > 1 every rank passes

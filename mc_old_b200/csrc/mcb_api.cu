@@ -2,7 +2,8 @@
 //
 // mcb_run_cycle() is the body of the reference's cycle loop (Simulator::start(), handler.cpp:14-44) for the
 // histories this rank owns: source resampling -> event loop on the GPU -> fission bank in canonical order ->
-// per-history close-outs -> (multi-GPU) NCCL all-reduce of the sums and all-gather of the bank -> k update.
+// per-history close-outs -> (multi-GPU) NCCL all-gather of the ranks' close-out sums; the bank stays in place and is
+// read by the peers over NVLink -> k update.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>

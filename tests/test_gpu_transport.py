@@ -29,7 +29,7 @@ def _close_frac(a, b, rtol=1e-9, atol=0.0):
 # ---------------------------------------------------------------------------------------------------------------
 # trajectory parity
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", ["fused", "split"])
+@pytest.mark.parametrize("mode", ["walk", "split"])
 def test_heu_history_parity(mode):
     """HEU sphere, 3 generations of 20000 histories: per-history k_C / k_TL (EstimatorK::end_history,
     Estimator.cpp:514-525), fission-bank size and sites, track / collision counts.  Generations are kept in lock
@@ -287,8 +287,8 @@ def test_batching_does_not_change_results():
         assert np.array_equal(out[0][1][0], bank[0]) and np.array_equal(out[0][1][1], bank[1])
 
 
-def test_split_and_fused_kernels_agree():
-    """the one-kernel-per-event-type mode and the fused multi-event kernel are the same computation"""
+def test_event_queue_and_walk_kernels_agree():
+    """the event-queue formulation (one kernel per event type) and the history-walk kernel are the same computation"""
     n = 30000
     deck = mcb.Deck(xml=decks.ucube(samples=n, active=1, passive=1))
     res = []
