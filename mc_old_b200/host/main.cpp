@@ -2,9 +2,16 @@
 // ./xs_library/<ZAID>.txt (relative to the CWD, setup.cpp:326; MCB_XS_LIBRARY overrides), runs the transport loop on
 // the GPU (mcb_run_cycle replaces Simulator::start(), handler.cpp:11-48), prints the reference's banners and
 // per-cycle lines (Estimator.cpp:536-554) and writes <dir>/output.h5 (report.cpp:9-52).
+//
+// Several GPUs: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (what torchrun, srun
+// or a shell loop provide); the histories of every generation are sharded over the ranks, rank 0 prints and writes
+// the output.  The 128-byte NCCL id travels through a file (MCB_ID_FILE, default /tmp/mcb_nccl_id.<MASTER_PORT>).
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -27,11 +34,35 @@ int main(int argc, char* argv[])
     const mcb_problem* p = mcbh_problem(deck);
     mcb_config cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.device = getenv("MCB_DEVICE") ? atoi(getenv("MCB_DEVICE")) : 0;
-    cfg.rank = 0; cfg.world = 1;
+    const int world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
+    const int rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
+    const bool root = rank == 0;
+    cfg.device = getenv("MCB_DEVICE") ? atoi(getenv("MCB_DEVICE")) : (getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : 0);
+    cfg.rank = rank; cfg.world = world > 1 ? world : 1;
     mcb_ctx* ctx = nullptr;
     if (mcb_create(p, &cfg, &ctx) != MCB_OK) { std::cout << mcb_last_error(nullptr) << "\n"; std::exit(EXIT_FAILURE); }
-    std::cout << "\nSimulation setup done,\nNow running the simulation...\n\n";
+    if (world > 1) {
+        const std::string id_file = getenv("MCB_ID_FILE") ? getenv("MCB_ID_FILE")
+                                    : std::string("/tmp/mcb_nccl_id.") + (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+        char id[128];
+        if (root) {
+            if (mcb_comm_unique_id(id) != MCB_OK) { std::cout << mcb_last_error(nullptr) << "\n"; std::exit(EXIT_FAILURE); }
+            std::ofstream f(id_file + ".tmp", std::ios::binary);
+            f.write(id, 128);
+            f.close();
+            std::rename((id_file + ".tmp").c_str(), id_file.c_str());
+        } else {
+            for (int tries = 0;; tries++) {
+                std::ifstream f(id_file, std::ios::binary);
+                if (f && f.read(id, 128)) break;
+                if (tries > 3000) { std::cout << "[ERROR] no NCCL id in " << id_file << "\n"; std::exit(EXIT_FAILURE); }
+                usleep(10000);
+            }
+        }
+        if (mcb_comm_init(ctx, id) != MCB_OK) { std::cout << mcb_last_error(ctx) << "\n"; std::exit(EXIT_FAILURE); }
+        if (root) std::remove(id_file.c_str());
+    }
+    if (root) std::cout << "\nSimulation setup done,\nNow running the simulation...\n\n";
 
     std::vector<double> k_cycle, H_cycle, k_avg, k_uncer;
     uint64_t n_track = 0;
@@ -41,13 +72,18 @@ int main(int argc, char* argv[])
         n_track += r.n_tracks;  // general.cpp:76
         if (p->ksearch) {       // EstimatorK::report_cycle (Estimator.cpp:526-561)
             k_cycle.push_back(r.k_cycle); H_cycle.push_back(r.H);
-            std::cout << icycle + 1 << "   " << r.k_cycle;
+            if (root) std::cout << icycle + 1 << "   " << r.k_cycle;
             if (icycle >= p->n_passive) {
                 k_avg.push_back(r.k_avg); k_uncer.push_back(r.k_uncer);
-                std::cout << "   " << r.k_avg << "   +/-   " << r.k_uncer;
+                if (root) std::cout << "   " << r.k_avg << "   +/-   " << r.k_uncer;
             }
-            std::cout << "   (" << r.H << ")\n";
+            if (root) std::cout << "   (" << r.H << ")" << std::endl;
         }
+    }
+    if (!root) {  // every rank holds the same global results; rank 0 reports them
+        mcb_destroy(ctx);
+        mcbh_free_deck(deck);
+        return 0;
     }
     std::cout << "Simulation done!\n\nReporting simulation output...\n";
     std::vector<double> mean((size_t)p->n_tallies), uncer((size_t)p->n_tallies);

@@ -201,3 +201,31 @@ def test_host_program_cli_and_output(tmp_path):
     # no argument: the reference's message and a failure exit code (Main.cpp:11-14)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode != 0 and "[ERROR] Please provide input.xml directory..." in out.stdout
+
+
+@pytest.mark.gpu
+def test_host_program_on_two_gpus(tmp_path):
+    """MCB.exe started once per GPU (RANK / WORLD_SIZE / LOCAL_RANK, NCCL id through a file): same cycle lines and
+    the same output.h5 as the single-GPU run, bit for bit (k, H, Ntrack; tallies to rounding)"""
+    if mcb.cuda_lib().mcb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "mc_old_b200", "MCB.exe")
+    xml = decks.heu_sphere(samples=40000, active=2, passive=2, entropy=True, estimators=True)
+    d1, d2 = str(tmp_path / "one"), str(tmp_path / "two")
+    decks.write(d1, xml); decks.write(d2, xml)
+    env = dict(os.environ, MCB_XS_LIBRARY=mcb.default_xs_dir())
+    one = subprocess.run([exe, d1], capture_output=True, text=True, env=env, timeout=300)
+    assert one.returncode == 0, one.stdout + one.stderr
+    idf = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([exe, d2], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              env=dict(env, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MCB_ID_FILE=idf)) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    lines = [l for l in outs[0].splitlines() if not l.startswith("NCCL version")]  # libnccl's own banner
+    assert lines == one.stdout.splitlines(), (outs[0], one.stdout)
+    assert outs[1] == ""
+    a, b = h5mini.File(os.path.join(d1, "output.h5")), h5mini.File(os.path.join(d2, "output.h5"))
+    for key in ("ksearch/k_cycle", "ksearch/H_cycle", "ksearch/k_active/mean", "ksearch/k_active/uncertainty"):
+        assert np.array_equal(a.root[key].value, b.root[key].value), key
+    assert a.root["summary/Ntrack"].value == b.root["summary/Ntrack"].value
+    assert np.allclose(a.root["sphere_rates/flux/mean"].value, b.root["sphere_rates/flux/mean"].value, rtol=1e-12, atol=0)
