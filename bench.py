@@ -13,9 +13,9 @@ reads the sites it draws in place over NVLink (CUDA IPC peer mappings, draws sor
 
 `value`  histories/s with the source bank resident in HBM (device time, CUDA events on the launch stream, max over
          ranks).
-`e2e`    the same step driven through the C-ABI with HOST buffers: every step uploads the global source bank from
-         pinned host memory (mcb_set_source_bank), runs the generation, and reads the new global bank back
-         (mcb_get_source_bank).
+`e2e`    the same step driven through the C-ABI with HOST buffers (mcb_run_cycle_host): every step takes the global
+         source bank from pinned host memory, runs the generation, and puts the new global bank back into pinned host
+         memory.
 `roofline`  the dominant stage kernel of the timed loop: algorithmic bytes per launch / mean launch time (CUDA events
          per launch in a separate pass, stage timing costs a few percent so it is off in the timed region).
 `cpu_baseline`  the compiled reference (oracle/_ref/MC_ref, single-threaded by construction) on the same deck at a
@@ -296,25 +296,25 @@ def main():
     e2e = None
     if not args.no_e2e:
         cap = 4 * n_sample + 4096 * world
-        sites = torch.empty((cap, 8), dtype=torch.float64, pin_memory=True).numpy()
-        cells = torch.empty((cap,), dtype=torch.int32, pin_memory=True).numpy()
-        s, c = ctx.source_bank(cap, sites, cells)
+        bufs = [(torch.empty((cap, 8), dtype=torch.float64, pin_memory=True).numpy(), torch.empty((cap,), dtype=torch.int32, pin_memory=True).numpy())
+                for _ in range(2)]
+        s, c = ctx.source_bank(cap, bufs[0][0], bufs[0][1])
         n_bank = s.shape[0]
         h2d = d2h = 0
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ctx.set_source_bank(sites[:n_bank], cells[:n_bank])
+        for i in range(args.steps):
+            src, dst = bufs[i & 1], bufs[(i + 1) & 1]
             h2d += n_bank * 68
-            r = ctx.run_cycle()
-            s, c = ctx.source_bank(cap, sites, cells)
+            r, s, c = ctx.run_cycle_host(src[0][:n_bank], src[1][:n_bank], dst[0], dst[1])
             n_bank = s.shape[0]
             d2h += n_bank * 68 + 176
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": args.steps * n_sample / dt, "unit": "histories/s", "h2d_bytes_per_step": h2d // args.steps,
                "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * dt / args.steps,
-               "what": "per step and per rank: mcb_set_source_bank (pinned host -> HBM) + mcb_run_cycle + mcb_get_source_bank (HBM -> pinned host)"}
+               "what": "per step and per rank: mcb_run_cycle_host = global source bank from pinned host memory -> HBM, the generation, "
+                       "the new global bank HBM -> pinned host memory (on one GPU the upload is pipelined with the walk)"}
 
     # ---- per-stage pass: CUDA events around every stage launch (rank-local), for the roofline of the dominant kernel ----
     ctx.reset_stage_times()

@@ -232,6 +232,14 @@ int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t m
  * last cycle produced: the host-buffer form of `Sbank = Fbank` (handler.cpp:16).  With world > 1 every rank passes
  * the same global bank. */
 int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells, int64_t n);
+/* One generation with the source bank in HOST buffers on both sides: equivalent to mcb_set_source_bank(in) +
+ * mcb_run_cycle + mcb_get_source_bank(out), the host-buffer form of one pass of the cycle body (handler.cpp:14-44 with
+ * Sbank / Fbank living in host RAM like the reference's).  On one GPU the three steps are pipelined: the draws are
+ * sorted by site index, the bank comes in over PCIe in pieces on a copy stream and the histories that drew from the
+ * pieces already there are walked meanwhile; the new bank goes back piece by piece.  Pinned buffers make the copies
+ * asynchronous.  *n_out = sites written (at most max_out). */
+int mcb_run_cycle_host(mcb_ctx* ctx, const double* in_sites8, const int32_t* in_cells, int64_t n_in, double* out_sites8,
+                       int32_t* out_cells, int64_t max_out, int64_t* n_out, mcb_cycle_result* out);
 /* per-history k scores of the last cycle on this rank, shard-local history order (EstimatorK::k_C / k_TL at
  * end_history, Estimator.cpp:514-525): parity tests compare them with the oracle history by history */
 int64_t mcb_get_history_k(mcb_ctx* ctx, double* kC, double* kTL, int64_t max_n);

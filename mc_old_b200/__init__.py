@@ -134,6 +134,7 @@ def cuda_lib():
         L.mcb_device_count.restype = C.c_int
         L.mcb_xs_lookup_batch.argtypes = [vp, i32, vp, i64, vp]
         L.mcb_xs_lookup_device.argtypes = [vp, i32, vp, i64, vp, C.POINTER(C.c_float)]
+        L.mcb_run_cycle_host.argtypes = [vp, vp, vp, i64, vp, vp, i64, C.POINTER(i64), vp]
         L.mcb_select_channel_batch.argtypes = [vp, i32, i32, vp, vp, i64, vp]
         L.mcb_rng_batch.argtypes = [vp, vp, i64, i32, vp]
         L.mcb_geometry_batch.argtypes = [vp, vp, vp, vp, i64, vp]
@@ -322,6 +323,17 @@ class Context:
         sites = np.ascontiguousarray(sites, dtype=np.float64).reshape(-1, 8)
         cells = np.ascontiguousarray(cells, dtype=np.int32)
         self._check(cuda_lib().mcb_set_source_bank(self._h, _ptr(sites), _ptr(cells), sites.shape[0]))
+
+    def run_cycle_host(self, sites_in: np.ndarray, cells_in: np.ndarray, sites_out: np.ndarray, cells_out: np.ndarray):
+        """One generation with the source bank in host arrays on both sides (pinned arrays make the copies
+        asynchronous); returns (CycleResult, new bank sites view, cells view)."""
+        r = CycleResult()
+        n_out = C.c_int64()
+        sites_in = np.ascontiguousarray(sites_in, dtype=np.float64).reshape(-1, 8)
+        cells_in = np.ascontiguousarray(cells_in, dtype=np.int32)
+        self._check(cuda_lib().mcb_run_cycle_host(self._h, _ptr(sites_in), _ptr(cells_in), sites_in.shape[0], _ptr(sites_out),
+                                                  _ptr(cells_out), sites_out.shape[0], C.byref(n_out), C.byref(r)))
+        return r, sites_out[:n_out.value], cells_out[:n_out.value]
 
     def history_k(self, n: int):
         kC = np.zeros(max(n, 1)); kTL = np.zeros(max(n, 1))

@@ -177,6 +177,15 @@ struct mcb_ctx {
     DevBuf<uint64_t> d_sort_rng;
     DevBuf<unsigned char> d_sort_temp;
     mcbk::SortScratch sort{};
+    // streamed host bank (mcb_run_cycle_host): the source bank arrives from pinned host memory in chunks while the
+    // histories that draw from the chunks already there are being walked
+    struct Streamed { const double* sites8; const int32_t* cells; uint64_t n; } const* streamed = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int N_CHUNK = 8;
+    cudaEvent_t ev_chunk[N_CHUNK] = {};
+    DevBuf<unsigned long long> d_chunk_lo;
+    DevBuf<uint32_t> d_chunk_pos;
+    uint32_t* h_chunk_pos = nullptr;  // pinned
     DevBuf<double> d_io_sites;       // staging for host-facing bank I/O (n x 8 doubles)
     DevBuf<int32_t> d_io_cells;
     uint64_t n_local_sites = 0;      // local bank of the last cycle
@@ -516,6 +525,9 @@ void mcb_destroy(mcb_ctx* ctx)
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     if (ctx->h_send) cudaFreeHost(ctx->h_send);
+    if (ctx->h_chunk_pos) cudaFreeHost(ctx->h_chunk_pos);
+    for (int i = 0; i < mcb_ctx::N_CHUNK; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_recv) cudaFreeHost(ctx->h_recv);
     for (int b = 0; b < 2; b++)
         for (int r = 0; r < ctx->world && r < MCB_MAX_WORLD; r++)
@@ -604,6 +616,87 @@ static double fx_to_double(unsigned long long lo, unsigned long long hi)
     return (double)(v / (long double)MCB_FX_SCALE);
 }
 
+static int ensure_sort_scratch(mcb_ctx* ctx)
+{
+    if (ctx->d_sort_key.p) return MCB_OK;
+    const size_t nbh = ctx->batch_hist;
+    CK(ctx->d_sort_key.alloc(2 * nbh)); CK(ctx->d_sort_val.alloc(2 * nbh)); CK(ctx->d_sort_rng.alloc(nbh));
+    CK(ctx->d_sort_temp.alloc(mcbk::sort_temp_bytes((uint32_t)nbh) + 256));
+    ctx->sort.key_in = ctx->d_sort_key.p; ctx->sort.key_out = ctx->d_sort_key.p + nbh;
+    ctx->sort.val_in = ctx->d_sort_val.p; ctx->sort.val_out = ctx->d_sort_val.p + nbh;
+    ctx->sort.rng_after = ctx->d_sort_rng.p; ctx->sort.temp = ctx->d_sort_temp.p; ctx->sort.temp_bytes = ctx->d_sort_temp.n;
+    return MCB_OK;
+}
+
+// One generation whose source bank is still on the host (mcb_run_cycle_host): the draws are made and sorted by site
+// index first; the bank then comes in over PCIe in N_CHUNK pieces on a copy stream, and as soon as piece c is there
+// the histories that drew from it are sourced and walked — the walk of piece c runs under the copy of piece c+1.
+static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_iterations)
+{
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    const DevProblem& P = ctx->P;
+    const uint64_t n = ctx->streamed->n;
+    constexpr int NC = mcb_ctx::N_CHUNK;
+    TallyAcc T;
+    T.acc = ctx->d_tally_acc.p; T.stride = ctx->batch_hist; T.first_hist = 0; T.on = tally_on && ctx->n_tallies > 0;
+    const uint64_t nps0 = ctx->icycle * ctx->n_sample + ctx->shard_begin;
+    Counters* C = ctx->d_counters.p;
+    Site* dst = ctx->d_local_bank[0].p;
+    SourceBankView V;
+    memset(&V, 0, sizeof(V));
+    V.flat = dst; V.dir_x = ctx->d_host_dirs.p; V.n = n;
+    { const int rc = ensure_sort_scratch(ctx); if (rc != MCB_OK) return rc; }
+    ctx->sort.rot = 0;
+    // the copies start right away ...
+    unsigned long long lo[NC + 1];
+    for (int c = 0; c <= NC; c++) lo[c] = n * (unsigned long long)c / NC;
+    for (int c = 0; c < NC; c++) {
+        const size_t cnt = (size_t)(lo[c + 1] - lo[c]);
+        if (cnt) {
+            CK(cudaMemcpyAsync(ctx->d_io_sites.p + 8 * lo[c], ctx->streamed->sites8 + 8 * lo[c], cnt * 8 * sizeof(double), cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(ctx->d_io_cells.p + lo[c], ctx->streamed->cells + lo[c], cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        }
+        CK(cudaEventRecord(ctx->ev_chunk[c], cs));
+    }
+    // ... while the draws are made, sorted, and cut where the site index crosses a chunk boundary
+    ctx->timer.begin(st, ST_SOURCE);
+    mcbk::pick_sort(st, P, 0, nb, nps0, n, &ctx->sort);
+    CK(cudaMemcpyAsync(ctx->d_chunk_lo.p, lo, (NC + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    mcbk::chunk_bounds(st, &ctx->sort, nb, ctx->d_chunk_lo.p, NC + 1, ctx->d_chunk_pos.p);
+    ctx->timer.end(st);
+    CK(cudaMemcpyAsync(ctx->h_chunk_pos, ctx->d_chunk_pos.p, (NC + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int max_nuc = ctx->mat_n_nuc.empty() ? 0 : *std::max_element(ctx->mat_n_nuc.begin(), ctx->mat_n_nuc.end());
+    (void)max_nuc;
+    for (int c = 0; c < NC; c++) {
+        const uint32_t q0 = ctx->h_chunk_pos[c], q1 = c + 1 < NC ? ctx->h_chunk_pos[c + 1] : nb;
+        const size_t cnt = (size_t)(lo[c + 1] - lo[c]);
+        CK(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+        ctx->timer.begin(st, ST_SOURCE);
+        if (cnt) mcbk::pack_sites(st, ctx->d_io_sites.p + 8 * lo[c], ctx->d_io_cells.p + lo[c], cnt, dst + lo[c], ctx->d_host_dirs.p + 3 * lo[c]);
+        mcbk::source_sorted_range(st, P, ctx->B, ctx->q_active, 0, q0, q1 - q0, nps0, V, C, &ctx->sort);
+        ctx->timer.end(st);
+        if (q1 > q0) {
+            CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
+            ctx->timer.begin(st, ST_STEP);
+            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->n_slots, ctx->k);
+            ctx->timer.end(st);
+            (*n_iterations)++;
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const Counters& hc = *ctx->h_counters;
+    if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
+    if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
+    if (T.on) {
+        ctx->timer.begin(st, ST_CLOSEOUT);
+        mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
+        ctx->timer.end(st);
+    }
+    return MCB_OK;
+}
+
 // the event loop over one batch of histories [h0, h0+nb) of the shard
 static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on, int* n_iterations)
 {
@@ -619,14 +712,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     ctx->timer.begin(st, ST_SOURCE);
     const mcbk::SortScratch* sort = nullptr;
     if (V.n && (!V.flat || getenv("MCB_FORCE_SORT"))) {  // bank spread over the ranks: read it in ascending order
-        if (!ctx->d_sort_key.p) {
-            const size_t nbh = ctx->batch_hist;
-            CK(ctx->d_sort_key.alloc(2 * nbh)); CK(ctx->d_sort_val.alloc(2 * nbh)); CK(ctx->d_sort_rng.alloc(nbh));
-            CK(ctx->d_sort_temp.alloc(mcbk::sort_temp_bytes((uint32_t)nbh) + 256));
-            ctx->sort.key_in = ctx->d_sort_key.p; ctx->sort.key_out = ctx->d_sort_key.p + nbh;
-            ctx->sort.val_in = ctx->d_sort_val.p; ctx->sort.val_out = ctx->d_sort_val.p + nbh;
-            ctx->sort.rng_after = ctx->d_sort_rng.p; ctx->sort.temp = ctx->d_sort_temp.p; ctx->sort.temp_bytes = ctx->d_sort_temp.n;
-        }
+        { const int rc = ensure_sort_scratch(ctx); if (rc != MCB_OK) return rc; }
         ctx->sort.rot = V.flat ? 0 : V.prefix[std::min(ctx->rank, V.n_seg - 1)];
         sort = &ctx->sort;
     }
@@ -745,7 +831,7 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     cudaStream_t st = ctx->stream;
     const bool tally_on = ctx->icycle >= ctx->n_passive;  // handler.cpp:15
     const uint64_t launches0 = mcbk::launch_count();
-    if (ctx->source_is_bank && ctx->view.n == 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
+    if (ctx->source_is_bank && ctx->view.n == 0 && !ctx->streamed) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
     if (ctx->world > 1 && !ctx->comm) return ctx->fail(MCB_ERR_COMM, "world > 1 but mcb_comm_init was not called");
     Counters* C = ctx->d_counters.p;
     CK(cudaEventRecord(ctx->ev0, st));
@@ -754,6 +840,10 @@ int mcb_run_cycle(mcb_ctx* ctx, mcb_cycle_result* out)
     CK(cudaMemsetAsync(ctx->d_hist_k.p, 0, 2 * nh * sizeof(double), st));
     CK(cudaMemsetAsync(ctx->d_nsite.p, 0, nh * sizeof(int32_t), st));
     int iterations = 0;
+    if (ctx->streamed) {
+        const int rc = transport_streamed(ctx, (uint32_t)ctx->shard_count, tally_on, &iterations);
+        if (rc != MCB_OK) return rc;
+    } else
     for (uint64_t h0 = 0; h0 < ctx->shard_count; h0 += ctx->batch_hist) {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(ctx->batch_hist, ctx->shard_count - h0);
         const int rc = transport_batch(ctx, (uint32_t)h0, nb, tally_on, &iterations);
@@ -1027,6 +1117,63 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
     memset(&ctx->view, 0, sizeof(ctx->view));
     ctx->view.flat = dst; ctx->view.dir_x = n ? ctx->d_host_dirs.p : nullptr; ctx->view.n = (uint64_t)n;
     ctx->source_is_bank = true;
+    return MCB_OK;
+}
+
+int mcb_run_cycle_host(mcb_ctx* ctx, const double* in_sites8, const int32_t* in_cells, int64_t n_in, double* out_sites8,
+                       int32_t* out_cells, int64_t max_out, int64_t* n_out, mcb_cycle_result* out)
+{
+    if (!ctx || n_in < 0 || !n_out) return MCB_ERR_ARG;
+    if (!ctx->ksearch) return ctx->fail(MCB_ERR_ARG, "mcb_run_cycle_host: not a k-eigenvalue problem");
+    if (n_in == 0) return ctx->fail(MCB_ERR_ARG, "[ERROR] Source bank is empty...");
+    CK(cudaSetDevice(ctx->device));
+    // the pipelined form needs one rank, one particle per history, one batch, the walk kernel; otherwise the three
+    // plain calls do the same thing one after the other
+    const bool pipelined = ctx->world == 1 && !ctx->P.shared_histories && ctx->walk_mode && ctx->shard_count <= ctx->batch_hist &&
+                           (uint64_t)n_in <= ctx->site_cap && !getenv("MCB_NO_STREAM");
+    if (!pipelined) {
+        int rc = mcb_set_source_bank(ctx, in_sites8, in_cells, n_in);
+        if (rc == MCB_OK) rc = mcb_run_cycle(ctx, out);
+        if (rc != MCB_OK) return rc;
+        const int64_t got = mcb_get_source_bank(ctx, out_sites8, out_cells, max_out);
+        if (got < 0) return (int)got;
+        *n_out = got;
+        return MCB_OK;
+    }
+    constexpr int NC = mcb_ctx::N_CHUNK;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int c = 0; c < NC; c++) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
+        CK(ctx->d_chunk_lo.alloc(NC + 1)); CK(ctx->d_chunk_pos.alloc(NC + 1));
+        CK(cudaMallocHost((void**)&ctx->h_chunk_pos, (NC + 1) * sizeof(uint32_t)));
+    }
+    const size_t need = (size_t)std::max<int64_t>(n_in, 1);
+    if (ctx->d_io_sites.n < need * 8) { const size_t cap = need + need / 4 + 1024; CK(ctx->d_io_sites.alloc(cap * 8)); CK(ctx->d_io_cells.alloc(cap)); }
+    if (ctx->d_host_dirs.n < need * 3) CK(ctx->d_host_dirs.alloc((need + need / 4 + 1024) * 3));
+    // everything queued on the launch stream so far must be done before the copy stream overwrites the staging buffers
+    CK(cudaStreamSynchronize(ctx->stream));
+    mcb_ctx::Streamed sd{in_sites8, in_cells, (uint64_t)n_in};
+    ctx->streamed = &sd;
+    const int rc = mcb_run_cycle(ctx, out);
+    ctx->streamed = nullptr;
+    if (rc != MCB_OK) return rc;
+    // the new bank goes back in pieces as well: piece c is unpacked while piece c-1 is on the wire
+    const int64_t n = std::min<int64_t>((int64_t)ctx->view.n, max_out);
+    if (ctx->d_io_sites.n < (size_t)std::max<int64_t>(n, 1) * 8) {
+        const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        CK(ctx->d_io_sites.alloc(cap * 8)); CK(ctx->d_io_cells.alloc(cap));
+    }
+    for (int c = 0; c < NC; c++) {
+        const uint64_t a = (uint64_t)n * c / NC, b = (uint64_t)n * (c + 1) / NC;
+        if (b == a) continue;
+        mcbk::unpack_sites(ctx->stream, ctx->view.flat + a, nullptr, b - a, ctx->d_io_sites.p + 8 * a, ctx->d_io_cells.p + a);
+        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+        if (out_sites8) CK(cudaMemcpyAsync(out_sites8 + 8 * a, ctx->d_io_sites.p + 8 * a, (b - a) * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_cells) CK(cudaMemcpyAsync(out_cells + a, ctx->d_io_cells.p + a, (b - a) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    *n_out = n;
     return MCB_OK;
 }
 

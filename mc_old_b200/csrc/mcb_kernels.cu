@@ -565,15 +565,17 @@ k_pick(uint64_t seed0, uint64_t nps0, int32_t first_hist, uint32_t count, unsign
 __global__ void __launch_bounds__(BLOCK)
 k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint32_t count, uint64_t nps0,
          const SourceBankView V, Counters* C, const unsigned long long* __restrict__ sorted_key,
-         const uint32_t* __restrict__ sorted_val, const uint64_t* __restrict__ rng_after, unsigned long long rot)
+         const uint32_t* __restrict__ sorted_val, const uint64_t* __restrict__ rng_after, unsigned long long rot, uint32_t q0)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    // q0 > 0: one chunk [q0, q0 + count) of a sorted sweep that is launched piece by piece (streamed host bank)
+    const uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x;
+    count += q0;
     if (q == 0) {  // queue state of the batch: `count` primaries in queue 0, slots behind them are free
         C->n_active[0] = count; C->n_active[1] = 0; C->n_active[2] = 0; C->q_collide = 0; C->q_cross = 0; C->slot_cursor = count;
     }
     __shared__ uint64_t s_base;  // stream of the block's first history; the others are a short skip away
     if (!sorted_key) {
-        if (threadIdx.x == 0) s_base = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)(first_hist + (int32_t)(blockIdx.x * blockDim.x)));
+        if (threadIdx.x == 0) s_base = mcb_rn_history_seed(P.seed0, nps0 + (uint64_t)(first_hist + (int32_t)(q0 + blockIdx.x * blockDim.x)));
         __syncthreads();
     }
     if (q >= count) return;
@@ -1278,11 +1280,45 @@ void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* activ
         size_t tb = sort->temp_bytes;
         cub::DeviceRadixSort::SortPairs(sort->temp, tb, sort->key_in, sort->key_out, sort->val_in, sort->val_out, (int)count, 0, bits, st);
         k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, sort->key_out,
-                                                                          sort->val_out, sort->rng_after, sort->rot);
+                                                                          sort->val_out, sort->rng_after, sort->rot, 0u);
         MCB_LAUNCHED(2 + (bits + 7) / 8 + 2);  // pick, source, the sort's histogram / onesweep passes
         return;
     }
-    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, nullptr, nullptr, nullptr, 0ull);
+    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, nullptr, nullptr, nullptr, 0ull, 0u);
+    MCB_LAUNCHED(1);
+}
+// the two halves of the sorted path on their own, for a bank that arrives from the host in chunks: draws + sort
+// first, then one k_source launch per chunk of the sweep
+void pick_sort(cudaStream_t st, const DevProblem& P, int32_t first_hist, uint32_t count, uint64_t nps0, uint64_t n_bank,
+               const SortScratch* sort)
+{
+    k_pick<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P.seed0, nps0, first_hist, count, n_bank, sort->rot, sort->key_in, sort->val_in, sort->rng_after);
+    int bits = 1;
+    while (bits < 64 && (n_bank >> bits)) bits++;
+    size_t tb = sort->temp_bytes;
+    cub::DeviceRadixSort::SortPairs(sort->temp, tb, sort->key_in, sort->key_out, sort->val_in, sort->val_out, (int)count, 0, bits, st);
+    MCB_LAUNCHED(1 + (bits + 7) / 8 + 2);
+}
+__global__ void k_chunk_bounds(const unsigned long long* __restrict__ sorted_key, uint32_t n, const unsigned long long* __restrict__ lo,
+                               int n_lo, uint32_t* pos)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_lo) return;
+    uint32_t a = 0, b = n;  // first position whose key is >= lo[c]
+    while (a < b) { const uint32_t m = (a + b) >> 1; if (sorted_key[m] < lo[c]) a = m + 1; else b = m; }
+    pos[c] = a;
+}
+void chunk_bounds(cudaStream_t st, const SortScratch* sort, uint32_t n, const unsigned long long* lo, int n_lo, uint32_t* pos)
+{
+    k_chunk_bounds<<<1, 64, 0, st>>>(sort->key_out, n, lo, n_lo, pos);
+    MCB_LAUNCHED(1);
+}
+void source_sorted_range(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t q0,
+                         uint32_t count, uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort)
+{
+    if (!count) return;
+    k_source<<<blocks_for(count, BLOCK), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, sort->key_out, sort->val_out,
+                                                         sort->rng_after, sort->rot, q0);
     MCB_LAUNCHED(1);
 }
 size_t sort_temp_bytes(uint32_t n)

@@ -21,6 +21,13 @@ struct SortScratch {
     unsigned long long rot;  // global index at which this rank's sweep over the bank starts
 };
 size_t sort_temp_bytes(uint32_t n);
+// the sorted path in pieces (bank streamed in from the host): draws + sort; positions in the sorted draws at which
+// the site index reaches lo[c]; k_source for positions [q0, q0 + count) of the sweep
+void pick_sort(cudaStream_t st, const DevProblem& P, int32_t first_hist, uint32_t count, uint64_t nps0, uint64_t n_bank,
+               const SortScratch* sort);
+void chunk_bounds(cudaStream_t st, const SortScratch* sort, uint32_t n, const unsigned long long* lo, int n_lo, uint32_t* pos);
+void source_sorted_range(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t q0,
+                         uint32_t count, uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort);
 // sort != nullptr: the draws are sorted by site index first and the bank is read in ascending order
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
             uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort);

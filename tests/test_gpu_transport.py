@@ -323,6 +323,29 @@ def test_source_bank_host_round_trip():
     a.close(); b.close()
 
 
+def test_host_bank_cycle_equals_the_three_plain_calls():
+    """mcb_run_cycle_host (bank in host buffers on both sides, upload pipelined with the walk through sorted draws) is
+    bit-identical to mcb_set_source_bank + mcb_run_cycle + mcb_get_source_bank"""
+    n = 50000
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=2, passive=1, entropy=True))
+    a = mcb.Context(deck, device=0); b = mcb.Context(deck, device=0)
+    ra = a.run_cycle(); rb = b.run_cycle()
+    sites, cells = a.source_bank(int(ra.n_sites))
+    for _ in range(2):
+        a.set_source_bank(sites, cells)
+        ra = a.run_cycle()
+        sa, ca = a.source_bank(int(ra.n_sites))
+        out_s = np.zeros((4 * n, 8)); out_c = np.zeros(4 * n, dtype=np.int32)
+        rb, sb, cb = b.run_cycle_host(sites, cells, out_s, out_c)
+        assert (ra.k_sum_C, ra.k_sum_TL, ra.k_sq_C, ra.H, ra.n_sites, ra.n_tracks, ra.n_collisions) == \
+               (rb.k_sum_C, rb.k_sum_TL, rb.k_sq_C, rb.H, rb.n_sites, rb.n_tracks, rb.n_collisions)
+        assert np.array_equal(sa, sb) and np.array_equal(ca, cb)
+        sites, cells = sa.copy(), ca.copy()
+    with pytest.raises(RuntimeError, match="Source bank is empty"):
+        b.run_cycle_host(np.zeros((0, 8)), np.zeros(0, dtype=np.int32), out_s, out_c)
+    a.close(); b.close()
+
+
 def test_capacity_and_lost_particle_errors():
     """a fission bank that overflows is an error, not a truncation; a particle that leaves every cell is the
     reference's "[WARNING] A particle is lost" (general.cpp:31-33) as a status code"""
