@@ -20,9 +20,19 @@
 #include "mcb_kernels.h"
 #include "mcb_tables.h"
 
+#include <chrono>
 namespace {
 
 thread_local std::string g_create_error;
+// MCB_TRACE_HOST=1: wall-clock marks of the host-bank cycle on stderr
+inline void trace_mark(const char* what)
+{
+    static const bool on = getenv("MCB_TRACE_HOST") != nullptr;
+    if (!on) return;
+    static auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[mcb trace] %10.3f ms  %s\n", ms, what);
+}
 
 // ---- NCCL is bound at run time so that a process that already holds a libnccl (e.g. torch's) shares it ----
 struct Nccl {
@@ -666,6 +676,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
     ctx->timer.end(st);
     CK(cudaMemcpyAsync(ctx->h_chunk_pos, ctx->d_chunk_pos.p, (NC + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    trace_mark("draws sorted, chunk bounds known");
     const int max_nuc = ctx->mat_n_nuc.empty() ? 0 : *std::max_element(ctx->mat_n_nuc.begin(), ctx->mat_n_nuc.end());
     (void)max_nuc;
     for (int c = 0; c < NC; c++) {
@@ -686,6 +697,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
     }
     CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    trace_mark("all chunks uploaded, sourced and walked");
     const Counters& hc = *ctx->h_counters;
     if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
     if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
@@ -1154,9 +1166,11 @@ int mcb_run_cycle_host(mcb_ctx* ctx, const double* in_sites8, const int32_t* in_
     CK(cudaStreamSynchronize(ctx->stream));
     mcb_ctx::Streamed sd{in_sites8, in_cells, (uint64_t)n_in};
     ctx->streamed = &sd;
+    trace_mark("host-bank cycle begins");
     const int rc = mcb_run_cycle(ctx, out);
     ctx->streamed = nullptr;
     if (rc != MCB_OK) return rc;
+    trace_mark("generation closed out");
     // the new bank goes back in pieces as well: piece c is unpacked while piece c-1 is on the wire
     const int64_t n = std::min<int64_t>((int64_t)ctx->view.n, max_out);
     if (ctx->d_io_sites.n < (size_t)std::max<int64_t>(n, 1) * 8) {
@@ -1173,6 +1187,7 @@ int mcb_run_cycle_host(mcb_ctx* ctx, const double* in_sites8, const int32_t* in_
         if (out_cells) CK(cudaMemcpyAsync(out_cells + a, ctx->d_io_cells.p + a, (b - a) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    trace_mark("new bank in host memory");
     *n_out = n;
     return MCB_OK;
 }
