@@ -327,11 +327,11 @@ def test_host_bank_cycle_equals_the_three_plain_calls():
     """mcb_run_cycle_host (bank in host buffers on both sides, upload pipelined with the walk through sorted draws) is
     bit-identical to mcb_set_source_bank + mcb_run_cycle + mcb_get_source_bank"""
     n = 50000
-    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=2, passive=1, entropy=True))
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=n, active=2, passive=1, entropy=True, estimators=True))
     a = mcb.Context(deck, device=0); b = mcb.Context(deck, device=0)
     ra = a.run_cycle(); rb = b.run_cycle()
     sites, cells = a.source_bank(int(ra.n_sites))
-    for _ in range(2):
+    for _ in range(2):  # the two active cycles: tallies are scored on both paths
         a.set_source_bank(sites, cells)
         ra = a.run_cycle()
         sa, ca = a.source_bank(int(ra.n_sites))
@@ -341,6 +341,8 @@ def test_host_bank_cycle_equals_the_three_plain_calls():
                (rb.k_sum_C, rb.k_sum_TL, rb.k_sq_C, rb.H, rb.n_sites, rb.n_tracks, rb.n_collisions)
         assert np.array_equal(sa, sb) and np.array_equal(ca, cb)
         sites, cells = sa.copy(), ca.copy()
+    ta, tb = a.tallies(), b.tallies()
+    assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1]) and np.count_nonzero(ta[0]) > 20
     with pytest.raises(RuntimeError, match="Source bank is empty"):
         b.run_cycle_host(np.zeros((0, 8)), np.zeros(0, dtype=np.int32), out_s, out_c)
     a.close(); b.close()
