@@ -25,7 +25,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef MCB_BLOCK
-#define MCB_BLOCK 128  // measured (tools/sweep.sh): 128 x 5 blocks per SM beats 256 x 2, 192 x 3 and 96 x 7 for the walk kernel
+#define MCB_BLOCK 128  // measured (tools/sweep.sh): 128 x 6 blocks per SM (85 registers) beats 128 x 5, 128 x 7, 256 x 2, 192 x 3 and 96 x 7 for the walk kernel
 #endif
 constexpr int BLOCK = MCB_BLOCK;
 constexpr int WARPS = BLOCK / 32;
@@ -797,7 +797,7 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
 }
 
 #ifndef MCB_STEP_MINB
-#define MCB_STEP_MINB 5
+#define MCB_STEP_MINB 6
 #endif
 
 // history walk: the whole event chain of a particle in registers, one launch per pass over bank slots
