@@ -29,9 +29,10 @@ IGNORE_TRMM = 1
 
 def default_xs_dir() -> str:
     """Directory holding <ZAID>.txt.  The reference reads ./xs_library relative to the CWD
-    (setup.cpp:326); MCB_XS_LIBRARY overrides; oracle/_ref/xs_library is where build() puts the data files."""
+    (setup.cpp:326); MCB_XS_LIBRARY overrides; data/xs_library is where build() puts a copy of the reference's
+    cross-section text files (data, git-ignored) when the reference tree is present."""
     for cand in (os.environ.get("MCB_XS_LIBRARY"), os.path.join(os.getcwd(), "xs_library"),
-                 os.path.join(REPO_ROOT, "oracle", "_ref", "xs_library")):
+                 os.path.join(REPO_ROOT, "data", "xs_library")):
         if cand and os.path.isdir(cand):
             return cand
     raise FileNotFoundError("xs_library not found (set MCB_XS_LIBRARY)")
