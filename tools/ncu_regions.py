@@ -25,7 +25,7 @@ def function_map(path):
             out[i] = cur
             continue
         m = DEF.match(re.sub(r'__launch_bounds__\([^)]*\)', '', pending + text))
-        if m is None and (pending + text).startswith("__global__"):
+        if m is None and "__global__" in (pending + text) and "(" not in re.sub(r'__launch_bounds__\([^)]*\)', '', pending + text):
             pending = pending + text + " "
             out[i] = cur
             continue
