@@ -268,6 +268,11 @@ int mcb_scatter_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, int64_
 /* DistributionWatt::sample (Distribution.cpp:34-73) for nuclide at incident E with the stream of nps[i] */
 int mcb_watt_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, const double* E, int64_t n, double* Eout);
 
+/* The kernels divide through a reciprocal shared between quotients of one denominator (interpolation weights, vector
+ * normalisations; csrc/mcb_physics.h): out_shared[i] = that form of a[i] / b[i], out_plain[i] = the compiler's IEEE
+ * division.  Cross sections are bit-exact against the reference's x86 divisions only if the two agree bit for bit. */
+int mcb_division_batch(mcb_ctx* ctx, const double* a, const double* b, int64_t n, double* out_shared, double* out_plain);
+
 /* history sharding rule shared by every rank: first history and count owned by `rank` */
 void mcb_shard_range(uint64_t n, int32_t rank, int32_t world, uint64_t* begin, uint64_t* count);
 

@@ -142,6 +142,7 @@ def cuda_lib():
         L.mcb_search_cell_batch.argtypes = [vp, vp, i64, vp]
         L.mcb_scatter_batch.argtypes = [vp, i32, vp, i64, vp]
         L.mcb_watt_batch.argtypes = [vp, i32, vp, vp, i64, vp]
+        L.mcb_division_batch.argtypes = [vp, vp, vp, i64, vp, vp]
         L.mcb_shard_range.argtypes = [u64, i32, i32, C.POINTER(u64), C.POINTER(u64)]
         L.mcb_shard_range.restype = None
         _cuda = L
@@ -397,6 +398,14 @@ class Context:
         out = np.empty(E.size)
         self._check(cuda_lib().mcb_watt_batch(self._h, nuclide, _ptr(nps), _ptr(E), E.size, _ptr(out)))
         return out
+
+
+    def division(self, a: np.ndarray, b: np.ndarray):
+        """a / b through the kernels' shared-reciprocal form and as the plain IEEE division (mcb_division_batch)"""
+        a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        o1, o2 = np.empty(a.size), np.empty(a.size)
+        self._check(cuda_lib().mcb_division_batch(self._h, _ptr(a), _ptr(b), a.size, _ptr(o1), _ptr(o2)))
+        return o1, o2
 
 
 def shard_range(n: int, rank: int, world: int):

@@ -165,6 +165,14 @@ struct mcb_ctx {
     cudaEvent_t ev_ring[MCB_RING] = {};
     uint64_t finish_below = 0;       // queue length under which the tail kernel takes over
     bool split_stages = false;       // event-queue mode: one kernel per event type (cross-check / profiling) instead of the walk kernel
+    mcbk::WalkPlan plan{};           // launch shape of the walk kernel on this device
+    int n_sm = 148;
+    DevBuf<StackRec> d_stack;        // per-context LIFO stacks of same-history secondaries (the reference's Pbank)
+    int stack_depth = 0;
+    DevBuf<uint32_t> d_tab_key;      // per-context tally tables of the walk kernel
+    DevBuf<double> d_tab_val;
+    DevBuf<uint16_t> d_tab_list;
+    uint32_t tab_size = 0;
     bool walk_mode = true;           // history walk (one launch per pass over the bank) instead of the event-queue loop
     // per-history accumulators
     DevBuf<double> d_hist_k;         // kC, kTL
@@ -314,6 +322,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         DevNuclide& D = nuc[n];
         D.rows = ctx->d_xs_rows.p + (size_t)N.row_begin * MCB_XS_ROW;
         D.n_rows = N.n_rows; D.has_delayed = N.has_delayed; D.A = N.A;
+        D.fg_beta = std::sqrt(2.0659834e-11 * N.A);  // Reaction.cpp:33; IEEE sqrt, the same number on the host and on the device
         memcpy(D.watt_a, N.watt_a, sizeof(D.watt_a)); memcpy(D.watt_b, N.watt_b, sizeof(D.watt_b)); memcpy(D.watt_g, N.watt_g, sizeof(D.watt_g));
         memcpy(D.lambda, N.lambda, sizeof(D.lambda)); memcpy(D.fraction, N.fraction, sizeof(D.fraction));
         D.chid_E = ctx->d_delayed.p ? ctx->d_delayed.p + N.chid_E_begin : nullptr;
@@ -413,47 +422,58 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     // ---- shard and banks ----
     mcb_shard_range(p->n_sample, ctx->rank, ctx->world, &ctx->shard_begin, &ctx->shard_count);
     if (ctx->shard_count >= (1ull << 31)) return ctx->fail(MCB_ERR_ARG, "more than 2^31 histories per GPU per generation");
-    // secondaries (same-history fission neutrons, splitting) need free slots behind the primaries of a batch
-    // (the walk kernel reuses the slots behind the running pass, so this bounds two consecutive passes, not a history)
-    const uint64_t per_hist = P.shared_histories ? 6 : 1;
+    ctx->split_stages = (cfg && (cfg->reserved & 2)) || (getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "split"));
+    ctx->walk_mode = !ctx->split_stages;
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ctx->device));
+        ctx->n_sm = prop.multiProcessorCount;
+    }
+    const bool split = ctx->split_stages;
+    // event-queue mode: secondaries (same-history fission neutrons, split copies) need free slots behind the primaries
+    // of a batch; the walk kernel keeps them on per-history stacks and needs one slot per source particle
+    const uint64_t per_hist = (split && P.shared_histories) ? 6 : 1;
     uint64_t cap = cfg && cfg->bank_capacity > 0 ? (uint64_t)cfg->bank_capacity : (1ull << 26);
     cap = std::min<uint64_t>(cap, (1ull << 31) - 1);
     uint64_t batch = std::max<uint64_t>(1, std::min<uint64_t>(ctx->shard_count, cap / per_hist));
-    if (p->n_tallies > 0) {
-        // dense per-history tally accumulators of a batch: keep them under ~8 GiB
+    if (split && p->n_tallies > 0) {
+        // event-queue mode: dense per-history tally accumulators of a batch, kept under ~8 GiB
         const uint64_t lim = std::max<uint64_t>(1024, (8ull << 30) / (8ull * (uint64_t)p->n_tallies));
         batch = std::min(batch, lim);
     }
     ctx->batch_hist = (uint32_t)batch;
     ctx->n_slots = (uint32_t)std::min<uint64_t>(batch * per_hist + 1024, (1ull << 31) - 1);
     const size_t ns = ctx->n_slots;
-    CK(ctx->d_bank_f64.alloc(15 * ns));
+    CK(ctx->d_bank_f64.alloc((split ? 15 : 10) * ns));
     CK(ctx->d_bank_rng.alloc(ns));
-    CK(ctx->d_bank_i32.alloc(4 * ns));
+    CK(ctx->d_bank_i32.alloc((split ? 4 : 2) * ns));
     {
         double* f = ctx->d_bank_f64.p;
         Bank& B = ctx->B;
         B.x = f; B.y = f + ns; B.z = f + 2 * ns; B.u = f + 3 * ns; B.v = f + 4 * ns; B.w = f + 5 * ns; B.E = f + 6 * ns;
         B.speed = f + 7 * ns; B.wgt = f + 8 * ns; B.t = f + 9 * ns;
-        B.St = f + 10 * ns; B.Ss = f + 11 * ns; B.Sc = f + 12 * ns; B.Sf = f + 13 * ns; B.nSf = f + 14 * ns;
+        B.St = B.Ss = B.Sc = B.Sf = B.nSf = nullptr;
+        if (split) { B.St = f + 10 * ns; B.Ss = f + 11 * ns; B.Sc = f + 12 * ns; B.Sf = f + 13 * ns; B.nSf = f + 14 * ns; }
         B.rng = ctx->d_bank_rng.p;
         int32_t* i = ctx->d_bank_i32.p;
-        B.cell = i; B.hist = i + ns; B.uidx = i + 2 * ns; B.surf = i + 3 * ns;
+        B.cell = i; B.hist = i + ns;
+        B.uidx = B.surf = nullptr;
+        if (split) { B.uidx = i + 2 * ns; B.surf = i + 3 * ns; }
         B.Eold = nullptr;
-        if (track_old) { CK(ctx->d_bank_eold.alloc(ns)); B.Eold = ctx->d_bank_eold.p; }
         B.told = nullptr;
-        if (track_time) { CK(ctx->d_bank_told.alloc(ns)); CK(cudaMemset(ctx->d_bank_told.p, 0, ns * sizeof(double))); B.told = ctx->d_bank_told.p; }
+        if (split && track_old) { CK(ctx->d_bank_eold.alloc(ns)); B.Eold = ctx->d_bank_eold.p; }
+        if (split && track_time) { CK(ctx->d_bank_told.alloc(ns)); CK(cudaMemset(ctx->d_bank_told.p, 0, ns * sizeof(double))); B.told = ctx->d_bank_told.p; }
     }
-    CK(ctx->d_queue.alloc(3 * ns));
-    ctx->q_active = ctx->d_queue.p; ctx->q_next = ctx->d_queue.p + ns; ctx->q_ev = ctx->d_queue.p + 2 * ns;
+    if (split) {
+        CK(ctx->d_queue.alloc(3 * ns));
+        ctx->q_active = ctx->d_queue.p; ctx->q_next = ctx->d_queue.p + ns; ctx->q_ev = ctx->d_queue.p + 2 * ns;
+    }
     CK(ctx->d_counters.alloc(1));
     CK(cudaMemset(ctx->d_counters.p, 0, sizeof(Counters)));
     CK(cudaMallocHost((void**)&ctx->h_counters, sizeof(Counters)));
     CK(cudaMallocHost((void**)&ctx->h_ring, MCB_RING * sizeof(unsigned long long)));
     for (int i = 0; i < MCB_RING; i++) CK(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
-    ctx->finish_below = getenv("MCB_FINISH_BELOW") ? strtoull(getenv("MCB_FINISH_BELOW"), nullptr, 10) : 148ull * 256ull;
-    ctx->split_stages = (cfg && (cfg->reserved & 2)) || (getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "split"));
-    ctx->walk_mode = !ctx->split_stages;
+    ctx->finish_below = getenv("MCB_FINISH_BELOW") ? strtoull(getenv("MCB_FINISH_BELOW"), nullptr, 10) : (uint64_t)ctx->n_sm * 256ull;
     const size_t nh = std::max<uint64_t>(ctx->shard_count, 1);
     CK(ctx->d_hist_k.alloc(2 * nh));
     CK(ctx->d_nsite.alloc(nh));
@@ -472,10 +492,34 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
             ctx->global_cap = cfg && cfg->site_capacity > 0 ? (uint64_t)cfg->site_capacity * ctx->world : 4 * p->n_sample + 4096ull * ctx->world;
         }
     }
+    if (!split) {
+        // walk kernel: launch shape on this device, per-context secondary stacks and tally tables
+        int det_nn = 1;
+        for (int m = 0; m < p->n_materials; m++) det_nn = std::max(det_nn, tabs[m].n_nuc);
+        const int rc = mcbk::walk_plan(P.shared_histories != 0, det_nn, p->n_tallies, ctx->n_sm, &ctx->plan);
+        if (rc != 0) return ctx->fail(MCB_ERR_CUDA, "walk kernel does not fit this device: %s", cudaGetErrorString((cudaError_t)rc));
+        const size_t n_ctx = (size_t)ctx->plan.n_contexts;
+        if (P.shared_histories) {
+            ctx->stack_depth = getenv("MCB_STACK_DEPTH") ? std::max(1, atoi(getenv("MCB_STACK_DEPTH"))) : 64;
+            CK(ctx->d_stack.alloc(n_ctx * (size_t)ctx->stack_depth));
+        }
+        if (p->n_tallies > 0) {
+            // table of a history: a power of two >= the number of tallies when that fits (then every tally has its own
+            // entry), at most 8192 entries and ~24 GiB in all
+            uint32_t size = 2;
+            while (size < (uint32_t)std::min<int64_t>(p->n_tallies, 8192)) size <<= 1;
+            while (size > 256 && n_ctx * (size_t)size * 14 > (24ull << 30)) size >>= 1;
+            ctx->tab_size = size;
+            CK(ctx->d_tab_key.alloc(n_ctx * size)); CK(ctx->d_tab_val.alloc(n_ctx * size)); CK(ctx->d_tab_list.alloc(n_ctx * size));
+            CK(cudaMemset(ctx->d_tab_key.p, 0, n_ctx * size * sizeof(uint32_t)));
+        }
+    }
     if (p->n_tallies > 0) {
-        CK(ctx->d_tally_acc.alloc((size_t)p->n_tallies * batch));
-        CK(cudaMemset(ctx->d_tally_acc.p, 0, (size_t)p->n_tallies * batch * sizeof(double)));
-        CK(ctx->d_tally_partial.alloc((size_t)p->n_tallies * mcbk::tally_chunks((uint32_t)batch) * 2));
+        if (split) {
+            CK(ctx->d_tally_acc.alloc((size_t)p->n_tallies * batch));
+            CK(cudaMemset(ctx->d_tally_acc.p, 0, (size_t)p->n_tallies * batch * sizeof(double)));
+            CK(ctx->d_tally_partial.alloc((size_t)p->n_tallies * mcbk::tally_chunks((uint32_t)batch) * 2));
+        }
         CK(ctx->d_tally_sum.alloc(p->n_tallies));
         CK(ctx->d_tally_sq.alloc(p->n_tallies));
         CK(cudaMemset(ctx->d_tally_sum.p, 0, p->n_tallies * sizeof(double)));
@@ -626,6 +670,32 @@ static double fx_to_double(unsigned long long lo, unsigned long long hi)
     return (double)(v / (long double)MCB_FX_SCALE);
 }
 
+static TallyAcc tally_acc(mcb_ctx* ctx, uint32_t h0, bool tally_on)
+{
+    TallyAcc T;
+    memset(&T, 0, sizeof(T));
+    T.acc = ctx->d_tally_acc.p;  // event-queue mode only (nullptr selects the per-history tables of the walk kernel)
+    T.stride = ctx->batch_hist; T.first_hist = (int32_t)h0; T.on = tally_on && ctx->n_tallies > 0;
+    T.tab_key = ctx->d_tab_key.p; T.tab_val = ctx->d_tab_val.p; T.tab_list = ctx->d_tab_list.p;
+    T.tab_mask = ctx->tab_size ? ctx->tab_size - 1 : 0; T.n_tallies = (int32_t)ctx->n_tallies;
+    T.sum = ctx->d_tally_sum.p; T.squared = ctx->d_tally_sq.p;
+    return T;
+}
+
+// launch errors of the stage kernels (an invalid configuration would otherwise pass silently) and the device-side
+// error flags, read once per batch from the counters
+static int check_batch(mcb_ctx* ctx, const Counters& hc)
+{
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return ctx->fail(MCB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(le));
+    if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
+    if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
+    if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
+    if (hc.overflow_stack) return ctx->fail(MCB_ERR_CAPACITY, "secondary stack overflow: a history had more than %d particles waiting (raise MCB_STACK_DEPTH)", ctx->stack_depth);
+    if (hc.overflow_tally) return ctx->fail(MCB_ERR_CAPACITY, "tally table overflow: a history touched more than %u tally bins", ctx->tab_size);
+    return MCB_OK;
+}
+
 static int ensure_sort_scratch(mcb_ctx* ctx)
 {
     if (ctx->d_sort_key.p) return MCB_OK;
@@ -647,8 +717,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
     const DevProblem& P = ctx->P;
     const uint64_t n = ctx->streamed->n;
     constexpr int NC = mcb_ctx::N_CHUNK;
-    TallyAcc T;
-    T.acc = ctx->d_tally_acc.p; T.stride = ctx->batch_hist; T.first_hist = 0; T.on = tally_on && ctx->n_tallies > 0;
+    const TallyAcc T = tally_acc(ctx, 0, tally_on);
     const uint64_t nps0 = ctx->icycle * ctx->n_sample + ctx->shard_begin;
     Counters* C = ctx->d_counters.p;
     Site* dst = ctx->d_local_bank[0].p;
@@ -690,7 +759,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
         if (q1 > q0) {
             CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
             ctx->timer.begin(st, ST_STEP);
-            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->n_slots, ctx->k);
+            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth);
             ctx->timer.end(st);
             (*n_iterations)++;
         }
@@ -698,15 +767,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
     CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     trace_mark("all chunks uploaded, sourced and walked");
-    const Counters& hc = *ctx->h_counters;
-    if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
-    if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
-    if (T.on) {
-        ctx->timer.begin(st, ST_CLOSEOUT);
-        mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
-        ctx->timer.end(st);
-    }
-    return MCB_OK;
+    return check_batch(ctx, *ctx->h_counters);
 }
 
 // the event loop over one batch of histories [h0, h0+nb) of the shard
@@ -714,8 +775,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
 {
     cudaStream_t st = ctx->stream;
     const DevProblem& P = ctx->P;
-    TallyAcc T;
-    T.acc = ctx->d_tally_acc.p; T.stride = ctx->batch_hist; T.first_hist = (int32_t)h0; T.on = tally_on && ctx->n_tallies > 0;
+    const TallyAcc T = tally_acc(ctx, h0, tally_on);
     const uint64_t nps0 = ctx->icycle * ctx->n_sample + ctx->shard_begin;
     SourceBankView V = ctx->view;
     if (!ctx->source_is_bank) { memset(&V, 0, sizeof(V)); }
@@ -732,35 +792,15 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     ctx->timer.end(st);
 
     if (ctx->walk_mode) {
-        // History walk: pass 0 follows the primaries in slots [0, nb) to the end of their chains; secondaries born on
-        // the way (fixed-source fission, splitting) land in slots >= nb and are walked by the next pass.
-        uint64_t begin = 0, end = nb;
-        int passes = 0;
-        while (begin < end) {
-            CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
-            ctx->timer.begin(st, ST_STEP);
-            mcbk::walk(st, P, ctx->B, begin, end, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->n_slots, ctx->k);
-            ctx->timer.end(st);
-            passes++;
-            if (!P.shared_histories) break;  // one particle per history: nothing can be born
-            CK(cudaMemcpyAsync(&ctx->h_ring[0], &C->slot_cursor, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            begin = end;
-            end = ctx->h_ring[0];
-        }
-        *n_iterations += passes;
+        // one launch follows the source particles in slots [0, nb) and every secondary of their histories to the end
+        CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
+        ctx->timer.begin(st, ST_STEP);
+        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth);
+        ctx->timer.end(st);
+        *n_iterations += 1;
         CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const Counters& hc = *ctx->h_counters;
-        if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
-        if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
-        if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
-        if (T.on) {
-            ctx->timer.begin(st, ST_CLOSEOUT);
-            mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
-            ctx->timer.end(st);
-        }
-        return MCB_OK;
+        return check_batch(ctx, *ctx->h_counters);
     }
 
     // Event loop.  Queue lengths live on the device; the host launches iterations ahead of what it knows and
@@ -824,14 +864,12 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     *n_iterations += it;
     CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const Counters& hc = *ctx->h_counters;
-    if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
-    if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
-    if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
+    { const int rc = check_batch(ctx, *ctx->h_counters); if (rc != MCB_OK) return rc; }
     if (T.on) {
         ctx->timer.begin(st, ST_CLOSEOUT);
         mcbk::tally_reduce(st, ctx->d_tally_acc.p, T.stride, nb, ctx->n_tallies, ctx->d_tally_partial.p, ctx->d_tally_sum.p, ctx->d_tally_sq.p);
         ctx->timer.end(st);
+        CK(cudaGetLastError());
     }
     return MCB_OK;
 }
@@ -1340,6 +1378,20 @@ int mcb_watt_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, const dou
         CK(dO.alloc((size_t)n));
         mcbk::watt(ctx->stream, ctx->P, nuclide, dN.p, dE.p, n, dO.p);
         D2H(Eout, dO, (size_t)n);
+        CK(cudaStreamSynchronize(ctx->stream));
+        return MCB_OK;
+    });
+}
+
+int mcb_division_batch(mcb_ctx* ctx, const double* a, const double* b, int64_t n, double* out_shared, double* out_plain)
+{
+    if (!ctx || n < 0) return MCB_ERR_ARG;
+    return with_buffers(ctx, [&]() -> int {
+        DevBuf<double> dA, dB, dS, dP;
+        H2D(dA, a, (size_t)n); H2D(dB, b, (size_t)n);
+        CK(dS.alloc((size_t)n)); CK(dP.alloc((size_t)n));
+        mcbk::division(ctx->stream, dA.p, dB.p, n, dS.p, dP.p);
+        D2H(out_shared, dS, (size_t)n); D2H(out_plain, dP, (size_t)n);
         CK(cudaStreamSynchronize(ctx->stream));
         return MCB_OK;
     });

@@ -27,6 +27,7 @@ struct DevNuclide {
     const double* rows;          // n_rows x {E, sigma_s, sigma_c, sigma_f, nu, beta}; 48-byte rows, 16-byte aligned
     int32_t n_rows, has_delayed;
     double A;
+    double fg_beta;              // sqrt(2.0659834e-11 * A): free-gas target speed parameter (Reaction.cpp:33), a per-nuclide constant
     double watt_a[3], watt_b[3], watt_g[3];
     // delayed neutrons (setup.cpp:377-412): decay constants, group fractions, tabulated emission spectra
     double lambda[6], fraction[6];
@@ -161,6 +162,7 @@ struct Counters {
     unsigned long long n_active[3];       // lengths of the particle queue: iteration i reads [i%3], fills [(i+1)%3], clears [(i+2)%3]
     unsigned long long q_collide, q_cross;// lengths of the two halves of the event queue
     int lost, overflow_sites, overflow_slots, overflow_fixed;
+    int overflow_tally, overflow_stack;   // walk kernel: a history's tally table / secondary stack is full
     double lost_pos[3];
     // exact (fixed-point, two-limb) sums over histories: k_C, k_TL, k_C^2, k_TL^2, H
     unsigned long long fx_lo[5], fx_hi[5];
@@ -172,13 +174,32 @@ struct HistoryAcc {
     int32_t* nsite;                       // fission sites banked by the history
 };
 
-// dense per-history tally accumulators of the current batch: acc[tally][batch history]
+// per-history tally accumulators.
+// Event-queue kernels: dense rows acc[tally][history of the batch] (acc != nullptr), reduced per batch by k_tally_*.
+// Walk kernel: one open-addressed table {tally index + 1 -> value} per history context (a history is followed by one
+// lane at a time), flushed when the history ends as sum += v, squared += v * v (Estimator.cpp:339-346) with
+// reductions into `sum` / `squared` (through block-private shared-memory bins when the problem has few tallies).
 struct TallyAcc {
     double* acc;
     int64_t stride;                       // histories per batch (row length)
     int32_t first_hist;                   // shard-local index of the batch's first history
     int32_t on;                           // tallies are being scored (active cycle, handler.cpp:15)
+    uint32_t* tab_key;                    // n_contexts x (tab_mask + 1)
+    double* tab_val;
+    uint16_t* tab_list;                   // positions in use, in order of first touch
+    uint32_t tab_mask;                    // table size - 1 (a power of two >= the number of tallies when that fits)
+    int32_t n_tallies;
+    double *sum, *squared;                // Tally::sum / squared of the cycle on this rank
 };
+
+// a same-history secondary waiting on its history's LIFO stack (the reference's Pbank, handler.cpp:20-29)
+struct alignas(16) StackRec {
+    double x, y, z, u, v, w, E, speed, wgt, t, Eold;
+    uint64_t rng;
+    int32_t cell, pad0;
+    double pad1;
+};
+static_assert(sizeof(StackRec) == 112, "StackRec is seven 16-byte words");
 
 #define MCB_FX_SCALE 17592186044416.0     /* 2^44: fixed-point scale of the exact history sums */
 
@@ -209,8 +230,11 @@ __device__ __forceinline__ void micro_xs(const DevNuclide& N, int idx, double E,
     const double2 a1 = ld_row2(r), b1 = ld_row2(r + 2), c1 = ld_row2(r + 4);
     const double2 a2 = ld_row2(r + 6), b2 = ld_row2(r + 8), c2 = ld_row2(r + 10);
     const double E1 = a1.x, E2 = a2.x;
-    const double f1 = (E - E2) / (E1 - E2);
-    const double f2 = (E - E1) / (E2 - E1);
+    // interpolate (Algorithm.cpp:103-105): E2 - E1 = -(E1 - E2) exactly and x / (-d) = -(x / d) exactly, so one
+    // reciprocal serves both weights (mcb_div_shared is bit-identical to the IEEE division)
+    const double d = E1 - E2, rd = mcb_rcp_shared(d);
+    const double f1 = mcb_div_shared(E - E2, d, rd);
+    const double f2 = -mcb_div_shared(E - E1, d, rd);
     m.s = f1 * a1.y + f2 * a2.y;
     m.c = f1 * b1.x + f2 * b2.x;
     m.f = f1 * b1.y + f2 * b2.y;
@@ -246,16 +270,30 @@ struct MacroXS { double t, s, c, f, nf; };
 
 // per-nuclide by-products of one macroscopic lookup.  The running sums ARE the partial sums that
 // Material::nuclide_scatter / nuclide_nufission (Material.cpp:106-125) rebuild, so a kernel that keeps them can
-// pick the reaction nuclide without evaluating the tables again.
+// pick the reaction nuclide without evaluating the tables again.  Detail types: set(n, ..) while the lookup runs,
+// cum_s(n) / cum_nf(n) / beta(n) afterwards; XSDetail keeps them in local memory, the walk kernel's SlotDetail in the
+// particle's shared-memory slot, NoDetail drops them.
 struct XSDetail {
-    double cum_s[MCB_MAX_MAT_NUCLIDES];   // Sigma_s after nuclides 0..n
-    double cum_nf[MCB_MAX_MAT_NUCLIDES];  // nuSigma_f after nuclides 0..n
-    double beta[MCB_MAX_MAT_NUCLIDES];    // beta_n(E)
+    static constexpr bool present = true;
+    double cs[MCB_MAX_MAT_NUCLIDES];      // Sigma_s after nuclides 0..n
+    double cnf[MCB_MAX_MAT_NUCLIDES];     // nuSigma_f after nuclides 0..n
+    double b[MCB_MAX_MAT_NUCLIDES];       // beta_n(E)
+    __device__ __forceinline__ void set(int n, double s, double nf, double be) { cs[n] = s; cnf[n] = nf; b[n] = be; }
+    __device__ __forceinline__ double cum_s(int n) const { return cs[n]; }
+    __device__ __forceinline__ double cum_nf(int n) const { return cnf[n]; }
+    __device__ __forceinline__ double beta(int n) const { return b[n]; }
+};
+struct NoDetail {
+    static constexpr bool present = false;
+    __device__ __forceinline__ void set(int, double, double, double) {}
+    __device__ __forceinline__ double cum_s(int) const { return 0.0; }
+    __device__ __forceinline__ double cum_nf(int) const { return 0.0; }
+    __device__ __forceinline__ double beta(int) const { return 0.0; }
 };
 
 // Material::SigmaT/S/C/F, nuSigmaF (Material.cpp:18-65): sums over nuclides in deck order, starting from 0.0
-template <bool DETAIL>
-__device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X, XSDetail* D)
+template <class DET>
+__device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X, DET& D)
 {
     X.t = 0.0; X.s = 0.0; X.c = 0.0; X.f = 0.0; X.nf = 0.0;
     for (int n = 0; n < M.n_nuc; n++) {
@@ -268,21 +306,23 @@ __device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMate
         X.c += m.c * dens;
         X.f += m.f * dens;
         X.nf += (m.f * m.nu) * dens;   // Nuclide::nusigmaF = sigmaF*nu (Nuclide.cpp:57-61)
-        if (DETAIL) { D->cum_s[n] = X.s; D->cum_nf[n] = X.nf; D->beta[n] = m.beta; }
+        if (DET::present) D.set(n, X.s, X.nf, m.beta);
     }
 }
 __device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X)
 {
-    macro_xs_impl<false>(P, M, u, E, X, nullptr);
+    NoDetail nd;
+    macro_xs_impl(P, M, u, E, X, nd);
 }
-// nuclide pick from kept partial sums: first n with cum[n] > total*xi (Material.cpp:106-125)
-__device__ __forceinline__ int select_from_detail(const DevProblem& P, const DevMaterial& M, const double* cum, double total,
+// nuclide pick from kept partial sums: first n with cum[n] > total*xi (Material.cpp:106-125); KIND 0 scatter, 1 nu-fission
+template <int KIND, class DET>
+__device__ __forceinline__ int select_from_detail(const DevProblem& P, const DevMaterial& M, const DET& D, double total,
                                                   double xi, int* local_n)
 {
     const double thr = total * xi;
     int sel = -1;
     for (int n = M.n_nuc - 1; n >= 0; n--)   // single exit; the last hit is the first nuclide with cum > thr
-        if (cum[n] > thr) sel = n;
+        if ((KIND == 0 ? D.cum_s(n) : D.cum_nf(n)) > thr) sel = n;
     if (sel < 0) return -1;
     *local_n = sel;
     return __ldg(&P.mat_nuclide[M.nuc_begin + sel]);
@@ -431,12 +471,14 @@ __device__ __forceinline__ double dist1_sample(const mcb_dist1& d, uint64_t& rng
 }
 
 // ReactionScatter::sample (Reaction.cpp:27-118): elastic scatter off a free-gas target at 293.6 K, isotropic in
-// the centre of mass.  In/out: direction, energy and speed of the neutron.
-__device__ __forceinline__ void scatter_sample(double A, double& dx, double& dy, double& dz, double& E, double& speed,
+// the centre of mass.  In/out: direction, energy and speed of the neutron.  Each three-component normalisation
+// divides by one number: the reciprocal is refined once (mcb_div_shared, bit-identical to three IEEE divisions).
+__device__ __forceinline__ void scatter_sample(const DevNuclide& N, double& dx, double& dy, double& dz, double& E, double& speed,
                                                uint64_t& rng)
 {
+    const double A = N.A;
     const double mu0 = 2.0 * mcb_urand(rng) - 1.0;  // DistributionIsotropicScatter (Distribution.cpp:74-77)
-    const double beta = sqrt(2.0659834e-11 * A);
+    const double beta = N.fg_beta;                  // sqrt(2.0659834e-11 * A)
     const double y = beta * speed;
     double V_tilda, mu_tilda, accept;
     do {
@@ -462,19 +504,22 @@ __device__ __forceinline__ void scatter_sample(double A, double& dx, double& dy,
     mcb_scatter_direction(dx, dy, dz, mu_tilda, mcb_urand(rng), nx, ny, nz);
     const double Vx = nx * V_tilda, Vy = ny * V_tilda, Vz = nz * V_tilda;
     double vx = speed * dx, vy = speed * dy, vz = speed * dz;
-    const double ux = (vx + A * Vx) / (1.0 + A);
-    const double uy = (vy + A * Vy) / (1.0 + A);
-    const double uz = (vz + A * Vz) / (1.0 + A);
+    const double A1 = 1.0 + A, rA1 = mcb_rcp_shared(A1);
+    const double ux = mcb_div_shared(vx + A * Vx, A1, rA1);
+    const double uy = mcb_div_shared(vy + A * Vy, A1, rA1);
+    const double uz = mcb_div_shared(vz + A * Vz, A1, rA1);
     double cx = vx - ux, cy = vy - uy, cz = vz - uz;
     const double speed_c = sqrt(cx * cx + cy * cy + cz * cz);
-    const double dcx = cx / speed_c, dcy = cy / speed_c, dcz = cz / speed_c;
+    const double rsc = mcb_rcp_shared(speed_c);
+    const double dcx = mcb_div_shared(cx, speed_c, rsc), dcy = mcb_div_shared(cy, speed_c, rsc), dcz = mcb_div_shared(cz, speed_c, rsc);
     double ex, ey, ez;
     mcb_scatter_direction(dcx, dcy, dcz, mu0, mcb_urand(rng), ex, ey, ez);
     cx = speed_c * ex; cy = speed_c * ey; cz = speed_c * ez;
     vx = cx + ux; vy = cy + uy; vz = cz + uz;
     speed = sqrt(vx * vx + vy * vy + vz * vz);  // Particle::set_speed (Particle.cpp:49-56)
     E = mcb_energy_of_speed(speed);
-    dx = vx / speed; dy = vy / speed; dz = vz / speed;
+    const double rsp = mcb_rcp_shared(speed);
+    dx = mcb_div_shared(vx, speed, rsp); dy = mcb_div_shared(vy, speed, rsp); dz = mcb_div_shared(vz, speed, rsp);
 }
 
 // surface_intersect (general.cpp:54-67): nearest surface of the cell along the flight direction

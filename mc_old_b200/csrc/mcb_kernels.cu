@@ -14,24 +14,16 @@
 //
 // Nothing here is GEMM-shaped: the loop is FP64 scalar work, L2-resident table gathers and HBM streams of the
 // bank, so tensor cores are unused on purpose.
-#include "mcb_kernels.h"
+#include "mcb_events.cuh"
 
 #include <algorithm>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+using namespace mcbe;
+
 namespace {
-
-constexpr unsigned FULL = 0xffffffffu;
-#ifndef MCB_BLOCK
-#define MCB_BLOCK 128  // measured (tools/sweep.sh): 128 x 6 blocks per SM (85 registers) beats 128 x 5, 128 x 7, 256 x 2, 192 x 3 and 96 x 7 for the walk kernel
-#endif
-constexpr int BLOCK = MCB_BLOCK;
-constexpr int WARPS = BLOCK / 32;
-
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
 // ---------------------------------------------------------------------------------------------
 // block-level stream compaction: every thread asks for n[c] consecutive positions behind cursor c; one
@@ -71,467 +63,42 @@ __device__ __forceinline__ void block_reserve(BlockScratch<NC>& S, const unsigne
 #pragma unroll
     for (int c = 0; c < NC; c++) pos[c] = S.base[c] + S.warp_tot[c][warp_id()] + (incl[c] - n[c]);
 }
-// block-wide event counter: one atomic per block
-__device__ __forceinline__ void block_count(unsigned long long* dst, bool pred)
+// particle <-> bank slot (event-queue kernels keep the particle in the SoA bank between events)
+__device__ __forceinline__ void load_particle(const DevProblem& P, const Bank& B, uint32_t i, Particle& p)
 {
-    const int c = __syncthreads_count(pred);
-    if (threadIdx.x == 0 && c) atomicAdd(dst, (unsigned long long)c);
+    p.cell = B.cell[i]; p.hist = B.hist[i]; p.row = p.hist; p.n_touched = 0;
+    p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
+    p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+    p.Eold = P.track_old ? B.Eold[i] : p.E;
+    p.told = P.track_time ? B.told[i] : p.t;
 }
-
-// per-history accumulators are bumped with reductions at L2 (RED, no return value): a read-modify-write in the
-// thread would stall the warp for a DRAM round trip on every event
-__device__ __forceinline__ void hist_add(double* p, double v) { atomicAdd(p, v); }
-
-// ---------------------------------------------------------------------------------------------
-// tally scoring (Estimator::score, Estimator.cpp:298-336, for filters that yield one bin: surface, cell, energy)
-// ---------------------------------------------------------------------------------------------
-struct ScoreState {   // the particle as Score / Filter / the simulating estimators see it
-    double w, E, E_old, speed, t, t_old;
-    double u, v, wd;  // direction
-    int cell, surface_old, material, uidx;
-    MacroXS X;        // macroscopic xs of `material` at E
-};
-
-__device__ __forceinline__ double kernel_value(int kernel, const ScoreState& s, double l)  // Estimator.cpp:17-41
-{
-    switch (kernel) {
-    case MCB_KERNEL_NEUTRON: return s.w;
-    case MCB_KERNEL_TRACK: return s.w * l;
-    case MCB_KERNEL_COLLISION: return s.w / s.X.t;
-    case MCB_KERNEL_VELOCITY: return s.w * s.speed;
-    default: return s.w * l * s.speed;
-    }
-}
-__device__ __forceinline__ double score_value(const DevProblem& P, const mcb_score& S, const ScoreState& s, double l, ChannelCache& CC)
-{  // Estimator.cpp:48-124
-    const double kv = kernel_value(S.kernel, s, l);
-    if (S.score == MCB_SCORE_FLUX) return kv;
-    if (S.score == MCB_SCORE_INVERSE_VELOCITY) return kv / s.speed;
-    if (s.material < 0) return 0.0;
-    const DevMaterial& M = P.materials[s.material];
-    switch (S.score) {
-    case MCB_SCORE_ABSORPTION: return macro_sigma_a(P, M, s.uidx, s.E) * kv;
-    case MCB_SCORE_SCATTER: return s.X.s * kv;
-    case MCB_SCORE_CAPTURE: return s.X.c * kv;
-    case MCB_SCORE_FISSION: return s.X.f * kv;
-    case MCB_SCORE_NU_FISSION: return s.X.nf * kv;
-    case MCB_SCORE_TOTAL: return s.X.t * kv;
-    // the "Old" scores of the TRMM tally set evaluate at Particle::energy_old (Estimator.cpp:96-118)
-    case MCB_SCORE_SCATTER_OLD: return macro_channel(P, s.material, s.E_old, 0, false, 0.0, nullptr, CC) * kv;
-    case MCB_SCORE_NU_FISSION_OLD: return macro_channel(P, s.material, s.E_old, 1, false, 0.0, nullptr, CC) * kv;
-    case MCB_SCORE_NU_FISSION_PROMPT_OLD: return macro_channel(P, s.material, s.E_old, 2, false, 0.0, nullptr, CC) * kv;
-    case MCB_SCORE_NU_FISSION_DELAYED_OLD: return macro_channel(P, s.material, s.E_old, 3 + S.group, false, 0.0, nullptr, CC) * kv;
-    case MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD: return macro_channel(P, s.material, s.E_old, 3 + S.group, true, 0.0, nullptr, CC) * kv;
-    default: return 0.0;
-    }
-}
-// Estimator::score (Estimator.cpp:298-336).  Surface / cell / energy / energy_old filters yield one bin; a time
-// filter (Estimator.cpp:199-246) splits the track [t_old, t] over the bins it spans, piece by piece; the loop scores
-// the shortest remaining piece of all filters, subtracts it everywhere and advances the exhausted ones, like the
-// reference's.  The time pieces are generated on demand.
-struct FilterCursor {
-    int idx;         // current bin
-    double l;        // remaining length of the current piece
-    int k, n;        // piece number, pieces in all
-    int loc1, loc2;  // time filter: bins of t_old and t
-    bool first;      // time filter: the piece of t_old's bin exists (loc1 >= 0)
-};
-__device__ __forceinline__ void time_piece(const mcb_filter& F, const double* g, const ScoreState& s, FilterCursor& c)
-{
-    const int Nbin = F.grid_n - 1;
-    int i = c.k;  // 0 = the piece in loc1 (when it exists), then the full bins, then the piece in loc2
-    if (c.first) {
-        if (i == 0) { c.idx = c.loc1; c.l = (g[c.loc1 + 1] - s.t_old) * s.speed; return; }
-        i--;
-    }
-    const int num_bin = c.loc2 - c.loc1 - 1;
-    if (i < num_bin) { c.idx = c.loc1 + i + 1; c.l = (g[c.loc1 + i + 2] - g[c.loc1 + i + 1]) * s.speed; return; }
-    (void)Nbin;
-    c.idx = c.loc2; c.l = (s.t - g[c.loc2]) * s.speed;
-}
-__device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, const mcb_estimator& E, const ScoreState& s,
-                                                      double l_in, int hist, ChannelCache& CC)
-{
-    constexpr int MAXF = 4;
-    FilterCursor cur[MAXF];
-    int64_t factor[MAXF + 1];  // idx_factor (Estimator.cpp:288-295)
-    const int nf = E.n_filters < MAXF ? E.n_filters : MAXF;
-    factor[nf] = 1;
-    for (int i = nf - 1; i >= 0; i--) factor[i] = factor[i + 1] * P.filters[E.filter_begin + i].size;
-    for (int i = 0; i < nf; i++) {
-        const mcb_filter F = P.filters[E.filter_begin + i];
-        const double* g = P.filter_grid + F.grid_begin;
-        FilterCursor& c = cur[i];
-        c.k = 0; c.n = 1; c.l = l_in; c.first = false; c.loc1 = c.loc2 = 0;
-        switch (F.type) {
-        case MCB_FILTER_SURFACE: c.idx = mcb_binary_search((double)s.surface_old, g, F.grid_n) + 1; break;  // Estimator.cpp:133-140
-        case MCB_FILTER_CELL: c.idx = mcb_binary_search((double)s.cell, g, F.grid_n) + 1; break;            // :141-148
-        case MCB_FILTER_ENERGY:
-        case MCB_FILTER_ENERGY_OLD:                                                                          // :149-179
-            c.idx = mcb_binary_search(F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, g, F.grid_n);
-            if (c.idx < 0 || c.idx >= F.grid_n - 1) return;
-            break;
-        default: {                                                                                           // time :199-246
-            const int Nbin = F.grid_n - 1;
-            c.loc1 = mcb_binary_search(s.t_old, g, F.grid_n);
-            c.loc2 = mcb_binary_search(s.t, g, F.grid_n);
-            if (c.loc1 == c.loc2) {
-                if (c.loc1 < 0 || c.loc1 >= Nbin) return;
-                c.idx = c.loc1;
-            } else {
-                c.first = c.loc1 >= 0;
-                c.n = (c.first ? 1 : 0) + (c.loc2 - c.loc1 - 1) + (c.loc2 < Nbin ? 1 : 0);
-                if (c.n == 0) return;
-                time_piece(F, g, s, c);
-            }
-        }
-        }
-    }
-    double* acc = T.acc + (int64_t)(hist - T.first_hist);
-    for (;;) {
-        double l = MCB_MAX_FLOAT;
-        int64_t idx_1D = 0;
-        for (int i = 0; i < nf; i++) { l = fmin(l, cur[i].l); idx_1D += (int64_t)cur[i].idx * factor[i + 1]; }
-        for (int k = 0; k < E.n_scores; k++) {
-            const double v = score_value(P, P.scores[E.score_begin + k], s, l, CC);
-            const int64_t t = E.tally_begin + idx_1D + (int64_t)k * factor[0];
-            if (t >= E.tally_begin && t < E.tally_begin + E.n_tallies) atomicAdd(acc + t * T.stride, v);
-        }
-        for (int i = 0; i < nf; i++) {
-            FilterCursor& c = cur[i];
-            c.l -= l;
-            if (c.l < MCB_EPSILON_FLOAT) {
-                if (c.k == c.n - 1) return;
-                c.k++;
-                const mcb_filter F = P.filters[E.filter_begin + i];
-                time_piece(F, P.filter_grid + F.grid_begin, s, c);
-            }
-        }
-        if (nf == 0) return;
-    }
-}
-// One estimator scores one event.  The TRMM estimators first let a COPY of the particle scatter / fission, drawing
-// from the particle's own stream like the reference draws from its global one (EstimatorScatter / FissionPrompt /
-// FissionDelayed::score, Estimator.cpp:441-482): energy_old = incident energy, energy and speed = outgoing.
-__device__ __forceinline__ void estimator_score(const DevProblem& P, const TallyAcc& T, int e, const ScoreState& s, uint64_t& rng, double l,
-                                             int hist, ChannelCache& CC)
-{
-    const mcb_estimator E = P.estimators[e];
-    if (E.simulate == MCB_SIM_NONE) { estimator_score_plain(P, T, E, s, l, hist, CC); return; }
-    if (s.material < 0) return;
-    const DevMaterial& M = P.materials[s.material];
-    ScoreState q = s;
-    int n = -1;
-    if (E.simulate == MCB_SIM_SCATTER) {
-        (void)macro_channel(P, s.material, s.E, 0, false, mcb_urand(rng), &n, CC);
-        if (n < 0) return;  // the reference dereferences a null nuclide here
-        scatter_sample(P.nuclides[n].A, q.u, q.v, q.wd, q.E, q.speed, rng);
-    } else if (E.simulate == MCB_SIM_FISSION || E.simulate == MCB_SIM_FISSION_PROMPT) {
-        (void)macro_channel(P, s.material, s.E, E.simulate == MCB_SIM_FISSION ? 1 : 2, false, mcb_urand(rng), &n, CC);
-        if (n < 0) return;
-        const DevNuclide& N = P.nuclides[n];
-        q.E = watt_sample(N.watt_a, N.watt_b, N.watt_g, s.E, rng);
-        q.speed = mcb_speed_of_energy(q.E);
-    } else {
-        const int g = E.simulate - MCB_SIM_FISSION_DELAYED;
-        (void)macro_channel(P, s.material, s.E, 3 + g, false, mcb_urand(rng), &n, CC);
-        if (n < 0) return;
-        q.E = chid_sample(P.nuclides[n], g, rng);
-        q.speed = mcb_speed_of_energy(q.E);
-    }
-    q.E_old = s.E;  // Particle::set_energy / set_speed (Particle.cpp:42-56)
-    // cross sections at the outgoing energy only when a score or kernel of this estimator reads them
-    bool needs_X = false;
-    for (int k = 0; k < E.n_scores; k++) {
-        const mcb_score& S = P.scores[E.score_begin + k];
-        if (S.kernel == MCB_KERNEL_COLLISION || (S.score >= MCB_SCORE_ABSORPTION && S.score <= MCB_SCORE_TOTAL)) needs_X = true;
-    }
-    if (needs_X) { q.uidx = union_index(M, q.E); macro_xs(P, M, q.uidx, q.E, q.X); }
-    estimator_score_plain(P, T, E, q, l, hist, CC);
-}
-__device__ __forceinline__ void score_attached(const DevProblem& P, const TallyAcc& T, int kind, int id,
-                                               const ScoreState& s, uint64_t& rng, double l, int hist)
-{
-    const int b = P.attach_begin[kind][id], e = P.attach_begin[kind][id + 1];
-    ChannelCache CC;  // microscopic data at the (at most two) energies the estimators of this event ask about
-    channel_cache_reset(CC);
-    for (int i = b; i < e; i++) estimator_score(P, T, P.attach_list[kind][i], s, rng, l, hist, CC);
-}
-__device__ __forceinline__ bool has_attached(const DevProblem& P, int kind, int id)
-{
-    return P.attach_begin[kind][id + 1] > P.attach_begin[kind][id];
-}
-
-// ---------------------------------------------------------------------------------------------
-// the events of one particle, on registers.  Stage kernels load/store the fields an event needs; k_finish keeps
-// the whole particle in registers and chains the events.
-// ---------------------------------------------------------------------------------------------
-struct Particle {
-    double x, y, z, u, v, w, E, speed, wgt, t;
-    uint64_t rng;
-    int cell, hist;
-    int slot;  // bank slot the particle was loaded from (addresses Bank::Eold)
-};
-// all estimators attached to surface / cell `id` score one event of particle p.  Cold and out of line, with every
-// input BY VALUE (no address of a register-resident particle escapes), so that the transport kernels' register
-// allocation is not shaped by it; returns the particle's stream state (the simulating estimators draw from it).
-// have_X = false (surface estimators): the cross sections of the cell the particle is now in are looked up here.
-__device__ __noinline__ uint64_t score_event(const DevProblem& P, const Bank& B, const TallyAcc& T, int kind, int id, double w, double E,
-                                             double speed, double t, double du, double dv, double dw, int cell, int hist, int slot, uint64_t rng,
-                                             int material, int uidx, bool have_X, double Xt, double Xs, double Xc, double Xf, double Xnf,
-                                             int surface_old, double l)
-{
-    ScoreState s;
-    s.w = w; s.E = E; s.speed = speed; s.u = du; s.v = dv; s.wd = dw;
-    s.E_old = P.track_old ? B.Eold[slot] : E;
-    s.t = t; s.t_old = P.track_time ? B.told[slot] : t;
-    s.cell = cell; s.surface_old = surface_old; s.material = material; s.uidx = uidx;
-    s.X = MacroXS{Xt, Xs, Xc, Xf, Xnf};
-    if (!have_X) {
-        s.uidx = -1;
-        if (material >= 0) { s.uidx = union_index(P.materials[material], E); macro_xs(P, P.materials[material], s.uidx, E, s.X); }
-    }
-    score_attached(P, T, kind, id, s, rng, l, hist);
-    return rng;
-}
-#define MCB_SCORE_EVENT(kind, id, p, material, uidx, have_X, X, surface_old, l)                                              \
-    (p).rng = score_event(P, B, T, kind, id, (p).wgt, (p).E, (p).speed, (p).t, (p).u, (p).v, (p).w, (p).cell, (p).hist, (p).slot, \
-                          (p).rng, material, uidx, have_X, (X).t, (X).s, (X).c, (X).f, (X).nf, surface_old, l)
-
-// xs_lookup event
-template <bool DETAIL>
-__device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p, MacroXS& X, int& uidx, XSDetail* D)
-{
-    const int m = P.cells[p.cell].material;
-    if (m < 0) return false;
-    const DevMaterial M = P.materials[m];
-    uidx = union_index(M, p.E);
-    macro_xs_impl<DETAIL>(P, M, uidx, p.E, X, D);
-    return true;
-}
-
-// flight event: surface_intersect + collision_distance + move_particle (general.cpp:40-83,177-207).
-// Returns true when the flight ends on a surface (S_hit), false when it ends in a collision.
-// A history whose particles never share it with others in flight (k-eigenvalue without splitting) can keep its
-// EstimatorK scores and its site count in registers (HistLocal) and store them once when it ends; otherwise they
-// are bumped in memory with reductions.
-struct HistLocal { double kC, kTL; int nsite; };
-
-template <bool TALLY>
-__device__ __forceinline__ bool ev_flight(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
-                                          const TallyAcc& T, int& S_hit, HistLocal* L = nullptr)
-{
-    const int m = P.cells[p.cell].material;
-    double dsurf;
-    S_hit = surface_intersect(P, p.cell, p.x, p.y, p.z, p.u, p.v, p.w, dsurf);
-    double dcol;
-    if (m >= 0) dcol = -log(mcb_urand(p.rng)) / X.t;   // exponential_sample (Algorithm.cpp:123-126)
-    else dcol = MCB_MAX_FLOAT_LESS;                      // vacuum (general.cpp:44-46)
-    const bool to_cross = dcol > dsurf;
-    const double l = to_cross ? dsurf : dcol;
-    // Particle::move (Particle.cpp:66-76)
-    p.x += p.u * l; p.y += p.v * l; p.z += p.w * l;
-    if (TALLY && P.track_time) B.told[p.slot] = p.t;
-    p.t += l / p.speed;
-    if (P.ksearch && m >= 0) {  // estimate_TL (Estimator.cpp:509-512)
-        if (L) L->kTL += X.nf * p.wgt * l;
-        else hist_add(&H.kTL[p.hist], X.nf * p.wgt * l);
-    }
-    if (TALLY && T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
-        MCB_SCORE_EVENT(MCB_ATTACH_CELL_TL, p.cell, p, m, uidx, true, X, -1, l);
-    }
-    return to_cross;
-}
-
-// collide event, first half: Simulator::collision up to the fission dispatch (general.cpp:121-150): collision
-// tallies, bank_nu, fissioning nuclide, prompt/delayed draw.  Tells how many fission sites (k-eigenvalue) or
-// same-history secondaries (fixed source) the second half will write.
-struct CollideCtx {
-    int m, N_fission;
-    unsigned n_sites, n_second;
-};
-template <bool TALLY>
-__device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
-                                               const TallyAcc& T, double k_eff, CollideCtx& c)
-{
-    c.m = P.cells[p.cell].material;
-    c.N_fission = -1; c.n_sites = 0; c.n_second = 0;
-    if (c.m < 0) { p.wgt = 0.0; return false; }  // vacuum: kill (general.cpp:124-128)
-    if (TALLY && T.on && has_attached(P, MCB_ATTACH_CELL_C, p.cell)) {
-        MCB_SCORE_EVENT(MCB_ATTACH_CELL_C, p.cell, p, c.m, uidx, true, X, -1, 0.0);
-    }
-    // floor( w/k * nuSigmaF / SigmaT + xi ) (general.cpp:135-136)
-    const double a = p.wgt / k_eff * X.nf / X.t;
-    const double bn = floor(a + mcb_urand(p.rng));
-    const unsigned bank_nu = bn > 0.0 ? (unsigned)bn : 0u;
-    const DevMaterial& M = P.materials[c.m];
-    int ln = 0;
-    const double xi_f = mcb_urand(p.rng);
-    c.N_fission = D ? select_from_detail(P, M, D->cum_nf, X.nf, xi_f, &ln)
-                    : select_nuclide(P, M, uidx, p.E, 1, X.nf, xi_f, &ln);  // Material.cpp:116-125
-    if (c.N_fission >= 0) {
-        // prompt or delayed (ksearch.cpp:24-38, fixed_source.cpp:12,41-52)
-        const double beta = D ? D->beta[ln] : micro_col(P.nuclides[c.N_fission], nuclide_index(M, uidx, ln), p.E, 1);
-        const bool prompt = mcb_urand(p.rng) > beta;
-        if (P.ksearch) {
-            if (!prompt) (void)mcb_urand(p.rng);  // precursor group pick, result unused
-            c.n_sites = bank_nu;
-        } else if (prompt) {
-            c.n_second = bank_nu;
-        } else {
-            // delayed, non-TDMC branch: draws are consumed, no neutron is banked (fixed_source.cpp:41-63)
-            (void)mcb_urand(p.rng);
-            for (unsigned b = 0; b < bank_nu; b++) { (void)mcb_urand(p.rng); (void)mcb_urand(p.rng); }
-        }
-    }
-    return true;
-}
-// collide event, banking part.  k-eigenvalue (ksearch.cpp:39-46): one request per fission site goes to
-// [site0, ..) of the request buffer; its Watt energy and isotropic direction are sampled by k_bank_sample_order
-// from the request's own stream.  Fixed source (fixed_source.cpp:12-22): same-history secondaries are written to
-// bank slots [slot0, ..), each sampled from, and continuing on, its own stream.  The parent's stream does not
-// advance.  Only lanes that bank anything call this; callers reconverge the warp afterwards.
-template <bool TALLY>
-__device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Bank& B, const Particle& p, const CollideCtx& c,
-                                                const HistoryAcc& H, Counters* C, SiteReq* reqs, uint64_t site_cap,
-                                                uint32_t n_slots, unsigned long long site0, unsigned long long slot0,
-                                                unsigned& n_second_ok, HistLocal* L = nullptr, unsigned long long ring_begin = 0)
-{
-    n_second_ok = 0;
-    uint64_t seed = p.rng;
-    if (c.n_sites) {
-        int seq0;
-        if (L) { seq0 = L->nsite; L->nsite += (int)c.n_sites; }
-        else seq0 = atomicAdd(&H.nsite[p.hist], (int)c.n_sites);
-        for (unsigned b = 0; b < c.n_sites; b++) {
-            seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
-            SiteReq r;
-            r.x = p.x; r.y = p.y; r.z = p.z; r.t = p.t; r.E_in = p.E; r.seed = seed;
-            r.cell = p.cell; r.seq = seq0 + (int)b; r.hist = p.hist; r.nuclide = c.N_fission;
-            if (site0 + b < site_cap) reqs[site0 + b] = r;
-            else C->overflow_sites = 1;
-        }
-    }
-    if (c.n_second) {
-        const DevNuclide& N = P.nuclides[c.N_fission];
-        for (unsigned b = 0; b < c.n_second; b++) {
-            seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
-            uint64_t rs = seed;
-            const double Es = watt_sample(N.watt_a, N.watt_b, N.watt_g, p.E, rs);   // energy first, then direction (App. D-4)
-            double du, dv, dw;
-            isotropic_direction(rs, du, dv, dw);
-            // the bank is a ring: positions grow without bound, slots behind the running pass (ring_begin) are reused
-            const unsigned long long pos = slot0 + b;
-            if (pos - ring_begin < n_slots) {
-                const uint32_t j = (uint32_t)(pos % n_slots);
-                B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = du; B.v[j] = dv; B.w[j] = dw;
-                B.E[j] = Es; B.speed[j] = mcb_speed_of_energy(Es); B.wgt[j] = 1.0; B.t[j] = p.t;
-                B.rng[j] = rs; B.cell[j] = p.cell; B.hist[j] = p.hist;
-                if (TALLY && P.track_old) B.Eold[j] = Es;
-                n_second_ok++;
-            } else C->overflow_slots = 1;
-        }
-    }
-}
-// collide event, last part: k_C, implicit capture, scatter, weight_roulette (general.cpp:146-163,
-// population_control.cpp:9-15).  Returns whether the particle survives.
-template <bool TALLY>
-__device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, const Bank& B, Particle& p, const MacroXS& X, int uidx, const XSDetail* D,
-                                                   const CollideCtx& c, const HistoryAcc& H, HistLocal* L = nullptr)
-{
-    if (P.ksearch && c.N_fission >= 0) {  // estimate_C (Estimator.cpp:503-507)
-        if (L) L->kC += X.nf * p.wgt / X.t;
-        else hist_add(&H.kC[p.hist], X.nf * p.wgt / X.t);
-    }
-    // implicit absorption (general.cpp:154-156)
-    const double implicit = X.c + X.f;
-    p.wgt = p.wgt * (X.t - implicit) / X.t;
-    const double xi_s = mcb_urand(p.rng);
-    int ln_s = 0;
-    const int N_scatter = D ? select_from_detail(P, P.materials[c.m], D->cum_s, X.s, xi_s, &ln_s)
-                            : select_nuclide(P, P.materials[c.m], uidx, p.E, 0, X.s, xi_s, &ln_s);  // Material.cpp:106-115
-    if (N_scatter >= 0) {
-        if (TALLY && P.track_old) B.Eold[p.slot] = p.E;  // Particle::set_speed keeps the pre-collision energy (Particle.cpp:49-56)
-        scatter_sample(P.nuclides[N_scatter].A, p.u, p.v, p.w, p.E, p.speed, p.rng);
-    }
-    // weight_roulette (population_control.cpp:9-15)
-    if (p.wgt < P.wr) {
-        if (mcb_urand(p.rng) < p.wgt / P.ws) p.wgt = P.ws;
-        else { p.wgt = 0.0; return false; }
-    }
-    return true;
-}
-
-// cross event, first half: surface_hit + cell_importance up to the split (general.cpp:89-115,
-// population_control.cpp:21-43).  n_copy = split copies the second half will write.
-template <bool TALLY>
-__device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, const Bank& B, Particle& p, int S, const TallyAcc& T, Counters* C, unsigned& n_copy)
-{
-    n_copy = 0;
-    if (S < 0) { p.wgt = 0.0; return false; }  // no surface ahead: cannot happen in a closed geometry
-    const mcb_surface& Sf = P.surfaces[S];
-    const int cell_old = p.cell;
-    bool alive = true;
-    if (Sf.bc == MCB_BC_TRANSMISSION) {
-        p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
-        if (TALLY && P.track_time) B.told[p.slot] = p.t;
-        p.t += MCB_EPSILON_FLOAT / p.speed;
-        const int cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, p.x, p.y, p.z);
-        if (cn < 0) {  // "[WARNING] A particle is lost" (general.cpp:31-33)
-            if (atomicExch(&C->lost, 1) == 0) { C->lost_pos[0] = p.x; C->lost_pos[1] = p.y; C->lost_pos[2] = p.z; }
-            alive = false; p.wgt = 0.0;
-        } else p.cell = cn;
-    } else if (Sf.bc == MCB_BC_VACUUM) {
-        alive = false; p.wgt = 0.0;
-    } else {
-        mcb_surf_reflect(Sf, p.u, p.v, p.w);
-        p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
-        if (TALLY && P.track_time) B.told[p.slot] = p.t;
-        p.t += MCB_EPSILON_FLOAT / p.speed;
-    }
-    if (TALLY && T.on && has_attached(P, MCB_ATTACH_SURFACE, S)) {
-        const MacroXS X0 = {0, 0, 0, 0, 0};
-        MCB_SCORE_EVENT(MCB_ATTACH_SURFACE, S, p, P.cells[p.cell].material, -1, false, X0, S, 0.0);
-    }
-    const double Iold = P.cells[cell_old].importance, Inew = P.cells[p.cell].importance;
-    if (Inew != Iold) {
-        const double rat = Inew / Iold;
-        if (rat < 1.0) {
-            if (mcb_urand(p.rng) < rat) p.wgt = p.wgt / rat;
-            else { alive = false; p.wgt = 0.0; }
-        } else {
-            const int ns = (int)floor(rat + mcb_urand(p.rng));
-            p.wgt = p.wgt / (double)ns;
-            n_copy = ns > 1 ? (unsigned)(ns - 1) : 0u;
-        }
-    }
-    return alive;
-}
-// cross event, second half: the split copies (population_control.cpp:44-48) and weight_roulette, which also
-// draws for a particle that was just killed (w = 0 < wr), like the reference
-template <bool TALLY>
-__device__ __forceinline__ bool ev_cross_post(const DevProblem& P, const Bank& B, Particle& p, bool alive, unsigned n_copy,
-                                              unsigned long long slot0, uint32_t n_slots, Counters* C, unsigned& n_copy_ok,
-                                              unsigned long long ring_begin = 0)
-{
-    n_copy_ok = 0;
-    for (unsigned b = 0; b < n_copy; b++) {
-        const unsigned long long pos = slot0 + b;
+// same-history secondaries of the event-queue kernels go to bank positions [slot0, ..): the bank is a ring, positions
+// grow without bound and slots behind the running pass (ring_begin) are reused
+struct BankSink {
+    const DevProblem& P;
+    const Bank& B;
+    unsigned long long slot0, ring_begin;
+    uint32_t n_slots;
+    Counters* C;
+    unsigned n_pushed, n_ok;
+    __device__ __forceinline__ BankSink(const DevProblem& P_, const Bank& B_, unsigned long long slot0_, uint32_t n_slots_, Counters* C_,
+                                        unsigned long long ring_begin_ = 0)
+        : P(P_), B(B_), slot0(slot0_), ring_begin(ring_begin_), n_slots(n_slots_), C(C_), n_pushed(0), n_ok(0) {}
+    __device__ __forceinline__ void push(const Particle& q)
+    {
+        const unsigned long long pos = slot0 + n_pushed;
+        n_pushed++;
         if (pos - ring_begin < n_slots) {
             const uint32_t j = (uint32_t)(pos % n_slots);
-            B.x[j] = p.x; B.y[j] = p.y; B.z[j] = p.z; B.u[j] = p.u; B.v[j] = p.v; B.w[j] = p.w;
-            B.E[j] = p.E; B.speed[j] = p.speed; B.wgt[j] = p.wgt; B.t[j] = p.t;
-            B.rng[j] = mcb_rn_child_seed(p.rng, b); B.cell[j] = p.cell; B.hist[j] = p.hist;
-            if (TALLY && P.track_old) B.Eold[j] = B.Eold[p.slot];
-            n_copy_ok++;
+            B.x[j] = q.x; B.y[j] = q.y; B.z[j] = q.z; B.u[j] = q.u; B.v[j] = q.v; B.w[j] = q.w;
+            B.E[j] = q.E; B.speed[j] = q.speed; B.wgt[j] = q.wgt; B.t[j] = q.t;
+            B.rng[j] = q.rng; B.cell[j] = q.cell; B.hist[j] = q.hist;
+            if (P.track_old) B.Eold[j] = q.Eold;
+            if (P.track_time) B.told[j] = q.told;
+            n_ok++;
         } else C->overflow_slots = 1;
     }
-    if (p.wgt < P.wr) {
-        if (mcb_urand(p.rng) < p.wgt / P.ws) p.wgt = P.ws;
-        else { p.wgt = 0.0; alive = false; }
-    }
-    return alive;
-}
+};
 
 // ---------------------------------------------------------------------------------------------
 // stage kernels
@@ -607,8 +174,9 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     B.x[q] = x; B.y[q] = y; B.z[q] = z; B.u[q] = u; B.v[q] = v; B.w[q] = w;
     B.E[q] = E; B.speed[q] = mcb_speed_of_energy(E); B.wgt[q] = 1.0; B.t[q] = t;
     B.rng[q] = rng; B.cell[q] = cell; B.hist[q] = h;
-    if (P.track_old) B.Eold[q] = E;  // the reference leaves energy_old uninitialised at birth; defined as E here
-    active[q] = q;
+    if (B.Eold) B.Eold[q] = E;  // the reference leaves energy_old uninitialised at birth; defined as E here
+    if (B.told) B.told[q] = t;
+    if (active) active[q] = q;  // event-queue mode: the first queue is the identity
 }
 
 // xs_lookup stage: macroscopic cross sections of every queued particle at its energy in its cell's material.
@@ -627,7 +195,8 @@ k_xs_stage(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int 
             p.cell = B.cell[i]; p.E = B.E[i];
             MacroXS X;
             int u;
-            if (ev_lookup<false>(P, p, X, u, nullptr)) {
+            NoDetail nd;
+            if (ev_lookup(P, p, X, u, nd)) {
                 B.St[i] = X.t; B.Ss[i] = X.s; B.Sc[i] = X.c; B.Sf[i] = X.f; B.nSf[i] = X.nf;
                 B.uidx[i] = u;
                 looked++;
@@ -663,16 +232,15 @@ k_flight(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
         if (valid) {
             i = active[q];
             Particle p;
-            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
-            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
-            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+            load_particle(P, B, i, p);
             MacroXS X;
             X.t = B.St[i]; X.nf = B.nSf[i];
             int uidx = 0;
             if (T.on) { X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; uidx = B.uidx[i]; }
             int S;
-            to_cross = ev_flight<true>(P, B, p, X, uidx, H, T, S);
+            to_cross = ev_flight<true>(P, p, X, uidx, H, T, C, S);
             B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.t[i] = p.t; B.rng[i] = p.rng; B.surf[i] = S;
+            if (P.track_time) B.told[i] = p.told;
             tracks++;
         }
         const unsigned cnt[2] = {valid && !to_cross ? 1u : 0u, valid && to_cross ? 1u : 0u};
@@ -697,22 +265,21 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
     unsigned long long* const next_len = &C->n_active[(cur + 1) % 3];
     unsigned collisions = 0;
     int it = 0;
+    const NoDetail nd;
     for (unsigned long long tile = blockIdx.x; tile * BLOCK < n; tile += gridDim.x, it++) {
         const unsigned long long q = tile * BLOCK + threadIdx.x;
         const bool valid = q < n;
         uint32_t i = 0;
         Particle p;
         MacroXS X = {0, 0, 0, 0, 0};
-        CollideCtx c = {-1, -1, 0, 0};
+        CollideCtx c = {-1, -1, 0, 0, 0.0};
         int uidx = -1;
         bool in_material = false;
         if (valid) {
             i = evq[q];
-            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
-            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
-            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+            load_particle(P, B, i, p);
             X.t = B.St[i]; X.s = B.Ss[i]; X.c = B.Sc[i]; X.f = B.Sf[i]; X.nf = B.nSf[i]; uidx = B.uidx[i];
-            in_material = ev_collide_pre<true>(P, B, p, X, uidx, nullptr, T, k_eff, c);
+            in_material = ev_collide_pre<true>(P, p, X, uidx, nd, T, C, k_eff, c);
             if (in_material) collisions++;
         }
         const unsigned cntA[2] = {c.n_sites, c.n_second};
@@ -720,22 +287,23 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
         unsigned long long posA[2];
         block_reserve<2>(scratchA[it & 1], cntA, curA, posA);
         bool alive = false;
-        unsigned n_second_ok = 0;
-        if (c.n_sites | c.n_second) ev_collide_bank<true>(P, B, p, c, H, C, reqs, site_cap, n_slots, posA[0], posA[1], n_second_ok);
+        BankSink sink(P, B, posA[1], n_slots, C);
+        if (c.n_sites | c.n_second) ev_collide_bank(P, p, c, H, C, reqs, site_cap, posA[0], sink);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (in_material) alive = ev_collide_scatter<true>(P, B, p, X, uidx, nullptr, c, H);
+        if (in_material) alive = ev_collide_scatter<true>(P, p, X, uidx, nd, c, H);
         __syncwarp();
         if (valid) {
             B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.E[i] = p.E; B.speed[i] = p.speed; B.wgt[i] = p.wgt; B.rng[i] = p.rng;
+            if (P.track_old) B.Eold[i] = p.Eold;
         }
         // survivors and their secondaries go to the next iteration's queue
-        const unsigned cntB[1] = {(alive ? 1u : 0u) + n_second_ok};
+        const unsigned cntB[1] = {(alive ? 1u : 0u) + sink.n_ok};
         unsigned long long* const curB[1] = {next_len};
         unsigned long long posB[1];
         block_reserve<1>(scratchB[it & 1], cntB, curB, posB);
         unsigned long long o = posB[0];
         if (alive) next[o++] = i;
-        for (unsigned b = 0; b < n_second_ok; b++) next[o++] = (uint32_t)(posA[1] + b);
+        for (unsigned b = 0; b < sink.n_ok; b++) next[o++] = (uint32_t)(posA[1] + b);
     }
     for (int d = 16; d; d >>= 1) collisions += __shfl_xor_sync(FULL, collisions, d);
     if (lane_id() == 0 && collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
@@ -762,10 +330,8 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
         unsigned n_copy = 0;
         if (valid) {
             i = evq[n_active - 1 - q];
-            p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
-            p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
-            p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
-            alive = ev_cross_pre<true>(P, B, p, B.surf[i], T, C, n_copy);
+            load_particle(P, B, i, p);
+            alive = ev_cross_pre<true>(P, p, B.surf[i], T, C, n_copy);
             crossings++;
         }
         unsigned long long slot0 = 0;
@@ -776,139 +342,25 @@ k_cross(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur, C
             block_reserve<1>(scratchA[it & 1], cntA, curA, posA);
             slot0 = posA[0];
         }
-        unsigned n_copy_ok = 0;
+        BankSink sink(P, B, slot0, n_slots, C);
         if (valid) {
-            alive = ev_cross_post<true>(P, B, p, alive, n_copy, slot0, n_slots, C, n_copy_ok);
+            alive = ev_cross_post(P, p, alive, n_copy, sink);
             if (alive) {
                 B.x[i] = p.x; B.y[i] = p.y; B.z[i] = p.z; B.u[i] = p.u; B.v[i] = p.v; B.w[i] = p.w; B.t[i] = p.t;
                 B.wgt[i] = p.wgt; B.rng[i] = p.rng; B.cell[i] = p.cell;
+                if (P.track_time) B.told[i] = p.told;
             }
         }
-        const unsigned cntB[1] = {(alive ? 1u : 0u) + n_copy_ok};
+        const unsigned cntB[1] = {(alive ? 1u : 0u) + sink.n_ok};
         unsigned long long* const curB[1] = {next_len};
         unsigned long long posB[1];
         block_reserve<1>(scratchB[it & 1], cntB, curB, posB);
         unsigned long long o = posB[0];
         if (alive) next[o++] = i;
-        for (unsigned b = 0; b < n_copy_ok; b++) next[o++] = (uint32_t)(slot0 + b);
+        for (unsigned b = 0; b < sink.n_ok; b++) next[o++] = (uint32_t)(slot0 + b);
     }
     for (int d = 16; d; d >>= 1) crossings += __shfl_xor_sync(FULL, crossings, d);
     if (lane_id() == 0 && crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
-}
-
-#ifndef MCB_STEP_MINB
-#define MCB_STEP_MINB 6
-#endif
-
-// history walk: the whole event chain of a particle in registers, one launch per pass over bank slots
-// [begin, end).  Every warp is autonomous (no block barriers): it draws slot indices in private chunks from a
-// global head counter and, at every iteration, refills the lanes whose particle has just ended with the next slots,
-// so lanes stay busy until the pass runs dry; fission-site requests are reserved with one cursor atomic per warp and
-// iteration.  Nothing but the site requests (and the rare secondaries, which go to slots >= end and are walked by
-// the next pass) is written back: the particle record is read once.  With one particle per history the EstimatorK
-// scores live in registers and are stored once when the history ends.
-template <bool TALLY, bool SHARED>
-__global__ void __launch_bounds__(BLOCK, MCB_STEP_MINB)
-k_walk(const DevProblem P, Bank B, unsigned long long begin, unsigned long long end, uint32_t chunk, Counters* C, HistoryAcc H, TallyAcc T,
-       SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
-{
-    const unsigned lane = lane_id();
-    const unsigned lt_mask = (1u << lane) - 1u;
-    constexpr bool local_acc = !SHARED;  // SHARED = DevProblem::shared_histories: secondaries / split copies can exist
-    unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
-    bool alive = false, exhausted = false;
-    Particle p;
-    HistLocal L = {0.0, 0.0, 0};
-    unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of bank positions
-    for (;;) {
-        // ---- refill the idle lanes
-        unsigned idle = __ballot_sync(FULL, !alive);
-        while (idle && !exhausted) {
-            if (chunk_next == chunk_end) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&C->walk_head, (unsigned long long)chunk);
-                base = __shfl_sync(FULL, base, 0);
-                const unsigned long long b = begin + base;
-                chunk_next = b < end ? b : end;
-                chunk_end = b + chunk < end ? b + chunk : end;
-                if (chunk_next == chunk_end) { exhausted = true; break; }
-            }
-            const unsigned take = min((unsigned)__popc(idle), (unsigned)(chunk_end - chunk_next));
-            const unsigned rank = __popc(idle & lt_mask);
-            if (!alive && rank < take) {
-                // ring: position -> slot (without secondaries positions never leave [0, n_slots))
-                const uint32_t j = SHARED ? (uint32_t)((chunk_next + rank) % n_slots) : (uint32_t)(chunk_next + rank);
-                p.cell = B.cell[j]; p.hist = B.hist[j]; p.slot = (int)j;
-                p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
-                p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
-                L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
-                alive = true;
-            }
-            chunk_next += take;
-            idle = __ballot_sync(FULL, !alive);
-        }
-#ifdef MCB_WALK_SYNC
-        // keep the warps of a block in phase: they then run the same stretch of this (large) loop body and share
-        // its instruction-cache lines instead of evicting each other's
-        if (!__syncthreads_or(idle != FULL)) break;
-#else
-        if (idle == FULL) break;  // nothing in flight and nothing left to draw
-#endif
-        // ---- one event per live lane
-        MacroXS X = {0, 0, 0, 0, 0};
-        XSDetail D;
-        CollideCtx c = {-1, -1, 0, 0};
-        int uidx = -1;
-        unsigned n_copy = 0;
-        bool to_cross = false, in_material = false;
-        const bool was_alive = alive;
-        if (alive) {
-            int S;
-            if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-            to_cross = ev_flight<TALLY>(P, B, p, X, uidx, H, T, S, local_acc ? &L : nullptr);
-            tracks++;
-            if (to_cross) { alive = ev_cross_pre<TALLY>(P, B, p, S, T, C, n_copy); crossings++; }
-            else { in_material = ev_collide_pre<TALLY>(P, B, p, X, uidx, &D, T, k_eff, c); if (in_material) collisions++; else alive = false; }
-        }
-        __syncwarp();
-        // fission-site requests: one reservation per warp
-        unsigned long long site0 = 0;
-        {
-            unsigned v = c.n_sites;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(FULL, v, d); if (lane >= (unsigned)d) v += t; }
-            const unsigned total = __shfl_sync(FULL, v, 31);
-            if (total) {
-                unsigned long long base = 0;
-                if (lane == 31) base = atomicAdd(&C->site_cursor, (unsigned long long)total);
-                site0 = __shfl_sync(FULL, base, 31) + (v - c.n_sites);
-            }
-        }
-        // secondaries (fixed-source fission neutrons, split copies) are rare: one slot reservation per lane
-        unsigned long long slot0 = 0;
-        if (!SHARED) { c.n_second = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
-        else if (c.n_second + n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)(c.n_second + n_copy));
-        unsigned n_new = 0;
-        if (c.n_sites | c.n_second) ev_collide_bank<TALLY>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new, local_acc ? &L : nullptr, begin);
-        __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (to_cross) alive = ev_cross_post<TALLY>(P, B, p, alive, n_copy, slot0, n_slots, C, n_new, begin);
-        __syncwarp();
-        if (in_material) alive = ev_collide_scatter<TALLY>(P, B, p, X, uidx, &D, c, H, local_acc ? &L : nullptr);
-        __syncwarp();
-        if (local_acc && was_alive && !alive) {  // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525)
-            H.kC[p.hist] = L.kC; H.kTL[p.hist] = L.kTL; H.nsite[p.hist] = L.nsite;
-        }
-    }
-    for (int d = 16; d; d >>= 1) {
-        tracks += __shfl_xor_sync(FULL, tracks, d); collisions += __shfl_xor_sync(FULL, collisions, d);
-        crossings += __shfl_xor_sync(FULL, crossings, d); lookups += __shfl_xor_sync(FULL, lookups, d);
-    }
-    if (lane == 0) {
-        if (tracks) atomicAdd(&C->n_tracks, (unsigned long long)tracks);
-        if (collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
-        if (crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
-        if (lookups) atomicAdd(&C->n_lookups, (unsigned long long)lookups);
-    }
 }
 
 // tail of a batch: every queued particle is followed to the end of its history in registers (the same events,
@@ -924,35 +376,37 @@ k_finish(const DevProblem P, Bank B, const uint32_t* __restrict__ active, int cu
     for (unsigned long long q = (unsigned long long)blockIdx.x * BLOCK + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * BLOCK) {
         const uint32_t i = active[q];
         Particle p;
-        p.cell = B.cell[i]; p.hist = B.hist[i]; p.slot = (int)i;
-        p.x = B.x[i]; p.y = B.y[i]; p.z = B.z[i]; p.u = B.u[i]; p.v = B.v[i]; p.w = B.w[i];
-        p.E = B.E[i]; p.speed = B.speed[i]; p.wgt = B.wgt[i]; p.t = B.t[i]; p.rng = B.rng[i];
+        load_particle(P, B, i, p);
         bool alive = true;
         while (alive) {
             MacroXS X = {0, 0, 0, 0, 0};
             XSDetail D;
             int uidx = -1, S;
-            if (ev_lookup<true>(P, p, X, uidx, &D)) lookups++;
-            const bool to_cross = ev_flight<true>(P, B, p, X, uidx, H, T, S);
+            if (ev_lookup(P, p, X, uidx, D)) lookups++;
+            const bool to_cross = ev_flight<true>(P, p, X, uidx, H, T, C, S);
             tracks++;
             unsigned n_new = 0;
             unsigned long long slot0 = 0;
             if (to_cross) {
                 unsigned n_copy;
-                alive = ev_cross_pre<true>(P, B, p, S, T, C, n_copy);
+                alive = ev_cross_pre<true>(P, p, S, T, C, n_copy);
                 crossings++;
                 if (n_copy) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)n_copy);
-                alive = ev_cross_post<true>(P, B, p, alive, n_copy, slot0, n_slots, C, n_new);
+                BankSink sink(P, B, slot0, n_slots, C);
+                alive = ev_cross_post(P, p, alive, n_copy, sink);
+                n_new = sink.n_ok;
             } else {
                 CollideCtx c;
-                alive = ev_collide_pre<true>(P, B, p, X, uidx, &D, T, k_eff, c);
+                alive = ev_collide_pre<true>(P, p, X, uidx, D, T, C, k_eff, c);
                 if (alive) {
                     collisions++;
                     unsigned long long site0 = 0;
                     if (c.n_sites) site0 = atomicAdd(&C->site_cursor, (unsigned long long)c.n_sites);
                     if (c.n_second) slot0 = atomicAdd(&C->slot_cursor, (unsigned long long)c.n_second);
-                    if (c.n_sites | c.n_second) ev_collide_bank<true>(P, B, p, c, H, C, reqs, site_cap, n_slots, site0, slot0, n_new);
-                    alive = ev_collide_scatter<true>(P, B, p, X, uidx, &D, c, H);
+                    BankSink sink(P, B, slot0, n_slots, C);
+                    if (c.n_sites | c.n_second) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink);
+                    n_new = sink.n_ok;
+                    alive = ev_collide_scatter<true>(P, p, X, uidx, D, c, H);
                 }
             }
             if (n_new) {
@@ -1090,8 +544,9 @@ __global__ void __launch_bounds__(256)
 k_tally_partial(double* acc, int64_t stride, uint32_t n_hist, double* partial /* [tally][chunk][2] */, int n_chunks)
 {
     __shared__ double ss[8], sq[8];
-    const int tally = blockIdx.y, chunk = blockIdx.x;
-    double* row = acc + (int64_t)tally * stride;
+    const int64_t tally = blockIdx.x;  // gridDim.x holds any number of tallies (gridDim.y stops at 65535)
+    const int chunk = blockIdx.y;
+    double* row = acc + tally * stride;
     double s = 0.0, q = 0.0;
     const uint32_t b = (uint32_t)chunk * TALLY_CHUNK;
     const uint32_t e = min(b + (uint32_t)TALLY_CHUNK, n_hist);
@@ -1105,8 +560,8 @@ k_tally_partial(double* acc, int64_t stride, uint32_t n_hist, double* partial /*
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < 8; i++) { s += ss[i]; q += sq[i]; }
-        partial[((int64_t)tally * n_chunks + chunk) * 2 + 0] = s;
-        partial[((int64_t)tally * n_chunks + chunk) * 2 + 1] = q;
+        partial[(tally * n_chunks + chunk) * 2 + 0] = s;
+        partial[(tally * n_chunks + chunk) * 2 + 1] = q;
     }
 }
 __global__ void k_tally_final(const double* partial, int n_chunks, int64_t n_tallies, double* sum, double* squared)
@@ -1238,7 +693,7 @@ __global__ void k_scatter(const DevProblem P, int nuclide, const uint64_t* nps, 
     uint64_t rng = mcb_rn_history_seed(P.seed0, nps[q]);
     double u = io5[5 * q], v = io5[5 * q + 1], w = io5[5 * q + 2], E = io5[5 * q + 3];
     double speed = mcb_speed_of_energy(E);
-    scatter_sample(P.nuclides[nuclide].A, u, v, w, E, speed, rng);
+    scatter_sample(P.nuclides[nuclide], u, v, w, E, speed, rng);
     io5[5 * q] = u; io5[5 * q + 1] = v; io5[5 * q + 2] = w; io5[5 * q + 3] = E; io5[5 * q + 4] = speed;
 }
 __global__ void k_watt(const DevProblem P, int nuclide, const uint64_t* nps, const double* E, int64_t n, double* out)
@@ -1250,6 +705,17 @@ __global__ void k_watt(const DevProblem P, int nuclide, const uint64_t* nps, con
     out[q] = watt_sample(N.watt_a, N.watt_b, N.watt_g, E[q], rng);
 }
 
+// a / b three ways: through one shared refined reciprocal (mcb_div_shared), as the zero-numerator shortcut where it applies
+// (mcb_div_zero_ok), and as the compiler's IEEE division: the first two must equal the third bit for bit
+__global__ void k_division(const double* a, const double* b, int64_t n, double* out_shared, double* out_plain)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double r = mcb_rcp_shared(b[q]);
+    out_shared[q] = (a[q] == 0.0 && b[q] > 0.0) ? mcb_div_zero_ok(a[q], b[q]) : mcb_div_shared(a[q], b[q], r);
+    out_plain[q] = a[q] / b[q];
+}
+
 inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -1259,7 +725,7 @@ inline unsigned blocks_for(uint64_t n, unsigned bs = 256) { return (unsigned)((n
 // ---------------------------------------------------------------------------------------------
 namespace mcbk {
 
-static thread_local uint64_t g_launches = 0;
+thread_local uint64_t g_launches = 0;  // also bumped by mcb_walk.cu
 uint64_t launch_count() { return g_launches; }
 #define MCB_LAUNCHED(k) (g_launches += (k))
 
@@ -1352,24 +818,6 @@ void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* 
     k_cross<<<grid_for(n_hint), BLOCK, 0, st>>>(P, B, evq, cur, C, next, T, n_slots);
     MCB_LAUNCHED(1);
 }
-void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff)
-{
-    if (end <= begin) return;
-    // persistent: every resident warp draws chunks of slots until the pass runs dry
-    const uint64_t n = end - begin;
-    const unsigned resident = 148u * MCB_STEP_MINB;
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + BLOCK - 1) / BLOCK, resident));
-    const uint64_t warps = (uint64_t)grid * WARPS;
-    const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
-    // two instances: the one for cycles that score nothing carries no estimator code (and no energy_old upkeep)
-    // and one pair for problems where nothing is born in flight (k-eigenvalue without splitting)
-#define MCB_WALK(TALLY, SHARED) k_walk<TALLY, SHARED><<<grid, BLOCK, 0, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, n_slots, k_eff)
-    if (T.on) { if (P.shared_histories) MCB_WALK(true, true); else MCB_WALK(true, false); }
-    else { if (P.shared_histories) MCB_WALK(false, true); else MCB_WALK(false, false); }
-#undef MCB_WALK
-    MCB_LAUNCHED(1);
-}
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff)
@@ -1410,7 +858,7 @@ void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist,
 {
     if (!n_hist || !n_tallies) return;
     const int nc = tally_chunks(n_hist);
-    k_tally_partial<<<dim3(nc, (unsigned)n_tallies), 256, 0, st>>>(acc, stride, n_hist, partial, nc);
+    k_tally_partial<<<dim3((unsigned)n_tallies, nc), 256, 0, st>>>(acc, stride, n_hist, partial, nc);
     k_tally_final<<<blocks_for(n_tallies, 128), 128, 0, st>>>(partial, nc, n_tallies, sum, squared);
     MCB_LAUNCHED(2);
 }
@@ -1460,6 +908,10 @@ void search_cell(cudaStream_t st, const DevProblem& P, const double* pos, int64_
 void scatter(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, int64_t n, double* io5)
 {
     if (n) { k_scatter<<<blocks_for(n), 256, 0, st>>>(P, nuclide, nps, n, io5); MCB_LAUNCHED(1); }
+}
+void division(cudaStream_t st, const double* a, const double* b, int64_t n, double* out_shared, double* out_plain)
+{
+    if (n) { k_division<<<blocks_for(n), 256, 0, st>>>(a, b, n, out_shared, out_plain); MCB_LAUNCHED(1); }
 }
 void watt(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, const double* E, int64_t n, double* out)
 {

@@ -39,11 +39,25 @@ void collide(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t
              uint64_t site_cap, uint32_t n_slots, double k_eff);
 void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* evq, int cur, uint64_t n_hint, Counters* C,
            uint32_t* next, const TallyAcc& T, uint32_t n_slots);
-// history walk: every particle in bank slots [begin, end) followed to the end of its chain in registers, lanes refilled
-// as particles end; secondaries born on the way land at positions >= end (Counters::slot_cursor) for the next pass.
-// The bank is a ring over positions: slot = position % n_slots, slots behind `begin` are reused
+// the walk kernel (mcb_walk.cu): every source particle in bank positions [begin, end) and all secondaries of its history
+// followed to the end; particles sorted by next event in shared-memory queues, 160 history contexts per thread block.
+// walk_plan() sizes the launch for this device (dynamic shared memory, blocks per SM of the scoring and non-scoring
+// instance) and tells how many history contexts exist at most: the caller owns the per-context secondary stacks
+// (n_contexts x stack_depth StackRec) and tally tables (TallyAcc::tab_*).
+struct WalkRes {        // kernel argument
+    StackRec* stack;
+    int32_t stack_depth, det_nn, n_pairs, priv_tallies;
+};
+struct WalkPlan {
+    int n_sm, det_nn, priv_tallies, max_grid;
+    bool shared;        // secondaries can be born in flight (fixed source / splitting)
+    int blocks_per_sm[2], n_pairs[2];   // [0] cycles that score nothing, [1] scoring cycles
+    size_t smem_bytes[2];
+    int64_t n_contexts;
+};
+int walk_plan(bool shared, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, uint32_t n_slots, double k_eff);
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth);
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff);
@@ -76,6 +90,7 @@ void geometry(cudaStream_t st, const DevProblem& P, const int32_t* cell, const d
               int64_t n, double* out3);
 void search_cell(cudaStream_t st, const DevProblem& P, const double* pos, int64_t n, int32_t* out);
 void scatter(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, int64_t n, double* io5);
+void division(cudaStream_t st, const double* a, const double* b, int64_t n, double* out_shared, double* out_plain);
 void watt(cudaStream_t st, const DevProblem& P, int nuclide, const uint64_t* nps, const double* E, int64_t n, double* out);
 
 }  // namespace mcbk

@@ -1,0 +1,428 @@
+// mcb_walk.cu — the transport loop of one generation: k_walk, an event-based particle queue held in shared memory.
+//
+// Reference: the body of the sample loop of Simulator::start() (handler.cpp:19-37): every source particle and the
+// secondaries of its history are followed through random_walk (general.cpp:177-211) until the history's particle
+// bank (Pbank) is empty, then the history is closed out (end_history).
+//
+// Design (B200: 148 SMs, 227 KB of shared memory per SM, FP64 scalar code bound by issue slots and latency):
+//  * Every thread block owns 160 particle SLOTS in shared memory (SoA, 16-byte pairs).  A slot is the home of one
+//    history from the moment it is drawn from the source bank until it ends: the particle in flight, its
+//    EstimatorK scores, the macroscopic cross sections and per-nuclide partial sums of its last lookup.
+//  * Particles are SORTED BY NEXT EVENT in two block-level queues of slot numbers: "collide" and "cross".
+//    A warp runs the common part (xs lookup + flight) on the 32 particles it holds, parks them in their slots,
+//    appends them to the queue of their next event and takes 32 slots of ONE kind back out, so the collision and
+//    crossing code runs on full warps (the history-per-lane formulation of round 1 ran collisions on 23 and
+//    crossings on 8 of 32 lanes).  With 128 threads and 160 slots at least 64 slots are queued whenever a warp
+//    asks, so one queue always holds a full warp.  Warps stay autonomous: the only synchronisation is a
+//    shared-memory lock around the few instructions that move queue heads and tails.
+//  * A lane whose history has ended draws the next source particle from the bank (chunks of a device-side head
+//    counter), so lanes stay busy until the bank runs dry.
+//  * Same-history secondaries (fixed-source fission neutrons, split copies) go to the history's own LIFO stack in
+//    global memory — the reference's Pbank — and are followed by whichever lane holds the history, so a history is
+//    always followed by one lane at a time: its k scores stay on registers, its tallies accumulate in a private
+//    table and there is no pass structure and no host round trip, however long the fission chain.
+//  * Fission sites leave the kernel as requests (one warp-aggregated cursor reservation per batch) and are sampled
+//    and put into canonical order by k_bank_sample_order.
+#include "mcb_events.cuh"
+
+#include <algorithm>
+
+using namespace mcbe;
+
+namespace {
+
+#ifndef MCB_WALK_MINB
+#define MCB_WALK_MINB 6
+#endif
+constexpr int WALK_RES = 32;                  // slots beyond one per thread: what makes a full batch always available
+constexpr int WALK_SLOTS = BLOCK + WALK_RES;  // 160
+constexpr int WALK_QCAP = 256;                // ring capacity of a queue (power of two >= WALK_SLOTS)
+static_assert(WALK_QCAP >= WALK_SLOTS && (WALK_QCAP & (WALK_QCAP - 1)) == 0, "queue ring");
+
+// slot state, pairs of doubles laid out [pair][slot] (a warp's 128-bit accesses fall on distinct banks for slots that
+// differ modulo 8)
+enum {
+    SP_XY = 0,    // x, y
+    SP_ZU,        // z, u
+    SP_VW,        // v, w
+    SP_ES,        // E, speed
+    SP_WT,        // weight, time
+    SP_RNG,       // stream state | (cell, history)
+    SP_K,         // k_C, k_TL of the history so far
+    SP_IDS,       // (sites banked by the history, depth of its secondary stack) | (surface ahead, union-grid index)
+    SP_XT,        // SigmaT, nuSigmaF
+    SP_XS,        // SigmaS, SigmaC
+    SP_XF,        // SigmaF, energy_old
+    SP_FIXED      // scoring instances add: time_old | (tally-table entries in use, -); then the per-nuclide detail
+};
+
+struct WalkQ {
+    unsigned lock;
+    unsigned headC, tailC, headX, tailX;
+    unsigned warps_done;
+    unsigned pad[2];
+    unsigned short qC[WALK_QCAP], qX[WALK_QCAP];
+};
+
+__device__ __forceinline__ double pack2i(int lo, int hi) { return __hiloint2double(hi, lo); }
+__device__ __forceinline__ int unpack_lo(double d) { return __double2loint(d); }
+__device__ __forceinline__ int unpack_hi(double d) { return __double2hiint(d); }
+
+// per-nuclide partial sums of the particle's last lookup, kept in its slot: (Sigma_s, nuSigma_f) after nuclides 0..n as
+// one pair per nuclide, then beta_n two to a pair
+struct SlotDetail {
+    static constexpr bool present = true;
+    double2* base;  // pair SP_DET of this slot
+    int nn;         // nuclides per material at most (problem-wide)
+    __device__ __forceinline__ void set(int n, double s, double nf, double be) const
+    {
+        base[n * WALK_SLOTS] = make_double2(s, nf);
+        reinterpret_cast<double*>(base + (nn + (n >> 1)) * WALK_SLOTS)[n & 1] = be;
+    }
+    __device__ __forceinline__ double cum_s(int n) const { return base[n * WALK_SLOTS].x; }
+    __device__ __forceinline__ double cum_nf(int n) const { return base[n * WALK_SLOTS].y; }
+    __device__ __forceinline__ double beta(int n) const { return reinterpret_cast<const double*>(base + (nn + (n >> 1)) * WALK_SLOTS)[n & 1]; }
+};
+
+// the history's LIFO stack of secondaries (the reference's Pbank, handler.cpp:20-29)
+struct StackSink {
+    StackRec* stk;
+    int& sp;
+    int depth;
+    Counters* C;
+    __device__ __forceinline__ void push(const Particle& q)
+    {
+        if (sp >= depth) { C->overflow_stack = 1; return; }
+        double2* r = reinterpret_cast<double2*>(stk + sp);
+        r[0] = make_double2(q.x, q.y); r[1] = make_double2(q.z, q.u); r[2] = make_double2(q.v, q.w);
+        r[3] = make_double2(q.E, q.speed); r[4] = make_double2(q.wgt, q.t);
+        r[5] = make_double2(q.Eold, __longlong_as_double((long long)q.rng));
+        r[6] = make_double2(pack2i(q.cell, 0), 0.0);
+        sp++;
+    }
+};
+__device__ __forceinline__ void stack_pop(const StackRec* stk, int& sp, Particle& p)
+{
+    sp--;
+    const double2* r = reinterpret_cast<const double2*>(stk + sp);
+    const double2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g = r[6];
+    p.x = a.x; p.y = a.y; p.z = b.x; p.u = b.y; p.v = c.x; p.w = c.y; p.E = d.x; p.speed = d.y; p.wgt = e.x; p.t = e.y;
+    p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x);
+    p.told = p.t;
+}
+
+__device__ __forceinline__ void lock_acquire(WalkQ& Q, unsigned lane)
+{
+    if (lane == 0) {
+        while (atomicCAS(&Q.lock, 0u, 1u) != 0u) __nanosleep(32);
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+__device__ __forceinline__ void lock_release(WalkQ& Q, unsigned lane)
+{
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(&Q.lock, 0u);
+}
+
+// Estimator::end_history for one history (Estimator.cpp:339-346): sum += hist, squared += hist^2 per touched bin
+__device__ __forceinline__ void flush_history_tallies(const TallyAcc& T, int row, int n_touched, double* s_sum, double* s_sq)
+{
+    const uint32_t size = T.tab_mask + 1u;
+    uint32_t* keys = T.tab_key + (size_t)row * size;
+    double* vals = T.tab_val + (size_t)row * size;
+    const uint16_t* list = T.tab_list + (size_t)row * size;
+    for (int i = 0; i < n_touched; i++) {
+        const uint32_t h = __ldcg(list + i);
+        const uint32_t t = __ldcg(keys + h) - 1u;
+        const double v = __ldcg(vals + h);
+        __stcg(keys + h, 0u);
+        if (s_sum) { atomicAdd(s_sum + t, v); atomicAdd(s_sq + t, v * v); }
+        else { atomicAdd(T.sum + t, v); atomicAdd(T.squared + t, v * v); }
+    }
+}
+
+template <bool TALLY, bool SHARED>
+__global__ void __launch_bounds__(BLOCK, MCB_WALK_MINB)
+k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long long end, uint32_t chunk, Counters* C, HistoryAcc H,
+       TallyAcc T, SiteReq* reqs, uint64_t site_cap, double k_eff, mcbk::WalkRes R)
+{
+    extern __shared__ double2 w_smem[];
+    constexpr int SP_DET = TALLY ? SP_FIXED + 1 : SP_FIXED;
+    double2* const st = w_smem;
+    WalkQ& Q = *reinterpret_cast<WalkQ*>(st + R.n_pairs * WALK_SLOTS);
+    double* const s_sum = (TALLY && R.priv_tallies) ? reinterpret_cast<double*>(&Q + 1) : nullptr;
+    double* const s_sq = s_sum ? s_sum + R.priv_tallies : nullptr;
+    if (threadIdx.x == 0) { Q.lock = 0; Q.headC = Q.tailC = Q.headX = Q.tailX = 0; Q.warps_done = 0; }
+    if (s_sum) for (int i = threadIdx.x; i < 2 * R.priv_tallies; i += BLOCK) s_sum[i] = 0.0;
+    __syncthreads();  // the only block-wide barrier: from here on the warps run on their own
+
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int ctx_base = blockIdx.x * WALK_SLOTS;
+    unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
+    int my_slot = threadIdx.x;            // the slot this lane parks its particle in (it moves with every claim)
+    bool have = false, exhausted = false;
+    bool second_batch = warp_id() == 0;   // warp 0 starts two batches: the block's 32 extra slots
+    Particle p;
+    HistLocal L = {0.0, 0.0, 0};
+    int sp = 0;                           // depth of the history's secondary stack
+    unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of bank positions
+    for (;;) {
+        // ---- lanes without a history draw the next source particles
+        unsigned idle = __ballot_sync(FULL, !have);
+        while (idle && !exhausted) {
+            if (chunk_next == chunk_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&C->walk_head, (unsigned long long)chunk);
+                base = __shfl_sync(FULL, base, 0);
+                const unsigned long long b = begin + base;
+                chunk_next = b < end ? b : end;
+                chunk_end = b + chunk < end ? b + chunk : end;
+                if (chunk_next == chunk_end) { exhausted = true; break; }
+            }
+            const unsigned take = min((unsigned)__popc(idle), (unsigned)(chunk_end - chunk_next));
+            const unsigned rank = __popc(idle & lt_mask);
+            if (!have && rank < take) {
+                const uint32_t j = (uint32_t)(chunk_next + rank);
+                p.cell = B.cell[j]; p.hist = B.hist[j];
+                p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
+                p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
+                p.Eold = p.E;  // the reference leaves energy_old uninitialised at birth; defined as E here
+                p.told = p.t;
+                p.n_touched = 0;
+                L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
+                sp = 0;
+                have = true;
+            }
+            chunk_next += take;
+            idle = __ballot_sync(FULL, !have);
+        }
+        // ---- common part of every track: xs lookup and flight; the particle is parked in its slot
+        bool to_cross = false;
+        if (have) {
+            p.row = ctx_base + my_slot;
+            MacroXS X = {0, 0, 0, 0, 0};
+            int uidx = -1, S = -1;
+            const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
+            if (ev_lookup(P, p, X, uidx, D)) lookups++;
+            to_cross = ev_flight<TALLY>(P, p, X, uidx, H, T, C, S, &L);
+            tracks++;
+            double2* s = st + my_slot;
+            s[SP_XY * WALK_SLOTS] = make_double2(p.x, p.y);
+            s[SP_ZU * WALK_SLOTS] = make_double2(p.z, p.u);
+            s[SP_VW * WALK_SLOTS] = make_double2(p.v, p.w);
+            s[SP_ES * WALK_SLOTS] = make_double2(p.E, p.speed);
+            s[SP_WT * WALK_SLOTS] = make_double2(p.wgt, p.t);
+            s[SP_RNG * WALK_SLOTS] = make_double2(__longlong_as_double((long long)p.rng), pack2i(p.cell, p.hist));
+            s[SP_K * WALK_SLOTS] = make_double2(L.kC, L.kTL);
+            s[SP_IDS * WALK_SLOTS] = make_double2(pack2i(L.nsite, sp), pack2i(S, uidx));
+            s[SP_XT * WALK_SLOTS] = make_double2(X.t, X.nf);
+            s[SP_XS * WALK_SLOTS] = make_double2(X.s, X.c);
+            s[SP_XF * WALK_SLOTS] = make_double2(X.f, p.Eold);
+            if (TALLY) s[SP_FIXED * WALK_SLOTS] = make_double2(p.told, pack2i(p.n_touched, 0));
+        }
+        // ---- event queues: append what this warp holds, take one batch of a kind back out
+        int kind = 0;  // 1 collide, 2 cross
+        lock_acquire(Q, lane);
+        {
+            const unsigned mC = __ballot_sync(FULL, have && !to_cross), mX = __ballot_sync(FULL, have && to_cross);
+            unsigned hC = Q.headC, tC = Q.tailC, hX = Q.headX, tX = Q.tailX;
+            if (have) {
+                if (!to_cross) Q.qC[(tC + __popc(mC & lt_mask)) & (WALK_QCAP - 1)] = (unsigned short)my_slot;
+                else Q.qX[(tX + __popc(mX & lt_mask)) & (WALK_QCAP - 1)] = (unsigned short)my_slot;
+            }
+            tC += __popc(mC); tX += __popc(mX);
+            __syncwarp();
+            unsigned nC = 0, nX = 0;
+            if (!second_batch) {
+                const unsigned aC = tC - hC, aX = tX - hX;
+                if (aX >= 32u) nX = 32u;
+                else if (aC >= 32u) nC = 32u;
+                else if (aC >= aX) { nC = aC; nX = min(aX, 32u - nC); }
+                else { nX = aX; nC = min(aC, 32u - nX); }
+                if (lane < nC) { my_slot = Q.qC[(hC + lane) & (WALK_QCAP - 1)]; kind = 1; }
+                else if (lane < nC + nX) { my_slot = Q.qX[(hX + lane - nC) & (WALK_QCAP - 1)]; kind = 2; }
+                hC += nC; hX += nX;
+            }
+            __syncwarp();
+            if (lane == 0) { Q.headC = hC; Q.tailC = tC; Q.headX = hX; Q.tailX = tX; }
+        }
+        lock_release(Q, lane);
+        if (second_batch) {  // warp 0, once: its first batch waits in the queues, the second goes to the extra slots
+            second_batch = false;
+            have = false;
+            my_slot = BLOCK + (int)lane;
+            continue;
+        }
+        const unsigned mK = __ballot_sync(FULL, kind != 0);
+        if (mK == 0u) {
+            if (exhausted) break;  // nothing held, nothing queued, nothing left to draw
+            continue;
+        }
+        have = kind != 0;
+        // ---- the event itself, on a batch of one kind (mixed only when the queues run low)
+        MacroXS X = {0, 0, 0, 0, 0};
+        CollideCtx c = {-1, -1, 0, 0, 0.0};
+        int uidx = -1, S = -1;
+        unsigned n_copy = 0;
+        bool alive = false, in_material = false;
+        const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
+        if (have) {
+            const double2* s = st + my_slot;
+            double2 v;
+            v = s[SP_XY * WALK_SLOTS]; p.x = v.x; p.y = v.y;
+            v = s[SP_ZU * WALK_SLOTS]; p.z = v.x; p.u = v.y;
+            v = s[SP_VW * WALK_SLOTS]; p.v = v.x; p.w = v.y;
+            v = s[SP_ES * WALK_SLOTS]; p.E = v.x; p.speed = v.y;
+            v = s[SP_WT * WALK_SLOTS]; p.wgt = v.x; p.t = v.y;
+            v = s[SP_RNG * WALK_SLOTS]; p.rng = (uint64_t)__double_as_longlong(v.x); p.cell = unpack_lo(v.y); p.hist = unpack_hi(v.y);
+            v = s[SP_K * WALK_SLOTS]; L.kC = v.x; L.kTL = v.y;
+            v = s[SP_IDS * WALK_SLOTS]; L.nsite = unpack_lo(v.x); sp = unpack_hi(v.x); S = unpack_lo(v.y); uidx = unpack_hi(v.y);
+            v = s[SP_XF * WALK_SLOTS]; X.f = v.x; p.Eold = v.y;
+            if (TALLY) { v = s[SP_FIXED * WALK_SLOTS]; p.told = v.x; p.n_touched = unpack_lo(v.y); }
+            else { p.told = p.t; p.n_touched = 0; }
+            p.row = ctx_base + my_slot;
+            if (kind == 1) {
+                v = s[SP_XT * WALK_SLOTS]; X.t = v.x; X.nf = v.y;
+                v = s[SP_XS * WALK_SLOTS]; X.s = v.x; X.c = v.y;
+                in_material = ev_collide_pre<TALLY>(P, p, X, uidx, D, T, C, k_eff, c);
+                if (in_material) collisions++;
+            } else {
+                alive = ev_cross_pre<TALLY>(P, p, S, T, C, n_copy);
+                crossings++;
+            }
+        }
+        __syncwarp();
+        // fission-site requests: one reservation per warp
+        unsigned long long site0 = 0;
+        if (__any_sync(FULL, c.n_sites != 0u)) {
+            unsigned v = c.n_sites;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(FULL, v, d); if (lane >= (unsigned)d) v += t; }
+            const unsigned total = __shfl_sync(FULL, v, 31);
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(&C->site_cursor, (unsigned long long)total);
+            site0 = __shfl_sync(FULL, base, 31) + (v - c.n_sites);
+        }
+        if (!SHARED) { c.n_second = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
+        StackRec* const stk = SHARED ? R.stack + (size_t)(ctx_base + my_slot) * R.stack_depth : nullptr;
+        StackSink sink = {stk, sp, R.stack_depth, C};
+        if (c.n_sites | c.n_second) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, &L);
+        __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
+        if (have && kind == 2) alive = ev_cross_post(P, p, alive, n_copy, sink);
+        if (in_material) alive = ev_collide_scatter<TALLY>(P, p, X, uidx, D, c, H, &L);
+        __syncwarp();
+        if (have && !alive) {
+            if (SHARED && sp > 0) {
+                stack_pop(stk, sp, p);  // the history goes on with its most recent secondary (handler.cpp:22)
+            } else {
+                // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525), Estimator::end_history
+                if (P.ksearch) { H.kC[p.hist] = L.kC; H.kTL[p.hist] = L.kTL; H.nsite[p.hist] = L.nsite; }
+                if (TALLY && p.n_touched) flush_history_tallies(T, p.row, p.n_touched, s_sum, s_sq);
+                have = false;
+            }
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        tracks += __shfl_xor_sync(FULL, tracks, d); collisions += __shfl_xor_sync(FULL, collisions, d);
+        crossings += __shfl_xor_sync(FULL, crossings, d); lookups += __shfl_xor_sync(FULL, lookups, d);
+    }
+    if (lane == 0) {
+        if (tracks) atomicAdd(&C->n_tracks, (unsigned long long)tracks);
+        if (collisions) atomicAdd(&C->n_collisions, (unsigned long long)collisions);
+        if (crossings) atomicAdd(&C->n_crossings, (unsigned long long)crossings);
+        if (lookups) atomicAdd(&C->n_lookups, (unsigned long long)lookups);
+    }
+    if (s_sum) {  // the last warp out adds the block's private bins to the cycle sums
+        unsigned done = 0;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) done = atomicAdd(&Q.warps_done, 1u);
+        done = __shfl_sync(FULL, done, 0);
+        if (done == (unsigned)WARPS - 1u) {
+            __threadfence_block();
+            for (int i = (int)lane; i < R.priv_tallies; i += 32) {
+                const double a = s_sum[i], b = s_sq[i];
+                if (a != 0.0) { atomicAdd(T.sum + i, a); atomicAdd(T.squared + i, b); }
+            }
+        }
+    }
+}
+
+template <bool TALLY, bool SHARED>
+cudaError_t plan_instance(int det_nn, int priv, int n_sm, int& blocks, size_t& smem)
+{
+    const int n_pairs = (TALLY ? SP_FIXED + 1 : SP_FIXED) + det_nn + (det_nn + 1) / 2;
+    smem = (size_t)n_pairs * WALK_SLOTS * sizeof(double2) + sizeof(WalkQ) + (TALLY ? (size_t)priv * 2 * sizeof(double) : 0);
+    // opt in to the device's full shared memory once (the attribute is per function, not per context)
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    if (smem > (size_t)optin) return cudaErrorInvalidConfiguration;
+    e = cudaFuncSetAttribute(k_walk<TALLY, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_walk<TALLY, SHARED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    blocks = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_walk<TALLY, SHARED>, BLOCK, smem);
+    (void)n_sm;
+    return e;
+}
+
+}  // namespace
+
+namespace mcbk {
+
+extern thread_local uint64_t g_launches;
+
+int walk_plan(bool shared, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out)
+{
+    WalkPlan& W = *out;
+    W.det_nn = std::max(det_nn, 1);
+    W.priv_tallies = (n_tallies > 0 && n_tallies <= 256) ? (int)n_tallies : 0;
+    W.n_sm = n_sm;
+    cudaError_t e;
+    for (int tally = 0; tally < 2; tally++) {
+        int blocks = 0;
+        size_t smem = 0;
+        if (tally) e = shared ? plan_instance<true, true>(W.det_nn, W.priv_tallies, n_sm, blocks, smem) : plan_instance<true, false>(W.det_nn, W.priv_tallies, n_sm, blocks, smem);
+        else e = shared ? plan_instance<false, true>(W.det_nn, W.priv_tallies, n_sm, blocks, smem) : plan_instance<false, false>(W.det_nn, W.priv_tallies, n_sm, blocks, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (blocks < 1) return (int)cudaErrorInvalidConfiguration;
+        W.blocks_per_sm[tally] = blocks;
+        W.smem_bytes[tally] = smem;
+        W.n_pairs[tally] = (tally ? SP_FIXED + 1 : SP_FIXED) + W.det_nn + (W.det_nn + 1) / 2;
+    }
+    W.max_grid = n_sm * std::max(W.blocks_per_sm[0], W.blocks_per_sm[1]);
+    W.n_contexts = (int64_t)W.max_grid * WALK_SLOTS;
+    W.shared = shared;
+    return 0;
+}
+
+void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth)
+{
+    if (end <= begin) return;
+    // persistent: every resident warp draws chunks of bank positions until the generation runs dry
+    const uint64_t n = end - begin;
+    const int ti = T.on ? 1 : 0;
+    const unsigned resident = (unsigned)(W.n_sm * W.blocks_per_sm[ti]);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + BLOCK - 1) / BLOCK, resident));
+    const uint64_t warps = (uint64_t)grid * WARPS;
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
+    WalkRes R;
+    R.stack = stack; R.stack_depth = stack_depth; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
+    const size_t smem = W.smem_bytes[ti];
+    // four instances: cycles that score nothing carry no estimator code, problems where nothing is born in flight
+    // (k-eigenvalue without splitting) no secondary stack
+#define MCB_WALK(TALLY, SHARED) k_walk<TALLY, SHARED><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R)
+    if (T.on) { if (W.shared) MCB_WALK(true, true); else MCB_WALK(true, false); }
+    else { if (W.shared) MCB_WALK(false, true); else MCB_WALK(false, false); }
+#undef MCB_WALK
+    g_launches += 1;
+}
+
+}  // namespace mcbk

@@ -256,3 +256,35 @@ def test_watt_spectrum_mean(ctxs):
     mean = a * (1.5 + a * b / 4.0) * 1e6
     sd = got.std() / np.sqrt(n)
     assert abs(got.mean() - mean) < 4 * sd
+
+
+def test_shared_reciprocal_division_is_ieee(ctxs):
+    """csrc/mcb_physics.h: quotients of one denominator share a refined reciprocal (interpolation weights of
+    XSTable::xs, vector normalisations of the scatter kinematics).  That form must be the IEEE division bit for bit,
+    or cross sections stop being bit-exact against the reference's x86 divisions: 4e6 random pairs over the whole
+    exponent range the path meets, grid-like nearly equal operands, exact quotients, zeros, denormals, infinities;
+    the GPU's plain division is in turn checked against numpy's."""
+    _, ctx = ctxs(sorted(FN_DECKS)[0])
+    rng = np.random.default_rng(20261018)
+    n = 1_000_000
+    a = np.concatenate([
+        rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n),
+        rng.uniform(1e-5, 2e7, n),                                   # energies
+        rng.uniform(-1, 1, n),                                       # direction components
+        (rng.integers(1, 1 << 20, n) * rng.integers(1, 1 << 20, n)).astype(np.float64),  # exact quotients
+        np.array([0.0, -0.0, 1e-310, 5e-324, 1e308, np.inf, 1.0, 3.0, 1e-300, 2.0 ** -969, 2.0 ** -970]),
+    ])
+    b = np.concatenate([
+        rng.standard_normal(n) * 10.0 ** rng.uniform(-30, 30, n),
+        rng.uniform(1e-5, 2e7, n) * (1 + rng.uniform(-1e-12, 1e-12, n)),
+        rng.uniform(1e-3, 1e9, n),
+        rng.integers(1, 1 << 20, n).astype(np.float64),
+        np.array([3.0, 7.0, 3.0, 3.0, 1e-10, 2.0, 1e-310, 0.0, 1e300, 3.0, 3.0]),
+    ])
+    b[b == 0.0] = 1.5
+    b[-4] = 0.0
+    shared, plain = ctx.division(a, b)
+    assert np.array_equal(shared.view(np.uint64), plain.view(np.uint64))
+    with np.errstate(all="ignore"):
+        want = a / b
+    assert np.array_equal(plain.view(np.uint64)[~np.isnan(want)], want.view(np.uint64)[~np.isnan(want)])

@@ -341,8 +341,10 @@ def test_host_bank_cycle_equals_the_three_plain_calls():
                (rb.k_sum_C, rb.k_sum_TL, rb.k_sq_C, rb.H, rb.n_sites, rb.n_tracks, rb.n_collisions)
         assert np.array_equal(sa, sb) and np.array_equal(ca, cb)
         sites, cells = sa.copy(), ca.copy()
+    # tallies: per-history scores are identical; the cycle sums are accumulated with floating-point reductions whose
+    # order is not fixed, so they agree to rounding
     ta, tb = a.tallies(), b.tallies()
-    assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1]) and np.count_nonzero(ta[0]) > 20
+    assert np.allclose(ta[0], tb[0], rtol=1e-12, atol=0) and np.allclose(ta[1], tb[1], rtol=1e-9, atol=0) and np.count_nonzero(ta[0]) > 20
     with pytest.raises(RuntimeError, match="Source bank is empty"):
         b.run_cycle_host(np.zeros((0, 8)), np.zeros(0, dtype=np.int32), out_s, out_c)
     a.close(); b.close()
