@@ -428,6 +428,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, ctx->device));
         ctx->n_sm = prop.multiProcessorCount;
+        mcbk::set_device_sms(ctx->n_sm);
     }
     const bool split = ctx->split_stages;
     // event-queue mode: secondaries (same-history fission neutrons, split copies) need free slots behind the primaries
@@ -617,9 +618,10 @@ int mcb_comm_init(mcb_ctx* ctx, const char id[128])
     NK(g_nccl.CommInitRank(&ctx->comm, ctx->world, uid, ctx->rank));
     // Map every peer's fission banks into this process (CUDA IPC over NVLink / NVSwitch): the source kernel then reads
     // the sites it draws straight from the HBM of the rank that banked them and the bank is never gathered.
-    // Measured on 8xB200 (NV18 all-to-all): with one peer the in-place reads cost 1.1 ms per 1e7 histories and beat the
-    // gather (9.4 vs 11.9 ms per generation); with 3 or 7 peers the same fine-grained reads collapse (63 / 134 ms), so
-    // from 4 ranks on the slices are gathered with NCCL instead unless MCB_P2P=1 forces the in-place path.
+    // Random peer reads thrash the address translation of the peer mappings once the banks exceed ~1 GB (134 ms per
+    // generation at 8 ranks), so the source step sorts its draws by site index and sweeps the global bank in ascending
+    // order, every rank starting at its own slice (k_pick / k_source): in place for any number of ranks.  MCB_NO_P2P=1
+    // (or a failed mapping) selects the NCCL gather of the slices instead.
     const bool want_p2p = getenv("MCB_P2P") ? atoi(getenv("MCB_P2P")) != 0 : true;
     if (ctx->ksearch && want_p2p && !getenv("MCB_NO_P2P")) {
         const int W = ctx->world;

@@ -729,11 +729,13 @@ thread_local uint64_t g_launches = 0;  // also bumped by mcb_walk.cu
 uint64_t launch_count() { return g_launches; }
 #define MCB_LAUNCHED(k) (g_launches += (k))
 
+static int g_n_sm = 148;  // multiprocessors of the device in use (cudaDeviceProp::multiProcessorCount)
+void set_device_sms(int n) { if (n > 0) g_n_sm = n; }
 static unsigned grid_for(uint64_t n_hint)
 {
     // persistent tile loops: enough blocks to fill the machine a few times over, never more than the work
     const uint64_t need = (n_hint + BLOCK - 1) / BLOCK;
-    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, 148ull * 16ull * (256 / BLOCK)));
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)g_n_sm * 16ull * (256 / BLOCK)));
 }
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
             uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort)
@@ -841,16 +843,16 @@ void scan_sites(cudaStream_t st, void* temp, size_t temp_bytes, const int32_t* n
 }
 void reduce_k(cudaStream_t st, const double* kC, const double* kTL, uint32_t n, Counters* C)
 {
-    if (n) { k_reduce_k<<<min(blocks_for(n), 148u * 8u), 256, 0, st>>>(kC, kTL, n, C); MCB_LAUNCHED(1); }
+    if (n) { k_reduce_k<<<min(blocks_for(n), (unsigned)g_n_sm * 8u), 256, 0, st>>>(kC, kTL, n, C); MCB_LAUNCHED(1); }
 }
 void entropy_history(cudaStream_t st, const DevProblem& P, const Site* bank, const uint32_t* offset,
                      const int32_t* nsite, uint32_t n_hist, Counters* C)
 {
-    if (n_hist) { k_entropy_history<<<min(blocks_for(n_hist), 148u * 8u), 256, 0, st>>>(P, bank, offset, nsite, n_hist, C); MCB_LAUNCHED(1); }
+    if (n_hist) { k_entropy_history<<<min(blocks_for(n_hist), (unsigned)g_n_sm * 8u), 256, 0, st>>>(P, bank, offset, nsite, n_hist, C); MCB_LAUNCHED(1); }
 }
 void entropy_histogram(cudaStream_t st, const DevProblem& P, const Site* bank, uint64_t n, unsigned long long* bins)
 {
-    if (n) { k_entropy_histogram<<<min(blocks_for(n), 148u * 8u), 256, 0, st>>>(P, bank, n, bins); MCB_LAUNCHED(1); }
+    if (n) { k_entropy_histogram<<<min(blocks_for(n), (unsigned)g_n_sm * 8u), 256, 0, st>>>(P, bank, n, bins); MCB_LAUNCHED(1); }
 }
 int tally_chunks(uint32_t n_hist) { return (int)((n_hist + TALLY_CHUNK - 1) / TALLY_CHUNK); }
 void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist, int64_t n_tallies, double* partial,

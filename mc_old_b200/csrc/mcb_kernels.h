@@ -6,6 +6,7 @@
 
 namespace mcbk {
 
+void set_device_sms(int n);  // grid sizing of the persistent kernels
 uint64_t launch_count();  // kernels launched by this thread through the launchers below
 
 // stages of one generation.  `cur` = iteration % 3 selects the queue-length counter the iteration reads

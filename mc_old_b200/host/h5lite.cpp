@@ -79,6 +79,7 @@ struct GlobalHeap {
 struct Writer {
     Image img;
     GlobalHeap gh;
+    std::string too_wide;  // first group with more members than one B-tree node addresses
 
     // ---- datatype messages (spec IV.A.2.d) ----
     static std::vector<uint8_t> datatype(Type t)
@@ -195,6 +196,12 @@ struct Writer {
         std::sort(kids.begin(), kids.end(), [](const Child& a, const Child& b) { return strcmp(a.name.c_str(), b.name.c_str()) < 0; });
         const size_t n = kids.size();
         const size_t n_snod = (n + 2 * LEAF_K - 1) / (2 * LEAF_K);
+        // one leaf-level B-tree node holds 2 * INTERNAL_K symbol nodes = 256 links; a larger group needs an internal
+        // level, which this writer does not emit: refuse instead of writing past the node
+        if (n_snod > (size_t)(2 * INTERNAL_K)) {
+            if (too_wide.empty()) too_wide = g.name.empty() ? "/" : g.name;
+            return;
+        }
         // local heap data segment: "" at offset 0, then the names
         std::vector<uint64_t> name_off(n);
         uint64_t heap_data = 8;
@@ -306,6 +313,7 @@ bool File::write(const std::string& path, std::string& error)
 {
     Writer w;
     w.run(*this);
+    if (!w.too_wide.empty()) { error = "group " + w.too_wide + " has more than 256 members (not supported by the built-in HDF5 writer)"; return false; }
     FILE* fp = fopen(path.c_str(), "wb");
     if (!fp) { error = "cannot open " + path + " for writing"; return false; }
     const size_t n = fwrite(w.img.b.data(), 1, w.img.b.size(), fp);

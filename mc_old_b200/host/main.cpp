@@ -5,7 +5,8 @@
 //
 // Several GPUs: start one process per GPU with RANK / WORLD_SIZE / LOCAL_RANK in the environment (what torchrun, srun
 // or a shell loop provide); the histories of every generation are sharded over the ranks, rank 0 prints and writes
-// the output.  The 128-byte NCCL id travels through a file (MCB_ID_FILE, default /tmp/mcb_nccl_id.<MASTER_PORT>).
+// the output.  The 128-byte NCCL id travels through a file (MCB_ID_FILE, default
+// $XDG_RUNTIME_DIR|$TMPDIR|/tmp/mcb_nccl_id.<run id>.<MASTER_PORT>.<uid>, tagged with the job so that a stale one is refused).
 #include <unistd.h>
 
 #include <cstdio>
@@ -17,6 +18,9 @@
 #include <vector>
 
 #include "mcb200.h"
+#include <sys/stat.h>
+#include <ctime>
+
 #include "mcb200_host.h"
 
 int main(int argc, char* argv[])
@@ -42,20 +46,36 @@ int main(int argc, char* argv[])
     mcb_ctx* ctx = nullptr;
     if (mcb_create(p, &cfg, &ctx) != MCB_OK) { std::cout << mcb_last_error(nullptr) << "\n"; std::exit(EXIT_FAILURE); }
     if (world > 1) {
-        const std::string id_file = getenv("MCB_ID_FILE") ? getenv("MCB_ID_FILE")
-                                    : std::string("/tmp/mcb_nccl_id.") + (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
-        char id[128];
+        // The NCCL unique id goes from rank 0 to the others through a file.  Its name carries the launcher's job
+        // identity (torchrun's TORCHELASTIC_RUN_ID / MASTER_PORT, or MCB_ID_FILE) and lives in a directory of the
+        // user's; the payload is tagged with the same job token, so an id left behind by a crashed run under the same
+        // name is not mistaken for this run's (rank 0 removes any such file before it writes, the others accept only
+        // a file written after they started waiting).
+        const char* tmpdir = getenv("XDG_RUNTIME_DIR") ? getenv("XDG_RUNTIME_DIR") : (getenv("TMPDIR") ? getenv("TMPDIR") : "/tmp");
+        const std::string job = std::string(getenv("TORCHELASTIC_RUN_ID") ? getenv("TORCHELASTIC_RUN_ID") : "none") + "." +
+                                (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0") + "." + std::to_string((long)getuid());
+        const std::string id_file = getenv("MCB_ID_FILE") ? getenv("MCB_ID_FILE") : std::string(tmpdir) + "/mcb_nccl_id." + job;
+        const time_t t_start = time(nullptr);
+        char id[128], tag[64];
+        memset(tag, 0, sizeof(tag));
+        snprintf(tag, sizeof(tag), "%s", job.c_str());
         if (root) {
+            std::remove(id_file.c_str());  // stale id of an earlier run
             if (mcb_comm_unique_id(id) != MCB_OK) { std::cout << mcb_last_error(nullptr) << "\n"; std::exit(EXIT_FAILURE); }
             std::ofstream f(id_file + ".tmp", std::ios::binary);
+            f.write(tag, sizeof(tag));
             f.write(id, 128);
             f.close();
             std::rename((id_file + ".tmp").c_str(), id_file.c_str());
         } else {
             for (int tries = 0;; tries++) {
+                struct stat sb;
+                char got[64];
                 std::ifstream f(id_file, std::ios::binary);
-                if (f && f.read(id, 128)) break;
-                if (tries > 3000) { std::cout << "[ERROR] no NCCL id in " << id_file << "\n"; std::exit(EXIT_FAILURE); }
+                // only a file with this job's tag that is not older than this process (minus clock slack)
+                if (f && stat(id_file.c_str(), &sb) == 0 && sb.st_mtime + 120 >= t_start && f.read(got, sizeof(got)) &&
+                    !memcmp(got, tag, sizeof(tag)) && f.read(id, 128)) break;
+                if (tries > 6000) { std::cout << "[ERROR] no NCCL id in " << id_file << "\n"; std::exit(EXIT_FAILURE); }
                 usleep(10000);
             }
         }

@@ -9,8 +9,8 @@ import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = {f: os.path.join(ROOT, d, f) for d, f in (("mc_old_b200/csrc", "mcb_kernels.cu"), ("mc_old_b200/csrc", "mcb_device.cuh"),
-                                                ("mc_old_b200/csrc", "mcb_physics.h"), ("mc_old_b200/csrc", "mcb_tables.h"))}
+SRC = {f: os.path.join(ROOT, "mc_old_b200/csrc", f) for f in ("mcb_kernels.cu", "mcb_walk.cu", "mcb_events.cuh", "mcb_device.cuh",
+                                                              "mcb_physics.h", "mcb_tables.h")}
 DEF = re.compile(r'^(?:static\s+)?(?:template\s*<[^>]*>\s*)?(?:__global__|__device__|MCB_HD|MCB_THD)[^;(]*?\b(\w+)\s*\(')
 
 
