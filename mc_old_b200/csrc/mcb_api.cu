@@ -142,6 +142,7 @@ struct mcb_ctx {
     DevBuf<DevMaterial> d_materials;
     DevBuf<DevNuclide> d_nuclides;
     DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid, d_delayed, d_bank_eold, d_bank_told;
+    DevBuf<int32_t> d_hrec;
     DevBuf<int32_t> d_map, d_hash, d_mat_nuclide, d_cell_surface, d_cell_sense, d_attach_begin[3], d_attach_list[3];
     DevBuf<mcb_surface> d_surfaces;
     DevBuf<mcb_cell> d_cells;
@@ -167,6 +168,7 @@ struct mcb_ctx {
     bool split_stages = false;       // event-queue mode: one kernel per event type (cross-check / profiling) instead of the walk kernel
     mcbk::WalkPlan plan{};           // launch shape of the walk kernel on this device
     int n_sm = 148;
+    DevBuf<double2> d_gstate;        // slot state of the walk kernel when it is kept in global memory (build option)
     DevBuf<StackRec> d_stack;        // per-context LIFO stacks of same-history secondaries (the reference's Pbank)
     int stack_depth = 0;
     DevBuf<uint32_t> d_tab_key;      // per-context tally tables of the walk kernel
@@ -336,12 +338,14 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         nU += tabs[m].U.size(); nmap += tabs[m].map.size(); nhash += tabs[m].hash.size();
         ctx->mat_n_nuc.push_back(tabs[m].n_nuc);
     }
-    std::vector<double> U; std::vector<int32_t> map, hash;
+    std::vector<double> U; std::vector<int32_t> map, hash, hrec;
     U.reserve(nU); map.reserve(nmap); hash.reserve(nhash);
     std::vector<DevMaterial> mats(p->n_materials);
-    std::vector<size_t> oU(p->n_materials), omap(p->n_materials), ohash(p->n_materials);
+    std::vector<size_t> oU(p->n_materials), omap(p->n_materials), ohash(p->n_materials), ohrec(p->n_materials);
     for (int m = 0; m < p->n_materials; m++) {
-        oU[m] = U.size(); omap[m] = map.size(); ohash[m] = hash.size();
+        oU[m] = U.size(); omap[m] = map.size(); ohash[m] = hash.size(); ohrec[m] = hrec.size();
+        hrec.insert(hrec.end(), tabs[m].hrec.begin(), tabs[m].hrec.end());
+        hrec.resize((hrec.size() + 3) & ~(size_t)3);  // every material's records start on a 16-byte boundary
         U.insert(U.end(), tabs[m].U.begin(), tabs[m].U.end());
         map.insert(map.end(), tabs[m].map.begin(), tabs[m].map.end());
         hash.insert(hash.end(), tabs[m].hash.begin(), tabs[m].hash.end());
@@ -349,12 +353,13 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     CK(ctx->d_union.upload(U.data(), U.size()));
     CK(ctx->d_map.upload(map.data(), map.size()));
     CK(ctx->d_hash.upload(hash.data(), hash.size()));
+    CK(ctx->d_hrec.upload(hrec.data(), hrec.size()));
     for (int m = 0; m < p->n_materials; m++) {
         DevMaterial& M = mats[m];
         M.nuc_begin = p->mat_begin[m]; M.n_nuc = tabs[m].n_nuc;
-        M.nU = (int32_t)tabs[m].U.size(); M.n_hash = tabs[m].n_hash; M.shift = tabs[m].shift; M.pad = 0;
+        M.nU = (int32_t)tabs[m].U.size(); M.n_hash = tabs[m].n_hash; M.shift = tabs[m].shift; M.hstride = tabs[m].hrec_stride;
         M.key_min = tabs[m].key_min;
-        M.U = ctx->d_union.p + oU[m]; M.map = ctx->d_map.p + omap[m]; M.hash = ctx->d_hash.p + ohash[m];
+        M.U = ctx->d_union.p + oU[m]; M.map = ctx->d_map.p + omap[m]; M.hash = ctx->d_hash.p + ohash[m]; M.hrec = ctx->d_hrec.p + ohrec[m];
     }
     CK(ctx->d_materials.upload(mats.data(), mats.size()));
     const int n_mat_nuc = p->mat_begin[p->n_materials];
@@ -497,9 +502,10 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         // walk kernel: launch shape on this device, per-context secondary stacks and tally tables
         int det_nn = 1;
         for (int m = 0; m < p->n_materials; m++) det_nn = std::max(det_nn, tabs[m].n_nuc);
-        const int rc = mcbk::walk_plan(P.shared_histories != 0, det_nn, p->n_tallies, ctx->n_sm, &ctx->plan);
+        const int rc = mcbk::walk_plan(P.shared_histories != 0, getenv("MCB_WALK_EXCHANGE") && atoi(getenv("MCB_WALK_EXCHANGE")) != 0, det_nn, p->n_tallies, ctx->n_sm, &ctx->plan);
         if (rc != 0) return ctx->fail(MCB_ERR_CUDA, "walk kernel does not fit this device: %s", cudaGetErrorString((cudaError_t)rc));
         const size_t n_ctx = (size_t)ctx->plan.n_contexts;
+        if (ctx->plan.gstate_pairs) CK(ctx->d_gstate.alloc(ctx->plan.gstate_pairs));
         if (P.shared_histories) {
             ctx->stack_depth = getenv("MCB_STACK_DEPTH") ? std::max(1, atoi(getenv("MCB_STACK_DEPTH"))) : 64;
             CK(ctx->d_stack.alloc(n_ctx * (size_t)ctx->stack_depth));
@@ -761,7 +767,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
         if (q1 > q0) {
             CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
             ctx->timer.begin(st, ST_STEP);
-            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth);
+            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth, ctx->d_gstate.p);
             ctx->timer.end(st);
             (*n_iterations)++;
         }
@@ -797,7 +803,7 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
         // one launch follows the source particles in slots [0, nb) and every secondary of their histories to the end
         CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
         ctx->timer.begin(st, ST_STEP);
-        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth);
+        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth, ctx->d_gstate.p);
         ctx->timer.end(st);
         *n_iterations += 1;
         CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));

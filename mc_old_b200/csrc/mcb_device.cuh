@@ -17,11 +17,12 @@
 // ---------------------------------------------------------------------------------------------
 struct DevMaterial {
     int32_t nuc_begin, n_nuc;    // range in mat_nuclide / mat_density (deck order = summation order)
-    int32_t nU, n_hash, shift, pad;
+    int32_t nU, n_hash, shift, hstride;
     int64_t key_min;
     const double* U;             // union grid
     const int32_t* map;          // nU x n_nuc
     const int32_t* hash;         // n_hash + 1
+    const int32_t* hrec;         // (n_hash + 2) bin records of hstride ints (mcb_tables.h)
 };
 struct DevNuclide {
     const double* rows;          // n_rows x {E, sigma_s, sigma_c, sigma_f, nu, beta}; 48-byte rows, 16-byte aligned
@@ -257,6 +258,27 @@ __device__ __forceinline__ double micro_col(const DevNuclide& N, int idx, double
     return mcb_interpolate(E, r1[0], r2[0], y1, y2);
 }
 
+// where an energy sits in the material's union grid: u = #{U < E} - 1 and the per-nuclide row indices, read from
+// the bin record when the energy lies below every grid point of its bin (mcb_union_lookup), else from map[u]
+struct UnionPos {
+    int u;
+    const int32_t* rec;   // bin record (indices at rec[2 + n])
+    const int32_t* row;   // map row of u when the record does not apply, else nullptr
+};
+__device__ __forceinline__ UnionPos union_pos(const DevMaterial& M, double E)
+{
+    UnionPos q;
+    bool from_rec;
+    const int lo = mcb_union_lookup(M.U, M.hrec, M.hstride, M.key_min, M.n_hash, M.shift, E, &q.rec, &from_rec);
+    q.u = lo - 1;
+    q.row = from_rec ? nullptr : M.map + (size_t)q.u * M.n_nuc;
+    return q;
+}
+__device__ __forceinline__ int nuclide_index(const UnionPos& q, int n)
+{
+    const int ir = __ldg(q.rec + 2 + n);  // issued whatever the outcome of the search in the bin
+    return q.row ? __ldg(q.row + n) : ir;
+}
 __device__ __forceinline__ int union_index(const DevMaterial& M, double E)
 {
     return mcb_union_count_less(M.U, M.hash, M.key_min, M.n_hash, M.shift, M.nU, E) - 1;
@@ -293,14 +315,14 @@ struct NoDetail {
 
 // Material::SigmaT/S/C/F, nuSigmaF (Material.cpp:18-65): sums over nuclides in deck order, starting from 0.0
 template <class DET>
-__device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X, DET& D)
+__device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMaterial& M, const UnionPos& q, double E, MacroXS& X, DET& D)
 {
     X.t = 0.0; X.s = 0.0; X.c = 0.0; X.f = 0.0; X.nf = 0.0;
     for (int n = 0; n < M.n_nuc; n++) {
         const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
         const double dens = __ldg(&P.mat_density[M.nuc_begin + n]);
         MicroXS m;
-        micro_xs(P.nuclides[gn], nuclide_index(M, u, n), E, m);
+        micro_xs(P.nuclides[gn], nuclide_index(q, n), E, m);
         X.t += m.t * dens;
         X.s += m.s * dens;
         X.c += m.c * dens;
@@ -309,10 +331,10 @@ __device__ __forceinline__ void macro_xs_impl(const DevProblem& P, const DevMate
         if (DET::present) D.set(n, X.s, X.nf, m.beta);
     }
 }
-__device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial& M, int u, double E, MacroXS& X)
+__device__ __forceinline__ void macro_xs(const DevProblem& P, const DevMaterial& M, const UnionPos& q, double E, MacroXS& X)
 {
     NoDetail nd;
-    macro_xs_impl(P, M, u, E, X, nd);
+    macro_xs_impl(P, M, q, E, X, nd);
 }
 // nuclide pick from kept partial sums: first n with cum[n] > total*xi (Material.cpp:106-125); KIND 0 scatter, 1 nu-fission
 template <int KIND, class DET>
@@ -382,10 +404,10 @@ __device__ __noinline__ static int channel_cache_get(const DevProblem& P, int ma
     const int i = C.used & 1;
     C.used++;
     const DevMaterial& M = P.materials[material];
-    const int u = union_index(M, E);
+    const UnionPos up = union_pos(M, E);
     for (int n = 0; n < M.n_nuc; n++) {
         const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
-        micro_xs(P.nuclides[gn], nuclide_index(M, u, n), E, C.m[i][n]);
+        micro_xs(P.nuclides[gn], nuclide_index(up, n), E, C.m[i][n]);
     }
     C.E[i] = E; C.mat[i] = material;
     return i;
@@ -446,9 +468,9 @@ __device__ __forceinline__ double watt_sample(const double* va, const double* vb
     }
     double Eout, C;
     do {
-        const double lx = log(mcb_urand(rng));
+        const double lx = mcb_log(mcb_urand(rng));
         Eout = -a * g * lx;
-        const double l2 = log(mcb_urand(rng));
+        const double l2 = mcb_log(mcb_urand(rng));
         C = (1.0 - g) * (1.0 - lx) - l2;
     } while (C * C > b * Eout);
     return Eout * 1.0e6;
@@ -485,15 +507,15 @@ __device__ __forceinline__ void scatter_sample(const DevNuclide& N, double& dx, 
         double x;
         if (mcb_urand(rng) < 2.0 / (2.0 + MCB_PI_SQRT * y)) {
             const double r1 = mcb_urand(rng), r2 = mcb_urand(rng);
-            x = sqrt(-log(r1 * r2));
+            x = sqrt(-mcb_log(r1 * r2));
         } else {
 #ifdef MCB_FAST_TRIG
             const double cos_val = cospi(0.5 * mcb_urand(rng));
 #else
             const double cos_val = cos(MCB_PI_HALF * mcb_urand(rng));
 #endif
-            const double l1 = log(mcb_urand(rng));
-            const double l2 = log(mcb_urand(rng));
+            const double l1 = mcb_log(mcb_urand(rng));
+            const double l2 = mcb_log(mcb_urand(rng));
             x = sqrt(-l1 - l2 * cos_val * cos_val);
         }
         V_tilda = x / beta;

@@ -214,7 +214,7 @@ __device__ __forceinline__ void estimator_score(const DevProblem& P, const Tally
         const mcb_score& S = P.scores[E.score_begin + k];
         if (S.kernel == MCB_KERNEL_COLLISION || (S.score >= MCB_SCORE_ABSORPTION && S.score <= MCB_SCORE_TOTAL)) needs_X = true;
     }
-    if (needs_X) { q.uidx = union_index(M, q.E); macro_xs(P, M, q.uidx, q.E, q.X); }
+    if (needs_X) { const UnionPos up = union_pos(M, q.E); q.uidx = up.u; macro_xs(P, M, up, q.E, q.X); }
     estimator_score_plain(P, T, C, E, q, l, row, n_touched, CC);
 }
 __device__ __forceinline__ bool has_attached(const DevProblem& P, int kind, int id)
@@ -252,7 +252,7 @@ static __device__ __noinline__ ScoreRet score_event(const DevProblem& P, const T
     s.X = MacroXS{Xt, Xs, Xc, Xf, Xnf};
     if (!have_X) {
         s.uidx = -1;
-        if (material >= 0) { s.uidx = union_index(P.materials[material], E); macro_xs(P, P.materials[material], s.uidx, E, s.X); }
+        if (material >= 0) { const UnionPos up = union_pos(P.materials[material], E); s.uidx = up.u; macro_xs(P, P.materials[material], up, E, s.X); }
     }
     const int b = P.attach_begin[kind][id], e = P.attach_begin[kind][id + 1];
     ChannelCache CC;  // microscopic data at the (at most two) energies the estimators of this event ask about
@@ -281,8 +281,9 @@ __device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p
     const int m = P.cells[p.cell].material;
     if (m < 0) return false;
     const DevMaterial M = P.materials[m];
-    uidx = union_index(M, p.E);
-    macro_xs_impl(P, M, uidx, p.E, X, D);
+    const UnionPos up = union_pos(M, p.E);
+    uidx = up.u;
+    macro_xs_impl(P, M, up, p.E, X, D);
     return true;
 }
 
@@ -300,7 +301,7 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, cons
     double dsurf;
     S_hit = surface_intersect(P, p.cell, p.x, p.y, p.z, p.u, p.v, p.w, dsurf);
     double dcol;
-    if (m >= 0) dcol = -log(mcb_urand(p.rng)) / X.t;   // exponential_sample (Algorithm.cpp:123-126)
+    if (m >= 0) dcol = -mcb_log(mcb_urand(p.rng)) / X.t;   // exponential_sample (Algorithm.cpp:123-126)
     else dcol = MCB_MAX_FLOAT_LESS;                      // vacuum (general.cpp:44-46)
     const bool to_cross = dcol > dsurf;
     const double l = to_cross ? dsurf : dcol;
@@ -468,11 +469,14 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
         // IEEE division routine down its slow path); same value, same draw
         const double rat = mcb_div_zero_ok(Inew, Iold);
         if (rat < 1.0) {
-            if (mcb_urand(p.rng) < rat) p.wgt = p.wgt / rat;
+            // the compiler evaluates this division whether or not the branch is taken; with rat = 0 (every leaking
+            // particle) a division by zero would go down the division routine's slow path, so it gets a harmless divisor
+            const double den = rat > 0.0 ? rat : 1.0;
+            if (mcb_urand(p.rng) < rat) p.wgt = p.wgt / den;
             else { alive = false; p.wgt = 0.0; }
         } else {
             const int ns = (int)floor(rat + mcb_urand(p.rng));
-            p.wgt = p.wgt / (double)ns;
+            p.wgt = p.wgt / (ns > 0 ? (double)ns : 1.0);  // ns >= 1 here; the guard is for the speculated evaluation (see above)
             n_copy = ns > 1 ? (unsigned)(ns - 1) : 0u;
         }
     }

@@ -629,9 +629,9 @@ k_xs_lookup(const DevProblem P, int material, const double* __restrict__ E, int6
     if (q < n) {
         const double e = __ldg(&E[q]);
         const DevMaterial M = P.materials[material];
-        const int u = union_index(M, e);
+        const UnionPos up = union_pos(M, e);
         MacroXS X;
-        macro_xs(P, M, u, e, X);
+        macro_xs(P, M, up, e, X);
         double* s = stage + threadIdx.x * 5;
         s[0] = X.t; s[1] = X.s; s[2] = X.c; s[3] = X.f; s[4] = X.nf;
     }
@@ -646,9 +646,10 @@ __global__ void k_select_channel(const DevProblem P, int material, int kind, con
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const DevMaterial M = P.materials[material];
-    const int u = union_index(M, E[q]);
+    const UnionPos up = union_pos(M, E[q]);
+    const int u = up.u;
     MacroXS X;
-    macro_xs(P, M, u, E[q], X);
+    macro_xs(P, M, up, E[q], X);
     out[q] = select_nuclide(P, M, u, E[q], kind, kind == 0 ? X.s : X.nf, xi[q], nullptr);
 }
 __global__ void k_beta(const DevProblem P, int material, int local_n, const double* E, int64_t n, double* out)

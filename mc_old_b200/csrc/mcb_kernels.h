@@ -47,18 +47,21 @@ void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* 
 // (n_contexts x stack_depth StackRec) and tally tables (TallyAcc::tab_*).
 struct WalkRes {        // kernel argument
     StackRec* stack;
+    double2* gstate;    // slot state in global memory (build option MCB_WALK_GLOBAL_STATE), else nullptr
     int32_t stack_depth, det_nn, n_pairs, priv_tallies;
 };
 struct WalkPlan {
     int n_sm, det_nn, priv_tallies, max_grid;
     bool shared;        // secondaries can be born in flight (fixed source / splitting)
+    bool exchange;      // event-sorted form (particles change lanes through shared-memory queues) or history per lane
     int blocks_per_sm[2], n_pairs[2];   // [0] cycles that score nothing, [1] scoring cycles
     size_t smem_bytes[2];
     int64_t n_contexts;
+    size_t gstate_pairs; // double2 elements of the global slot-state array the caller allocates (0: state in shared memory)
 };
-int walk_plan(bool shared, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
+int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth);
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth, double2* gstate);
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff);

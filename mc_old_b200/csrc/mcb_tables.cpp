@@ -45,7 +45,13 @@ void build_material_tables(const mcb_problem* p, int material, int max_mant_bits
             T.map[(size_t)u * T.n_nuc + (i - nb)] = r - 1;
         }
     }
-    if (nU == 0) { T.hash.assign(1, 0); return; }
+    if (nU == 0) {
+        T.hash.assign(1, 0);
+        T.hrec_stride = (2 + T.n_nuc + 1) & ~1;
+        T.hrec.assign((size_t)2 * T.hrec_stride, 0);
+        for (int r = 0; r < 2; r++) for (int n = 0; n < T.n_nuc; n++) T.hrec[(size_t)r * T.hrec_stride + 2 + n] = -1;
+        return;
+    }
     // hash on the bit pattern; keep the table at most ~4 entries per grid point
     const int64_t cap = std::max<int64_t>(4 * (int64_t)nU + 1024, 4096);
     int bits = std::min(std::max(max_mant_bits, 0), 20);
@@ -66,6 +72,21 @@ void build_material_tables(const mcb_problem* p, int material, int max_mant_bits
         }
     }
     for (int64_t b = 0; b < T.n_hash; b++) T.max_bin = std::max(T.max_bin, T.hash[b + 1] - T.hash[b]);
+    // bin records (see mcb_union_lookup): the search window and the per-nuclide indices below it in one place
+    T.hrec_stride = (2 + T.n_nuc + 1) & ~1;  // whole 8-byte words
+    T.hrec.assign((size_t)(T.n_hash + 2) * T.hrec_stride, 0);
+    auto fill = [&](int64_t r, int u0, int cnt) {
+        int32_t* rec = T.hrec.data() + (size_t)r * T.hrec_stride;
+        rec[0] = u0; rec[1] = cnt;
+        for (int n = 0; n < T.n_nuc; n++) rec[2 + n] = u0 > 0 ? T.map[(size_t)(u0 - 1) * T.n_nuc + n] : -1;
+    };
+    for (int64_t b = 0; b < T.n_hash; b++) fill(b, T.hash[(size_t)b], T.hash[(size_t)b + 1] - T.hash[(size_t)b]);
+    fill(T.n_hash, nU, 0);      // above the last bin
+    fill(T.n_hash + 1, 0, 0);   // below the first
+    for (int n = 0; n < T.n_nuc; n++)  // a grid that is not ascending is bisected whatever the energy
+        if (nU && T.map[n] == MCB_MAP_BISECT)
+            for (int64_t r = 0; r < T.n_hash + 2; r++)
+                if (T.hrec[(size_t)r * T.hrec_stride] > 0) T.hrec[(size_t)r * T.hrec_stride + 2 + n] = MCB_MAP_BISECT;
 }
 
 }  // namespace mcb

@@ -49,6 +49,42 @@ MCB_THD int mcb_union_count_less(const double* U, const int32_t* hash, int64_t k
     return lo;
 }
 
+// The same search through the bin RECORDS: record key = { u0 = #{U < lower edge of bin key}, cnt = points of U inside
+// the bin, idx_n = map[(u0 - 1) * Nn + n] (-1 for u0 = 0) }, `stride` ints apiece; two more records stand for energies
+// above the last bin (index n_hash) and below the first (index n_hash + 1).  Most bins hold no grid point (HEU: 204 k
+// points in 672 k bins; none at all above the resolved resonances, where a fast system spends its collisions), and for
+// those the per-nuclide indices come straight from the record: the chain hash -> union grid -> map -> rows of
+// dependent loads becomes record -> rows.  Returns lo = #{U < E}; *rec_out = the record; *from_rec tells whether
+// the record's indices apply (else read map[(lo - 1) * Nn + n]).
+MCB_THD int mcb_union_lookup(const double* U, const int32_t* hrec, int32_t stride, int64_t key_min, int32_t n_hash, int32_t shift,
+                             double E, const int32_t** rec_out, bool* from_rec)
+{
+    int64_t bits;
+#if defined(__CUDA_ARCH__)
+    bits = __double_as_longlong(E);
+#else
+    memcpy(&bits, &E, sizeof(bits));
+#endif
+    int64_t key = (bits >> shift) - key_min;
+    if (key < 0) key = (int64_t)n_hash + 1;
+    else if (key > n_hash) key = n_hash;
+    const int32_t* rec = hrec + (size_t)key * stride;
+    *rec_out = rec;
+#if defined(__CUDA_ARCH__)
+    const int2 h = __ldg(reinterpret_cast<const int2*>(rec));
+    const int u0 = h.x, cnt = h.y;
+#else
+    const int u0 = rec[0], cnt = rec[1];
+#endif
+    int lo = u0, hi = u0 + cnt;
+    while (lo < hi) {  // lower_bound inside the bin: first element not < E
+        const int mid = (lo + hi) >> 1;
+        if (U[mid] < E) lo = mid + 1; else hi = mid;
+    }
+    *from_rec = lo == u0;
+    return lo;
+}
+
 // binary_search (Algorithm.cpp:46-64) over column 0 of n rows of MCB_XS_ROW doubles: the probe sequence of the
 // reference, whatever the order of the grid
 MCB_THD int mcb_row_bisect(const double* rows, int n, double E)
@@ -69,6 +105,8 @@ struct MaterialTables {
     std::vector<double> U;       // distinct energies of all nuclides of the material, ascending
     std::vector<int32_t> map;    // nU x n_nuc
     std::vector<int32_t> hash;   // n_hash + 1
+    std::vector<int32_t> hrec;   // (n_hash + 2) bin records of hrec_stride ints: { u0, cnt, idx_0 .. idx_{Nn-1}, pad }
+    int32_t hrec_stride = 0;
     int64_t key_min = 0;
     int32_t n_hash = 0, shift = 0, n_nuc = 0;
     int32_t n_bisect = 0;        // nuclides whose grid is not ascending

@@ -32,11 +32,12 @@ using namespace mcbe;
 namespace {
 
 #ifndef MCB_WALK_MINB
-#define MCB_WALK_MINB 6
+#define MCB_WALK_MINB 4  // measured (tools/sweep.sh): 4 blocks of 128 threads per SM (128 registers) beat 3, 5 and 6 for both forms
 #endif
 constexpr int WALK_RES = 32;                  // slots beyond one per thread: what makes a full batch always available
 constexpr int WALK_SLOTS = BLOCK + WALK_RES;  // 160
-constexpr int WALK_QCAP = 256;                // ring capacity of a queue (power of two >= WALK_SLOTS)
+constexpr int pow2_at_least(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+constexpr int WALK_QCAP = pow2_at_least(WALK_SLOTS);  // ring capacity of a queue
 static_assert(WALK_QCAP >= WALK_SLOTS && (WALK_QCAP & (WALK_QCAP - 1)) == 0, "queue ring");
 
 // slot state, pairs of doubles laid out [pair][slot] (a warp's 128-bit accesses fall on distinct banks for slots that
@@ -64,6 +65,15 @@ struct WalkQ {
     unsigned short qC[WALK_QCAP], qX[WALK_QCAP];
 };
 
+// slot state lives in shared memory, or (MCB_WALK_GLOBAL_STATE) in a per-block global array that stays in L2, read and
+// written around L1 so that L1 keeps serving the cross-section gathers
+#ifdef MCB_WALK_GLOBAL_STATE
+__device__ __forceinline__ void st_pair(double2* p, double2 v) { __stcg(p, v); }
+__device__ __forceinline__ double2 ld_pair(const double2* p) { return __ldcg(p); }
+#else
+__device__ __forceinline__ void st_pair(double2* p, double2 v) { *p = v; }
+__device__ __forceinline__ double2 ld_pair(const double2* p) { return *p; }
+#endif
 __device__ __forceinline__ double pack2i(int lo, int hi) { return __hiloint2double(hi, lo); }
 __device__ __forceinline__ int unpack_lo(double d) { return __double2loint(d); }
 __device__ __forceinline__ int unpack_hi(double d) { return __double2hiint(d); }
@@ -76,12 +86,20 @@ struct SlotDetail {
     int nn;         // nuclides per material at most (problem-wide)
     __device__ __forceinline__ void set(int n, double s, double nf, double be) const
     {
-        base[n * WALK_SLOTS] = make_double2(s, nf);
+        st_pair(base + n * WALK_SLOTS, make_double2(s, nf));
+#ifdef MCB_WALK_GLOBAL_STATE
+        __stcg(reinterpret_cast<double*>(base + (nn + (n >> 1)) * WALK_SLOTS) + (n & 1), be);
+#else
         reinterpret_cast<double*>(base + (nn + (n >> 1)) * WALK_SLOTS)[n & 1] = be;
+#endif
     }
-    __device__ __forceinline__ double cum_s(int n) const { return base[n * WALK_SLOTS].x; }
-    __device__ __forceinline__ double cum_nf(int n) const { return base[n * WALK_SLOTS].y; }
-    __device__ __forceinline__ double beta(int n) const { return reinterpret_cast<const double*>(base + (nn + (n >> 1)) * WALK_SLOTS)[n & 1]; }
+    __device__ __forceinline__ double cum_s(int n) const { return ld_pair(base + n * WALK_SLOTS).x; }
+    __device__ __forceinline__ double cum_nf(int n) const { return ld_pair(base + n * WALK_SLOTS).y; }
+    __device__ __forceinline__ double beta(int n) const
+    {
+        const double2 v = ld_pair(base + (nn + (n >> 1)) * WALK_SLOTS);
+        return (n & 1) ? v.y : v.x;
+    }
 };
 
 // the history's LIFO stack of secondaries (the reference's Pbank, handler.cpp:20-29)
@@ -143,15 +161,25 @@ __device__ __forceinline__ void flush_history_tallies(const TallyAcc& T, int row
     }
 }
 
-template <bool TALLY, bool SHARED>
+// EXCH = true: the event-sorted form described above.  EXCH = false: every lane keeps its history from the source bank to
+// its end and runs its own next event (collide and cross lanes of a warp diverge): no slot traffic and no queue, every
+// warp streams through one loop body.  Which one wins is a matter of the instruction cache: the loop is ~70 KB of code
+// against a 32 KB per-SM instruction cache, and warps scattered over three code regions (EXCH) fetch from the GPC-level
+// cache at its limit (ncu: gcc instruction requests 98 % of peak, sm__icc hit rate 61 %), see DESIGN.md.
+template <bool TALLY, bool SHARED, bool EXCH>
 __global__ void __launch_bounds__(BLOCK, MCB_WALK_MINB)
 k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long long end, uint32_t chunk, Counters* C, HistoryAcc H,
        TallyAcc T, SiteReq* reqs, uint64_t site_cap, double k_eff, mcbk::WalkRes R)
 {
     extern __shared__ double2 w_smem[];
-    constexpr int SP_DET = TALLY ? SP_FIXED + 1 : SP_FIXED;
+    constexpr int SP_DET = !EXCH ? 0 : (TALLY ? SP_FIXED + 1 : SP_FIXED);  // without the exchange a slot holds the detail only
+#ifdef MCB_WALK_GLOBAL_STATE
+    double2* const st = R.gstate + (size_t)blockIdx.x * R.n_pairs * WALK_SLOTS;
+    WalkQ& Q = *reinterpret_cast<WalkQ*>(w_smem);
+#else
     double2* const st = w_smem;
     WalkQ& Q = *reinterpret_cast<WalkQ*>(st + R.n_pairs * WALK_SLOTS);
+#endif
     double* const s_sum = (TALLY && R.priv_tallies) ? reinterpret_cast<double*>(&Q + 1) : nullptr;
     double* const s_sq = s_sum ? s_sum + R.priv_tallies : nullptr;
     if (threadIdx.x == 0) { Q.lock = 0; Q.headC = Q.tailC = Q.headX = Q.tailX = 0; Q.warps_done = 0; }
@@ -164,7 +192,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
     unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
     int my_slot = threadIdx.x;            // the slot this lane parks its particle in (it moves with every claim)
     bool have = false, exhausted = false;
-    bool second_batch = warp_id() == 0;   // warp 0 starts two batches: the block's 32 extra slots
+    bool second_batch = EXCH && warp_id() == 0;   // warp 0 starts two batches: the block's 32 extra slots
     Particle p;
     HistLocal L = {0.0, 0.0, 0};
     int sp = 0;                           // depth of the history's secondary stack
@@ -201,32 +229,35 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         }
         // ---- common part of every track: xs lookup and flight; the particle is parked in its slot
         bool to_cross = false;
+        MacroXS X = {0, 0, 0, 0, 0};
+        int uidx = -1, S = -1;
         if (have) {
             p.row = ctx_base + my_slot;
-            MacroXS X = {0, 0, 0, 0, 0};
-            int uidx = -1, S = -1;
             const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
             if (ev_lookup(P, p, X, uidx, D)) lookups++;
             to_cross = ev_flight<TALLY>(P, p, X, uidx, H, T, C, S, &L);
             tracks++;
+        }
+        if (EXCH && have) {
             double2* s = st + my_slot;
-            s[SP_XY * WALK_SLOTS] = make_double2(p.x, p.y);
-            s[SP_ZU * WALK_SLOTS] = make_double2(p.z, p.u);
-            s[SP_VW * WALK_SLOTS] = make_double2(p.v, p.w);
-            s[SP_ES * WALK_SLOTS] = make_double2(p.E, p.speed);
-            s[SP_WT * WALK_SLOTS] = make_double2(p.wgt, p.t);
-            s[SP_RNG * WALK_SLOTS] = make_double2(__longlong_as_double((long long)p.rng), pack2i(p.cell, p.hist));
-            s[SP_K * WALK_SLOTS] = make_double2(L.kC, L.kTL);
-            s[SP_IDS * WALK_SLOTS] = make_double2(pack2i(L.nsite, sp), pack2i(S, uidx));
-            s[SP_XT * WALK_SLOTS] = make_double2(X.t, X.nf);
-            s[SP_XS * WALK_SLOTS] = make_double2(X.s, X.c);
-            s[SP_XF * WALK_SLOTS] = make_double2(X.f, p.Eold);
-            if (TALLY) s[SP_FIXED * WALK_SLOTS] = make_double2(p.told, pack2i(p.n_touched, 0));
+            st_pair(s + SP_XY * WALK_SLOTS, make_double2(p.x, p.y));
+            st_pair(s + SP_ZU * WALK_SLOTS, make_double2(p.z, p.u));
+            st_pair(s + SP_VW * WALK_SLOTS, make_double2(p.v, p.w));
+            st_pair(s + SP_ES * WALK_SLOTS, make_double2(p.E, p.speed));
+            st_pair(s + SP_WT * WALK_SLOTS, make_double2(p.wgt, p.t));
+            st_pair(s + SP_RNG * WALK_SLOTS, make_double2(__longlong_as_double((long long)p.rng), pack2i(p.cell, p.hist)));
+            st_pair(s + SP_K * WALK_SLOTS, make_double2(L.kC, L.kTL));
+            st_pair(s + SP_IDS * WALK_SLOTS, make_double2(pack2i(L.nsite, sp), pack2i(S, uidx)));
+            st_pair(s + SP_XT * WALK_SLOTS, make_double2(X.t, X.nf));
+            st_pair(s + SP_XS * WALK_SLOTS, make_double2(X.s, X.c));
+            st_pair(s + SP_XF * WALK_SLOTS, make_double2(X.f, p.Eold));
+            if (TALLY) st_pair(s + SP_FIXED * WALK_SLOTS, make_double2(p.told, pack2i(p.n_touched, 0)));
         }
         // ---- event queues: append what this warp holds, take one batch of a kind back out
         int kind = 0;  // 1 collide, 2 cross
-        lock_acquire(Q, lane);
-        {
+        if (!EXCH) kind = have ? (to_cross ? 2 : 1) : 0;
+        if (EXCH) lock_acquire(Q, lane);
+        if (EXCH) {
             const unsigned mC = __ballot_sync(FULL, have && !to_cross), mX = __ballot_sync(FULL, have && to_cross);
             unsigned hC = Q.headC, tC = Q.tailC, hX = Q.headX, tX = Q.tailX;
             if (have) {
@@ -249,44 +280,52 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             __syncwarp();
             if (lane == 0) { Q.headC = hC; Q.tailC = tC; Q.headX = hX; Q.tailX = tX; }
         }
-        lock_release(Q, lane);
-        if (second_batch) {  // warp 0, once: its first batch waits in the queues, the second goes to the extra slots
+        if (EXCH) lock_release(Q, lane);
+        if (EXCH && second_batch) {  // warp 0, once: its first batch waits in the queues, the second goes to the extra slots
             second_batch = false;
             have = false;
             my_slot = BLOCK + (int)lane;
             continue;
         }
         const unsigned mK = __ballot_sync(FULL, kind != 0);
+#ifdef MCB_WALK_SYNC
+        // history-per-lane form with the warps of a block kept in step: they then run the same stretch of the loop body
+        // at the same time and share its instruction-cache lines (the per-SM instruction cache serves one miss for all)
+        if (!EXCH) { if (!__syncthreads_or(mK != 0u || !exhausted)) break; }
+        else
+#endif
         if (mK == 0u) {
             if (exhausted) break;  // nothing held, nothing queued, nothing left to draw
             continue;
         }
         have = kind != 0;
         // ---- the event itself, on a batch of one kind (mixed only when the queues run low)
-        MacroXS X = {0, 0, 0, 0, 0};
         CollideCtx c = {-1, -1, 0, 0, 0.0};
-        int uidx = -1, S = -1;
         unsigned n_copy = 0;
         bool alive = false, in_material = false;
         const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
-        if (have) {
+        if (EXCH && have) {
             const double2* s = st + my_slot;
             double2 v;
-            v = s[SP_XY * WALK_SLOTS]; p.x = v.x; p.y = v.y;
-            v = s[SP_ZU * WALK_SLOTS]; p.z = v.x; p.u = v.y;
-            v = s[SP_VW * WALK_SLOTS]; p.v = v.x; p.w = v.y;
-            v = s[SP_ES * WALK_SLOTS]; p.E = v.x; p.speed = v.y;
-            v = s[SP_WT * WALK_SLOTS]; p.wgt = v.x; p.t = v.y;
-            v = s[SP_RNG * WALK_SLOTS]; p.rng = (uint64_t)__double_as_longlong(v.x); p.cell = unpack_lo(v.y); p.hist = unpack_hi(v.y);
-            v = s[SP_K * WALK_SLOTS]; L.kC = v.x; L.kTL = v.y;
-            v = s[SP_IDS * WALK_SLOTS]; L.nsite = unpack_lo(v.x); sp = unpack_hi(v.x); S = unpack_lo(v.y); uidx = unpack_hi(v.y);
-            v = s[SP_XF * WALK_SLOTS]; X.f = v.x; p.Eold = v.y;
-            if (TALLY) { v = s[SP_FIXED * WALK_SLOTS]; p.told = v.x; p.n_touched = unpack_lo(v.y); }
+            v = ld_pair(s + SP_XY * WALK_SLOTS); p.x = v.x; p.y = v.y;
+            v = ld_pair(s + SP_ZU * WALK_SLOTS); p.z = v.x; p.u = v.y;
+            v = ld_pair(s + SP_VW * WALK_SLOTS); p.v = v.x; p.w = v.y;
+            v = ld_pair(s + SP_ES * WALK_SLOTS); p.E = v.x; p.speed = v.y;
+            v = ld_pair(s + SP_WT * WALK_SLOTS); p.wgt = v.x; p.t = v.y;
+            v = ld_pair(s + SP_RNG * WALK_SLOTS); p.rng = (uint64_t)__double_as_longlong(v.x); p.cell = unpack_lo(v.y); p.hist = unpack_hi(v.y);
+            v = ld_pair(s + SP_K * WALK_SLOTS); L.kC = v.x; L.kTL = v.y;
+            v = ld_pair(s + SP_IDS * WALK_SLOTS); L.nsite = unpack_lo(v.x); sp = unpack_hi(v.x); S = unpack_lo(v.y); uidx = unpack_hi(v.y);
+            v = ld_pair(s + SP_XF * WALK_SLOTS); X.f = v.x; p.Eold = v.y;
+            if (TALLY) { v = ld_pair(s + SP_FIXED * WALK_SLOTS); p.told = v.x; p.n_touched = unpack_lo(v.y); }
             else { p.told = p.t; p.n_touched = 0; }
             p.row = ctx_base + my_slot;
             if (kind == 1) {
-                v = s[SP_XT * WALK_SLOTS]; X.t = v.x; X.nf = v.y;
-                v = s[SP_XS * WALK_SLOTS]; X.s = v.x; X.c = v.y;
+                v = ld_pair(s + SP_XT * WALK_SLOTS); X.t = v.x; X.nf = v.y;
+                v = ld_pair(s + SP_XS * WALK_SLOTS); X.s = v.x; X.c = v.y;
+            }
+        }
+        if (have) {
+            if (kind == 1) {
                 in_material = ev_collide_pre<TALLY>(P, p, X, uidx, D, T, C, k_eff, c);
                 if (in_material) collisions++;
             } else {
@@ -351,23 +390,31 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
     }
 }
 
-template <bool TALLY, bool SHARED>
-cudaError_t plan_instance(int det_nn, int priv, int n_sm, int& blocks, size_t& smem)
+template <bool TALLY, bool SHARED, bool EXCH>
+cudaError_t plan_instance(int det_nn, int priv, int n_sm, int& blocks, size_t& smem, int& n_pairs)
 {
-    const int n_pairs = (TALLY ? SP_FIXED + 1 : SP_FIXED) + det_nn + (det_nn + 1) / 2;
+    n_pairs = (!EXCH ? 0 : (TALLY ? SP_FIXED + 1 : SP_FIXED)) + det_nn + (det_nn + 1) / 2;
+#ifdef MCB_WALK_GLOBAL_STATE
+    smem = sizeof(WalkQ) + (TALLY ? (size_t)priv * 2 * sizeof(double) : 0);
+#else
     smem = (size_t)n_pairs * WALK_SLOTS * sizeof(double2) + sizeof(WalkQ) + (TALLY ? (size_t)priv * 2 * sizeof(double) : 0);
+#endif
     // opt in to the device's full shared memory once (the attribute is per function, not per context)
     int dev = 0, optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess) return e;
     if (smem > (size_t)optin) return cudaErrorInvalidConfiguration;
-    e = cudaFuncSetAttribute(k_walk<TALLY, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    e = cudaFuncSetAttribute(k_walk<TALLY, SHARED, EXCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_walk<TALLY, SHARED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+#ifndef MCB_WALK_GLOBAL_STATE
+    if (EXCH) {
+        e = cudaFuncSetAttribute(k_walk<TALLY, SHARED, EXCH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+#endif
     blocks = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_walk<TALLY, SHARED>, BLOCK, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_walk<TALLY, SHARED, EXCH>, BLOCK, smem);
     (void)n_sm;
     return e;
 }
@@ -378,32 +425,45 @@ namespace mcbk {
 
 extern thread_local uint64_t g_launches;
 
-int walk_plan(bool shared, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out)
+int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out)
 {
     WalkPlan& W = *out;
     W.det_nn = std::max(det_nn, 1);
     W.priv_tallies = (n_tallies > 0 && n_tallies <= 256) ? (int)n_tallies : 0;
     W.n_sm = n_sm;
+    W.exchange = exchange;
     cudaError_t e;
     for (int tally = 0; tally < 2; tally++) {
-        int blocks = 0;
+        int blocks = 0, n_pairs = 0;
         size_t smem = 0;
-        if (tally) e = shared ? plan_instance<true, true>(W.det_nn, W.priv_tallies, n_sm, blocks, smem) : plan_instance<true, false>(W.det_nn, W.priv_tallies, n_sm, blocks, smem);
-        else e = shared ? plan_instance<false, true>(W.det_nn, W.priv_tallies, n_sm, blocks, smem) : plan_instance<false, false>(W.det_nn, W.priv_tallies, n_sm, blocks, smem);
+#define MCB_PLAN(T_, S_, E_) plan_instance<T_, S_, E_>(W.det_nn, W.priv_tallies, n_sm, blocks, smem, n_pairs)
+        if (exchange) {
+            if (tally) e = shared ? MCB_PLAN(true, true, true) : MCB_PLAN(true, false, true);
+            else e = shared ? MCB_PLAN(false, true, true) : MCB_PLAN(false, false, true);
+        } else {
+            if (tally) e = shared ? MCB_PLAN(true, true, false) : MCB_PLAN(true, false, false);
+            else e = shared ? MCB_PLAN(false, true, false) : MCB_PLAN(false, false, false);
+        }
+#undef MCB_PLAN
         if (e != cudaSuccess) return (int)e;
         if (blocks < 1) return (int)cudaErrorInvalidConfiguration;
-        W.blocks_per_sm[tally] = blocks;
+        W.blocks_per_sm[tally] = std::min(blocks, MCB_WALK_MINB);
         W.smem_bytes[tally] = smem;
-        W.n_pairs[tally] = (tally ? SP_FIXED + 1 : SP_FIXED) + W.det_nn + (W.det_nn + 1) / 2;
+        W.n_pairs[tally] = n_pairs;
     }
     W.max_grid = n_sm * std::max(W.blocks_per_sm[0], W.blocks_per_sm[1]);
     W.n_contexts = (int64_t)W.max_grid * WALK_SLOTS;
     W.shared = shared;
+#ifdef MCB_WALK_GLOBAL_STATE
+    W.gstate_pairs = (size_t)W.max_grid * std::max(W.n_pairs[0], W.n_pairs[1]) * WALK_SLOTS;
+#else
+    W.gstate_pairs = 0;
+#endif
     return 0;
 }
 
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth)
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth, double2* gstate)
 {
     if (end <= begin) return;
     // persistent: every resident warp draws chunks of bank positions until the generation runs dry
@@ -414,13 +474,18 @@ void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, u
     const uint64_t warps = (uint64_t)grid * WARPS;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
     WalkRes R;
-    R.stack = stack; R.stack_depth = stack_depth; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
+    R.stack = stack; R.gstate = gstate; R.stack_depth = stack_depth; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
     const size_t smem = W.smem_bytes[ti];
     // four instances: cycles that score nothing carry no estimator code, problems where nothing is born in flight
     // (k-eigenvalue without splitting) no secondary stack
-#define MCB_WALK(TALLY, SHARED) k_walk<TALLY, SHARED><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R)
-    if (T.on) { if (W.shared) MCB_WALK(true, true); else MCB_WALK(true, false); }
-    else { if (W.shared) MCB_WALK(false, true); else MCB_WALK(false, false); }
+#define MCB_WALK(T_, S_, E_) k_walk<T_, S_, E_><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R)
+    if (W.exchange) {
+        if (T.on) { if (W.shared) MCB_WALK(true, true, true); else MCB_WALK(true, false, true); }
+        else { if (W.shared) MCB_WALK(false, true, true); else MCB_WALK(false, false, true); }
+    } else {
+        if (T.on) { if (W.shared) MCB_WALK(true, true, false); else MCB_WALK(true, false, false); }
+        else { if (W.shared) MCB_WALK(false, true, false); else MCB_WALK(false, false, false); }
+    }
 #undef MCB_WALK
     g_launches += 1;
 }

@@ -219,8 +219,14 @@ int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, i
     mcb::build_material_tables(p, material, 14, T);
     for (int64_t i = 0; i < n; i++) {
         const int u = mcb_union_count_less(T.U.data(), T.hash.data(), T.key_min, T.n_hash, T.shift, (int32_t)T.U.size(), E[i]) - 1;
+        // the device reads the indices through the bin records (mcb_union_lookup): both routes must agree
+        const int32_t* rec = nullptr;
+        bool from_rec = false;
+        const int lo = mcb_union_lookup(T.U.data(), T.hrec.data(), T.hrec_stride, T.key_min, T.n_hash, T.shift, E[i], &rec, &from_rec);
+        if (lo - 1 != u) return -2;
         for (int k = 0; k < T.n_nuc; k++) {
             int idx = u < 0 ? -1 : T.map[(size_t)u * T.n_nuc + k];
+            if ((from_rec ? rec[2 + k] : T.map[(size_t)u * T.n_nuc + k]) != idx) return -2;
             if (idx == MCB_MAP_BISECT) {
                 const mcb_nuclide& N = p->nuclides[p->mat_nuclide[p->mat_begin[material] + k]];
                 idx = mcb_row_bisect(p->xs_rows + (size_t)N.row_begin * MCB_XS_ROW, N.n_rows, E[i]);
