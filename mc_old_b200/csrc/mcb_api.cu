@@ -170,7 +170,13 @@ struct mcb_ctx {
     int n_sm = 148;
     DevBuf<double2> d_gstate;        // slot state of the walk kernel when it is kept in global memory (build option)
     DevBuf<StackRec> d_stack;        // per-context LIFO stacks of same-history secondaries (the reference's Pbank)
-    int stack_depth = 0;
+    DevBuf<unsigned short> d_chunk_tab;
+    DevBuf<DonationQueue> d_donq;    // work sharing between lanes (fixed-source problems): ring of handed-over secondaries
+    DevBuf<unsigned long long> d_donq_seq;
+    DevBuf<StackRec> d_donq_recs;
+    DevBuf<double> d_dense;          // dense tally rows of histories shared between lanes
+    DevBuf<int32_t> d_dense_pending; // [0 .. rows) pending units, [rows] the row cursor
+    int dense_rows = 0;
     DevBuf<uint32_t> d_tab_key;      // per-context tally tables of the walk kernel
     DevBuf<double> d_tab_val;
     DevBuf<uint16_t> d_tab_list;
@@ -506,9 +512,26 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         if (rc != 0) return ctx->fail(MCB_ERR_CUDA, "walk kernel does not fit this device: %s", cudaGetErrorString((cudaError_t)rc));
         const size_t n_ctx = (size_t)ctx->plan.n_contexts;
         if (ctx->plan.gstate_pairs) CK(ctx->d_gstate.alloc(ctx->plan.gstate_pairs));
-        if (P.shared_histories) {
-            ctx->stack_depth = getenv("MCB_STACK_DEPTH") ? std::max(1, atoi(getenv("MCB_STACK_DEPTH"))) : 64;
-            CK(ctx->d_stack.alloc(n_ctx * (size_t)ctx->stack_depth));
+        if (ctx->plan.stack_records) { CK(ctx->d_stack.alloc(ctx->plan.stack_records)); CK(ctx->d_chunk_tab.alloc(ctx->plan.chunk_tab_entries)); }
+        if (P.shared_histories && !p->ksearch && !getenv("MCB_NO_SHARING")) {
+            // fixed-source problems: lanes hand waiting secondaries to idle lanes (k-eigenvalue problems only split, their
+            // families are small, and their fission sites keep the order of one lane)
+            const uint32_t cap = 1u << 16;
+            std::vector<unsigned long long> seq(cap);
+            for (uint32_t i = 0; i < cap; i++) seq[i] = i;
+            CK(ctx->d_donq_seq.upload(seq.data(), cap));
+            CK(ctx->d_donq_recs.alloc(cap));
+            DonationQueue dq;
+            memset(&dq, 0, sizeof(dq));
+            dq.seq = ctx->d_donq_seq.p; dq.recs = ctx->d_donq_recs.p; dq.cap_mask = cap - 1;
+            CK(ctx->d_donq.upload(&dq, 1));
+            if (p->n_tallies > 0) {
+                ctx->dense_rows = (int)std::max<int64_t>(64, std::min<int64_t>(65536, (int64_t)(1ull << 31) / (8 * p->n_tallies)));
+                CK(ctx->d_dense.alloc((size_t)ctx->dense_rows * p->n_tallies));
+                CK(cudaMemset(ctx->d_dense.p, 0, (size_t)ctx->dense_rows * p->n_tallies * sizeof(double)));
+                CK(ctx->d_dense_pending.alloc((size_t)ctx->dense_rows + 1));
+                CK(cudaMemset(ctx->d_dense_pending.p, 0, ((size_t)ctx->dense_rows + 1) * sizeof(int32_t)));
+            }
         }
         if (p->n_tallies > 0) {
             // table of a history: a power of two >= the number of tallies when that fits (then every tally has its own
@@ -687,6 +710,8 @@ static TallyAcc tally_acc(mcb_ctx* ctx, uint32_t h0, bool tally_on)
     T.tab_key = ctx->d_tab_key.p; T.tab_val = ctx->d_tab_val.p; T.tab_list = ctx->d_tab_list.p;
     T.tab_mask = ctx->tab_size ? ctx->tab_size - 1 : 0; T.n_tallies = (int32_t)ctx->n_tallies;
     T.sum = ctx->d_tally_sum.p; T.squared = ctx->d_tally_sq.p;
+    T.dense = ctx->d_dense.p; T.dense_pending = ctx->d_dense_pending.p; T.dense_rows = ctx->dense_rows;
+    T.dense_cursor = ctx->d_dense_pending.p ? ctx->d_dense_pending.p + ctx->dense_rows : nullptr;
     return T;
 }
 
@@ -699,7 +724,8 @@ static int check_batch(mcb_ctx* ctx, const Counters& hc)
     if (hc.lost) return ctx->fail(MCB_ERR_LOST, "[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )", hc.lost_pos[0], hc.lost_pos[1], hc.lost_pos[2]);
     if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
     if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
-    if (hc.overflow_stack) return ctx->fail(MCB_ERR_CAPACITY, "secondary stack overflow: a history had more than %d particles waiting (raise MCB_STACK_DEPTH)", ctx->stack_depth);
+    if (hc.overflow_stack) return ctx->fail(MCB_ERR_CAPACITY, "secondary stack overflow: a history had more than %d particles waiting, or the block's spare chunks ran out", ctx->plan.stack_max);
+    if (hc.hang) return ctx->fail(MCB_ERR_CUDA, "walk kernel: a bounded wait ran out (work-sharing protocol)");
     if (hc.overflow_tally) return ctx->fail(MCB_ERR_CAPACITY, "tally table overflow: a history touched more than %u tally bins", ctx->tab_size);
     return MCB_OK;
 }
@@ -767,7 +793,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
         if (q1 > q0) {
             CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
             ctx->timer.begin(st, ST_STEP);
-            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth, ctx->d_gstate.p);
+            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p);
             ctx->timer.end(st);
             (*n_iterations)++;
         }
@@ -802,12 +828,14 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     if (ctx->walk_mode) {
         // one launch follows the source particles in slots [0, nb) and every secondary of their histories to the end
         CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
+        if (ctx->d_dense_pending.p) CK(cudaMemsetAsync(ctx->d_dense_pending.p + ctx->dense_rows, 0, sizeof(int32_t), st));
         ctx->timer.begin(st, ST_STEP);
-        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->stack_depth, ctx->d_gstate.p);
+        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p);
         ctx->timer.end(st);
         *n_iterations += 1;
         CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (getenv("MCB_TRACE_SHARING")) fprintf(stderr, "[mcb sharing] donated %llu  shared histories %llu  refused %llu  idle waits %llu  tracks %llu\n", ctx->h_counters->n_donated, ctx->h_counters->n_shared_hist, ctx->h_counters->n_donate_refused, ctx->h_counters->n_idle_waits, ctx->h_counters->n_tracks);
         return check_batch(ctx, *ctx->h_counters);
     }
 

@@ -164,6 +164,9 @@ struct Counters {
     unsigned long long q_collide, q_cross;// lengths of the two halves of the event queue
     int lost, overflow_sites, overflow_slots, overflow_fixed;
     int overflow_tally, overflow_stack;   // walk kernel: a history's tally table / secondary stack is full
+    int hang, pad_i;                      // walk kernel: a bounded wait ran out (never expected; reported as an error)
+    long long live;                       // walk kernel: work units alive on this GPU (histories + donated secondaries)
+    unsigned long long n_donated, n_shared_hist, n_donate_refused, n_idle_waits;  // work-sharing statistics
     double lost_pos[3];
     // exact (fixed-point, two-limb) sums over histories: k_C, k_TL, k_C^2, k_TL^2, H
     unsigned long long fx_lo[5], fx_hi[5];
@@ -191,7 +194,14 @@ struct TallyAcc {
     uint32_t tab_mask;                    // table size - 1 (a power of two >= the number of tallies when that fits)
     int32_t n_tallies;
     double *sum, *squared;                // Tally::sum / squared of the cycle on this rank
+    // histories whose secondaries were handed to other lanes (long fission chains): their units merge into one dense
+    // row each; the unit that finishes last (pending reaches 0) turns the row into sum / squared
+    double* dense;                        // dense_rows x n_tallies
+    int32_t* dense_pending;
+    int32_t* dense_cursor;                // rows handed out in this launch
+    int32_t dense_rows, pad;
 };
+
 
 // a same-history secondary waiting on its history's LIFO stack (the reference's Pbank, handler.cpp:20-29)
 struct alignas(16) StackRec {
@@ -201,6 +211,16 @@ struct alignas(16) StackRec {
     double pad1;
 };
 static_assert(sizeof(StackRec) == 112, "StackRec is seven 16-byte words");
+
+// secondaries handed over between lanes (work sharing for long fixed-source fission chains): a bounded multi-producer
+// multi-consumer ring in global memory, one sequence number per cell (free for ticket t when seq = t, filled when t + 1)
+struct DonationQueue {
+    unsigned long long head, tail;
+    int avail, count;
+    unsigned long long* seq;
+    StackRec* recs;
+    uint32_t cap_mask, pad;
+};
 
 #define MCB_FX_SCALE 17592186044416.0     /* 2^44: fixed-point scale of the exact history sums */
 

@@ -32,6 +32,8 @@ __device__ __forceinline__ void hist_add(double* p, double v) { atomicAdd(p, v);
 //    {tally index -> value} in global memory (row = the history's context), touched entries listed for the flush;
 //  * event-queue kernels: particles of one history are spread over threads: dense rows acc[tally][history of batch].
 // ---------------------------------------------------------------------------------------------
+// A history's table is only ever touched from one SM (the lane, or the lanes of one block, that follow it), so plain
+// cached accesses are coherent and most probes are L1 hits.
 __device__ __forceinline__ void tally_add(const TallyAcc& T, Counters* C, int row, int& n_touched, int64_t t, double v)
 {
     if (T.acc) { atomicAdd(T.acc + t * T.stride + (int64_t)(row - T.first_hist), v); return; }
@@ -40,12 +42,12 @@ __device__ __forceinline__ void tally_add(const TallyAcc& T, Counters* C, int ro
     double* vals = T.tab_val + (size_t)row * (mask + 1u);
     uint32_t h = (uint32_t)t & mask;
     for (uint32_t probe = 0; probe <= mask; probe++, h = (h + 1u) & mask) {
-        const uint32_t k = __ldcg(keys + h);
-        if (k == (uint32_t)t + 1u) { __stcg(vals + h, __ldcg(vals + h) + v); return; }
+        const uint32_t k = keys[h];
+        if (k == (uint32_t)t + 1u) { vals[h] += v; return; }
         if (k == 0u) {
-            __stcg(keys + h, (uint32_t)t + 1u);
-            __stcg(vals + h, v);
-            __stcg(T.tab_list + (size_t)row * (mask + 1u) + n_touched, (uint16_t)h);
+            keys[h] = (uint32_t)t + 1u;
+            vals[h] = v;
+            T.tab_list[(size_t)row * (mask + 1u) + n_touched] = (uint16_t)h;
             n_touched++;
             return;
         }
@@ -232,6 +234,7 @@ struct Particle {
     int cell, hist;
     int row;        // tally accumulator row of the history: context (walk kernel) or shard-local history index (dense rows)
     int n_touched;  // entries of the history's tally table in use (walk kernel)
+    int drow;       // dense tally row of a history that is shared between lanes, -1 while a history is followed by one lane
 };
 // all estimators attached to surface / cell `id` score one event of particle p.  Cold and out of line, with every
 // input BY VALUE (no address of a register-resident particle escapes), so that the transport kernels' register

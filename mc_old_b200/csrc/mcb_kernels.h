@@ -44,11 +44,13 @@ void cross(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* 
 // followed to the end; particles sorted by next event in shared-memory queues, 160 history contexts per thread block.
 // walk_plan() sizes the launch for this device (dynamic shared memory, blocks per SM of the scoring and non-scoring
 // instance) and tells how many history contexts exist at most: the caller owns the per-context secondary stacks
-// (n_contexts x stack_depth StackRec) and tally tables (TallyAcc::tab_*).
+// (WalkPlan::stack_records StackRec, chunk table) and tally tables (TallyAcc::tab_*).
 struct WalkRes {        // kernel argument
     StackRec* stack;
+    unsigned short* chunk_tab;  // n_contexts x 32: borrowed stack chunks of every history
+    DonationQueue* donq;        // secondaries handed over between lanes (nullptr: every history stays with one lane)
     double2* gstate;    // slot state in global memory (build option MCB_WALK_GLOBAL_STATE), else nullptr
-    int32_t stack_depth, det_nn, n_pairs, priv_tallies;
+    int32_t det_nn, n_pairs, priv_tallies;
 };
 struct WalkPlan {
     int n_sm, det_nn, priv_tallies, max_grid;
@@ -57,11 +59,13 @@ struct WalkPlan {
     int blocks_per_sm[2], n_pairs[2];   // [0] cycles that score nothing, [1] scoring cycles
     size_t smem_bytes[2];
     int64_t n_contexts;
+    size_t stack_records, chunk_tab_entries;  // sizes of the secondary-stack arrays the caller allocates (0: no secondaries)
+    int stack_max;       // particles one history can have waiting
     size_t gstate_pairs; // double2 elements of the global slot-state array the caller allocates (0: state in shared memory)
 };
 int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth, double2* gstate);
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate);
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff);

@@ -36,6 +36,11 @@ namespace {
 #endif
 constexpr int WALK_RES = 32;                  // slots beyond one per thread: what makes a full batch always available
 constexpr int WALK_SLOTS = BLOCK + WALK_RES;  // 160
+// secondary stacks: chunks of 32 records.  Every slot owns one chunk for good (a history rarely has more than a few
+// particles waiting); a history that needs more borrows chunks from its block's pool and returns them when it ends
+constexpr int STACK_CHUNK = 32;
+constexpr int WALK_EXTRA = 256;               // spare chunks per block
+constexpr int STACK_MAXCH = 32;               // chunks per history at most (1024 particles waiting)
 constexpr int pow2_at_least(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 constexpr int WALK_QCAP = pow2_at_least(WALK_SLOTS);  // ring capacity of a queue
 static_assert(WALK_QCAP >= WALK_SLOTS && (WALK_QCAP & (WALK_QCAP - 1)) == 0, "queue ring");
@@ -61,8 +66,10 @@ struct WalkQ {
     unsigned lock;
     unsigned headC, tailC, headX, tailX;
     unsigned warps_done;
-    unsigned pad[2];
+    unsigned alloc_lock;
+    int n_free;                               // spare stack chunks in free_list
     unsigned short qC[WALK_QCAP], qX[WALK_QCAP];
+    unsigned short free_list[WALK_EXTRA];
 };
 
 // slot state lives in shared memory, or (MCB_WALK_GLOBAL_STATE) in a per-block global array that stays in L2, read and
@@ -102,31 +109,100 @@ struct SlotDetail {
     }
 };
 
-// the history's LIFO stack of secondaries (the reference's Pbank, handler.cpp:20-29)
+// the history's LIFO stack of secondaries (the reference's Pbank, handler.cpp:20-29): record i lives in chunk i / 32 of
+// the history (chunk 0 = the slot's own, the others listed in its row of the chunk table)
 struct StackSink {
-    StackRec* stk;
-    int& sp;
-    int depth;
+    StackRec* blk;              // this block's chunks
+    const unsigned short* tab;  // chunk table row of the history
+    int own;                    // the slot's own chunk
+    int& sp;                    // records on the stack
+    int nch;                    // chunks the history holds
     Counters* C;
+    __device__ __forceinline__ StackRec* rec(int i) const
+    {
+        const int k = i / STACK_CHUNK;
+        const int id = k == 0 ? own : (int)__ldcg(tab + k);
+        return blk + (size_t)id * STACK_CHUNK + (i % STACK_CHUNK);
+    }
     __device__ __forceinline__ void push(const Particle& q)
     {
-        if (sp >= depth) { C->overflow_stack = 1; return; }
-        double2* r = reinterpret_cast<double2*>(stk + sp);
+        if (sp >= nch * STACK_CHUNK) { C->overflow_stack = 1; return; }
+        double2* r = reinterpret_cast<double2*>(rec(sp));
         r[0] = make_double2(q.x, q.y); r[1] = make_double2(q.z, q.u); r[2] = make_double2(q.v, q.w);
         r[3] = make_double2(q.E, q.speed); r[4] = make_double2(q.wgt, q.t);
         r[5] = make_double2(q.Eold, __longlong_as_double((long long)q.rng));
-        r[6] = make_double2(pack2i(q.cell, 0), 0.0);
+        r[6] = make_double2(pack2i(q.cell, q.hist), pack2i(q.drow, 0));
         sp++;
     }
+    __device__ __forceinline__ void pop(Particle& p)
+    {
+        sp--;
+        const double2* r = reinterpret_cast<const double2*>(rec(sp));
+        const double2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g = r[6];
+        p.x = a.x; p.y = a.y; p.z = b.x; p.u = b.y; p.v = c.x; p.w = c.y; p.E = d.x; p.speed = d.y; p.wgt = e.x; p.t = e.y;
+        p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x);
+        p.told = p.t;
+    }
 };
-__device__ __forceinline__ void stack_pop(const StackRec* stk, int& sp, Particle& p)
+
+// ---- work sharing: secondaries handed to other lanes through a global ring (DonationQueue)
+constexpr int WAIT_LIMIT = 1 << 22;  // bounded waits: a protocol error becomes an error code, never a hung GPU
+__device__ __forceinline__ bool donation_push(DonationQueue* D, const Particle& q, Counters* C)
 {
-    sp--;
-    const double2* r = reinterpret_cast<const double2*>(stk + sp);
-    const double2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g = r[6];
+    if (atomicAdd(&D->count, 1) >= (int)D->cap_mask) { atomicSub(&D->count, 1); return false; }
+    const unsigned long long pos = atomicAdd(&D->tail, 1ull);
+    const uint32_t cell = (uint32_t)pos & D->cap_mask;
+    volatile unsigned long long* seq = D->seq + cell;
+    int spins = 0;
+    while (*seq != pos) { if (++spins > WAIT_LIMIT) { C->hang = 1; return true; } __nanosleep(64); }
+    double2* r = reinterpret_cast<double2*>(D->recs + cell);
+    __stcg(r + 0, make_double2(q.x, q.y)); __stcg(r + 1, make_double2(q.z, q.u)); __stcg(r + 2, make_double2(q.v, q.w));
+    __stcg(r + 3, make_double2(q.E, q.speed)); __stcg(r + 4, make_double2(q.wgt, q.t));
+    __stcg(r + 5, make_double2(q.Eold, __longlong_as_double((long long)q.rng)));
+    __stcg(r + 6, make_double2(pack2i(q.cell, q.hist), pack2i(q.drow, 0)));
+    __threadfence();
+    *seq = pos + 1ull;
+    atomicAdd(&D->avail, 1);
+    return true;
+}
+__device__ __forceinline__ bool donation_pop(DonationQueue* D, Particle& p, Counters* C)
+{
+    if (atomicSub(&D->avail, 1) <= 0) { atomicAdd(&D->avail, 1); return false; }
+    const unsigned long long pos = atomicAdd(&D->head, 1ull);
+    const uint32_t cell = (uint32_t)pos & D->cap_mask;
+    volatile unsigned long long* seq = D->seq + cell;
+    int spins = 0;
+    while (*seq != pos + 1ull) { if (++spins > WAIT_LIMIT) { C->hang = 1; return false; } __nanosleep(64); }
+    __threadfence();
+    const double2* r = reinterpret_cast<const double2*>(D->recs + cell);
+    const double2 a = __ldcg(r + 0), b = __ldcg(r + 1), c = __ldcg(r + 2), d = __ldcg(r + 3), e = __ldcg(r + 4), f = __ldcg(r + 5), g = __ldcg(r + 6);
     p.x = a.x; p.y = a.y; p.z = b.x; p.u = b.y; p.v = c.x; p.w = c.y; p.E = d.x; p.speed = d.y; p.wgt = e.x; p.t = e.y;
-    p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x);
+    p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x); p.hist = unpack_hi(g.x); p.drow = unpack_lo(g.y);
     p.told = p.t;
+    __threadfence();
+    *seq = pos + (unsigned long long)D->cap_mask + 1ull;
+    atomicSub(&D->count, 1);
+    return true;
+}
+// chunk pool of the block: taken and returned by single lanes under a lock of its own (rare: only histories with more
+// than 32 particles waiting get here); callers serialise the lanes of a warp
+__device__ __forceinline__ int chunks_take(WalkQ& Q, unsigned short* tab, int nch, int want)
+{
+    while (atomicCAS(&Q.alloc_lock, 0u, 1u) != 0u) __nanosleep(64);
+    __threadfence_block();
+    int got = 0;
+    while (got < want && Q.n_free > 0 && nch + got < STACK_MAXCH) { __stcg(tab + nch + got, Q.free_list[--Q.n_free]); got++; }
+    __threadfence_block();
+    atomicExch(&Q.alloc_lock, 0u);
+    return got;
+}
+__device__ __forceinline__ void chunks_give(WalkQ& Q, const unsigned short* tab, int nch)
+{
+    while (atomicCAS(&Q.alloc_lock, 0u, 1u) != 0u) __nanosleep(64);
+    __threadfence_block();
+    for (int k = 1; k < nch; k++) Q.free_list[Q.n_free++] = __ldcg(tab + k);
+    __threadfence_block();
+    atomicExch(&Q.alloc_lock, 0u);
 }
 
 __device__ __forceinline__ void lock_acquire(WalkQ& Q, unsigned lane)
@@ -144,21 +220,56 @@ __device__ __forceinline__ void lock_release(WalkQ& Q, unsigned lane)
     if (lane == 0) atomicExch(&Q.lock, 0u);
 }
 
-// Estimator::end_history for one history (Estimator.cpp:339-346): sum += hist, squared += hist^2 per touched bin
-__device__ __forceinline__ void flush_history_tallies(const TallyAcc& T, int row, int n_touched, double* s_sum, double* s_sq)
+// Estimator::end_history for one history (Estimator.cpp:339-346): sum += hist, squared += hist^2 per touched bin.
+// The whole warp works on the table of the lane whose history ended (histories end on one or two lanes at a time).
+__device__ __forceinline__ void flush_history_tallies(const TallyAcc& T, int row, int n_touched, double* s_sum, double* s_sq, unsigned lane)
 {
     const uint32_t size = T.tab_mask + 1u;
     uint32_t* keys = T.tab_key + (size_t)row * size;
     double* vals = T.tab_val + (size_t)row * size;
     const uint16_t* list = T.tab_list + (size_t)row * size;
-    for (int i = 0; i < n_touched; i++) {
-        const uint32_t h = __ldcg(list + i);
-        const uint32_t t = __ldcg(keys + h) - 1u;
-        const double v = __ldcg(vals + h);
-        __stcg(keys + h, 0u);
+    for (int i = (int)lane; i < n_touched; i += 32) {
+        const uint32_t h = list[i];
+        const uint32_t t = keys[h] - 1u;
+        const double v = vals[h];
+        keys[h] = 0u;
         if (s_sum) { atomicAdd(s_sum + t, v); atomicAdd(s_sq + t, v * v); }
         else { atomicAdd(T.sum + t, v); atomicAdd(T.squared + t, v * v); }
     }
+}
+// a unit of a shared history ends: its private table goes into the history's dense row; the last unit out turns the row
+// into sum / squared.  Warp-cooperative like the flush.
+__device__ __forceinline__ void merge_shared_tallies(const TallyAcc& T, int row, int n_touched, int drow, double* s_sum, double* s_sq, unsigned lane)
+{
+    const uint32_t size = T.tab_mask + 1u;
+    uint32_t* keys = T.tab_key + (size_t)row * size;
+    double* vals = T.tab_val + (size_t)row * size;
+    const uint16_t* list = T.tab_list + (size_t)row * size;
+    double* dense = T.dense + (size_t)drow * T.n_tallies;
+    for (int i = (int)lane; i < n_touched; i += 32) {
+        const uint32_t h = list[i];
+        const uint32_t t = keys[h] - 1u;
+        atomicAdd(dense + t, vals[h]);
+        keys[h] = 0u;
+    }
+    __threadfence();
+    __syncwarp();
+    int left = 0;
+    if (lane == 0) left = atomicSub(T.dense_pending + drow, 1) - 1;
+    left = __shfl_sync(FULL, left, 0);
+    if (left != 0) return;
+    __threadfence();
+    for (int t = (int)lane; t < T.n_tallies; t += 32) {
+        const double v = __ldcg(dense + t);
+        if (v != 0.0) {
+            __stcg(dense + t, 0.0);
+            if (s_sum) { atomicAdd(s_sum + t, v); atomicAdd(s_sq + t, v * v); }
+            else { atomicAdd(T.sum + t, v); atomicAdd(T.squared + t, v * v); }
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(T.dense_pending + drow, -1);  // the row is clean again: free for another history
 }
 
 // EXCH = true: the event-sorted form described above.  EXCH = false: every lane keeps its history from the source bank to
@@ -182,7 +293,8 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
 #endif
     double* const s_sum = (TALLY && R.priv_tallies) ? reinterpret_cast<double*>(&Q + 1) : nullptr;
     double* const s_sq = s_sum ? s_sum + R.priv_tallies : nullptr;
-    if (threadIdx.x == 0) { Q.lock = 0; Q.headC = Q.tailC = Q.headX = Q.tailX = 0; Q.warps_done = 0; }
+    if (threadIdx.x == 0) { Q.lock = 0; Q.headC = Q.tailC = Q.headX = Q.tailX = 0; Q.warps_done = 0; Q.alloc_lock = 0; Q.n_free = SHARED ? WALK_EXTRA : 0; }
+    if (SHARED) for (int i = threadIdx.x; i < WALK_EXTRA; i += BLOCK) Q.free_list[i] = (unsigned short)(WALK_SLOTS + i);
     if (s_sum) for (int i = threadIdx.x; i < 2 * R.priv_tallies; i += BLOCK) s_sum[i] = 0.0;
     __syncthreads();  // the only block-wide barrier: from here on the warps run on their own
 
@@ -192,11 +304,13 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
     unsigned tracks = 0, collisions = 0, crossings = 0, lookups = 0;
     int my_slot = threadIdx.x;            // the slot this lane parks its particle in (it moves with every claim)
     bool have = false, exhausted = false;
+    bool own = true;                      // event-sorted form: this lane holds a slot to park a particle in
     bool second_batch = EXCH && warp_id() == 0;   // warp 0 starts two batches: the block's 32 extra slots
     Particle p;
     HistLocal L = {0.0, 0.0, 0};
-    int sp = 0;                           // depth of the history's secondary stack
+    int sp = 0, nch = 1;                  // records on the history's secondary stack, chunks it holds
     unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of bank positions
+    int idle_spins = 0;
     for (;;) {
         // ---- lanes without a history draw the next source particles
         unsigned idle = __ballot_sync(FULL, !have);
@@ -219,13 +333,26 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
                 p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
                 p.Eold = p.E;  // the reference leaves energy_old uninitialised at birth; defined as E here
                 p.told = p.t;
-                p.n_touched = 0;
+                p.n_touched = 0; p.drow = -1;
                 L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
-                sp = 0;
+                sp = 0; nch = 1;
                 have = true;
             }
             chunk_next += take;
+            if (SHARED && R.donq && lane == 0) atomicAdd((unsigned long long*)&C->live, (unsigned long long)take);
             idle = __ballot_sync(FULL, !have);
+        }
+        if (SHARED && R.donq && exhausted && idle) {  // the bank is dry: idle lanes take secondaries other lanes handed over
+            int av = 0;
+            if (lane == 0) av = __ldcg(&R.donq->avail);
+            av = __shfl_sync(FULL, av, 0);
+            if (av > 0 && !have && own && donation_pop(R.donq, p, C)) {
+                p.n_touched = 0;
+                L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
+                sp = 0; nch = 1;
+                have = true;
+            }
+            __syncwarp();
         }
         // ---- common part of every track: xs lookup and flight; the particle is parked in its slot
         bool to_cross = false;
@@ -247,11 +374,11 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             st_pair(s + SP_WT * WALK_SLOTS, make_double2(p.wgt, p.t));
             st_pair(s + SP_RNG * WALK_SLOTS, make_double2(__longlong_as_double((long long)p.rng), pack2i(p.cell, p.hist)));
             st_pair(s + SP_K * WALK_SLOTS, make_double2(L.kC, L.kTL));
-            st_pair(s + SP_IDS * WALK_SLOTS, make_double2(pack2i(L.nsite, sp), pack2i(S, uidx)));
+            st_pair(s + SP_IDS * WALK_SLOTS, make_double2(pack2i(L.nsite, sp | (nch << 16)), pack2i(S, uidx)));
             st_pair(s + SP_XT * WALK_SLOTS, make_double2(X.t, X.nf));
             st_pair(s + SP_XS * WALK_SLOTS, make_double2(X.s, X.c));
             st_pair(s + SP_XF * WALK_SLOTS, make_double2(X.f, p.Eold));
-            if (TALLY) st_pair(s + SP_FIXED * WALK_SLOTS, make_double2(p.told, pack2i(p.n_touched, 0)));
+            if (TALLY) st_pair(s + SP_FIXED * WALK_SLOTS, make_double2(p.told, pack2i(p.n_touched, p.drow)));
         }
         // ---- event queues: append what this warp holds, take one batch of a kind back out
         int kind = 0;  // 1 collide, 2 cross
@@ -261,6 +388,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             const unsigned mC = __ballot_sync(FULL, have && !to_cross), mX = __ballot_sync(FULL, have && to_cross);
             unsigned hC = Q.headC, tC = Q.tailC, hX = Q.headX, tX = Q.tailX;
             if (have) {
+                own = false;  // the slot goes into a queue with its particle
                 if (!to_cross) Q.qC[(tC + __popc(mC & lt_mask)) & (WALK_QCAP - 1)] = (unsigned short)my_slot;
                 else Q.qX[(tX + __popc(mX & lt_mask)) & (WALK_QCAP - 1)] = (unsigned short)my_slot;
             }
@@ -273,8 +401,8 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
                 else if (aC >= 32u) nC = 32u;
                 else if (aC >= aX) { nC = aC; nX = min(aX, 32u - nC); }
                 else { nX = aX; nC = min(aC, 32u - nX); }
-                if (lane < nC) { my_slot = Q.qC[(hC + lane) & (WALK_QCAP - 1)]; kind = 1; }
-                else if (lane < nC + nX) { my_slot = Q.qX[(hX + lane - nC) & (WALK_QCAP - 1)]; kind = 2; }
+                if (lane < nC) { my_slot = Q.qC[(hC + lane) & (WALK_QCAP - 1)]; kind = 1; own = true; }
+                else if (lane < nC + nX) { my_slot = Q.qX[(hX + lane - nC) & (WALK_QCAP - 1)]; kind = 2; own = true; }
                 hC += nC; hX += nX;
             }
             __syncwarp();
@@ -285,6 +413,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             second_batch = false;
             have = false;
             my_slot = BLOCK + (int)lane;
+            own = true;
             continue;
         }
         const unsigned mK = __ballot_sync(FULL, kind != 0);
@@ -295,14 +424,22 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         else
 #endif
         if (mK == 0u) {
-            if (exhausted) break;  // nothing held, nothing queued, nothing left to draw
+            if (!exhausted) continue;
+            if (!(SHARED && R.donq)) break;  // nothing held, nothing queued, nothing left to draw
+            // work sharing: other lanes may still hand secondaries over; leave when no unit is alive anywhere
+            long long lv = 0;
+            if (lane == 0) lv = (long long)__ldcg((const unsigned long long*)&C->live);
+            lv = __shfl_sync(FULL, lv, 0);
+            if (lv <= 0) break;
+            if (++idle_spins > WAIT_LIMIT) { C->hang = 1; break; }
+            __nanosleep(4000);
             continue;
         }
         have = kind != 0;
         // ---- the event itself, on a batch of one kind (mixed only when the queues run low)
         CollideCtx c = {-1, -1, 0, 0, 0.0};
         unsigned n_copy = 0;
-        bool alive = false, in_material = false;
+        bool alive = false, in_material = false, unit_ended = false;
         const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
         if (EXCH && have) {
             const double2* s = st + my_slot;
@@ -314,10 +451,10 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             v = ld_pair(s + SP_WT * WALK_SLOTS); p.wgt = v.x; p.t = v.y;
             v = ld_pair(s + SP_RNG * WALK_SLOTS); p.rng = (uint64_t)__double_as_longlong(v.x); p.cell = unpack_lo(v.y); p.hist = unpack_hi(v.y);
             v = ld_pair(s + SP_K * WALK_SLOTS); L.kC = v.x; L.kTL = v.y;
-            v = ld_pair(s + SP_IDS * WALK_SLOTS); L.nsite = unpack_lo(v.x); sp = unpack_hi(v.x); S = unpack_lo(v.y); uidx = unpack_hi(v.y);
+            v = ld_pair(s + SP_IDS * WALK_SLOTS); L.nsite = unpack_lo(v.x); sp = unpack_hi(v.x) & 0xffff; nch = unpack_hi(v.x) >> 16; S = unpack_lo(v.y); uidx = unpack_hi(v.y);
             v = ld_pair(s + SP_XF * WALK_SLOTS); X.f = v.x; p.Eold = v.y;
-            if (TALLY) { v = ld_pair(s + SP_FIXED * WALK_SLOTS); p.told = v.x; p.n_touched = unpack_lo(v.y); }
-            else { p.told = p.t; p.n_touched = 0; }
+            if (TALLY) { v = ld_pair(s + SP_FIXED * WALK_SLOTS); p.told = v.x; p.n_touched = unpack_lo(v.y); p.drow = unpack_hi(v.y); }
+            else { p.told = p.t; p.n_touched = 0; p.drow = -1; }
             p.row = ctx_base + my_slot;
             if (kind == 1) {
                 v = ld_pair(s + SP_XT * WALK_SLOTS); X.t = v.x; X.nf = v.y;
@@ -346,8 +483,18 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             site0 = __shfl_sync(FULL, base, 31) + (v - c.n_sites);
         }
         if (!SHARED) { c.n_second = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
-        StackRec* const stk = SHARED ? R.stack + (size_t)(ctx_base + my_slot) * R.stack_depth : nullptr;
-        StackSink sink = {stk, sp, R.stack_depth, C};
+        unsigned short* const tab = SHARED ? R.chunk_tab + (size_t)(ctx_base + my_slot) * STACK_MAXCH : nullptr;
+        if (SHARED) {  // room for the particles about to be born: borrow chunks (lane by lane; rare)
+            const int need = (sp + (int)(c.n_second + n_copy) + STACK_CHUNK - 1) / STACK_CHUNK;
+            unsigned m = __ballot_sync(FULL, have && need > nch);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                if ((int)lane == src) nch += chunks_take(Q, tab, nch, need - nch);
+                __syncwarp();
+            }
+        }
+        StackSink sink = {SHARED ? R.stack + (size_t)blockIdx.x * (WALK_SLOTS + WALK_EXTRA) * STACK_CHUNK : nullptr, tab, my_slot, sp, nch, C};
         if (c.n_sites | c.n_second) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, &L);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
         if (have && kind == 2) alive = ev_cross_post(P, p, alive, n_copy, sink);
@@ -355,12 +502,87 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         __syncwarp();
         if (have && !alive) {
             if (SHARED && sp > 0) {
-                stack_pop(stk, sp, p);  // the history goes on with its most recent secondary (handler.cpp:22)
+                sink.pop(p);  // the history goes on with its most recent secondary (handler.cpp:22)
             } else {
                 // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525), Estimator::end_history
                 if (P.ksearch) { H.kC[p.hist] = L.kC; H.kTL[p.hist] = L.kTL; H.nsite[p.hist] = L.nsite; }
-                if (TALLY && p.n_touched) flush_history_tallies(T, p.row, p.n_touched, s_sum, s_sq);
                 have = false;
+                unit_ended = true;
+            }
+        }
+        if (TALLY) {  // Estimator::end_history of the histories (or shared units) that ended, one after the other, by the whole warp
+            unsigned m = __ballot_sync(FULL, unit_ended && (p.n_touched > 0 || p.drow >= 0));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int row = __shfl_sync(FULL, p.row, src), nt = __shfl_sync(FULL, p.n_touched, src), dr = __shfl_sync(FULL, p.drow, src);
+                if (dr >= 0) merge_shared_tallies(T, row, nt, dr, s_sum, s_sq, lane);
+                else flush_history_tallies(T, row, nt, s_sum, s_sq, lane);
+                __syncwarp();
+            }
+        }
+        if (SHARED && R.donq) {
+            const unsigned n_end = __popc(__ballot_sync(FULL, unit_ended));
+            if (lane == 0 && n_end) atomicAdd((unsigned long long*)&C->live, (unsigned long long)(-(long long)n_end));
+            // Work sharing.  A fission chain followed by one lane can be arbitrarily long (HEU_sphere_leakage: 170 tracks
+            // per history on average, a heavy tail far beyond): once the source bank is dry a history keeps one waiting
+            // secondary and hands the others to idle lanes; before that only a stack that has grown deep is relieved.
+            // Hand-over is driven by demand: while the source bank still has particles every lane is busy and only a
+            // stack that has grown deep is relieved; once the bank is dry a history keeps one waiting secondary and gives
+            // the others away, as long as the ring is not already stocked for the idle lanes.
+            bool dry = exhausted;  // this warp's own view; a warp whose lanes are all busy never asks the bank, so look
+            bool stocked = false;
+            if (__any_sync(FULL, have && sp > 1)) {
+                unsigned long long wh = 0;
+                int av = 0;
+                if (lane == 0) { wh = __ldcg(&C->walk_head); av = __ldcg(&R.donq->avail); }
+                dry = dry || __shfl_sync(FULL, wh, 0) >= end - begin;
+                stocked = __shfl_sync(FULL, av, 0) >= 4096;
+            }
+            const int thr = dry ? (stocked ? 24 : 1) : 24;
+            if (have && sp > thr) {
+                if (TALLY && p.drow < 0) {  // the history becomes shared: its units meet in a dense tally row
+                    int r = -1;
+                    if (__ldcg(T.dense_cursor) < T.dense_rows) {
+                        r = atomicAdd(T.dense_cursor, 1);
+                        if (r >= T.dense_rows) r = -1;
+                    }
+                    if (r < 0) {  // all rows handed out once: take one that its history has given back (pending = -1)
+                        unsigned probe = (unsigned)p.rng;
+                        for (int k = 0; k < 8 && r < 0; k++) {
+                            probe = probe * 1664525u + 1013904223u;
+                            const int cand = (int)(probe % (unsigned)T.dense_rows);
+                            if (__ldcg(T.dense_pending + cand) == -1 && atomicCAS(T.dense_pending + cand, -1, 1) == -1) r = cand;
+                        }
+                    } else T.dense_pending[r] = 1;
+                    if (r >= 0) { __threadfence(); p.drow = r; atomicAdd(&C->n_shared_hist, 1ull); }
+                    else atomicAdd(&C->n_donate_refused, 1ull);
+                }
+                if (!TALLY || p.drow >= 0) {
+                    while (sp > thr) {
+                        Particle q = p;
+                        sink.pop(q);
+                        if (TALLY) atomicAdd(T.dense_pending + p.drow, 1);
+                        atomicAdd((unsigned long long*)&C->live, 1ull);
+                        atomicAdd(&C->n_donated, 1ull);
+                        if (!donation_push(R.donq, q, C)) {  // ring full: keep it
+                            atomicAdd(&C->n_donate_refused, 1ull);
+                            atomicAdd((unsigned long long*)&C->live, (unsigned long long)(-1ll));
+                            if (TALLY) atomicSub(T.dense_pending + p.drow, 1);
+                            sink.push(q);
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        if (SHARED) {  // histories that ended holding borrowed chunks return them
+            unsigned m = __ballot_sync(FULL, !have && nch > 1);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                if ((int)lane == src) { chunks_give(Q, tab, nch); nch = 1; }
+                __syncwarp();
             }
         }
     }
@@ -454,6 +676,9 @@ int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_s
     W.max_grid = n_sm * std::max(W.blocks_per_sm[0], W.blocks_per_sm[1]);
     W.n_contexts = (int64_t)W.max_grid * WALK_SLOTS;
     W.shared = shared;
+    W.stack_records = shared ? (size_t)W.max_grid * (WALK_SLOTS + WALK_EXTRA) * STACK_CHUNK : 0;
+    W.chunk_tab_entries = shared ? (size_t)W.n_contexts * STACK_MAXCH : 0;
+    W.stack_max = STACK_MAXCH * STACK_CHUNK;
 #ifdef MCB_WALK_GLOBAL_STATE
     W.gstate_pairs = (size_t)W.max_grid * std::max(W.n_pairs[0], W.n_pairs[1]) * WALK_SLOTS;
 #else
@@ -463,7 +688,7 @@ int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_s
 }
 
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, int stack_depth, double2* gstate)
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate)
 {
     if (end <= begin) return;
     // persistent: every resident warp draws chunks of bank positions until the generation runs dry
@@ -474,7 +699,7 @@ void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, u
     const uint64_t warps = (uint64_t)grid * WARPS;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
     WalkRes R;
-    R.stack = stack; R.gstate = gstate; R.stack_depth = stack_depth; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
+    R.stack = stack; R.chunk_tab = chunk_tab; R.donq = donq; R.gstate = gstate; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
     const size_t smem = W.smem_bytes[ti];
     // four instances: cycles that score nothing carry no estimator code, problems where nothing is born in flight
     // (k-eigenvalue without splitting) no secondary stack

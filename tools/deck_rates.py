@@ -6,9 +6,9 @@ import mc_old_b200 as mcb
 from mc_old_b200 import decks
 cases = [("slab_analytic", decks.slab(samples=10_000_000), 2), ("shielding_vReduction", decks.shielding(samples=10_000_000), 2),
          ("infinite_GCR (k only)", decks.gcr(samples=200_000, active=0, passive=3), 3),
-         ("infinite_GCR_TRMM", decks.gcr(samples=20_000, active=2, passive=1, trmm=True), 3),
+         ("infinite_GCR_TRMM", decks.gcr(samples=200_000, active=2, passive=1, trmm=True), 3),
          ("UCube", decks.ucube(samples=2_000_000, active=2, passive=2), 4),
-         ("HEU_sphere_leakage", decks.heu_leakage(samples=1_000_000), 2)]
+         ("HEU_sphere_leakage", decks.heu_leakage(samples=4_000_000), 2)]
 for name, xml, cycles in cases:
     deck = mcb.Deck(xml=xml)
     if not deck.info["ksearch"]:

@@ -5,7 +5,7 @@ set -u
 TAG=$1; K=${2:-k_walk}; shift; shift
 mkdir -p gpurun_out
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$K -c 1 \
-    -f -o gpurun_out/$TAG python tools/prof_driver.py --samples 1e7 --cycles 3 --profile-cycle 2 "$@" > gpurun_out/${TAG}_ncu.log 2>&1
+    -f -o gpurun_out/$TAG python tools/prof_driver.py --cycles 3 --profile-cycle 2 "$@" > gpurun_out/${TAG}_ncu.log 2>&1
 ncu -i gpurun_out/$TAG.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>/dev/null
 python tools/ncu_summary.py raw gpurun_out/${TAG}_raw.csv > gpurun_out/${TAG}_summary.txt 2>&1
 cat gpurun_out/${TAG}_summary.txt

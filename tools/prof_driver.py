@@ -16,8 +16,13 @@ ap.add_argument("--profile-cycle", type=int, default=-1, help="cudaProfilerStart
 a = ap.parse_args()
 xml = {"heu": lambda: decks.heu_sphere(samples=int(a.samples), active=a.cycles, passive=0),
        "ucube": lambda: decks.ucube(samples=int(a.samples), active=a.cycles, passive=0),
-       "gcr": lambda: decks.gcr(samples=int(a.samples), active=a.cycles, passive=0)}[a.deck]()
+       "gcr": lambda: decks.gcr(samples=int(a.samples), active=a.cycles, passive=0),
+       "gcr_trmm": lambda: decks.gcr(samples=int(a.samples), active=a.cycles, passive=0, trmm=True),
+       "shield": lambda: decks.shielding(samples=int(a.samples)),
+       "leak": lambda: decks.heu_leakage(samples=int(a.samples))}[a.deck]()
 deck = mcb.Deck(xml=xml)
+if not deck.info["ksearch"]:
+    deck.set_run(n_cycle=a.cycles, n_passive=0)
 ctx = mcb.Context(deck)
 import ctypes
 rt = ctypes.CDLL("libcudart.so")
