@@ -209,6 +209,8 @@ struct mcb_ctx {
     cudaStream_t copy_stream = nullptr;
     static constexpr int N_CHUNK = 8;
     cudaEvent_t ev_chunk[N_CHUNK] = {};
+    cudaStream_t side_stream = nullptr;   // the peer-bank sweep of chunk c + 1 runs here beside the walk of chunk c
+    cudaEvent_t ev_side[N_CHUNK + 1] = {};
     DevBuf<unsigned long long> d_chunk_lo;
     DevBuf<uint32_t> d_chunk_pos;
     uint32_t* h_chunk_pos = nullptr;  // pinned
@@ -612,6 +614,8 @@ void mcb_destroy(mcb_ctx* ctx)
     if (ctx->h_chunk_pos) cudaFreeHost(ctx->h_chunk_pos);
     for (int i = 0; i < mcb_ctx::N_CHUNK; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i <= mcb_ctx::N_CHUNK; i++) if (ctx->ev_side[i]) cudaEventDestroy(ctx->ev_side[i]);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->h_recv) cudaFreeHost(ctx->h_recv);
     for (int b = 0; b < 2; b++)
         for (int r = 0; r < ctx->world && r < MCB_MAX_WORLD; r++)
@@ -725,9 +729,21 @@ static int check_batch(mcb_ctx* ctx, const Counters& hc)
     if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
     if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
     if (hc.overflow_stack) return ctx->fail(MCB_ERR_CAPACITY, "secondary stack overflow: a history had more than %d particles waiting, or the block's spare chunks ran out", ctx->plan.stack_max);
-    if (hc.hang) return ctx->fail(MCB_ERR_CUDA, "walk kernel: a bounded wait ran out (work-sharing protocol)");
+    if (hc.hang) return ctx->fail(MCB_ERR_CUDA, "walk kernel: a bounded wait ran out (%s; src_ready %llu, walk_head %llu)", hc.hang == 4 ? "source sweep beside the walk" : hc.hang == 3 ? "idle warps waiting for shared work" : "ring of handed-over secondaries", hc.src_ready, hc.walk_head);
     if (hc.overflow_tally) return ctx->fail(MCB_ERR_CAPACITY, "tally table overflow: a history touched more than %u tally bins", ctx->tab_size);
     return MCB_OK;
+}
+
+static mcbk::WalkSource walk_source(mcb_ctx* ctx, const SourceBankView* V, int32_t first_hist, uint64_t nps0, const mcbk::SortScratch* sort)
+{
+    mcbk::WalkSource S;
+    memset(&S, 0, sizeof(S));
+    S.first_hist = first_hist; S.nps0 = nps0; S.seed0 = ctx->P.seed0;
+    if (V && V->n) {
+        S.fused = 1; S.V = *V;
+        if (sort) { S.sorted_key = sort->key_out; S.sorted_val = sort->val_out; S.rng_after = sort->rng_after; S.rot = sort->rot; S.key32 = sort->key32; }
+    }
+    return S;
 }
 
 static int ensure_sort_scratch(mcb_ctx* ctx)
@@ -760,6 +776,7 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
     V.flat = dst; V.dir_x = ctx->d_host_dirs.p; V.n = n;
     { const int rc = ensure_sort_scratch(ctx); if (rc != MCB_OK) return rc; }
     ctx->sort.rot = 0;
+    ctx->sort.key32 = n < (1ull << 32) ? 1 : 0;
     // the copies start right away ...
     unsigned long long lo[NC + 1];
     for (int c = 0; c <= NC; c++) lo[c] = n * (unsigned long long)c / NC;
@@ -788,12 +805,12 @@ static int transport_streamed(mcb_ctx* ctx, uint32_t nb, bool tally_on, int* n_i
         CK(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
         ctx->timer.begin(st, ST_SOURCE);
         if (cnt) mcbk::pack_sites(st, ctx->d_io_sites.p + 8 * lo[c], ctx->d_io_cells.p + lo[c], cnt, dst + lo[c], ctx->d_host_dirs.p + 3 * lo[c]);
-        mcbk::source_sorted_range(st, P, ctx->B, ctx->q_active, 0, q0, q1 - q0, nps0, V, C, &ctx->sort);
         ctx->timer.end(st);
         if (q1 > q0) {
             CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
             ctx->timer.begin(st, ST_STEP);
-            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p);
+            mcbk::walk(st, P, ctx->B, q0, q1, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p,
+                       walk_source(ctx, &V, 0, nps0, &ctx->sort));
             ctx->timer.end(st);
             (*n_iterations)++;
         }
@@ -822,15 +839,72 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
         ctx->sort.rot = V.flat ? 0 : V.prefix[std::min(ctx->rank, V.n_seg - 1)];
         sort = &ctx->sort;
     }
-    mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, V, C, sort);
+    if (sort) ctx->sort.key32 = V.n < (1ull << 32) ? 1 : 0;
+    // the walk kernel sources its lanes itself from a fission bank (only the draws are made and sorted beforehand when the
+    // bank is spread over several GPUs); the deck's <sources> of the first cycle / of fixed-source decks are sampled by k_source
+    // (measured on one B200: with a flat local bank k_source + k_walk take 0.42 + 5.67 ms, the fused form 6.36 ms — the site
+    // reads sit on the critical path of the refilled lanes; across GPUs the fused form takes the NVLink sweep off the
+    // critical path instead.  MCB_FUSED_SOURCE=0/1 overrides.)
+    const bool fused_default = false;
+    const bool fused = ctx->walk_mode && V.n > 0 && (getenv("MCB_FUSED_SOURCE") ? atoi(getenv("MCB_FUSED_SOURCE")) != 0 : fused_default);
+    // Experimental (MCB_SOURCE_OVERLAP_SMS=n, off by default): the sorted sweep over the peers' banks runs piece by piece on a
+    // side stream beside ONE walk launch that vacates n SMs and takes bank positions as they are published.  In this
+    // library the side-stream kernels do not start until the walk kernel has ended (a standalone two-kernel experiment,
+    // tools/exp/concurrency.cu, does run them side by side), so the walk's bounded wait reports an error; left for the next
+    // round.
+    const int overlap_sms = getenv("MCB_SOURCE_OVERLAP_SMS") ? atoi(getenv("MCB_SOURCE_OVERLAP_SMS")) : 0;
+    const bool piecewise = ctx->walk_mode && !fused && sort && (!V.flat || getenv("MCB_FORCE_SORT")) && overlap_sms > 0 && nb >= (1u << 16);
+    if (fused) { if (sort) mcbk::pick_sort(st, P, (int32_t)h0, nb, nps0, V.n, sort); }
+    else if (piecewise) mcbk::pick_sort(st, P, (int32_t)h0, nb, nps0, V.n, sort);
+    else mcbk::source(st, P, ctx->B, queue[0], (int32_t)h0, nb, nps0, V, C, sort);
     ctx->timer.end(st);
+
+    if (piecewise) {
+        // the sweep runs on a side stream, piece by piece, and publishes how far it has got; the walk kernel, launched
+        // first and a few block slots short of the machine, takes bank positions as they become ready
+        constexpr int NC = mcb_ctx::N_CHUNK;
+        if (!ctx->side_stream) {
+            // highest priority: its blocks go first wherever an SM has room, and priority streams get a hardware queue of
+            // their own (two streams that share a queue run one after the other, whatever their dependencies say)
+            int prio_lo = 0, prio_hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CK(cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi));
+            for (int i = 0; i <= NC; i++) CK(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
+        }
+        if (getenv("MCB_DEBUG_OVERLAP") && atoi(getenv("MCB_DEBUG_OVERLAP")) == 1)  // debug: whole sweep first, only the publishing runs beside
+            mcbk::source_sorted_range(st, P, ctx->B, nullptr, (int32_t)h0, 0, nb, nps0, V, C, sort);
+        CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(&C->src_ready, 0, sizeof(unsigned long long), st));
+        CK(cudaEventRecord(ctx->ev_side[NC], st));
+        ctx->plan.reserve_sms = overlap_sms;
+        mcbk::WalkSource ws = walk_source(ctx, nullptr, (int32_t)h0, nps0, nullptr);
+        ws.ready = &C->src_ready;
+        ctx->timer.begin(st, ST_STEP);
+        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p, ws);
+        ctx->timer.end(st);
+        ctx->plan.reserve_sms = 0;
+        *n_iterations += 1;
+        CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_side[NC], 0));
+        const int dbg = getenv("MCB_DEBUG_OVERLAP") ? atoi(getenv("MCB_DEBUG_OVERLAP")) : 0;
+        for (int c = 0; c < NC; c++) {
+            const uint32_t q0 = (uint32_t)((uint64_t)nb * c / NC), q1 = (uint32_t)((uint64_t)nb * (c + 1) / NC);
+            if (dbg != 1) mcbk::source_sorted_range(ctx->side_stream, P, ctx->B, nullptr, (int32_t)h0, q0, q1 - q0, nps0, V, C, sort);
+            mcbk::publish(ctx->side_stream, &C->src_ready, q1);
+        }
+        CK(cudaEventRecord(ctx->ev_side[0], ctx->side_stream));
+        CK(cudaStreamWaitEvent(st, ctx->ev_side[0], 0));
+        CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return check_batch(ctx, *ctx->h_counters);
+    }
 
     if (ctx->walk_mode) {
         // one launch follows the source particles in slots [0, nb) and every secondary of their histories to the end
         CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
         if (ctx->d_dense_pending.p) CK(cudaMemsetAsync(ctx->d_dense_pending.p + ctx->dense_rows, 0, sizeof(int32_t), st));
         ctx->timer.begin(st, ST_STEP);
-        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p);
+        mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p,
+                   walk_source(ctx, fused ? &V : nullptr, (int32_t)h0, nps0, sort));
         ctx->timer.end(st);
         *n_iterations += 1;
         CK(cudaMemcpyAsync(ctx->h_counters, C, sizeof(Counters), cudaMemcpyDeviceToHost, st));

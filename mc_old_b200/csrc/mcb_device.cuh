@@ -160,6 +160,7 @@ struct Counters {
     unsigned long long site_cursor;       // unordered fission sites banked this cycle
     unsigned long long slot_cursor;       // bank slots in use (primaries + secondaries of the batch)
     unsigned long long walk_head;         // history walk: slots of the current pass handed out so far
+    unsigned long long src_ready;         // bank positions k_source has filled so far (sweep running beside the walk)
     unsigned long long n_active[3];       // lengths of the particle queue: iteration i reads [i%3], fills [(i+1)%3], clears [(i+2)%3]
     unsigned long long q_collide, q_cross;// lengths of the two halves of the event queue
     int lost, overflow_sites, overflow_slots, overflow_fixed;

@@ -113,7 +113,7 @@ struct BankSink {
 // peer page is visited once, neighbouring threads read neighbouring (or the same) sites.
 __global__ void __launch_bounds__(BLOCK)
 k_pick(uint64_t seed0, uint64_t nps0, int32_t first_hist, uint32_t count, unsigned long long n_bank, unsigned long long rot,
-       unsigned long long* key, uint32_t* val, uint64_t* rng_after)
+       unsigned long long* key, uint32_t* val, uint64_t* rng_after, int key32)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ uint64_t s_base;  // stream of the block's first history; the others are a short skip away
@@ -126,13 +126,15 @@ k_pick(uint64_t seed0, uint64_t nps0, int32_t first_hist, uint32_t count, unsign
     if (j >= n_bank) j = n_bank - 1;
     // the sweep of rank r starts at its own slice (rot = global index of its first site) and wraps around: at any
     // moment the ranks read from different peers instead of all queueing at rank 0's HBM
-    key[q] = j >= rot ? j - rot : j + n_bank - rot; val[q] = q; rng_after[q] = rng;
+    const unsigned long long kq = j >= rot ? j - rot : j + n_bank - rot;
+    if (key32) reinterpret_cast<uint32_t*>(key)[q] = (uint32_t)kq; else key[q] = kq;
+    val[q] = q; rng_after[q] = rng;
 }
 
 __global__ void __launch_bounds__(BLOCK)
 k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint32_t count, uint64_t nps0,
          const SourceBankView V, Counters* C, const unsigned long long* __restrict__ sorted_key,
-         const uint32_t* __restrict__ sorted_val, const uint64_t* __restrict__ rng_after, unsigned long long rot, uint32_t q0)
+         const uint32_t* __restrict__ sorted_val, const uint64_t* __restrict__ rng_after, unsigned long long rot, uint32_t q0, int key32)
 {
     // q0 > 0: one chunk [q0, q0 + count) of a sorted sweep that is launched piece by piece (streamed host bank)
     const uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,7 +157,7 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     int cell;
     if (V.n) {
         uint64_t j;
-        if (sorted_key) { j = sorted_key[q] + rot; if (j >= V.n) j -= V.n; }
+        if (sorted_key) { j = (key32 ? (uint64_t)reinterpret_cast<const uint32_t*>(sorted_key)[q] : sorted_key[q]) + rot; if (j >= V.n) j -= V.n; }
         else { j = (uint64_t)(xi * (double)V.n); if (j >= V.n) j = V.n - 1; }
         const Site s = source_bank_site(V, j);  // local HBM, or a peer's HBM over NVLink
         x = s.x; y = s.y; z = s.z; E = s.E; t = s.t; cell = s.cell;
@@ -738,22 +740,31 @@ static unsigned grid_for(uint64_t n_hint)
     const uint64_t need = (n_hint + BLOCK - 1) / BLOCK;
     return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)g_n_sm * 16ull * (256 / BLOCK)));
 }
+static void sort_draws(cudaStream_t st, const SortScratch* sort, uint32_t count, uint64_t n_bank)
+{
+    int bits = 1;
+    while (bits < 64 && (n_bank >> bits)) bits++;
+    size_t tb = sort->temp_bytes;
+    if (sort->key32)
+        cub::DeviceRadixSort::SortPairs(sort->temp, tb, reinterpret_cast<const uint32_t*>(sort->key_in), reinterpret_cast<uint32_t*>(sort->key_out),
+                                        sort->val_in, sort->val_out, (int)count, 0, std::min(bits, 32), st);
+    else
+        cub::DeviceRadixSort::SortPairs(sort->temp, tb, sort->key_in, sort->key_out, sort->val_in, sort->val_out, (int)count, 0, bits, st);
+    MCB_LAUNCHED((std::min(bits, sort->key32 ? 32 : 64) + 7) / 8 + 2);  // the sort's histogram / onesweep passes
+}
 void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t count,
             uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort)
 {
     if (sort && V.n) {
         // draws -> sorted by site index -> the bank is read in ascending order
-        k_pick<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P.seed0, nps0, first_hist, count, V.n, sort->rot, sort->key_in, sort->val_in, sort->rng_after);
-        int bits = 1;
-        while (bits < 64 && (V.n >> bits)) bits++;
-        size_t tb = sort->temp_bytes;
-        cub::DeviceRadixSort::SortPairs(sort->temp, tb, sort->key_in, sort->key_out, sort->val_in, sort->val_out, (int)count, 0, bits, st);
+        k_pick<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P.seed0, nps0, first_hist, count, V.n, sort->rot, sort->key_in, sort->val_in, sort->rng_after, sort->key32);
+        sort_draws(st, sort, count, V.n);
         k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, sort->key_out,
-                                                                          sort->val_out, sort->rng_after, sort->rot, 0u);
-        MCB_LAUNCHED(2 + (bits + 7) / 8 + 2);  // pick, source, the sort's histogram / onesweep passes
+                                                                          sort->val_out, sort->rng_after, sort->rot, 0u, sort->key32);
+        MCB_LAUNCHED(2);
         return;
     }
-    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, nullptr, nullptr, nullptr, 0ull, 0u);
+    k_source<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, nullptr, nullptr, nullptr, 0ull, 0u, 0);
     MCB_LAUNCHED(1);
 }
 // the two halves of the sorted path on their own, for a bank that arrives from the host in chunks: draws + sort
@@ -761,25 +772,32 @@ void source(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* activ
 void pick_sort(cudaStream_t st, const DevProblem& P, int32_t first_hist, uint32_t count, uint64_t nps0, uint64_t n_bank,
                const SortScratch* sort)
 {
-    k_pick<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P.seed0, nps0, first_hist, count, n_bank, sort->rot, sort->key_in, sort->val_in, sort->rng_after);
-    int bits = 1;
-    while (bits < 64 && (n_bank >> bits)) bits++;
-    size_t tb = sort->temp_bytes;
-    cub::DeviceRadixSort::SortPairs(sort->temp, tb, sort->key_in, sort->key_out, sort->val_in, sort->val_out, (int)count, 0, bits, st);
-    MCB_LAUNCHED(1 + (bits + 7) / 8 + 2);
+    k_pick<<<std::max(1u, blocks_for(count, BLOCK)), BLOCK, 0, st>>>(P.seed0, nps0, first_hist, count, n_bank, sort->rot, sort->key_in, sort->val_in, sort->rng_after, sort->key32);
+    sort_draws(st, sort, count, n_bank);
+    MCB_LAUNCHED(1);
 }
 __global__ void k_chunk_bounds(const unsigned long long* __restrict__ sorted_key, uint32_t n, const unsigned long long* __restrict__ lo,
-                               int n_lo, uint32_t* pos)
+                               int n_lo, uint32_t* pos, int key32)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_lo) return;
     uint32_t a = 0, b = n;  // first position whose key is >= lo[c]
-    while (a < b) { const uint32_t m = (a + b) >> 1; if (sorted_key[m] < lo[c]) a = m + 1; else b = m; }
+    while (a < b) {
+        const uint32_t m = (a + b) >> 1;
+        const unsigned long long km = key32 ? (unsigned long long)reinterpret_cast<const uint32_t*>(sorted_key)[m] : sorted_key[m];
+        if (km < lo[c]) a = m + 1; else b = m;
+    }
     pos[c] = a;
+}
+__global__ void k_publish(unsigned long long* dst, unsigned long long value) { __threadfence(); *dst = value; }
+void publish(cudaStream_t st, unsigned long long* dst, unsigned long long value)
+{
+    k_publish<<<1, 1, 0, st>>>(dst, value);
+    MCB_LAUNCHED(1);
 }
 void chunk_bounds(cudaStream_t st, const SortScratch* sort, uint32_t n, const unsigned long long* lo, int n_lo, uint32_t* pos)
 {
-    k_chunk_bounds<<<1, 64, 0, st>>>(sort->key_out, n, lo, n_lo, pos);
+    k_chunk_bounds<<<1, 64, 0, st>>>(sort->key_out, n, lo, n_lo, pos, sort->key32);
     MCB_LAUNCHED(1);
 }
 void source_sorted_range(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t q0,
@@ -787,7 +805,7 @@ void source_sorted_range(cudaStream_t st, const DevProblem& P, const Bank& B, ui
 {
     if (!count) return;
     k_source<<<blocks_for(count, BLOCK), BLOCK, 0, st>>>(P, B, active, first_hist, count, nps0, V, C, sort->key_out, sort->val_out,
-                                                         sort->rng_after, sort->rot, q0);
+                                                         sort->rng_after, sort->rot, q0, sort->key32);
     MCB_LAUNCHED(1);
 }
 size_t sort_temp_bytes(uint32_t n)

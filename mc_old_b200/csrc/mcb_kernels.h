@@ -20,12 +20,14 @@ struct SortScratch {
     void* temp;
     size_t temp_bytes;
     unsigned long long rot;  // global index at which this rank's sweep over the bank starts
+    int key32;               // keys are 32-bit (bank below 2^32 sites): half the sort
 };
 size_t sort_temp_bytes(uint32_t n);
 // the sorted path in pieces (bank streamed in from the host): draws + sort; positions in the sorted draws at which
 // the site index reaches lo[c]; k_source for positions [q0, q0 + count) of the sweep
 void pick_sort(cudaStream_t st, const DevProblem& P, int32_t first_hist, uint32_t count, uint64_t nps0, uint64_t n_bank,
                const SortScratch* sort);
+void publish(cudaStream_t st, unsigned long long* dst, unsigned long long value);  // *dst = value in stream order
 void chunk_bounds(cudaStream_t st, const SortScratch* sort, uint32_t n, const unsigned long long* lo, int n_lo, uint32_t* pos);
 void source_sorted_range(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t q0,
                          uint32_t count, uint64_t nps0, const SourceBankView& V, Counters* C, const SortScratch* sort);
@@ -51,9 +53,26 @@ struct WalkRes {        // kernel argument
     DonationQueue* donq;        // secondaries handed over between lanes (nullptr: every history stays with one lane)
     double2* gstate;    // slot state in global memory (build option MCB_WALK_GLOBAL_STATE), else nullptr
     int32_t det_nn, n_pairs, priv_tallies;
+    int32_t sm_limit;   // blocks that land on an SM with id >= sm_limit leave at once: those SMs stay free for a kernel running beside (0: none)
+};
+// where the lanes of the walk kernel get their source particles from: the particle bank k_source filled (first cycle,
+// fixed-source decks: the deck's <sources> are sampled there), or — fused — straight from the fission bank of the last
+// generation: SourceBank::get_source (Source.cpp:42-46) happens in the lane that is about to follow the history, local
+// HBM or a peer's over NVLink, and the latency of those reads hides under the transport of the other warps.
+struct WalkSource {
+    int32_t fused, first_hist;
+    uint64_t nps0, seed0;
+    const void* sorted_key;      // sorted draws (bank spread over several GPUs / streamed from the host), else nullptr
+    const uint32_t* sorted_val;
+    const uint64_t* rng_after;
+    unsigned long long rot;
+    int32_t key32, pad;          // the sorted keys are 32-bit
+    const unsigned long long* ready;  // bank positions filled so far by a k_source running beside the walk (nullptr: all)
+    SourceBankView V;
 };
 struct WalkPlan {
     int n_sm, det_nn, priv_tallies, max_grid;
+    int reserve_sms;     // SMs the next launch leaves to a kernel running beside it (set by the caller per launch, default 0)
     bool shared;        // secondaries can be born in flight (fixed source / splitting)
     bool exchange;      // event-sorted form (particles change lanes through shared-memory queues) or history per lane
     int blocks_per_sm[2], n_pairs[2];   // [0] cycles that score nothing, [1] scoring cycles
@@ -65,7 +84,8 @@ struct WalkPlan {
 };
 int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate);
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate,
+          const WalkSource& src);
 void finish(cudaStream_t st, const DevProblem& P, const Bank& B, const uint32_t* active, int cur, uint64_t n_hint, Counters* C,
             uint32_t* next, const HistoryAcc& H, const TallyAcc& T, SiteReq* reqs, uint64_t site_cap,
             uint32_t n_slots, double k_eff);

@@ -146,7 +146,7 @@ struct StackSink {
 };
 
 // ---- work sharing: secondaries handed to other lanes through a global ring (DonationQueue)
-constexpr int WAIT_LIMIT = 1 << 22;  // bounded waits: a protocol error becomes an error code, never a hung GPU
+constexpr int WAIT_LIMIT = 1 << 19;  // bounded waits: a protocol error becomes an error code, never a hung GPU
 __device__ __forceinline__ bool donation_push(DonationQueue* D, const Particle& q, Counters* C)
 {
     if (atomicAdd(&D->count, 1) >= (int)D->cap_mask) { atomicSub(&D->count, 1); return false; }
@@ -172,7 +172,7 @@ __device__ __forceinline__ bool donation_pop(DonationQueue* D, Particle& p, Coun
     const uint32_t cell = (uint32_t)pos & D->cap_mask;
     volatile unsigned long long* seq = D->seq + cell;
     int spins = 0;
-    while (*seq != pos + 1ull) { if (++spins > WAIT_LIMIT) { C->hang = 1; return false; } __nanosleep(64); }
+    while (*seq != pos + 1ull) { if (++spins > WAIT_LIMIT) { C->hang = 2; return false; } __nanosleep(64); }
     __threadfence();
     const double2* r = reinterpret_cast<const double2*>(D->recs + cell);
     const double2 a = __ldcg(r + 0), b = __ldcg(r + 1), c = __ldcg(r + 2), d = __ldcg(r + 3), e = __ldcg(r + 4), f = __ldcg(r + 5), g = __ldcg(r + 6);
@@ -280,8 +280,13 @@ __device__ __forceinline__ void merge_shared_tallies(const TallyAcc& T, int row,
 template <bool TALLY, bool SHARED, bool EXCH>
 __global__ void __launch_bounds__(BLOCK, MCB_WALK_MINB)
 k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long long end, uint32_t chunk, Counters* C, HistoryAcc H,
-       TallyAcc T, SiteReq* reqs, uint64_t site_cap, double k_eff, mcbk::WalkRes R)
+       TallyAcc T, SiteReq* reqs, uint64_t site_cap, double k_eff, mcbk::WalkRes R, const __grid_constant__ mcbk::WalkSource SRC)
 {
+    if (R.sm_limit > 0) {  // whole SMs are left to the kernel that runs beside this one (kernels of different shared-memory
+        unsigned smid;     // configurations do not share an SM, so free block slots would not do)
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((int)smid >= R.sm_limit) return;
+    }
     extern __shared__ double2 w_smem[];
     constexpr int SP_DET = !EXCH ? 0 : (TALLY ? SP_FIXED + 1 : SP_FIXED);  // without the exchange a slot holds the detail only
 #ifdef MCB_WALK_GLOBAL_STATE
@@ -311,6 +316,8 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
     int sp = 0, nch = 1;                  // records on the history's secondary stack, chunks it holds
     unsigned long long chunk_next = 0, chunk_end = 0;  // warp-uniform: this warp's private range of bank positions
     int idle_spins = 0;
+    unsigned long long chunk_begin = 0;
+    uint64_t chunk_seed = 0;
     for (;;) {
         // ---- lanes without a history draw the next source particles
         unsigned idle = __ballot_sync(FULL, !have);
@@ -323,14 +330,58 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
                 chunk_next = b < end ? b : end;
                 chunk_end = b + chunk < end ? b + chunk : end;
                 if (chunk_next == chunk_end) { exhausted = true; break; }
+                if (SRC.ready) {  // the bank is being filled beside this kernel, in ascending order: wait for this chunk
+                    // (one lane polls, with a growing pause: thousands of warps hammering one address would starve the
+                    // very store they are waiting for)
+                    int spins = 0;
+                    unsigned pause = 250;
+                    for (;;) {
+                        unsigned long long got = 0;
+                        if (lane == 0) got = *(volatile const unsigned long long*)SRC.ready;
+                        got = __shfl_sync(FULL, got, 0);
+                        if (got >= chunk_end) break;
+                        if (++spins > WAIT_LIMIT) { C->hang = 4; break; }
+                        __nanosleep(pause);
+                        if (pause < 8000) pause *= 2;
+                    }
+                    __threadfence();
+                }
+                if (SRC.fused && !SRC.sorted_key) {  // stream of the chunk's first history; the others are a short skip away
+                    chunk_begin = chunk_next;
+                    chunk_seed = mcb_rn_history_seed(SRC.seed0, SRC.nps0 + (uint64_t)((long long)SRC.first_hist + (long long)chunk_next));
+                }
             }
             const unsigned take = min((unsigned)__popc(idle), (unsigned)(chunk_end - chunk_next));
             const unsigned rank = __popc(idle & lt_mask);
             if (!have && rank < take) {
                 const uint32_t j = (uint32_t)(chunk_next + rank);
-                p.cell = B.cell[j]; p.hist = B.hist[j];
-                p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
-                p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
+                if (SRC.fused) {
+                    // SourceBank::get_source (Source.cpp:42-46) with site index floor(xi N): history h draws from the
+                    // stream of nps = cycle * Nsample + h (RN_init_particle, Random.cpp:196-204)
+                    unsigned long long site;
+                    if (SRC.sorted_key) {  // the draws were made and sorted by site index beforehand (k_pick)
+                        const uint32_t sv = __ldg(SRC.sorted_val + j);
+                        p.hist = SRC.first_hist + (int32_t)sv;
+                        p.rng = __ldg(SRC.rng_after + sv);
+                        site = (SRC.key32 ? (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(SRC.sorted_key) + j)
+                                          : __ldg(reinterpret_cast<const unsigned long long*>(SRC.sorted_key) + j)) + SRC.rot;
+                        if (site >= SRC.V.n) site -= SRC.V.n;
+                    } else {
+                        p.hist = SRC.first_hist + (int32_t)j;
+                        p.rng = mcb_rn_history_seed_from(chunk_seed, (uint32_t)(j - chunk_begin));
+                        const double xi = mcb_urand(p.rng);
+                        site = (unsigned long long)(xi * (double)SRC.V.n);
+                        if (site >= SRC.V.n) site = SRC.V.n - 1;
+                    }
+                    const Site sx = source_bank_site(SRC.V, site);  // local HBM, or a peer's HBM over NVLink
+                    p.x = sx.x; p.y = sx.y; p.z = sx.z; p.E = sx.E; p.t = sx.t; p.cell = sx.cell;
+                    source_bank_direction(SRC.V, site, sx, p.u, p.v, p.w);
+                    p.speed = mcb_speed_of_energy(p.E); p.wgt = 1.0;
+                } else {
+                    p.cell = B.cell[j]; p.hist = B.hist[j];
+                    p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
+                    p.E = B.E[j]; p.speed = B.speed[j]; p.wgt = B.wgt[j]; p.t = B.t[j]; p.rng = B.rng[j];
+                }
                 p.Eold = p.E;  // the reference leaves energy_old uninitialised at birth; defined as E here
                 p.told = p.t;
                 p.n_touched = 0; p.drow = -1;
@@ -431,7 +482,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             if (lane == 0) lv = (long long)__ldcg((const unsigned long long*)&C->live);
             lv = __shfl_sync(FULL, lv, 0);
             if (lv <= 0) break;
-            if (++idle_spins > WAIT_LIMIT) { C->hang = 1; break; }
+            if (++idle_spins > WAIT_LIMIT) { C->hang = 3; break; }
             __nanosleep(4000);
             continue;
         }
@@ -653,6 +704,7 @@ int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_s
     W.det_nn = std::max(det_nn, 1);
     W.priv_tallies = (n_tallies > 0 && n_tallies <= 256) ? (int)n_tallies : 0;
     W.n_sm = n_sm;
+    W.reserve_sms = 0;
     W.exchange = exchange;
     cudaError_t e;
     for (int tally = 0; tally < 2; tally++) {
@@ -688,7 +740,8 @@ int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_s
 }
 
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
-          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate)
+          const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate,
+          const WalkSource& src)
 {
     if (end <= begin) return;
     // persistent: every resident warp draws chunks of bank positions until the generation runs dry
@@ -699,11 +752,11 @@ void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, u
     const uint64_t warps = (uint64_t)grid * WARPS;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
     WalkRes R;
-    R.stack = stack; R.chunk_tab = chunk_tab; R.donq = donq; R.gstate = gstate; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
+    R.stack = stack; R.chunk_tab = chunk_tab; R.donq = donq; R.gstate = gstate; R.sm_limit = W.reserve_sms > 0 ? std::max(1, W.n_sm - W.reserve_sms) : 0; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
     const size_t smem = W.smem_bytes[ti];
     // four instances: cycles that score nothing carry no estimator code, problems where nothing is born in flight
     // (k-eigenvalue without splitting) no secondary stack
-#define MCB_WALK(T_, S_, E_) k_walk<T_, S_, E_><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R)
+#define MCB_WALK(T_, S_, E_) k_walk<T_, S_, E_><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R, src)
     if (W.exchange) {
         if (T.on) { if (W.shared) MCB_WALK(true, true, true); else MCB_WALK(true, false, true); }
         else { if (W.shared) MCB_WALK(false, true, true); else MCB_WALK(false, false, true); }
