@@ -33,6 +33,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "HEU_sphere_criticality"
+# Results must not depend on the number of GPUs (per-history streams, canonical bank order, exact integer sums): two
+# generations of the HEU sphere at 4e4 histories, k per generation as hex and the fission-bank size, recorded from a
+# 1-GPU run (tests/golden/g_independence.json, written by `bench.py --record-g-independence`); every run at any GPU
+# count repeats them and must reproduce them bit for bit.
+G_IND_FILE = os.path.join(ROOT, "tests", "golden", "g_independence.json")
+G_IND_SAMPLES, G_IND_CYCLES = 40000, 2
 # algorithmic bytes per unit of each stage kernel; Nn = nuclides of the material (HEU: 2)
 BYTES_LOOKUP = lambda nn: 72 + 100 * nn   # E + mat 12, hash 4, bracket 16, Nn x (idx 4 + 2 rows x 48), 5 Sigma out 40
 BYTES_FLIGHT = 180                        # queue 4 + state in 112 + state out 44 + k_TL rmw 16 + event queue 4
@@ -51,22 +57,36 @@ def peaks():
         return 6650.0, "fallback"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, launch=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the newest committed
-    `ncu --set full` summary under profiles/ (same workload: 1e7 histories per generation); None when absent."""
+    `ncu --set full` summary under profiles/ (same workload: 1e7 histories per generation).  A capture whose launch
+    shape (registers per thread, grid) differs from the kernel that is running is stale and is refused: returns
+    (None, path, why).  None when there is no capture."""
     import glob
     import re
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_ncu_full_summary.txt" % kernel))):
-        tot, seen = 0.0, 0
+        tot, seen, regs, grid = 0.0, 0, None, None
         for line in open(path):
             m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
             if m:
                 tot += float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 0.0)
                 seen += 1
+            m = re.match(r"\s*launch__registers_per_thread\s+([0-9]+)", line)
+            if m:
+                regs = int(m.group(1))
+            m = re.match(r"\s*launch__grid_size\s+([0-9]+)", line)
+            if m:
+                grid = int(m.group(1))
         if seen == 2:
-            best = (tot, os.path.relpath(path, ROOT))
-    return best
+            best = (tot, os.path.relpath(path, ROOT), regs, grid)
+    if best is None:
+        return None
+    tot, path, regs, grid = best
+    if launch is not None and (regs != launch["registers"] or grid != launch["grid"]):
+        return (None, path, "stale capture: %s registers / grid %s, running kernel %d registers / grid %d" %
+                (regs, grid, launch["registers"], launch["grid"]))
+    return (tot, path, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -130,6 +150,10 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "histories_per_generation": samples, "note": "bounded sample of the same deck"},
+        "reference_histories_per_generation": samples,
+        "why_not_the_gpu_size": "the reference holds two banks of heap-allocated particles (~350 B per site): 1e7 histories per generation need ~7 GB and "
+                                "~40 s per generation on one core (BASELINE.md section 2); histories/s is normalised by size and falls slowly with it "
+                                "(see cpu_baseline.points of the GPU arm: 2e5 and 1e6 per generation)",
         "cpu_baseline": {"value": value, "unit": "histories/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -223,6 +247,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-xs", action="store_true", help="skip the xs_lookup microbench")
+    ap.add_argument("--record-g-independence", action="store_true", help="write tests/golden/g_independence.json from this (1-GPU) run")
     args = ap.parse_args()
     args.ref_samples = int(args.ref_samples)
     if args.warmup < 3:
@@ -270,6 +295,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- GPU-count independence check (untimed) ----
+    gdeck = mcb.Deck(xml=decks.heu_sphere(samples=G_IND_SAMPLES, active=1, passive=G_IND_CYCLES - 1))
+    gctx = mcb.Context(gdeck, device=local_rank, rank=rank, world=world, stream=stream.cuda_stream)
+    if world > 1:
+        uid = [mcb.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gctx.comm_init(uid[0])
+    g_got = []
+    for _ in range(G_IND_CYCLES):
+        r = gctx.run_cycle()
+        g_got.append([float(r.k_cycle).hex(), int(r.n_sites), int(r.n_tracks)])
+    gctx.close()
+    g_independent, g_expected = None, None
+    if args.record_g_independence and world == 1:
+        with open(G_IND_FILE, "w") as f:
+            json.dump({"samples": G_IND_SAMPLES, "cycles": G_IND_CYCLES, "deck": "HEU_sphere_criticality", "recorded_with_gpus": 1,
+                       "k_cycle_hex_n_sites_n_tracks": g_got}, f, indent=1)
+    if os.path.exists(G_IND_FILE):
+        g_expected = json.load(open(G_IND_FILE))["k_cycle_hex_n_sites_n_tracks"]
+        g_independent = g_got == g_expected
+
     for _ in range(args.warmup):
         ctx.run_cycle()
 
@@ -295,7 +341,7 @@ def main():
     # ---- e2e: the same step with the source bank crossing the host boundary both ways ----
     e2e = None
     if not args.no_e2e:
-        cap = 4 * n_sample + 4096 * world
+        cap = (4 if world == 1 else 2) * n_sample + 4096 * world
         bufs = [(torch.empty((cap, 8), dtype=torch.float64, pin_memory=True).numpy(), torch.empty((cap,), dtype=torch.int32, pin_memory=True).numpy())
                 for _ in range(2)]
         s, c = ctx.source_bank(cap, bufs[0][0], bufs[0][1])
@@ -309,18 +355,21 @@ def main():
         t0 = time.perf_counter()
         for i in range(args.steps):
             src, dst = bufs[i & 1], bufs[(i + 1) & 1]
-            h2d += n_bank * 68
+            h2d += mcb.shard_range(n_bank, rank, world)[1] * 68   # with several GPUs every rank moves only its slice
             r, s, c = ctx.run_cycle_host(src[0][:n_bank], src[1][:n_bank], dst[0], dst[1])
             n_bank = s.shape[0]
-            d2h += n_bank * 68 + 176
+            d2h += mcb.shard_range(n_bank, rank, world)[1] * 68 + 176
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": args.steps * n_sample / dt, "unit": "histories/s", "h2d_bytes_per_step": h2d // args.steps,
                "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * dt / args.steps,
-               "what": "per step and per rank: mcb_run_cycle_host = global source bank from pinned host memory -> HBM, the generation, "
-                       "the new global bank HBM -> pinned host memory (on one GPU the upload is pipelined with the walk)"}
+               "what": "per step and per rank: mcb_run_cycle_host = source bank from pinned host memory -> HBM, the generation, the new "
+                       "bank HBM -> pinned host memory.  One GPU: the whole bank, upload pipelined with the walk.  Several GPUs: the "
+                       "host bank is one array of which every rank moves its 1/W slice each way (bytes are per rank); the slices "
+                       "are read in place over NVLink"}
 
     # ---- per-stage pass: CUDA events around every stage launch (rank-local), for the roofline of the dominant kernel ----
+    ctx_launch = ctx.walk_launch_info(False)
     ctx.reset_stage_times()
     ctx.set_stage_timing(True)
     for _ in range(2):
@@ -344,10 +393,12 @@ def main():
         total_bytes = 2.0 * per_gen[dominant] * per_unit[dominant]
         achieved = total_bytes / (stages[dominant]["ms"] * 1e-3) / 1e9
         kname = "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" else dominant))
-        tr = ncu_traffic(kname) if int(args.samples) == 10000000 else None
+        launch = ctx_launch if dominant == "step" else None
+        tr = ncu_traffic(kname, launch) if int(args.samples) == 10000000 else None
         roofline = {"bound": "hbm", "kernel": "k_" + ("xs_stage" if dominant == "lookup" else ("walk" if dominant == "step" else dominant)), "unit_name": "lookup" if dominant == "lookup" else ("collision" if dominant == "collide" else "track"), "achieved": achieved,
                     "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None,
+                    "traffic": tr[0] if tr else None, "traffic_source": tr[1] if tr else None, "traffic_refused": tr[2] if tr else None,
+                    "launch": launch,
                     "algorithmic_bytes_per_launch": total_bytes / max(stages[dominant]["launches"], 1),
                     "bytes_per_unit": per_unit[dominant], "units_per_launch": 2.0 * per_gen[dominant] / max(stages[dominant]["launches"], 1),
                     "avg_launch_ms": stages[dominant]["ms"] / max(stages[dominant]["launches"], 1),
@@ -380,7 +431,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         r = run_reference_cpu(args.ref_samples, 1, 4)
         if r is not None:
-            cpu = {"value": r[0], "unit": "histories/s", "cores": r[1], "kind": "reference", "sample": r[2]}
+            cpu = {"value": r[0], "unit": "histories/s", "cores": r[1], "kind": "reference", "sample": r[2],
+                   "reference_histories_per_generation": args.ref_samples,
+                   "why_not_the_gpu_size": "the reference needs ~7 GB and ~40 s per generation at 1e7 histories per generation (BASELINE.md section 2)",
+                   "points": [{"histories_per_generation": args.ref_samples, "histories_per_second": r[0]}]}
+            r2 = run_reference_cpu(1000000, 1, 2)  # a second size, so that the size dependence is data, not a claim
+            if r2 is not None:
+                cpu["points"].append({"histories_per_generation": 1000000, "histories_per_second": r2[0]})
 
     if rank == 0:
         line = {
@@ -395,6 +452,7 @@ def main():
             "xs_lookup_algorithmic_GBps": lookups * BYTES_LOOKUP(2) / world / (ms * 1e-3) / 1e9,
             "xs_lookup_microbench": xs_micro,
             "k_cycle_last": res[-1].k_cycle, "event_loop_iterations_per_step": sum(r.n_iterations for r in res) / args.steps,
+            "g_independent": g_independent, "g_independence": {"got": g_got, "expected": g_expected, "golden": os.path.relpath(G_IND_FILE, ROOT)},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "stages_ms_2_generations": stages,
             "cpu_baseline": cpu,
         }
@@ -402,6 +460,9 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if g_independent is False:
+        sys.stderr.write("bench.py: results depend on the GPU count: got %r, expected %r\n" % (g_got, g_expected))
+        return 3
     return 0
 
 

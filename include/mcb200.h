@@ -237,7 +237,11 @@ int mcb_set_source_bank(mcb_ctx* ctx, const double* sites8, const int32_t* cells
  * Sbank / Fbank living in host RAM like the reference's).  On one GPU the three steps are pipelined: the draws are
  * sorted by site index, the bank comes in over PCIe in pieces on a copy stream and the histories that drew from the
  * pieces already there are walked meanwhile; the new bank goes back piece by piece.  Pinned buffers make the copies
- * asynchronous.  *n_out = sites written (at most max_out). */
+ * asynchronous.  *n_out = sites written (at most max_out).
+ * Several GPUs (world > 1, banks peer-mapped): the host bank is one array of which rank r owns the slice
+ * [n r / W, n (r + 1) / W): every rank passes pointers to the WHOLE arrays (same layout on every rank) but reads only its
+ * slice of `in` and writes only slice [n' r / W, n' (r + 1) / W) of the new bank (n' sites) into `out`, at its global
+ * offset; *n_out = n'.  Per rank 1/W of the bytes cross the host boundary. */
 int mcb_run_cycle_host(mcb_ctx* ctx, const double* in_sites8, const int32_t* in_cells, int64_t n_in, double* out_sites8,
                        int32_t* out_cells, int64_t max_out, int64_t* n_out, mcb_cycle_result* out);
 /* per-history k scores of the last cycle on this rank, shard-local history order (EstimatorK::k_C / k_TL at
@@ -272,6 +276,11 @@ int mcb_watt_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, const dou
  * normalisations; csrc/mcb_physics.h): out_shared[i] = that form of a[i] / b[i], out_plain[i] = the compiler's IEEE
  * division.  Cross sections are bit-exact against the reference's x86 divisions only if the two agree bit for bit. */
 int mcb_division_batch(mcb_ctx* ctx, const double* a, const double* b, int64_t n, double* out_shared, double* out_plain);
+
+/* launch shape of the walk kernel (the dominant kernel) as it runs on this device: out4 = {registers per thread, grid,
+ * block, dynamic shared memory}; scoring = 1 for the instance of tally-scoring cycles.  bench.py checks the committed
+ * ncu capture against it before quoting the capture's DRAM traffic. */
+int mcb_walk_launch_info(mcb_ctx* ctx, int32_t scoring, int32_t out4[4]);
 
 /* history sharding rule shared by every rank: first history and count owned by `rank` */
 void mcb_shard_range(uint64_t n, int32_t rank, int32_t world, uint64_t* begin, uint64_t* count);

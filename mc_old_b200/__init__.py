@@ -143,6 +143,7 @@ def cuda_lib():
         L.mcb_scatter_batch.argtypes = [vp, i32, vp, i64, vp]
         L.mcb_watt_batch.argtypes = [vp, i32, vp, vp, i64, vp]
         L.mcb_division_batch.argtypes = [vp, vp, vp, i64, vp, vp]
+        L.mcb_walk_launch_info.argtypes = [vp, i32, vp]
         L.mcb_shard_range.argtypes = [u64, i32, i32, C.POINTER(u64), C.POINTER(u64)]
         L.mcb_shard_range.restype = None
         _cuda = L
@@ -399,6 +400,12 @@ class Context:
         self._check(cuda_lib().mcb_watt_batch(self._h, nuclide, _ptr(nps), _ptr(E), E.size, _ptr(out)))
         return out
 
+
+    def walk_launch_info(self, scoring=False):
+        """{registers, grid, block, smem} of the walk kernel as launched on this device"""
+        out = np.zeros(4, dtype=np.int32)
+        self._check(cuda_lib().mcb_walk_launch_info(self._h, 1 if scoring else 0, _ptr(out)))
+        return dict(zip(("registers", "grid", "block", "smem"), (int(x) for x in out)))
 
     def division(self, a: np.ndarray, b: np.ndarray):
         """a / b through the kernels' shared-reciprocal form and as the plain IEEE division (mcb_division_batch)"""

@@ -195,6 +195,8 @@ struct mcb_ctx {
     DevBuf<Site> d_global_bank;      // the whole bank in one array: only for banks set / read through the host API, or without P2P
     DevBuf<double> d_host_dirs;      // explicit directions of a bank set through the host API (n x 3)
     int bank_w = 0;                  // d_local_bank[bank_w] is the one the running cycle writes
+    DevBuf<double> d_slice_dirs;     // explicit directions of this rank's slice of a bank handed in from the host (world > 1)
+    double* peer_dirs[MCB_MAX_WORLD] = {};   // the ranks' d_slice_dirs mapped here (CUDA IPC)
     Site* peer_bank[2][MCB_MAX_WORLD] = {};  // peer_bank[b][r] = rank r's d_local_bank[b] mapped here (CUDA IPC); [rank] = own
     bool p2p = false;                // the peers' banks are mapped: source sites are read in place over NVLink
     SourceBankView view{};           // the bank the next cycle samples (n = 0: the deck's sources)
@@ -620,6 +622,7 @@ void mcb_destroy(mcb_ctx* ctx)
     for (int b = 0; b < 2; b++)
         for (int r = 0; r < ctx->world && r < MCB_MAX_WORLD; r++)
             if (r != ctx->rank && ctx->peer_bank[b][r]) cudaIpcCloseMemHandle(ctx->peer_bank[b][r]);
+    for (int r = 0; r < ctx->world && r < MCB_MAX_WORLD; r++) if (r != ctx->rank && ctx->peer_dirs[r]) cudaIpcCloseMemHandle(ctx->peer_dirs[r]);
     for (int i = 0; i < MCB_RING; i++) if (ctx->ev_ring[i]) cudaEventDestroy(ctx->ev_ring[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -658,30 +661,39 @@ int mcb_comm_init(mcb_ctx* ctx, const char id[128])
     const bool want_p2p = getenv("MCB_P2P") ? atoi(getenv("MCB_P2P")) != 0 : true;
     if (ctx->ksearch && want_p2p && !getenv("MCB_NO_P2P")) {
         const int W = ctx->world;
-        cudaIpcMemHandle_t mine[2];
+        // three mappings per peer: its two (alternating) fission banks and the direction array of host-provided slices
+        if (cudaMalloc((void**)&ctx->d_slice_dirs.p, ctx->site_cap * 3 * sizeof(double)) == cudaSuccess) ctx->d_slice_dirs.n = ctx->site_cap * 3;
+        else { ctx->d_slice_dirs.p = nullptr; cudaGetLastError(); }
+        constexpr int NH = 3;
+        cudaIpcMemHandle_t mine[NH];
+        memset(mine, 0, sizeof(mine));
         bool ok = cudaIpcGetMemHandle(&mine[0], ctx->d_local_bank[0].p) == cudaSuccess &&
-                  cudaIpcGetMemHandle(&mine[1], ctx->d_local_bank[1].p) == cudaSuccess;
+                  cudaIpcGetMemHandle(&mine[1], ctx->d_local_bank[1].p) == cudaSuccess &&
+                  ctx->d_slice_dirs.p && cudaIpcGetMemHandle(&mine[2], ctx->d_slice_dirs.p) == cudaSuccess;
         cudaGetLastError();
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-        const size_t rec = 2 * sizeof(cudaIpcMemHandle_t) + 8;  // two handles + "I could export" flag
+        const size_t rec = NH * sizeof(cudaIpcMemHandle_t) + 8;  // the handles + "I could export" flag
         DevBuf<unsigned char> d_mine, d_all;
         std::vector<unsigned char> h_mine(rec, 0), h_all(rec * W, 0);
-        memcpy(h_mine.data(), mine, 2 * sizeof(cudaIpcMemHandle_t));
-        h_mine[2 * sizeof(cudaIpcMemHandle_t)] = ok ? 1 : 0;
+        memcpy(h_mine.data(), mine, NH * sizeof(cudaIpcMemHandle_t));
+        h_mine[NH * sizeof(cudaIpcMemHandle_t)] = ok ? 1 : 0;
         CK(d_mine.upload(h_mine.data(), rec));
         CK(d_all.alloc(rec * W));
         NK(g_nccl.AllGather(d_mine.p, d_all.p, rec, ncclChar, ctx->comm, ctx->stream));
         CK(cudaMemcpyAsync(h_all.data(), d_all.p, rec * W, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        for (int r = 0; r < W; r++) ok = ok && h_all[r * rec + 2 * sizeof(cudaIpcMemHandle_t)] == 1;
+        for (int r = 0; r < W; r++) ok = ok && h_all[r * rec + NH * sizeof(cudaIpcMemHandle_t)] == 1;
         for (int r = 0; r < W && ok; r++) {
-            for (int b = 0; b < 2; b++) {
-                if (r == ctx->rank) { ctx->peer_bank[b][r] = ctx->d_local_bank[b].p; continue; }
+            for (int b = 0; b < NH; b++) {
+                if (r == ctx->rank) {
+                    if (b < 2) ctx->peer_bank[b][r] = ctx->d_local_bank[b].p; else ctx->peer_dirs[r] = ctx->d_slice_dirs.p;
+                    continue;
+                }
                 cudaIpcMemHandle_t h;
                 memcpy(&h, h_all.data() + r * rec + b * sizeof(cudaIpcMemHandle_t), sizeof(h));
                 void* ptr = nullptr;
                 if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
-                ctx->peer_bank[b][r] = (Site*)ptr;
+                if (b < 2) ctx->peer_bank[b][r] = (Site*)ptr; else ctx->peer_dirs[r] = (double*)ptr;
             }
         }
         // every rank must take the same path: agree on the outcome
@@ -1247,7 +1259,7 @@ int64_t mcb_get_source_bank(mcb_ctx* ctx, double* out, int32_t* cells, int64_t m
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MCB_ERR_CUDA;
     if (ctx->d_global_bank.n < (size_t)n && ctx->d_global_bank.alloc((size_t)n) != cudaSuccess)
         return ctx->fail(MCB_ERR_CUDA, "out of device memory for the gathered bank");
-    mcbk::gather_sites(ctx->stream, ctx->view, (uint64_t)n, ctx->d_global_bank.p);
+    mcbk::gather_sites(ctx->stream, ctx->view, 0, (uint64_t)n, ctx->d_global_bank.p);
     return read_bank(ctx, ctx->d_global_bank.p, nullptr, (uint64_t)n, out, cells, max_n);
 }
 
@@ -1291,6 +1303,53 @@ int mcb_run_cycle_host(mcb_ctx* ctx, const double* in_sites8, const int32_t* in_
     // plain calls do the same thing one after the other
     const bool pipelined = ctx->world == 1 && !ctx->P.shared_histories && ctx->walk_mode && ctx->shard_count <= ctx->batch_hist &&
                            (uint64_t)n_in <= ctx->site_cap && !getenv("MCB_NO_STREAM");
+    if (ctx->world > 1 && ctx->p2p && ctx->walk_mode && !getenv("MCB_NO_SLICES")) {
+        // Several GPUs: the host bank is one array of which every rank owns a slice.  Rank r uploads sites
+        // [n r / W, n (r + 1) / W) into its own (peer-mapped) bank buffer, the generation reads the slices in place over
+        // NVLink like it reads the banks it made itself, and rank r writes its canonical slice of the new bank back at
+        // its global offset: per rank 1/W of the bytes each way, whatever W.
+        const int W = ctx->world;
+        const int src = ctx->bank_w ^ 1;  // the buffer the running cycle does not write
+        uint64_t a = 0, cnt = 0;
+        mcb_shard_range((uint64_t)n_in, ctx->rank, W, &a, &cnt);
+        if (cnt > ctx->site_cap) return ctx->fail(MCB_ERR_CAPACITY, "source bank slice of %llu sites exceeds the capacity %llu", (unsigned long long)cnt, (unsigned long long)ctx->site_cap);
+        if (ctx->d_io_sites.n < (size_t)std::max<uint64_t>(cnt, 1) * 8) { const size_t cap = cnt + cnt / 4 + 1024; CK(ctx->d_io_sites.alloc(cap * 8)); CK(ctx->d_io_cells.alloc(cap)); }
+        if (cnt) {
+            CK(cudaMemcpyAsync(ctx->d_io_sites.p, in_sites8 + 8 * a, cnt * 8 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_io_cells.p, in_cells + a, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            mcbk::pack_sites(ctx->stream, ctx->d_io_sites.p, ctx->d_io_cells.p, cnt, ctx->d_local_bank[src].p, ctx->d_slice_dirs.p);
+        }
+        // nobody reads a slice before its owner has written it
+        NK(g_nccl.AllReduce(ctx->d_send.p, ctx->d_send.p, 1, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+        memset(&ctx->view, 0, sizeof(ctx->view));
+        ctx->view.n_seg = W; ctx->view.n = (uint64_t)n_in;
+        for (int r = 0; r < W; r++) {
+            uint64_t b0 = 0, c0 = 0;
+            mcb_shard_range((uint64_t)n_in, r, W, &b0, &c0);
+            ctx->view.seg[r] = ctx->peer_bank[src][r]; ctx->view.seg_dir[r] = ctx->peer_dirs[r]; ctx->view.prefix[r] = b0;
+        }
+        ctx->view.prefix[W] = (uint64_t)n_in;
+        ctx->source_is_bank = true;
+        const int rc = mcb_run_cycle(ctx, out);
+        if (rc != MCB_OK) return rc;
+        // this rank's slice [n' r / W, n' (r + 1) / W) of the new bank (its own sites but for a few at the ends, which it
+        // reads from its neighbours in place), written at its global offset: the slices of the next call
+        const uint64_t total = ctx->view.n;
+        if ((int64_t)total > max_out) return ctx->fail(MCB_ERR_CAPACITY, "the new bank has %llu sites, the output buffers hold %lld", (unsigned long long)total, (long long)max_out);
+        uint64_t off = 0, mine = 0;
+        mcb_shard_range(total, ctx->rank, W, &off, &mine);
+        if (mine) {
+            if (ctx->d_io_sites.n < (size_t)mine * 8) { const size_t cap = mine + mine / 4 + 1024; CK(ctx->d_io_sites.alloc(cap * 8)); CK(ctx->d_io_cells.alloc(cap)); }
+            if (ctx->d_global_bank.n < (size_t)mine) CK(ctx->d_global_bank.alloc((size_t)mine + (size_t)mine / 4 + 1024));
+            mcbk::gather_sites(ctx->stream, ctx->view, off, mine, ctx->d_global_bank.p);
+            mcbk::unpack_sites(ctx->stream, ctx->d_global_bank.p, nullptr, mine, ctx->d_io_sites.p, ctx->d_io_cells.p);
+            if (out_sites8) CK(cudaMemcpyAsync(out_sites8 + 8 * off, ctx->d_io_sites.p, mine * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_cells) CK(cudaMemcpyAsync(out_cells + off, ctx->d_io_cells.p, mine * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        *n_out = (int64_t)total;
+        return MCB_OK;
+    }
     if (!pipelined) {
         int rc = mcb_set_source_bank(ctx, in_sites8, in_cells, n_in);
         if (rc == MCB_OK) rc = mcb_run_cycle(ctx, out);
@@ -1491,6 +1550,18 @@ int mcb_watt_batch(mcb_ctx* ctx, int32_t nuclide, const uint64_t* nps, const dou
         CK(cudaStreamSynchronize(ctx->stream));
         return MCB_OK;
     });
+}
+
+int mcb_walk_launch_info(mcb_ctx* ctx, int32_t scoring, int32_t out4[4])
+{
+    if (!ctx || !out4) return MCB_ERR_ARG;
+    if (!ctx->walk_mode) return ctx->fail(MCB_ERR_ARG, "event-queue mode has no walk kernel");
+    CK(cudaSetDevice(ctx->device));
+    int o[4];
+    const int rc = mcbk::walk_launch_info(ctx->plan, scoring != 0, o);
+    if (rc != 0) return ctx->fail(MCB_ERR_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString((cudaError_t)rc));
+    for (int i = 0; i < 4; i++) out4[i] = o[i];
+    return MCB_OK;
 }
 
 int mcb_division_batch(mcb_ctx* ctx, const double* a, const double* b, int64_t n, double* out_shared, double* out_plain)

@@ -129,22 +129,36 @@ struct SourceBankView {
     const Site* flat;
     const double* dir_x;                  // flat banks handed in from the host: n x 3 explicit directions (else nullptr)
     const Site* seg[MCB_MAX_WORLD];
+    const double* seg_dir[MCB_MAX_WORLD]; // slices handed in from the host, one per rank: explicit directions (else nullptr)
     unsigned long long prefix[MCB_MAX_WORLD + 1];
     int32_t n_seg, pad;
     unsigned long long n;                 // total sites; 0 with flat == nullptr and n_seg == 0 -> sample the deck's sources
 };
-__device__ __forceinline__ Site source_bank_site(const SourceBankView& V, unsigned long long j)
+__device__ __forceinline__ int source_bank_locate(const SourceBankView& V, unsigned long long j, unsigned long long& local)
 {
-    if (V.flat) return load_site(V.flat + j);
+    if (V.flat) { local = j; return -1; }
     int r = 0;
     while (r + 1 < V.n_seg && j >= V.prefix[r + 1]) r++;
-    return load_site(V.seg[r] + (j - V.prefix[r]));
+    local = j - V.prefix[r];
+    return r;
+}
+__device__ __forceinline__ Site source_bank_site(const SourceBankView& V, unsigned long long j)
+{
+    unsigned long long local;
+    const int r = source_bank_locate(V, j, local);
+    return load_site((r < 0 ? V.flat : V.seg[r]) + local);
 }
 __device__ __forceinline__ void source_bank_direction(const SourceBankView& V, unsigned long long j, const Site& s, double& u, double& v,
                                                       double& w)
 {
-    if (V.dir_x) { u = V.dir_x[3 * j]; v = V.dir_x[3 * j + 1]; w = V.dir_x[3 * j + 2]; }
-    else direction_from_draws(s.mu, s.xi, u, v, w);
+    if (V.dir_x) { u = V.dir_x[3 * j]; v = V.dir_x[3 * j + 1]; w = V.dir_x[3 * j + 2]; return; }
+    if (!V.flat) {
+        unsigned long long local;
+        const int r = source_bank_locate(V, j, local);
+        const double* d = V.seg_dir[r];
+        if (d) { u = d[3 * local]; v = d[3 * local + 1]; w = d[3 * local + 2]; return; }
+    }
+    direction_from_draws(s.mu, s.xi, u, v, w);
 }
 
 // a fission site as the collision leaves it: where, from what, and the stream it will be sampled from.  The

@@ -605,10 +605,10 @@ k_unpack_sites(const Site* __restrict__ in, const double* __restrict__ dir_x, ui
 
 // the global bank of a multi-GPU run, materialised on demand (host read-back): out[q] = site q of the view
 __global__ void __launch_bounds__(256)
-k_gather_sites(const SourceBankView V, uint64_t n, Site* out)
+k_gather_sites(const SourceBankView V, uint64_t q0, uint64_t n, Site* out)
 {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) store_site(out + q, source_bank_site(V, q));
+    if (q < n) store_site(out + q, source_bank_site(V, q0 + q));
 }
 
 __global__ void k_iota(uint32_t* a, uint32_t n)
@@ -891,9 +891,9 @@ void unpack_sites(cudaStream_t st, const Site* in, const double* dir_x, uint64_t
 {
     if (n) { k_unpack_sites<<<blocks_for(n), 256, 0, st>>>(in, dir_x, n, s8, cells); MCB_LAUNCHED(1); }
 }
-void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t n, Site* out)
+void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t q0, uint64_t n, Site* out)
 {
-    if (n) { k_gather_sites<<<blocks_for(n), 256, 0, st>>>(V, n, out); MCB_LAUNCHED(1); }
+    if (n) { k_gather_sites<<<blocks_for(n), 256, 0, st>>>(V, q0, n, out); MCB_LAUNCHED(1); }
 }
 void iota(cudaStream_t st, uint32_t* a, uint32_t n)
 {

@@ -83,6 +83,7 @@ struct WalkPlan {
     size_t gstate_pairs; // double2 elements of the global slot-state array the caller allocates (0: state in shared memory)
 };
 int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
+int walk_launch_info(const WalkPlan& W, bool tally, int out[4]);  // registers per thread, full grid, block size, dynamic smem
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
           const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate,
           const WalkSource& src);
@@ -101,7 +102,7 @@ void entropy_histogram(cudaStream_t st, const DevProblem& P, const Site* bank, u
 int tally_chunks(uint32_t n_hist);
 void tally_reduce(cudaStream_t st, double* acc, int64_t stride, uint32_t n_hist, int64_t n_tallies, double* partial,
                   double* sum, double* squared);
-void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t n, Site* out);
+void gather_sites(cudaStream_t st, const SourceBankView& V, uint64_t q0, uint64_t n, Site* out);  // out[q] = site q0 + q of the view
 void iota(cudaStream_t st, uint32_t* a, uint32_t n);
 // host-facing bank layout (n x 8 doubles + n cells) <-> Site records; dir_x = n x 3 explicit directions of a bank that
 // came from the host (nullptr for banks the device made: their directions are rebuilt from the stored draws)

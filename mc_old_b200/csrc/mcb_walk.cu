@@ -739,6 +739,24 @@ int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_s
     return 0;
 }
 
+int walk_launch_info(const WalkPlan& W, bool tally, int out[4])
+{
+    cudaFuncAttributes a;
+    cudaError_t e;
+#define MCB_ATTR(T_, S_, E_) cudaFuncGetAttributes(&a, k_walk<T_, S_, E_>)
+    if (W.exchange) {
+        if (tally) e = W.shared ? MCB_ATTR(true, true, true) : MCB_ATTR(true, false, true);
+        else e = W.shared ? MCB_ATTR(false, true, true) : MCB_ATTR(false, false, true);
+    } else {
+        if (tally) e = W.shared ? MCB_ATTR(true, true, false) : MCB_ATTR(true, false, false);
+        else e = W.shared ? MCB_ATTR(false, true, false) : MCB_ATTR(false, false, false);
+    }
+#undef MCB_ATTR
+    if (e != cudaSuccess) return (int)e;
+    out[0] = a.numRegs; out[1] = W.n_sm * W.blocks_per_sm[tally ? 1 : 0]; out[2] = BLOCK; out[3] = (int)W.smem_bytes[tally ? 1 : 0];
+    return 0;
+}
+
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
           const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate,
           const WalkSource& src)

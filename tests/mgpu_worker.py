@@ -33,6 +33,22 @@ out = {"k_cycle_hex": [r.k_cycle.hex() for r in rs], "n_sites": [int(r.n_sites) 
        "H_hex": [r.H.hex() for r in rs], "n_tracks": [int(r.n_tracks) for r in rs],
        "bank_energy_sum_hex": float(np.sum(sites[:, 6])).hex(),
        "tally_mean": [float(x) for x in mean], "tally_uncer": [float(x) for x in uncer]}
+# host-bank cycles (mcb_run_cycle_host): every rank reads its slice of the global host bank and writes its slice of the new one
+cells = ctx.source_bank(int(rs[-1].n_sites))[1]
+hk = []
+for _ in range(2):
+    out_s = np.zeros((4 * a.samples, 8)); out_c = np.zeros(4 * a.samples, dtype=np.int32)
+    r, s_new, c_new = ctx.run_cycle_host(sites, cells, out_s, out_c)
+    parts = [None] * world
+    dist.all_gather_object(parts, (s_new.copy(), c_new.copy()))
+    if os.environ.get("MCB_NO_P2P"):   # no peer mappings: every rank moved the whole bank
+        sites, cells = parts[0]
+    else:                               # the slices are disjoint, the rest of every rank's array is zero
+        sites = sum(p[0] for p in parts)
+        cells = sum(p[1] for p in parts).astype(np.int32)
+    hk.append([r.k_cycle.hex(), int(r.n_sites), int(r.n_tracks)])
+out["host_cycles"] = hk
+out["host_bank_sum_hex"] = [float(np.sum(sites[:, i])).hex() for i in range(8)]
 gathered = [None] * world
 dist.all_gather_object(gathered, out)
 assert all(g == gathered[0] for g in gathered), "ranks disagree on the global results"

@@ -426,12 +426,21 @@ def test_multi_gpu_matches_single_gpu(bank):
     deck = mcb.Deck(xml=decks.heu_sphere(samples=40000, active=2, passive=1, entropy=True, estimators=True))
     ctx = mcb.Context(deck, device=0)
     rs = [ctx.run_cycle() for _ in range(3)]
-    sites, _ = ctx.source_bank(int(rs[-1].n_sites))
+    sites, cells = ctx.source_bank(int(rs[-1].n_sites))
     mean, uncer = ctx.tallies()
+    bank_energy_sum = float(np.sum(sites[:, 6])).hex()
+    hk = []
+    for _ in range(2):  # host-bank cycles: on several GPUs every rank moves only its slice of the bank (peer reads path)
+        out_s = np.zeros((4 * 40000, 8)); out_c = np.zeros(4 * 40000, dtype=np.int32)
+        r, s_new, c_new = ctx.run_cycle_host(sites, cells, out_s, out_c)
+        sites, cells = s_new.copy(), c_new.copy()
+        hk.append([r.k_cycle.hex(), int(r.n_sites), int(r.n_tracks)])
     ctx.close()
+    assert hk == multi["host_cycles"]
+    assert [float(np.sum(sites[:, i])).hex() for i in range(8)] == multi["host_bank_sum_hex"]
     assert [r.H.hex() for r in rs] == multi["H_hex"]
     assert [int(r.n_tracks) for r in rs] == multi["n_tracks"]
     assert np.allclose(mean, multi["tally_mean"], rtol=1e-12, atol=0) and np.allclose(uncer, multi["tally_uncer"], rtol=1e-9, atol=0)
     assert [r.k_cycle.hex() for r in rs] == multi["k_cycle_hex"]
     assert [int(r.n_sites) for r in rs] == multi["n_sites"]
-    assert float(np.sum(sites[:, 6])).hex() == multi["bank_energy_sum_hex"]
+    assert bank_energy_sum == multi["bank_energy_sum_hex"]
