@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 1
+#define MCB_ABI_VERSION 2
 #define MCB_MAX_MAT_NUCLIDES 8 /* nuclides per material handled in registers */
 #define MCB_XS_ROW 6           /* doubles per xs row: E, sigma_s, sigma_c, sigma_f, nu, beta */
 
@@ -164,6 +164,9 @@ typedef struct mcb_problem {
     int32_t entropy_on;
     int32_t entropy_n[3];        /* number of grid points per axis (bins + 1) */
     const double* entropy_grid;  /* x grid, then y grid, then z grid */
+    /* particle comb (setup.cpp:57-67, population_control.cpp:55-84): after every random walk, a history whose particle
+     * bank holds bank_max or more waiting particles is combed down to `teeth` particles of equal weight */
+    int32_t comb_on, comb_bank_max, comb_teeth, reserved2;
 } mcb_problem;
 
 /* ---- per-process device context ---- */

@@ -425,6 +425,8 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     P.shared_histories = (!p->ksearch || splitting) ? 1 : 0;
     P.track_old = track_old ? 1 : 0;
     P.track_time = track_time ? 1 : 0; P.pad = 0;
+    P.comb_teeth = p->comb_on ? p->comb_teeth : 0; P.comb_bank_max = p->comb_bank_max;
+    if (p->comb_on && (p->comb_teeth < 1 || p->comb_teeth > 256 || p->comb_bank_max < 1)) return ctx->fail(MCB_ERR_ARG, "particle comb: bank_max >= 1 and 1 <= teeth <= 256");
     P.wr = p->wr; P.ws = p->ws; P.seed0 = ctx->seed; P.n_sample = p->n_sample;
     P.materials = ctx->d_materials.p; P.nuclides = ctx->d_nuclides.p; P.mat_nuclide = ctx->d_mat_nuclide.p; P.mat_density = ctx->d_mat_density.p;
     P.surfaces = ctx->d_surfaces.p; P.cells = ctx->d_cells.p; P.cell_surface = ctx->d_cell_surface.p; P.cell_sense = ctx->d_cell_sense.p;
@@ -517,7 +519,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         const size_t n_ctx = (size_t)ctx->plan.n_contexts;
         if (ctx->plan.gstate_pairs) CK(ctx->d_gstate.alloc(ctx->plan.gstate_pairs));
         if (ctx->plan.stack_records) { CK(ctx->d_stack.alloc(ctx->plan.stack_records)); CK(ctx->d_chunk_tab.alloc(ctx->plan.chunk_tab_entries)); }
-        if (P.shared_histories && !p->ksearch && !getenv("MCB_NO_SHARING")) {
+        if (P.shared_histories && !p->ksearch && !p->comb_on && !getenv("MCB_NO_SHARING")) {  // (the comb works on a history's whole bank)
             // fixed-source problems: lanes hand waiting secondaries to idle lanes (k-eigenvalue problems only split, their
             // families are small, and their fission sites keep the order of one lane)
             const uint32_t cap = 1u << 16;

@@ -40,7 +40,9 @@ struct DevProblem {
     int32_t ksearch, n_materials, n_nuclides, n_surfaces, n_cells, n_sources, n_estimators, entropy_on;
     int32_t shared_histories;    // several particles of one history can be in flight (secondaries / splitting)
     int32_t track_old;           // some estimator reads Particle::energy_old (TRMM tally set): Bank::Eold is maintained
-    int32_t track_time, pad;     // some estimator has a time filter: Bank::told (Particle::time_old) is maintained
+    int32_t track_time;          // some estimator has a time filter: Bank::told (Particle::time_old) is maintained
+    int32_t comb_teeth;          // particle comb (population_control.cpp:55-84): 0 = off
+    int32_t comb_bank_max, pad;
     double wr, ws;
     uint64_t seed0, n_sample;
     const DevMaterial* materials;

@@ -205,6 +205,39 @@ __device__ __forceinline__ void chunks_give(WalkQ& Q, const unsigned short* tab,
     atomicExch(&Q.alloc_lock, 0u);
 }
 
+// particle_comb (population_control.cpp:55-84) on the history's stack, by the lane that follows the history (rare and
+// short: banks of a few dozen particles).  The one draw comes from the stream of the particle whose walk just ended.  As
+// in the reference: a particle takes at most one tooth; the new bank starts as `teeth` copies of the first particle, and
+// teeth the loop does not reach keep that copy with its original weight (their streams are set (q + 1) * 2^40 draws on,
+// so that the copies do not repeat each other); a tooth past the end is dropped.
+__device__ __noinline__ static void comb_stack(StackSink sink, int teeth, uint64_t& rng_done, int* sp_out)
+{
+    const int n = sink.sp;
+    double W = 0.0;
+    for (int i = 0; i < n; i++) W += reinterpret_cast<const double2*>(sink.rec(i))[4].x;
+    const double w_avg = W / (double)teeth;
+    double tooth = mcb_urand(rng_done) * w_avg, sum = 0.0;
+    auto copy = [&](int from, int to) {
+        const double2* a = reinterpret_cast<const double2*>(sink.rec(from));
+        double2* b = reinterpret_cast<double2*>(sink.rec(to));
+        for (int k = 0; k < 7; k++) b[k] = a[k];
+    };
+    for (int q = 0; q < teeth; q++) copy(0, n + q);
+    int j = 0;
+    for (int i = 0; i < n; i++) {
+        sum += reinterpret_cast<const double2*>(sink.rec(i))[4].x;
+        if (sum > tooth) {
+            if (j < teeth) { copy(i, n + j); reinterpret_cast<double2*>(sink.rec(n + j))[4].x = w_avg; }
+            tooth += w_avg; j++;
+        }
+    }
+    const uint64_t rng0 = (uint64_t)__double_as_longlong(reinterpret_cast<const double2*>(sink.rec(0))[5].y);
+    for (int q = j; q < teeth; q++)
+        reinterpret_cast<double2*>(sink.rec(n + q))[5].y = __longlong_as_double((long long)mcb_rn_skip(rng0, ((uint64_t)(q + 1)) << 40));
+    for (int q = 0; q < teeth; q++) copy(n + q, q);
+    *sp_out = teeth;
+}
+
 __device__ __forceinline__ void lock_acquire(WalkQ& Q, unsigned lane)
 {
     if (lane == 0) {
@@ -553,6 +586,12 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         __syncwarp();
         if (have && !alive) {
             if (SHARED && sp > 0) {
+                if (P.comb_teeth && sp >= P.comb_bank_max) {  // handler.cpp:27-28
+                    const int need = (sp + P.comb_teeth + STACK_CHUNK - 1) / STACK_CHUNK;
+                    if (need > nch) { nch += chunks_take(Q, tab, nch, need - nch); sink.nch = nch; }
+                    if (need <= nch) comb_stack(sink, P.comb_teeth, p.rng, &sp);
+                    else C->overflow_stack = 1;
+                }
                 sink.pop(p);  // the history goes on with its most recent secondary (handler.cpp:22)
             } else {
                 // end of the history: EstimatorK::end_history inputs (Estimator.cpp:514-525), Estimator::end_history

@@ -304,14 +304,19 @@ def shielding(samples=20000, split=False):
 """
 
 
-def fixed_source_fissile(samples=2000):
+def fixed_source_fissile(samples=2000, comb=None):
     """A fixed-source deck in fissile material (same-history fission secondaries, fixed_source.cpp:12-22),
     generic plane + cylinder_x surfaces, a uniform source energy and an independentXYZ direction, with
-    TL / collision / surface estimators and an energy filter — exercises the paths the example decks leave out."""
+    TL / collision / surface estimators and an energy filter — exercises the paths the example decks leave out.
+    comb = (bank_max, teeth) adds <population_control><particle_comb/> (population_control.cpp:55-84)."""
+    ctrl = "" if comb is None else f"""
+<population_control>
+    <particle_comb bank_max="{comb[0]}" teeth="{comb[1]}"/>
+</population_control>"""
     return HEAD + f"""
 <simulation>
     <description name="subcritical block" samples="{samples:g}"/>
-</simulation>
+</simulation>{ctrl}
 <distributions>
     <uniform name="ux" datatype="double" a="0.2" b="0.9"/>
     <uniform name="uy" datatype="double" a="-0.3" b="0.3"/>

@@ -194,9 +194,14 @@ bool Deck::load_string(const std::string& xml_text, const std::string& xs_dir, i
 
     // ---- population control (setup.cpp:57-67) ----
     if (const XmlNode* ctrl = doc.child("population_control")) {
-        if (ctrl->child("particle_comb")) {
-            error = "unsupported: particle_comb (only the TDMC decks use it; SURVEY.md §8f-3)";
-            return false;
+        if (const XmlNode* comb = ctrl->child("particle_comb")) {
+            p.comb_on = 1;
+            p.comb_bank_max = comb->attribute("bank_max").as_int();
+            p.comb_teeth = comb->attribute("teeth").as_int();
+            if (p.comb_teeth < 1 || p.comb_teeth > 256 || p.comb_bank_max < 1) {
+                error = "[INPUT ERROR] <particle_comb> needs bank_max >= 1 and 1 <= teeth <= 256";
+                return false;
+            }
         }
     }
 

@@ -911,6 +911,36 @@ static void collision(mco_ctx* c, particle* P) /* general.cpp:121-163 */
         scatter_sample(p->nuclides[N_scatter].A, P, &r);
     }
 }
+/* particle_comb (population_control.cpp:55-84), called after every random walk (handler.cpp:27-28).  The comb's one
+ * draw comes from the global stream (MCO_RNG_GLOBAL) or from the stream of the particle whose walk just ended
+ * (MCO_RNG_HISTORY).  Reproduced as it is: `if`, not `while`, so a heavy particle takes one tooth; the new bank starts as
+ * `teeth` copies of Pbank[0], and teeth the loop does not reach keep that copy with its ORIGINAL weight; a tooth past
+ * the end (the reference writes out of bounds there) is dropped.  MCO_RNG_HISTORY: a combed particle keeps the stream
+ * of the particle it copies; the leftover copies of Pbank[0] get streams of their own, (q + 1) * 2^40 draws on. */
+static void particle_comb(mco_ctx* c, particle* done)
+{
+    const mcb_problem* p = c->p;
+    const size_t teeth = (size_t)p->comb_teeth;
+    double W = 0.0, w_avg, tooth, sum = 0.0;
+    particle tmp[256];
+    size_t i, j = 0, q;
+    if (!p->comb_on || c->Pn < (size_t)p->comb_bank_max) return;
+    for (i = 0; i < c->Pn; i++) W += c->Pbank[i].w;
+    w_avg = W / (double)p->comb_teeth;
+    tooth = urand(c, done) * w_avg;
+    for (q = 0; q < teeth; q++) tmp[q] = c->Pbank[0];
+    for (i = 0; i < c->Pn; i++) {
+        sum += c->Pbank[i].w;
+        if (sum > tooth) {
+            if (j < teeth) { tmp[j] = c->Pbank[i]; tmp[j].w = w_avg; }
+            tooth += w_avg; j++;
+        }
+    }
+    if (c->rng_mode == MCO_RNG_HISTORY)
+        for (q = j; q < teeth; q++) tmp[q].rng = mco_lcg_skip(c->Pbank[0].rng, ((uint64_t)(q + 1)) << 40);
+    c->Pn = 0;
+    for (q = 0; q < teeth; q++) push(&c->Pbank, &c->Pn, &c->Pcap, &tmp[q]);
+}
 static int random_walk(mco_ctx* c, particle* P) /* general.cpp:177-211 */
 {
     const mcb_problem* p = c->p;
@@ -1034,6 +1064,7 @@ int mco_transport_cycle(mco_ctx* c)
         while (c->Pn) {                                    /* handler.cpp:22-29 */
             particle P = c->Pbank[--c->Pn];
             if (random_walk(c, &P) != 0) return -1;
+            particle_comb(c, &P);                          /* handler.cpp:27-28 */
         }
         if (c->tally_on) {                                 /* Estimator::end_history (Estimator.cpp:339-346) */
             int64_t t;

@@ -35,6 +35,7 @@ def run_decks():
         "shield": (decks.shielding(samples=4000), True),
         "shield_split": (decks.shielding(samples=3000, split=True), True),
         "fsf": (decks.fixed_source_fissile(samples=2000), True),
+        "fsf_comb": (decks.fixed_source_fissile(samples=2000, comb=(3, 2)), True),
         "leak_time": (decks.heu_leakage(samples=3000), False),
     }
 

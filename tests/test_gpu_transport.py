@@ -81,18 +81,20 @@ def test_heu_entropy_history_parity():
     ctx.close()
 
 
-@pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("heu_tallies", 10000),
-                                    ("gcr_trmm", 400), ("leak_time", 20000)])
+@pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("fsf_comb", 20000),
+                                    ("heu_tallies", 10000), ("gcr_trmm", 400), ("leak_time", 20000)])
 def test_tallies_history_parity(name, n):
     """Estimator::score / end_history / end_cycle / end_simulation (Estimator.cpp:298-367) on every deck family:
     surface, cell-TL and cell-C estimators, energy filters, splitting (cell_importance, population_control.cpp:21-49)
     and same-history fission secondaries (fixed_source.cpp:12-22); the TRMM tally set of infinite_GCR_TRMM (3500 bins:
     energy_initial x energy matrices filled by simulate-then-score estimators, Estimator.cpp:441-482, delayed-neutron
     scores at energy_old); time filters that split a track over the bins it spans (examples/HEU_sphere_leakage,
-    Estimator.cpp:199-246).  Same per-history streams on both sides, so the
+    Estimator.cpp:199-246); the particle comb (population_control.cpp:55-84, fsf_comb: banks of 3 or more waiting particles
+    combed to 2).  Same per-history streams on both sides, so the
     per-bin means agree far inside their statistical error: |gpu - oracle| <= 0.2 sigma + 1e-9 relative."""
     xml = {"slab": lambda: decks.slab(samples=n), "shield": lambda: decks.shielding(samples=n),
            "shield_split": lambda: decks.shielding(samples=n, split=True), "fsf": lambda: decks.fixed_source_fissile(samples=n),
+           "fsf_comb": lambda: decks.fixed_source_fissile(samples=n, comb=(3, 2)),
            "heu_tallies": lambda: decks.heu_sphere(samples=n, active=1, passive=0, estimators=True),
            "gcr_trmm": lambda: decks.gcr(samples=n, active=1, passive=0, trmm=True),
            "leak_time": lambda: decks.heu_leakage(samples=n)}[name]()
@@ -224,6 +226,76 @@ def test_tallies_chi_square_k_mode():
     nz = (ov > 0) & (gv > 0)
     z = np.abs(gm[nz] - om[nz]) / np.sqrt(gv[nz] + ov[nz])
     assert z.max() < 5.0, z
+
+
+def test_gcr_trmm_statistical_gate():
+    """BASELINE.json config 2 (examples/infinite_GCR_TRMM: 4 nuclides, reflective planes, the nine TRMM estimators =
+    3500 bins that report.cpp:53-158 assembles into the transition-rate matrix): k within 3 sigma combined of the
+    reference-identical oracle (RNG_GLOBAL / PICK_CDF, bit-identical to the compiled reference), and a chi-square over
+    the tally bins.  Reference side: tests/golden/gcr_trmm_global_4000.npz, 4000 x (5 + 10), made by
+    tests/golden/make_gcr_trmm_golden.py (the deck's own 400 histories per generation carry a population-size bias a
+    2e4-per-generation run resolves: GPU at N = 400 against the N = 400 reference gives chi2 / dof 1.05 - 1.25, at
+    N = 2e4 against the same 2.2 - 2.5).  GPU: 2e4 x (5 + 10), independent streams.
+
+    What the chi-square runs over.  In a k-eigenvalue run all bins of an estimator share the generation-to-generation
+    fluctuation of the source (two reference-identical runs differ by ~2 % in EVERY bin at once), and the twelve
+    NuFissionDelayed* scores of TRM_simple are one score times constants; a chi-square over the raw 3500 bins counts that
+    one fluctuation hundreds of times.  So each (estimator, score) vector is compared as a SHAPE (bins divided by their
+    sum), one representative score per family.  Calibration with the oracle alone (two GLOBAL runs of different seeds,
+    and GLOBAL against per-history streams, all at N = 400): chi2 / dof = 1.10 ... 1.26 over ~1100 bins — the reported
+    per-bin uncertainties leave out the correlation between generations — hence the bound 1.5."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gcr_trmm_global_4000.npz"))
+    om, ou = gold["mean"], gold["uncer"]
+    ko = gold["k_cycle"][5:]
+    k_o, s_o = float(gold["k_avg"]), max(float(gold["k_uncer"]), float(ko.std(ddof=1) / np.sqrt(ko.size)))
+    deck = mcb.Deck(xml=decks.gcr(samples=20000, active=10, passive=5, trmm=True))
+    ctx = mcb.Context(deck, device=0)
+    rs = [ctx.run_cycle() for _ in range(15)]
+    gm, gu = ctx.tallies()
+    ctx.close()
+    s_g = _k_sigma(rs, 5)
+    assert abs(rs[-1].k_avg - k_o) <= 3 * np.hypot(s_g, s_o), (rs[-1].k_avg, s_g, k_o, s_o)
+    assert gm.size == om.size == 3500
+    x2, dof = 0.0, 0
+    for e in deck.estimators():
+        per = e["n_tallies"] // len(e["scores"])
+        for k, sc in enumerate(e["scores"]):
+            if e["name"] == "TRM_simple" and sc not in ("flux", "NuFissionDelayed_1", "inverse_speed"):
+                continue
+            sl = slice(e["tally_begin"] + k * per, e["tally_begin"] + (k + 1) * per)
+            ok = (ou[sl] > 0) & (gu[sl] > 0)
+            if ok.sum() < 2:
+                continue
+            so, sg = om[sl][ok].sum(), gm[sl][ok].sum()
+            x2 += float(np.sum((gm[sl][ok] / sg - om[sl][ok] / so) ** 2 / ((gu[sl][ok] / sg) ** 2 + (ou[sl][ok] / so) ** 2)))
+            dof += int(ok.sum()) - 1
+            # the totals themselves: within 10 % (the oracle's 4000 active histories fix them to ~2 %)
+            assert abs(sg - so) <= 0.10 * so, (e["name"], sc, sg, so)
+    assert dof > 900
+    assert x2 < 1.5 * dof, (x2, dof)
+    # bins the oracle's 4000 active histories never reached carry little weight on the GPU side as well
+    rare = (ou == 0) & (gm > 0)
+    assert gm[rare].sum() <= 0.02 * gm.sum()
+
+
+def test_keff_of_the_scaled_up_generation_size():
+    """north_star target: HEU_sphere_criticality at 1e8 histories per generation with k-eff within 3 sigma of the
+    reference.  The reference cannot run that size; its k is pinned by an ensemble of eight
+    reference-identical runs at the deck's size (tests/golden/k_ensemble.json, made by tests/golden/make_k_ensemble.py:
+    8 seeds x 1e4 x (10 + 190)).  GPU: 1e8 histories per generation x (6 + 8) generations on one GPU, in bank batches."""
+    import json
+    import os
+    ens = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "k_ensemble.json")))
+    k_ref, s_ref = ens["ensemble_mean"], ens["ensemble_std_of_mean"]
+    deck = mcb.Deck(xml=decks.heu_sphere(samples=100_000_000, active=8, passive=6))
+    ctx = mcb.Context(deck, device=0)
+    rs = [ctx.run_cycle() for _ in range(14)]
+    ctx.close()
+    assert rs[-1].n_histories == 100_000_000
+    s_g = _k_sigma(rs, 6)
+    assert abs(rs[-1].k_avg - k_ref) <= 3 * np.hypot(s_g, s_ref), (rs[-1].k_avg, s_g, k_ref, s_ref)
+    assert s_g < 1e-4 < s_ref   # the comparison is limited by what the reference can afford, not by the GPU run
 
 
 def test_slab_analytic_1e7():
