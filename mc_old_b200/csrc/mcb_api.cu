@@ -587,6 +587,9 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
             cudaGetLastError();
         }
     }
+    // Kernels are loaded lazily, and loading one waits for every running kernel to end: a kernel first launched BESIDE a
+    // persistent kernel that waits for it would never start.  Everything the side stream launches is launched once here.
+    mcbk::preload_side_kernels(ctx->stream, &ctx->d_counters.p->src_ready);
     CK(cudaStreamSynchronize(ctx->stream));
     return MCB_OK;
 }
@@ -861,12 +864,12 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
     // critical path instead.  MCB_FUSED_SOURCE=0/1 overrides.)
     const bool fused_default = false;
     const bool fused = ctx->walk_mode && V.n > 0 && (getenv("MCB_FUSED_SOURCE") ? atoi(getenv("MCB_FUSED_SOURCE")) != 0 : fused_default);
-    // Experimental (MCB_SOURCE_OVERLAP_SMS=n, off by default): the sorted sweep over the peers' banks runs piece by piece on a
-    // side stream beside ONE walk launch that vacates n SMs and takes bank positions as they are published.  In this
-    // library the side-stream kernels do not start until the walk kernel has ended (a standalone two-kernel experiment,
-    // tools/exp/concurrency.cu, does run them side by side), so the walk's bounded wait reports an error; left for the next
-    // round.
-    const int overlap_sms = getenv("MCB_SOURCE_OVERLAP_SMS") ? atoi(getenv("MCB_SOURCE_OVERLAP_SMS")) : 0;
+    // Bank spread over several GPUs: the sorted sweep over the peers' banks runs piece by piece on a side stream BESIDE one
+    // walk launch that vacates a few SMs and takes bank positions as they are published (k_publish).  Measured on 8 x B200:
+    // 9.07 -> 8.52 ms per generation with 16 SMs left to the sweep (24: 8.80); on 2 GPUs the sweep is short and the walk's
+    // loss of SMs eats the gain (8.33 -> 8.43), so it is on from 4 ranks.  The sweep needs that many SMs because a peer
+    // read keeps a thread waiting for microseconds: bytes in flight per SM, not NVLink, bound it there.
+    const int overlap_sms = getenv("MCB_SOURCE_OVERLAP_SMS") ? atoi(getenv("MCB_SOURCE_OVERLAP_SMS")) : (ctx->world >= 4 ? 16 : 0);
     const bool piecewise = ctx->walk_mode && !fused && sort && (!V.flat || getenv("MCB_FORCE_SORT")) && overlap_sms > 0 && nb >= (1u << 16);
     if (fused) { if (sort) mcbk::pick_sort(st, P, (int32_t)h0, nb, nps0, V.n, sort); }
     else if (piecewise) mcbk::pick_sort(st, P, (int32_t)h0, nb, nps0, V.n, sort);
@@ -902,7 +905,8 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
         const int dbg = getenv("MCB_DEBUG_OVERLAP") ? atoi(getenv("MCB_DEBUG_OVERLAP")) : 0;
         for (int c = 0; c < NC; c++) {
             const uint32_t q0 = (uint32_t)((uint64_t)nb * c / NC), q1 = (uint32_t)((uint64_t)nb * (c + 1) / NC);
-            if (dbg != 1) mcbk::source_sorted_range(ctx->side_stream, P, ctx->B, nullptr, (int32_t)h0, q0, q1 - q0, nps0, V, C, sort);
+            if (dbg == 2) mcbk::source_sweep(ctx->side_stream, ctx->B, (int32_t)h0, q0, q1 - q0, V, sort);  // several sites per thread (measured slower)
+            else if (dbg != 1) mcbk::source_sorted_range(ctx->side_stream, P, ctx->B, nullptr, (int32_t)h0, q0, q1 - q0, nps0, V, C, sort);
             mcbk::publish(ctx->side_stream, &C->src_ready, q1);
         }
         CK(cudaEventRecord(ctx->ev_side[0], ctx->side_stream));

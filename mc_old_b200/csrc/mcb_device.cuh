@@ -305,10 +305,16 @@ struct UnionPos {
 __device__ __forceinline__ UnionPos union_pos(const DevMaterial& M, double E)
 {
     UnionPos q;
+#ifdef MCB_OLD_LOOKUP
+    q.u = mcb_union_count_less(M.U, M.hash, M.key_min, M.n_hash, M.shift, M.nU, E) - 1;
+    q.rec = M.hrec + (size_t)(M.n_hash + 1) * M.hstride;  // the "below the grid" record: indices -1
+    q.row = q.u < 0 ? nullptr : M.map + (size_t)q.u * M.n_nuc;
+#else
     bool from_rec;
     const int lo = mcb_union_lookup(M.U, M.hrec, M.hstride, M.key_min, M.n_hash, M.shift, E, &q.rec, &from_rec);
     q.u = lo - 1;
     q.row = from_rec ? nullptr : M.map + (size_t)q.u * M.n_nuc;
+#endif
     return q;
 }
 __device__ __forceinline__ int nuclide_index(const UnionPos& q, int n)

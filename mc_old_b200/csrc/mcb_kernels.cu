@@ -17,6 +17,7 @@
 #include "mcb_events.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -179,6 +180,47 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
     if (B.Eold) B.Eold[q] = E;  // the reference leaves energy_old uninitialised at birth; defined as E here
     if (B.told) B.told[q] = t;
     if (active) active[q] = q;  // event-queue mode: the first queue is the identity
+}
+
+// The sorted sweep over a bank spread over several GPUs, for a launch that shares the machine with the walk kernel and
+// gets only a few SMs: every thread fetches ITEMS sites with all their loads in flight at once (ITEMS x 64 B per thread,
+// 0.5 MB per SM), so that a handful of SMs keep NVLink as busy as the whole GPU does with one site per thread.
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+k_source_sweep(Bank B, int32_t first_hist, uint32_t q_begin, uint32_t q_end, const SourceBankView V,
+               const void* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_val, const uint64_t* __restrict__ rng_after,
+               unsigned long long rot, int key32)
+{
+    const uint32_t tile = q_begin + (blockIdx.x * 256u) * ITEMS + threadIdx.x;
+    uint32_t sv[ITEMS];
+    unsigned long long j[ITEMS];
+    Site s[ITEMS];
+    uint64_t rng[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint32_t q = tile + k * 256u;
+        if (q < q_end) {
+            sv[k] = sorted_val[q];
+            j[k] = (key32 ? (unsigned long long)reinterpret_cast<const uint32_t*>(sorted_key)[q] : reinterpret_cast<const unsigned long long*>(sorted_key)[q]) + rot;
+            if (j[k] >= V.n) j[k] -= V.n;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint32_t q = tile + k * 256u;
+        if (q < q_end) { s[k] = source_bank_site(V, j[k]); rng[k] = rng_after[sv[k]]; }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint32_t q = tile + k * 256u;
+        if (q < q_end) {
+            double u, v, w;
+            source_bank_direction(V, j[k], s[k], u, v, w);
+            B.x[q] = s[k].x; B.y[q] = s[k].y; B.z[q] = s[k].z; B.u[q] = u; B.v[q] = v; B.w[q] = w;
+            B.E[q] = s[k].E; B.speed[q] = mcb_speed_of_energy(s[k].E); B.wgt[q] = 1.0; B.t[q] = s[k].t;
+            B.rng[q] = rng[k]; B.cell[q] = s[k].cell; B.hist[q] = first_hist + (int32_t)sv[k];
+        }
+    }
 }
 
 // xs_lookup stage: macroscopic cross sections of every queued particle at its energy in its cell's material.
@@ -794,6 +836,25 @@ void publish(cudaStream_t st, unsigned long long* dst, unsigned long long value)
 {
     k_publish<<<1, 1, 0, st>>>(dst, value);
     MCB_LAUNCHED(1);
+}
+void source_sweep(cudaStream_t st, const Bank& B, int32_t first_hist, uint32_t q0, uint32_t count, const SourceBankView& V, const SortScratch* sort)
+{
+    if (!count) return;
+    constexpr int ITEMS = 4;
+    k_source_sweep<ITEMS><<<blocks_for(count, 256 * ITEMS), 256, 0, st>>>(B, first_hist, q0, q0 + count, V, sort->key_out, sort->val_out, sort->rng_after,
+                                                                        sort->rot, sort->key32);
+    MCB_LAUNCHED(1);
+}
+void preload_side_kernels(cudaStream_t st, unsigned long long* scratch)
+{
+    // lazy loading: a kernel's first launch waits for every running kernel to end, so the kernels that are meant to run
+    // BESIDE the persistent walk kernel are launched once (on nothing) when the context is made
+    SourceBankView V;
+    memset(&V, 0, sizeof(V));
+    Bank B;
+    memset(&B, 0, sizeof(B));
+    k_source_sweep<4><<<1, 256, 0, st>>>(B, 0, 0u, 0u, V, nullptr, nullptr, nullptr, 0ull, 0);
+    k_publish<<<1, 1, 0, st>>>(scratch, 0ull);
 }
 void chunk_bounds(cudaStream_t st, const SortScratch* sort, uint32_t n, const unsigned long long* lo, int n_lo, uint32_t* pos)
 {

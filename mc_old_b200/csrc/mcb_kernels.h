@@ -27,6 +27,9 @@ size_t sort_temp_bytes(uint32_t n);
 // the site index reaches lo[c]; k_source for positions [q0, q0 + count) of the sweep
 void pick_sort(cudaStream_t st, const DevProblem& P, int32_t first_hist, uint32_t count, uint64_t nps0, uint64_t n_bank,
                const SortScratch* sort);
+// the sorted sweep for positions [q0, q0 + count) with several sites in flight per thread (walk mode: no queue, no energy_old arrays)
+void source_sweep(cudaStream_t st, const Bank& B, int32_t first_hist, uint32_t q0, uint32_t count, const SourceBankView& V, const SortScratch* sort);
+void preload_side_kernels(cudaStream_t st, unsigned long long* scratch);
 void publish(cudaStream_t st, unsigned long long* dst, unsigned long long value);  // *dst = value in stream order
 void chunk_bounds(cudaStream_t st, const SortScratch* sort, uint32_t n, const unsigned long long* lo, int n_lo, uint32_t* pos);
 void source_sorted_range(cudaStream_t st, const DevProblem& P, const Bank& B, uint32_t* active, int32_t first_hist, uint32_t q0,

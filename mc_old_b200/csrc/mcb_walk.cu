@@ -305,6 +305,33 @@ __device__ __forceinline__ void merge_shared_tallies(const TallyAcc& T, int row,
     if (lane == 0) atomicExch(T.dense_pending + drow, -1);  // the row is clean again: free for another history
 }
 
+// SourceBank::get_source (Source.cpp:42-46) in the lane that is about to follow the history, with site index floor(xi N):
+// history h draws from the stream of nps = cycle * Nsample + h (RN_init_particle, Random.cpp:196-204).
+// (inlined: an out-of-line callee that writes the particle through a reference pins the whole record to local memory:
+// measured 5.68 -> 6.52 ms per generation.)
+__device__ __forceinline__ void fused_source(const mcbk::WalkSource& SRC, uint32_t j, uint64_t chunk_seed, unsigned long long chunk_begin, Particle& p)
+{
+    unsigned long long site;
+    if (SRC.sorted_key) {  // the draws were made and sorted by site index beforehand (k_pick)
+        const uint32_t sv = __ldg(SRC.sorted_val + j);
+        p.hist = SRC.first_hist + (int32_t)sv;
+        p.rng = __ldg(SRC.rng_after + sv);
+        site = (SRC.key32 ? (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(SRC.sorted_key) + j)
+                          : __ldg(reinterpret_cast<const unsigned long long*>(SRC.sorted_key) + j)) + SRC.rot;
+        if (site >= SRC.V.n) site -= SRC.V.n;
+    } else {
+        p.hist = SRC.first_hist + (int32_t)j;
+        p.rng = mcb_rn_history_seed_from(chunk_seed, (uint32_t)(j - chunk_begin));
+        const double xi = mcb_urand(p.rng);
+        site = (unsigned long long)(xi * (double)SRC.V.n);
+        if (site >= SRC.V.n) site = SRC.V.n - 1;
+    }
+    const Site sx = source_bank_site(SRC.V, site);  // local HBM, or a peer's HBM over NVLink
+    p.x = sx.x; p.y = sx.y; p.z = sx.z; p.E = sx.E; p.t = sx.t; p.cell = sx.cell;
+    source_bank_direction(SRC.V, site, sx, p.u, p.v, p.w);
+    p.speed = mcb_speed_of_energy(p.E); p.wgt = 1.0;
+}
+
 // EXCH = true: the event-sorted form described above.  EXCH = false: every lane keeps its history from the source bank to
 // its end and runs its own next event (collide and cross lanes of a warp diverge): no slot traffic and no queue, every
 // warp streams through one loop body.  Which one wins is a matter of the instruction cache: the loop is ~70 KB of code
@@ -389,27 +416,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             if (!have && rank < take) {
                 const uint32_t j = (uint32_t)(chunk_next + rank);
                 if (SRC.fused) {
-                    // SourceBank::get_source (Source.cpp:42-46) with site index floor(xi N): history h draws from the
-                    // stream of nps = cycle * Nsample + h (RN_init_particle, Random.cpp:196-204)
-                    unsigned long long site;
-                    if (SRC.sorted_key) {  // the draws were made and sorted by site index beforehand (k_pick)
-                        const uint32_t sv = __ldg(SRC.sorted_val + j);
-                        p.hist = SRC.first_hist + (int32_t)sv;
-                        p.rng = __ldg(SRC.rng_after + sv);
-                        site = (SRC.key32 ? (unsigned long long)__ldg(reinterpret_cast<const uint32_t*>(SRC.sorted_key) + j)
-                                          : __ldg(reinterpret_cast<const unsigned long long*>(SRC.sorted_key) + j)) + SRC.rot;
-                        if (site >= SRC.V.n) site -= SRC.V.n;
-                    } else {
-                        p.hist = SRC.first_hist + (int32_t)j;
-                        p.rng = mcb_rn_history_seed_from(chunk_seed, (uint32_t)(j - chunk_begin));
-                        const double xi = mcb_urand(p.rng);
-                        site = (unsigned long long)(xi * (double)SRC.V.n);
-                        if (site >= SRC.V.n) site = SRC.V.n - 1;
-                    }
-                    const Site sx = source_bank_site(SRC.V, site);  // local HBM, or a peer's HBM over NVLink
-                    p.x = sx.x; p.y = sx.y; p.z = sx.z; p.E = sx.E; p.t = sx.t; p.cell = sx.cell;
-                    source_bank_direction(SRC.V, site, sx, p.u, p.v, p.w);
-                    p.speed = mcb_speed_of_energy(p.E); p.wgt = 1.0;
+                    fused_source(SRC, j, chunk_seed, chunk_begin, p);
                 } else {
                     p.cell = B.cell[j]; p.hist = B.hist[j];
                     p.x = B.x[j]; p.y = B.y[j]; p.z = B.z[j]; p.u = B.u[j]; p.v = B.v[j]; p.w = B.w[j];
