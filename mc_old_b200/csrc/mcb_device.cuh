@@ -305,7 +305,8 @@ struct UnionPos {
 __device__ __forceinline__ UnionPos union_pos(const DevMaterial& M, double E)
 {
     UnionPos q;
-#ifdef MCB_OLD_LOOKUP
+#ifndef MCB_HREC_LOOKUP  // measured: the record form changes nothing in the walk kernel (5.74 ms either way) and costs the
+                         // lookup microbench 10 % (its table is four times the hash), so the plain hash stays the default
     q.u = mcb_union_count_less(M.U, M.hash, M.key_min, M.n_hash, M.shift, M.nU, E) - 1;
     q.rec = M.hrec + (size_t)(M.n_hash + 1) * M.hstride;  // the "below the grid" record: indices -1
     q.row = q.u < 0 ? nullptr : M.map + (size_t)q.u * M.n_nuc;
