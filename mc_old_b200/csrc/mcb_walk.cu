@@ -253,23 +253,6 @@ __device__ __forceinline__ void lock_release(WalkQ& Q, unsigned lane)
     if (lane == 0) atomicExch(&Q.lock, 0u);
 }
 
-// Estimator::end_history for one history (Estimator.cpp:339-346): sum += hist, squared += hist^2 per touched bin.
-// The whole warp works on the table of the lane whose history ended (histories end on one or two lanes at a time).
-__device__ __forceinline__ void flush_history_tallies(const TallyAcc& T, int row, int n_touched, double* s_sum, double* s_sq, unsigned lane)
-{
-    const uint32_t size = T.tab_mask + 1u;
-    uint32_t* keys = T.tab_key + (size_t)row * size;
-    double* vals = T.tab_val + (size_t)row * size;
-    const uint16_t* list = T.tab_list + (size_t)row * size;
-    for (int i = (int)lane; i < n_touched; i += 32) {
-        const uint32_t h = list[i];
-        const uint32_t t = keys[h] - 1u;
-        const double v = vals[h];
-        keys[h] = 0u;
-        if (s_sum) { atomicAdd(s_sum + t, v); atomicAdd(s_sq + t, v * v); }
-        else { atomicAdd(T.sum + t, v); atomicAdd(T.squared + t, v * v); }
-    }
-}
 // a unit of a shared history ends: its private table goes into the history's dense row; the last unit out turns the row
 // into sum / squared.  Warp-cooperative like the flush.
 __device__ __forceinline__ void merge_shared_tallies(const TallyAcc& T, int row, int n_touched, int drow, double* s_sum, double* s_sq, unsigned lane)

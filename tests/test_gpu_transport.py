@@ -378,24 +378,28 @@ def test_event_queue_and_walk_kernels_agree():
 @pytest.mark.parametrize("deck_name", ["ucube", "shield_split"])
 def test_walk_forms_agree(deck_name, monkeypatch):
     """the two forms of the walk kernel — history per lane, and particles sorted by next event through the
-    shared-memory collide / cross queues (MCB_WALK_EXCHANGE=1) — are the same computation: identical k sums, entropy,
+    shared-memory collide / cross queues (MCB_WALK_EXCHANGE=1), and SMs specialised by event type with particles handed over
+    through global rings (MCB_WALK_FORM=roles) — are the same computation: identical k sums, entropy,
     counts and fission bank; tallies to rounding"""
     xml = decks.ucube(samples=30000, active=1, passive=1) if deck_name == "ucube" else decks.shielding(samples=20000, split=True)
     deck = mcb.Deck(xml=xml)
     res = []
-    for exch in ("0", "1"):
+    forms = [("0", ""), ("1", "")] + ([("0", "roles")] if deck_name == "ucube" else [])  # roles: one particle per history only
+    for exch, form in forms:
         monkeypatch.setenv("MCB_WALK_EXCHANGE", exch)
+        monkeypatch.setenv("MCB_WALK_FORM", form)
         ctx = mcb.Context(deck, device=0)
         rs = [ctx.run_cycle() for _ in range(deck.info["n_cycle"] if deck_name != "ucube" else 2)]
         bank = ctx.fission_bank(int(rs[-1].n_sites)) if deck_name == "ucube" else None
         res.append((rs, bank, ctx.tallies()))
         ctx.close()
-    for a, b in zip(res[0][0], res[1][0]):
-        assert (a.k_sum_C, a.k_sum_TL, a.H, a.n_sites, a.n_tracks, a.n_collisions, a.n_crossings) == \
-               (b.k_sum_C, b.k_sum_TL, b.H, b.n_sites, b.n_tracks, b.n_collisions, b.n_crossings)
-    if res[0][1] is not None:
-        assert np.array_equal(res[0][1][0], res[1][1][0])
-    assert np.allclose(res[0][2][0], res[1][2][0], rtol=1e-12, atol=0)
+    for other in res[1:]:
+        for a, b in zip(res[0][0], other[0]):
+            assert (a.k_sum_C, a.k_sum_TL, a.H, a.n_sites, a.n_tracks, a.n_collisions, a.n_crossings) == \
+                   (b.k_sum_C, b.k_sum_TL, b.H, b.n_sites, b.n_tracks, b.n_collisions, b.n_crossings)
+        if res[0][1] is not None:
+            assert np.array_equal(res[0][1][0], other[1][0])
+        assert np.allclose(res[0][2][0], other[2][0], rtol=1e-12, atol=0)
 
 
 def test_source_bank_host_round_trip():
