@@ -167,13 +167,6 @@ struct mcb_ctx {
     uint64_t finish_below = 0;       // queue length under which the tail kernel takes over
     bool split_stages = false;       // event-queue mode: one kernel per event type (cross-check / profiling) instead of the walk kernel
     mcbk::WalkPlan plan{};           // launch shape of the walk kernel on this device
-    bool roles = false;              // MCB_WALK_FORM=roles: SMs specialised by event type (k_walk_roles)
-    mcbk::RolesPlan rplan{};
-    mcbk::RolesRes rres{};
-    DevBuf<double2> d_rstate;
-    DevBuf<mcbk::RoleQueue> d_rq;
-    DevBuf<unsigned long long> d_rq_seq;
-    DevBuf<uint32_t> d_rq_ids, d_rq_cnt;
     int n_sm = 148;
     DevBuf<double2> d_gstate;        // slot state of the walk kernel when it is kept in global memory (build option)
     DevBuf<StackRec> d_stack;        // per-context LIFO stacks of same-history secondaries (the reference's Pbank)
@@ -523,26 +516,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         for (int m = 0; m < p->n_materials; m++) det_nn = std::max(det_nn, tabs[m].n_nuc);
         const int rc = mcbk::walk_plan(P.shared_histories != 0, getenv("MCB_WALK_EXCHANGE") && atoi(getenv("MCB_WALK_EXCHANGE")) != 0, det_nn, p->n_tallies, ctx->n_sm, &ctx->plan);
         if (rc != 0) return ctx->fail(MCB_ERR_CUDA, "walk kernel does not fit this device: %s", cudaGetErrorString((cudaError_t)rc));
-        size_t n_ctx = (size_t)ctx->plan.n_contexts;
-        if (!P.shared_histories && getenv("MCB_WALK_FORM") && !strcmp(getenv("MCB_WALK_FORM"), "roles")) {
-            const int rr = mcbk::roles_plan(det_nn, p->n_tallies, ctx->n_sm, &ctx->rplan);
-            if (rr != 0) return ctx->fail(MCB_ERR_CUDA, "roles form does not fit this device: %s", cudaGetErrorString((cudaError_t)rr));
-            ctx->roles = true;
-            const size_t NP = ctx->rplan.n_slots, cap = ctx->rplan.queue_cap;
-            const int NS = getenv("MCB_ROLE_SHARDS") ? std::max(1, atoi(getenv("MCB_ROLE_SHARDS"))) : 32;
-            n_ctx = std::max(n_ctx, NP);
-            CK(ctx->d_rstate.alloc((size_t)ctx->rplan.n_pairs * NP));
-            std::vector<unsigned long long> seq(2 * NS * cap);
-            for (size_t i = 0; i < seq.size(); i++) seq[i] = i % cap;
-            CK(ctx->d_rq_seq.upload(seq.data(), seq.size()));
-            CK(ctx->d_rq_ids.alloc(2 * NS * cap * 32)); CK(ctx->d_rq_cnt.alloc(2 * NS * cap));
-            std::vector<mcbk::RoleQueue> q(2 * NS);
-            memset(q.data(), 0, q.size() * sizeof(mcbk::RoleQueue));
-            for (int i = 0; i < 2 * NS; i++) { q[i].seq = ctx->d_rq_seq.p + i * cap; q[i].ids = ctx->d_rq_ids.p + i * cap * 32; q[i].cnt = ctx->d_rq_cnt.p + i * cap; q[i].cap_mask = (uint32_t)cap - 1; }
-            CK(ctx->d_rq.upload(q.data(), q.size()));
-            ctx->rres.state = ctx->d_rstate.p; ctx->rres.qF = ctx->d_rq.p; ctx->rres.qC = ctx->d_rq.p + NS; ctx->rres.n_shards = NS;
-            ctx->rres.c_pct = getenv("MCB_ROLE_C_PCT") ? atoi(getenv("MCB_ROLE_C_PCT")) : 50;
-        }
+        const size_t n_ctx = (size_t)ctx->plan.n_contexts;
         if (ctx->plan.gstate_pairs) CK(ctx->d_gstate.alloc(ctx->plan.gstate_pairs));
         if (ctx->plan.stack_records) { CK(ctx->d_stack.alloc(ctx->plan.stack_records)); CK(ctx->d_chunk_tab.alloc(ctx->plan.chunk_tab_entries)); }
         if (P.shared_histories && !p->ksearch && !p->comb_on && !getenv("MCB_NO_SHARING")) {  // (the comb works on a history's whole bank)
@@ -772,7 +746,7 @@ static int check_batch(mcb_ctx* ctx, const Counters& hc)
     if (hc.overflow_sites) return ctx->fail(MCB_ERR_CAPACITY, "fission bank overflow: more than %llu sites on rank %d (raise mcb_config.site_capacity)", (unsigned long long)ctx->site_cap, ctx->rank);
     if (hc.overflow_slots) return ctx->fail(MCB_ERR_CAPACITY, "particle bank overflow: more than %u slots (raise mcb_config.bank_capacity)", ctx->n_slots);
     if (hc.overflow_stack) return ctx->fail(MCB_ERR_CAPACITY, "secondary stack overflow: a history had more than %d particles waiting, or the block's spare chunks ran out", ctx->plan.stack_max);
-    if (hc.hang) return ctx->fail(MCB_ERR_CUDA, "walk kernel: a bounded wait ran out (code %d live %lld: %s; src_ready %llu, walk_head %llu)", hc.hang, hc.live, hc.hang == 4 ? "source sweep beside the walk" : hc.hang == 3 ? "idle warps waiting for shared work" : hc.hang >= 5 ? "rings of the roles form" : "ring of handed-over secondaries", hc.src_ready, hc.walk_head);
+    if (hc.hang) return ctx->fail(MCB_ERR_CUDA, "walk kernel: a bounded wait ran out (code %d live %lld: %s; src_ready %llu, walk_head %llu)", hc.hang, hc.live, hc.hang == 4 ? "source sweep beside the walk" : hc.hang == 3 ? "idle warps waiting for shared work" : "ring of handed-over secondaries", hc.src_ready, hc.walk_head);
     if (hc.overflow_tally) return ctx->fail(MCB_ERR_CAPACITY, "tally table overflow: a history touched more than %u tally bins", ctx->tab_size);
     return MCB_OK;
 }
@@ -947,9 +921,6 @@ static int transport_batch(mcb_ctx* ctx, uint32_t h0, uint32_t nb, bool tally_on
         CK(cudaMemsetAsync(&C->walk_head, 0, sizeof(unsigned long long), st));
         if (ctx->d_dense_pending.p) CK(cudaMemsetAsync(ctx->d_dense_pending.p + ctx->dense_rows, 0, sizeof(int32_t), st));
         ctx->timer.begin(st, ST_STEP);
-        if (ctx->roles && !fused)
-            mcbk::walk_roles(st, P, ctx->B, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->rplan, ctx->rres);
-        else
         mcbk::walk(st, P, ctx->B, 0, nb, C, ctx->H, T, ctx->d_site_reqs.p, ctx->site_cap, ctx->k, ctx->plan, ctx->d_stack.p, ctx->d_chunk_tab.p, ctx->d_donq.p, ctx->d_gstate.p,
                    walk_source(ctx, fused ? &V : nullptr, (int32_t)h0, nps0, sort));
         ctx->timer.end(st);

@@ -86,33 +86,6 @@ struct WalkPlan {
     size_t gstate_pairs; // double2 elements of the global slot-state array the caller allocates (0: state in shared memory)
 };
 int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out);  // 0 or a cudaError_t
-// k_walk_roles (mcb_walk_roles.cu): SMs specialised by event type, particles handed over through global rings of tiles
-struct alignas(128) RoleQueue { // bounded multi-producer multi-consumer ring of tiles of up to 32 slot numbers; the three
-    unsigned long long head;    // counters sit in cache lines of their own, and every kind of queue is sharded
-    unsigned long long pad0[15];// (contended atomics on one sector top out near 250 M/s)
-    unsigned long long tail;
-    unsigned long long pad1[15];
-    int avail, pad2[31];
-    unsigned long long* seq;    // cell c is free for ticket t when seq[c] = t, filled when t + 1
-    uint32_t* ids;              // cap x 32
-    uint32_t* cnt;              // cap
-    uint32_t cap_mask, pad3;
-    unsigned long long pad4[12];
-};
-struct RolesRes {             // kernel argument
-    double2* state;           // n_pairs x n_slots
-    RoleQueue *qF, *qC;         // n_shards queues of each kind
-    uint32_t NP;
-    int32_t n_shards;
-    int32_t det_nn, n_pairs, c_pct, priv_tallies;
-};
-struct RolesPlan {
-    int n_sm, det_nn, priv_tallies, blocks_per_sm, grid, n_pairs;
-    uint32_t n_slots, queue_cap;
-};
-int roles_plan(int det_nn, int64_t n_tallies, int n_sm, RolesPlan* out);
-void walk_roles(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t n_bank, Counters* C, const HistoryAcc& H, const TallyAcc& T,
-                SiteReq* reqs, uint64_t site_cap, double k_eff, const RolesPlan& W, const RolesRes& res);
 int walk_launch_info(const WalkPlan& W, bool tally, int out[4]);  // registers per thread, full grid, block size, dynamic smem
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
           const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack, unsigned short* chunk_tab, DonationQueue* donq, double2* gstate,

@@ -378,16 +378,13 @@ def test_event_queue_and_walk_kernels_agree():
 @pytest.mark.parametrize("deck_name", ["ucube", "shield_split"])
 def test_walk_forms_agree(deck_name, monkeypatch):
     """the two forms of the walk kernel — history per lane, and particles sorted by next event through the
-    shared-memory collide / cross queues (MCB_WALK_EXCHANGE=1), and SMs specialised by event type with particles handed over
-    through global rings (MCB_WALK_FORM=roles) — are the same computation: identical k sums, entropy,
+    shared-memory collide / cross queues (MCB_WALK_EXCHANGE=1) — are the same computation: identical k sums, entropy,
     counts and fission bank; tallies to rounding"""
     xml = decks.ucube(samples=30000, active=1, passive=1) if deck_name == "ucube" else decks.shielding(samples=20000, split=True)
     deck = mcb.Deck(xml=xml)
     res = []
-    forms = [("0", ""), ("1", "")] + ([("0", "roles")] if deck_name == "ucube" else [])  # roles: one particle per history only
-    for exch, form in forms:
+    for exch in ("0", "1"):
         monkeypatch.setenv("MCB_WALK_EXCHANGE", exch)
-        monkeypatch.setenv("MCB_WALK_FORM", form)
         ctx = mcb.Context(deck, device=0)
         rs = [ctx.run_cycle() for _ in range(deck.info["n_cycle"] if deck_name != "ucube" else 2)]
         bank = ctx.fission_bank(int(rs[-1].n_sites)) if deck_name == "ucube" else None
