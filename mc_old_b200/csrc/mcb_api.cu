@@ -181,6 +181,7 @@ struct mcb_ctx {
     DevBuf<double> d_tab_val;
     DevBuf<uint16_t> d_tab_list;
     uint32_t tab_size = 0;
+    bool tab_direct = false;
     bool walk_mode = true;           // history walk (one launch per pass over the bank) instead of the event-queue loop
     // per-history accumulators
     DevBuf<double> d_hist_k;         // kC, kTL
@@ -383,7 +384,19 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     CK(ctx->d_sources.upload(p->sources, p->n_sources));
     CK(ctx->d_estimators.upload(p->estimators, p->n_estimators));
     CK(ctx->d_scores.upload(p->scores, p->n_scores));
-    CK(ctx->d_filters.upload(p->filters, p->n_filters));
+    {
+        // filters with the same grid share one copy on the device: the walk kernel's bin cache (filter_bin) is keyed by
+        // the grid, and the estimators of a TRMM tally set all carry the same energy grid
+        std::vector<mcb_filter> fl(p->filters, p->filters + p->n_filters);
+        for (int f = 1; f < p->n_filters; f++)
+            for (int g = 0; g < f; g++)
+                if (fl[g].grid_n == fl[f].grid_n &&
+                    !memcmp(p->filter_grid + fl[g].grid_begin, p->filter_grid + p->filters[f].grid_begin, sizeof(double) * (size_t)fl[f].grid_n)) {
+                    fl[f].grid_begin = fl[g].grid_begin;
+                    break;
+                }
+        CK(ctx->d_filters.upload(fl.data(), p->n_filters));
+    }
     CK(ctx->d_filter_grid.upload(p->filter_grid, p->n_filter_grid));
     bool splitting = false;
     {
@@ -540,14 +553,23 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
             }
         }
         if (p->n_tallies > 0) {
-            // table of a history: a power of two >= the number of tallies when that fits (then every tally has its own
-            // entry), at most 8192 entries and ~24 GiB in all
-            uint32_t size = 2;
-            while (size < (uint32_t)std::min<int64_t>(p->n_tallies, 8192)) size <<= 1;
-            while (size > 256 && n_ctx * (size_t)size * 14 > (24ull << 30)) size >>= 1;
+            // table of a history: direct (one position per tally, values only) while that stays under ~24 GiB in all
+            // and positions fit the 16-bit touched list; else open-addressed, a power of two of at most 8192 entries
+            const uint64_t dsize = ((uint64_t)p->n_tallies + 15) & ~15ull;
+            ctx->tab_direct = dsize <= 65536 && n_ctx * dsize * 10 <= (24ull << 30) && !getenv("MCB_HASHED_TALLIES");
+            uint32_t size = (uint32_t)dsize;
+            if (!ctx->tab_direct) {
+                size = 2;
+                while (size < (uint32_t)std::min<int64_t>(p->n_tallies, 8192)) size <<= 1;
+                while (size > 256 && n_ctx * (size_t)size * 14 > (24ull << 30)) size >>= 1;
+            }
             ctx->tab_size = size;
-            CK(ctx->d_tab_key.alloc(n_ctx * size)); CK(ctx->d_tab_val.alloc(n_ctx * size)); CK(ctx->d_tab_list.alloc(n_ctx * size));
-            CK(cudaMemset(ctx->d_tab_key.p, 0, n_ctx * size * sizeof(uint32_t)));
+            CK(ctx->d_tab_val.alloc(n_ctx * size)); CK(ctx->d_tab_list.alloc(n_ctx * size));
+            if (ctx->tab_direct) CK(cudaMemset(ctx->d_tab_val.p, 0, n_ctx * size * sizeof(double)));
+            else {
+                CK(ctx->d_tab_key.alloc(n_ctx * size));
+                CK(cudaMemset(ctx->d_tab_key.p, 0, n_ctx * size * sizeof(uint32_t)));
+            }
         }
     }
     if (p->n_tallies > 0) {
@@ -729,7 +751,7 @@ static TallyAcc tally_acc(mcb_ctx* ctx, uint32_t h0, bool tally_on)
     T.acc = ctx->d_tally_acc.p;  // event-queue mode only (nullptr selects the per-history tables of the walk kernel)
     T.stride = ctx->batch_hist; T.first_hist = (int32_t)h0; T.on = tally_on && ctx->n_tallies > 0;
     T.tab_key = ctx->d_tab_key.p; T.tab_val = ctx->d_tab_val.p; T.tab_list = ctx->d_tab_list.p;
-    T.tab_mask = ctx->tab_size ? ctx->tab_size - 1 : 0; T.n_tallies = (int32_t)ctx->n_tallies;
+    T.tab_mask = ctx->tab_size ? ctx->tab_size - 1 : 0; T.n_tallies = (int32_t)ctx->n_tallies; T.direct = ctx->tab_direct ? 1 : 0;
     T.sum = ctx->d_tally_sum.p; T.squared = ctx->d_tally_sq.p;
     T.dense = ctx->d_dense.p; T.dense_pending = ctx->d_dense_pending.p; T.dense_rows = ctx->dense_rows;
     T.dense_cursor = ctx->d_dense_pending.p ? ctx->d_dense_pending.p + ctx->dense_rows : nullptr;

@@ -197,8 +197,9 @@ struct HistoryAcc {
 
 // per-history tally accumulators.
 // Event-queue kernels: dense rows acc[tally][history of the batch] (acc != nullptr), reduced per batch by k_tally_*.
-// Walk kernel: one open-addressed table {tally index + 1 -> value} per history context (a history is followed by one
-// lane at a time), flushed when the history ends as sum += v, squared += v * v (Estimator.cpp:339-346) with
+// Walk kernel: one table per history context (a history is followed by one lane at a time): direct ({position ->
+// value}, every tally its own position) when the problem has at most 8192 tallies, else open-addressed {tally index
+// + 1 -> value}; flushed when the history ends as sum += v, squared += v * v (Estimator.cpp:339-346) with
 // reductions into `sum` / `squared` (through block-private shared-memory bins when the problem has few tallies).
 struct TallyAcc {
     double* acc;
@@ -216,7 +217,8 @@ struct TallyAcc {
     double* dense;                        // dense_rows x n_tallies
     int32_t* dense_pending;
     int32_t* dense_cursor;                // rows handed out in this launch
-    int32_t dense_rows, pad;
+    int32_t dense_rows;
+    int32_t direct;                       // tables hold every tally at its own position (no keys), see tally_slot
 };
 
 
@@ -439,9 +441,15 @@ __device__ __forceinline__ double micro_channel(const DevNuclide& N, const Micro
 struct ChannelCache {
     double E[2];
     int32_t mat[2], used;
+    uint32_t valid[2];                       // channel sums already formed at E[i]: bit kind, bit 9 + g for the decay sums
     MicroXS m[2][MCB_MAX_MAT_NUCLIDES];
+    double sums[2][15];
+    // bins of the last two (energy filter grid, energy) pairs searched, most recent first: the estimators of one event
+    // look up the same energy in the same grid again and again
+    double fb_val[2];
+    int32_t fb_grid[2], fb_idx[2];
 };
-__device__ __forceinline__ void channel_cache_reset(ChannelCache& C) { C.mat[0] = C.mat[1] = -1; C.used = 0; }
+__device__ __forceinline__ void channel_cache_reset(ChannelCache& C) { C.mat[0] = C.mat[1] = -1; C.used = 0; C.fb_grid[0] = C.fb_grid[1] = -1; }
 __device__ __noinline__ static int channel_cache_get(const DevProblem& P, int material, double E, ChannelCache& C)
 {
     for (int i = 0; i < 2; i++) if (C.mat[i] == material && C.E[i] == E) return i;
@@ -453,8 +461,19 @@ __device__ __noinline__ static int channel_cache_get(const DevProblem& P, int ma
         const int gn = __ldg(&P.mat_nuclide[M.nuc_begin + n]);
         micro_xs(P.nuclides[gn], nuclide_index(up, n), E, C.m[i][n]);
     }
-    C.E[i] = E; C.mat[i] = material;
+    C.E[i] = E; C.mat[i] = material; C.valid[i] = 0u;
     return i;
+}
+// mcb_binary_search(x, grid, n) of a filter grid through the two-entry cache
+__device__ __forceinline__ int filter_bin(const DevProblem& P, int grid_begin, int n, double x, ChannelCache& C)
+{
+    if (C.fb_grid[0] == grid_begin && C.fb_val[0] == x) return C.fb_idx[0];
+    int idx;
+    if (C.fb_grid[1] == grid_begin && C.fb_val[1] == x) idx = C.fb_idx[1];
+    else idx = mcb_binary_search(x, P.filter_grid + grid_begin, n);
+    C.fb_grid[1] = C.fb_grid[0]; C.fb_val[1] = C.fb_val[0]; C.fb_idx[1] = C.fb_idx[0];
+    C.fb_grid[0] = grid_begin; C.fb_val[0] = x; C.fb_idx[0] = idx;
+    return idx;
 }
 // Material::SigmaS / nuSigmaF / nuSigmaF_prompt / nuSigmaF_delayed (Material.cpp:26-82) at any energy; with `picked`
 // also Material::nuclide_scatter / _nufission / _nufission_prompt / _nufission_delayed (Material.cpp:106-146): *picked =
@@ -463,12 +482,20 @@ __device__ __noinline__ static double macro_channel(const DevProblem& P, int mat
                                                     int* picked, ChannelCache& C)
 {
     const DevMaterial& M = P.materials[material];
-    const MicroXS* m = C.m[channel_cache_get(P, material, E, C)];
-    double sum = 0.0;
-    for (int n = 0; n < M.n_nuc; n++) {
-        const DevNuclide& N = P.nuclides[__ldg(&P.mat_nuclide[M.nuc_begin + n])];
-        const double v = micro_channel(N, m[n], kind);
-        sum += (decay ? v / N.lambda[kind - 3] : v) * __ldg(&P.mat_density[M.nuc_begin + n]);
+    const int ci = channel_cache_get(P, material, E, C);
+    const MicroXS* m = C.m[ci];
+    const int slot = decay ? kind + 6 : kind;
+    double sum;
+    if (C.valid[ci] >> slot & 1u) sum = C.sums[ci][slot];
+    else {
+        sum = 0.0;
+        for (int n = 0; n < M.n_nuc; n++) {
+            const DevNuclide& N = P.nuclides[__ldg(&P.mat_nuclide[M.nuc_begin + n])];
+            const double v = micro_channel(N, m[n], kind);
+            sum += (decay ? v / N.lambda[kind - 3] : v) * __ldg(&P.mat_density[M.nuc_begin + n]);
+        }
+        C.sums[ci][slot] = sum;
+        C.valid[ci] |= 1u << slot;
     }
     if (picked) {
         const double thr = sum * xi;

@@ -38,8 +38,23 @@ __device__ __forceinline__ void tally_add(const TallyAcc& T, Counters* C, int ro
 {
     if (T.acc) { atomicAdd(T.acc + t * T.stride + (int64_t)(row - T.first_hist), v); return; }
     const uint32_t mask = T.tab_mask;
-    uint32_t* keys = T.tab_key + (size_t)row * (mask + 1u);
     double* vals = T.tab_val + (size_t)row * (mask + 1u);
+    if (T.direct) {
+        // every tally has its own entry (t is the table position, see tally_slot): the value itself says whether the
+        // entry is in use, so an add is one read-modify-write of one sector and a zero score touches nothing
+        if (v == 0.0) return;
+#ifdef MCB_TALLY_CG
+        const double old = __ldcg(vals + t);
+        if (old == 0.0 && n_touched <= (int)mask) { __stcg(T.tab_list + (size_t)row * (mask + 1u) + n_touched, (uint16_t)t); n_touched++; }
+        __stcg(vals + t, old + v);
+#else
+        const double old = vals[t];
+        if (old == 0.0 && n_touched <= (int)mask) { T.tab_list[(size_t)row * (mask + 1u) + n_touched] = (uint16_t)t; n_touched++; }
+        vals[t] = old + v;
+#endif
+        return;
+    }
+    uint32_t* keys = T.tab_key + (size_t)row * (mask + 1u);
     uint32_t h = (uint32_t)t & mask;
     for (uint32_t probe = 0; probe <= mask; probe++, h = (h + 1u) & mask) {
         const uint32_t k = keys[h];
@@ -53,6 +68,40 @@ __device__ __forceinline__ void tally_add(const TallyAcc& T, Counters* C, int ro
         }
     }
     C->overflow_tally = 1;  // a history touched more bins than a table holds
+}
+// Position of tally (estimator E, flat filter bin idx, score k) in a history's table.  Tally::sum is laid out
+// [score][bin] (Estimator.cpp:288-295), but one event adds to all scores of ONE bin: direct tables keep an estimator's
+// scores of a bin side by side ([bin][score]) so that those adds fall into one or two sectors instead of one each.
+__device__ __forceinline__ int64_t tally_slot(const TallyAcc& T, const mcb_estimator& E, int64_t idx, int k, int64_t bins)
+{
+    return T.direct ? E.tally_begin + idx * E.n_scores + k : E.tally_begin + idx + (int64_t)k * bins;
+}
+// ... and back: the index into Tally::sum of the table position `pos` of a direct table
+__device__ __forceinline__ uint32_t tally_of_slot(const DevProblem& P, uint32_t pos)
+{
+    int e = 0;
+    while (e + 1 < P.n_estimators && (int64_t)pos >= P.estimators[e + 1].tally_begin) e++;
+    const int64_t begin = P.estimators[e].tally_begin, S = P.estimators[e].n_scores;
+    const int64_t local = (int64_t)pos - begin, bins = P.estimators[e].n_tallies / S;
+    return (uint32_t)(begin + (local % S) * bins + local / S);
+}
+// takes entry i of a history's touched list out of its table: {index into Tally::sum, value}
+__device__ __forceinline__ bool tally_take(const DevProblem& P, const TallyAcc& T, int row, int i, uint32_t& t, double& v)
+{
+    const uint32_t size = T.tab_mask + 1u;
+    const uint32_t h = T.tab_list[(size_t)row * size + i];
+    double* val = T.tab_val + (size_t)row * size + h;
+    if (T.direct) {
+        v = __longlong_as_double((long long)atomicExch((unsigned long long*)val, 0ull));  // a position listed twice is taken once
+        if (v == 0.0) return false;
+        t = tally_of_slot(P, h);
+        return true;
+    }
+    uint32_t* key = T.tab_key + (size_t)row * size + h;
+    t = *key - 1u;
+    v = *val;
+    *key = 0u;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -120,13 +169,14 @@ __device__ __forceinline__ void time_piece(const mcb_filter& F, const double* g,
     if (i < num_bin) { c.idx = c.loc1 + i + 1; c.l = (g[c.loc1 + i + 2] - g[c.loc1 + i + 1]) * s.speed; return; }
     c.idx = c.loc2; c.l = (s.t - g[c.loc2]) * s.speed;
 }
-__device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, Counters* C, const mcb_estimator& E,
-                                                      const ScoreState& s, double l_in, int row, int& n_touched, ChannelCache& CC)
+// the general form: a time filter splits the track into pieces
+__device__ __noinline__ static int estimator_score_pieces(const DevProblem& P, const TallyAcc& T, Counters* C, const mcb_estimator& E,
+                                                          const ScoreState& s, double l_in, int row, int n_touched, ChannelCache& CC)
 {
     constexpr int MAXF = 4;
+    const int nf = E.n_filters < MAXF ? E.n_filters : MAXF;
     FilterCursor cur[MAXF];
     int64_t factor[MAXF + 1];  // idx_factor (Estimator.cpp:288-295)
-    const int nf = E.n_filters < MAXF ? E.n_filters : MAXF;
     factor[nf] = 1;
     for (int i = nf - 1; i >= 0; i--) factor[i] = factor[i + 1] * P.filters[E.filter_begin + i].size;
     for (int i = 0; i < nf; i++) {
@@ -140,19 +190,19 @@ __device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const
         case MCB_FILTER_ENERGY:
         case MCB_FILTER_ENERGY_OLD:                                                                          // :149-179
             c.idx = mcb_binary_search(F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, g, F.grid_n);
-            if (c.idx < 0 || c.idx >= F.grid_n - 1) return;
+            if (c.idx < 0 || c.idx >= F.grid_n - 1) return n_touched;
             break;
         default: {                                                                                           // time :199-246
             const int Nbin = F.grid_n - 1;
             c.loc1 = mcb_binary_search(s.t_old, g, F.grid_n);
             c.loc2 = mcb_binary_search(s.t, g, F.grid_n);
             if (c.loc1 == c.loc2) {
-                if (c.loc1 < 0 || c.loc1 >= Nbin) return;
+                if (c.loc1 < 0 || c.loc1 >= Nbin) return n_touched;
                 c.idx = c.loc1;
             } else {
                 c.first = c.loc1 >= 0;
                 c.n = (c.first ? 1 : 0) + (c.loc2 - c.loc1 - 1) + (c.loc2 < Nbin ? 1 : 0);
-                if (c.n == 0) return;
+                if (c.n == 0) return n_touched;
                 time_piece(F, g, s, c);
             }
         }
@@ -164,21 +214,62 @@ __device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const
         for (int i = 0; i < nf; i++) { l = fmin(l, cur[i].l); idx_1D += (int64_t)cur[i].idx * factor[i + 1]; }
         for (int k = 0; k < E.n_scores; k++) {
             const double v = score_value(P, P.scores[E.score_begin + k], s, l, CC);
-            const int64_t t = E.tally_begin + idx_1D + (int64_t)k * factor[0];
-            if (t >= E.tally_begin && t < E.tally_begin + E.n_tallies) tally_add(T, C, row, n_touched, t, v);
+            if (idx_1D >= 0 && idx_1D < factor[0]) tally_add(T, C, row, n_touched, tally_slot(T, E, idx_1D, k, factor[0]), v);
+            else {  // a bin index past its filter lands in a neighbouring score's bins, as long as it stays inside e_tally
+                const int64_t local = idx_1D + (int64_t)k * factor[0];
+                if (local >= 0 && local < E.n_tallies)
+                    tally_add(T, C, row, n_touched, tally_slot(T, E, local % factor[0], (int)(local / factor[0]), factor[0]), v);
+            }
         }
         for (int i = 0; i < nf; i++) {
             FilterCursor& c = cur[i];
             c.l -= l;
             if (c.l < MCB_EPSILON_FLOAT) {
-                if (c.k == c.n - 1) return;
+                if (c.k == c.n - 1) return n_touched;
                 c.k++;
                 const mcb_filter F = P.filters[E.filter_begin + i];
                 time_piece(F, P.filter_grid + F.grid_begin, s, c);
             }
         }
-        if (nf == 0) return;
+        if (nf == 0) return n_touched;
     }
+    return n_touched;
+}
+__device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const TallyAcc& T, Counters* C, const mcb_estimator& E,
+                                                      const ScoreState& s, double l_in, int row, int& n_touched, ChannelCache& CC)
+{
+    constexpr int MAXF = 4;
+    const int nf = E.n_filters < MAXF ? E.n_filters : MAXF;
+    bool pieces = false;
+    for (int i = 0; i < nf; i++) pieces |= P.filters[E.filter_begin + i].type == MCB_FILTER_TIME;
+    if (!pieces) {
+        // no time filter: every filter yields one bin and the whole length, one pass of the loop below
+        int64_t idx_1D = 0, bins = 1;
+        for (int i = 0; i < nf; i++) {
+            const mcb_filter F = P.filters[E.filter_begin + i];
+            int idx;
+            switch (F.type) {
+            case MCB_FILTER_SURFACE: idx = mcb_binary_search((double)s.surface_old, P.filter_grid + F.grid_begin, F.grid_n) + 1; break;
+            case MCB_FILTER_CELL: idx = mcb_binary_search((double)s.cell, P.filter_grid + F.grid_begin, F.grid_n) + 1; break;
+            default:
+                idx = filter_bin(P, F.grid_begin, F.grid_n, F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, CC);
+                if (idx < 0 || idx >= F.grid_n - 1) return;
+            }
+            idx_1D = idx_1D * F.size + idx;
+            bins *= F.size;
+        }
+        const double l = fmin(MCB_MAX_FLOAT, l_in);
+        for (int k = 0; k < E.n_scores; k++) {
+            const double v = score_value(P, P.scores[E.score_begin + k], s, l, CC);
+            if (idx_1D >= 0 && idx_1D < bins) tally_add(T, C, row, n_touched, tally_slot(T, E, idx_1D, k, bins), v);
+            else {
+                const int64_t local = idx_1D + (int64_t)k * bins;
+                if (local >= 0 && local < E.n_tallies) tally_add(T, C, row, n_touched, tally_slot(T, E, local % bins, (int)(local / bins), bins), v);
+            }
+        }
+        return;
+    }
+    n_touched = estimator_score_pieces(P, T, C, E, s, l_in, row, n_touched, CC);
 }
 // One estimator scores one event.  The TRMM estimators first let a COPY of the particle scatter / fission, drawing
 // from the particle's own stream like the reference draws from its global one (EstimatorScatter / FissionPrompt /
@@ -504,17 +595,13 @@ __device__ __forceinline__ bool ev_cross_post(const DevProblem& P, Particle& p, 
 
 // Estimator::end_history for one history (Estimator.cpp:339-346): sum += hist, squared += hist^2 per touched bin.
 // The whole warp works on the table of the lane whose history ended (histories end on one or two lanes at a time).
-__device__ __forceinline__ void flush_history_tallies(const TallyAcc& T, int row, int n_touched, double* s_sum, double* s_sq, unsigned lane)
+__device__ __forceinline__ void flush_history_tallies(const DevProblem& P, const TallyAcc& T, int row, int n_touched, double* s_sum, double* s_sq,
+                                                      unsigned lane)
 {
-    const uint32_t size = T.tab_mask + 1u;
-    uint32_t* keys = T.tab_key + (size_t)row * size;
-    double* vals = T.tab_val + (size_t)row * size;
-    const uint16_t* list = T.tab_list + (size_t)row * size;
     for (int i = (int)lane; i < n_touched; i += 32) {
-        const uint32_t h = list[i];
-        const uint32_t t = keys[h] - 1u;
-        const double v = vals[h];
-        keys[h] = 0u;
+        uint32_t t;
+        double v;
+        if (!tally_take(P, T, row, i, t, v)) continue;
         if (s_sum) { atomicAdd(s_sum + t, v); atomicAdd(s_sq + t, v * v); }
         else { atomicAdd(T.sum + t, v); atomicAdd(T.squared + t, v * v); }
     }

@@ -79,6 +79,7 @@ struct WalkPlan {
     bool shared;        // secondaries can be born in flight (fixed source / splitting)
     bool exchange;      // event-sorted form (particles change lanes through shared-memory queues) or history per lane
     int blocks_per_sm[2], n_pairs[2];   // [0] cycles that score nothing, [1] scoring cycles
+    int block[2];                       // threads per block
     size_t smem_bytes[2];
     int64_t n_contexts;
     size_t stack_records, chunk_tab_entries;  // sizes of the secondary-stack arrays the caller allocates (0: no secondaries)

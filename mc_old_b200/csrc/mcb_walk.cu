@@ -23,6 +23,17 @@
 //    table and there is no pass structure and no host round trip, however long the fission chain.
 //  * Fission sites leave the kernel as requests (one warp-aggregated cursor reservation per batch) and are sampled
 //    and put into canonical order by k_bank_sample_order.
+//
+// The file is compiled twice (two "flavours"), one kernel family each:
+//  * flavour 0 (this file): cycles that score no tallies: blocks of 128 threads, 4 per SM, warps free-running;
+//  * flavour 1 (mcb_walk_tally.cu includes this file): scoring cycles.  The estimator code makes the loop body several
+//    times larger than the instruction caches, and warps that run free each stream it from L2 on their own (ncu:
+//    stall_no_inst 30 %, sm__icc_request_hit_rate 59 %).  One block of 512 threads per SM whose warps meet at a
+//    barrier once per track run the same stretch of code at the same time and share the fetched lines: +47 % on the
+//    TRMM tally set (profiles/README.md, round 2e).  The barrier does not pay without estimators (measured).
+#ifndef MCB_WALK_FLAVOUR
+#define MCB_WALK_FLAVOUR 0
+#endif
 #include "mcb_events.cuh"
 
 #include <algorithm>
@@ -39,7 +50,7 @@ constexpr int WALK_SLOTS = BLOCK + WALK_RES;  // 160
 // secondary stacks: chunks of 32 records.  Every slot owns one chunk for good (a history rarely has more than a few
 // particles waiting); a history that needs more borrows chunks from its block's pool and returns them when it ends
 constexpr int STACK_CHUNK = 32;
-constexpr int WALK_EXTRA = 256;               // spare chunks per block
+constexpr int WALK_EXTRA = 2 * BLOCK;         // spare chunks per block
 constexpr int STACK_MAXCH = 32;               // chunks per history at most (1024 particles waiting)
 constexpr int pow2_at_least(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 constexpr int WALK_QCAP = pow2_at_least(WALK_SLOTS);  // ring capacity of a queue
@@ -255,18 +266,13 @@ __device__ __forceinline__ void lock_release(WalkQ& Q, unsigned lane)
 
 // a unit of a shared history ends: its private table goes into the history's dense row; the last unit out turns the row
 // into sum / squared.  Warp-cooperative like the flush.
-__device__ __forceinline__ void merge_shared_tallies(const TallyAcc& T, int row, int n_touched, int drow, double* s_sum, double* s_sq, unsigned lane)
+__device__ __forceinline__ void merge_shared_tallies(const DevProblem& P, const TallyAcc& T, int row, int n_touched, int drow, double* s_sum, double* s_sq, unsigned lane)
 {
-    const uint32_t size = T.tab_mask + 1u;
-    uint32_t* keys = T.tab_key + (size_t)row * size;
-    double* vals = T.tab_val + (size_t)row * size;
-    const uint16_t* list = T.tab_list + (size_t)row * size;
     double* dense = T.dense + (size_t)drow * T.n_tallies;
     for (int i = (int)lane; i < n_touched; i += 32) {
-        const uint32_t h = list[i];
-        const uint32_t t = keys[h] - 1u;
-        atomicAdd(dense + t, vals[h]);
-        keys[h] = 0u;
+        uint32_t t;
+        double v;
+        if (tally_take(P, T, row, i, t, v)) atomicAdd(dense + t, v);
     }
     __threadfence();
     __syncwarp();
@@ -494,8 +500,19 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
 #ifdef MCB_WALK_SYNC
         // history-per-lane form with the warps of a block kept in step: they then run the same stretch of the loop body
         // at the same time and share its instruction-cache lines (the per-SM instruction cache serves one miss for all)
-        if (!EXCH) { if (!__syncthreads_or(mK != 0u || !exhausted)) break; }
-        else
+        if (!EXCH) {
+            if (!__syncthreads_or(mK != 0u || !exhausted)) {
+                // the whole block is idle and the bank is dry
+                if (!(SHARED && R.donq)) break;
+                // work sharing: other blocks may still hand secondaries over; leave when no unit is alive anywhere
+                long long lv = 0;
+                if (threadIdx.x == 0) lv = (long long)__ldcg((const unsigned long long*)&C->live);
+                if (threadIdx.x == 0 && lv > 0 && ++idle_spins > WAIT_LIMIT) { C->hang = 3; lv = 0; }
+                if (!__syncthreads_or(lv > 0)) break;
+                __nanosleep(4000);
+                continue;
+            }
+        } else
 #endif
         if (mK == 0u) {
             if (!exhausted) continue;
@@ -596,8 +613,8 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const int row = __shfl_sync(FULL, p.row, src), nt = __shfl_sync(FULL, p.n_touched, src), dr = __shfl_sync(FULL, p.drow, src);
-                if (dr >= 0) merge_shared_tallies(T, row, nt, dr, s_sum, s_sq, lane);
-                else flush_history_tallies(T, row, nt, s_sum, s_sq, lane);
+                if (dr >= 0) merge_shared_tallies(P, T, row, nt, dr, s_sum, s_sq, lane);
+                else flush_history_tallies(P, T, row, nt, s_sum, s_sq, lane);
                 __syncwarp();
             }
         }
@@ -727,6 +744,82 @@ namespace mcbk {
 
 extern thread_local uint64_t g_launches;
 
+#define MCB_CAT2(a, b) a##b
+#define MCB_CAT(a, b) MCB_CAT2(a, b)
+#define MCB_FLAVOURED(name) MCB_CAT(name, MCB_WALK_FLAVOUR)
+constexpr bool FT = MCB_WALK_FLAVOUR != 0;  // this flavour's kernels score tallies
+
+// this flavour's share of the plan: fields [FT] of the per-instance arrays, and its sizes folded into the common ones
+int MCB_FLAVOURED(walk_plan_part)(WalkPlan& W)
+{
+    int blocks = 0, n_pairs = 0;
+    size_t smem = 0;
+    cudaError_t e;
+#define MCB_PLAN(S_, E_) plan_instance<FT, S_, E_>(W.det_nn, W.priv_tallies, W.n_sm, blocks, smem, n_pairs)
+    if (W.exchange) e = W.shared ? MCB_PLAN(true, true) : MCB_PLAN(false, true);
+    else e = W.shared ? MCB_PLAN(true, false) : MCB_PLAN(false, false);
+#undef MCB_PLAN
+    if (e != cudaSuccess) return (int)e;
+    if (blocks < 1) return (int)cudaErrorInvalidConfiguration;
+    W.blocks_per_sm[FT] = std::min(blocks, MCB_WALK_MINB);
+    W.smem_bytes[FT] = smem;
+    W.n_pairs[FT] = n_pairs;
+    W.block[FT] = BLOCK;
+    const int grid = W.n_sm * W.blocks_per_sm[FT];
+    W.max_grid = std::max(W.max_grid, grid);
+    W.n_contexts = std::max<int64_t>(W.n_contexts, (int64_t)grid * WALK_SLOTS);
+    if (W.shared) {
+        W.stack_records = std::max(W.stack_records, (size_t)grid * (WALK_SLOTS + WALK_EXTRA) * STACK_CHUNK);
+        W.chunk_tab_entries = std::max(W.chunk_tab_entries, (size_t)grid * WALK_SLOTS * STACK_MAXCH);
+    }
+    W.stack_max = STACK_MAXCH * STACK_CHUNK;
+#ifdef MCB_WALK_GLOBAL_STATE
+    W.gstate_pairs = std::max(W.gstate_pairs, (size_t)grid * n_pairs * WALK_SLOTS);
+#endif
+    return 0;
+}
+
+int MCB_FLAVOURED(walk_launch_info_part)(const WalkPlan& W, int out[4])
+{
+    cudaFuncAttributes a;
+    cudaError_t e;
+#define MCB_ATTR(S_, E_) cudaFuncGetAttributes(&a, k_walk<FT, S_, E_>)
+    if (W.exchange) e = W.shared ? MCB_ATTR(true, true) : MCB_ATTR(false, true);
+    else e = W.shared ? MCB_ATTR(true, false) : MCB_ATTR(false, false);
+#undef MCB_ATTR
+    if (e != cudaSuccess) return (int)e;
+    out[0] = a.numRegs; out[1] = W.n_sm * W.blocks_per_sm[FT]; out[2] = BLOCK; out[3] = (int)W.smem_bytes[FT];
+    return 0;
+}
+
+void MCB_FLAVOURED(walk_part)(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
+                              const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack,
+                              unsigned short* chunk_tab, DonationQueue* donq, double2* gstate, const WalkSource& src)
+{
+    // persistent: every resident warp draws chunks of bank positions until the generation runs dry
+    const uint64_t n = end - begin;
+    const unsigned resident = (unsigned)(W.n_sm * W.blocks_per_sm[FT]);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + BLOCK - 1) / BLOCK, resident));
+    const uint64_t warps = (uint64_t)grid * WARPS;
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
+    WalkRes R;
+    R.stack = stack; R.chunk_tab = chunk_tab; R.donq = donq; R.gstate = gstate; R.sm_limit = W.reserve_sms > 0 ? std::max(1, W.n_sm - W.reserve_sms) : 0; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[FT]; R.priv_tallies = FT ? W.priv_tallies : 0;
+    const size_t smem = W.smem_bytes[FT];
+    // per flavour four instances: problems where nothing is born in flight (k-eigenvalue without splitting) carry no
+    // secondary stack; the event-sorted form is a run-time option
+#define MCB_WALK(S_, E_) k_walk<FT, S_, E_><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R, src)
+    if (W.exchange) { if (W.shared) MCB_WALK(true, true); else MCB_WALK(false, true); }
+    else { if (W.shared) MCB_WALK(true, false); else MCB_WALK(false, false); }
+#undef MCB_WALK
+}
+
+#if MCB_WALK_FLAVOUR == 0
+int walk_plan_part1(WalkPlan& W);
+int walk_launch_info_part1(const WalkPlan& W, int out[4]);
+void walk_part1(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
+                const TallyAcc& T, SiteReq* reqs, uint64_t site_cap, double k_eff, const WalkPlan& W, StackRec* stack,
+                unsigned short* chunk_tab, DonationQueue* donq, double2* gstate, const WalkSource& src);
+
 int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_sm, WalkPlan* out)
 {
     WalkPlan& W = *out;
@@ -735,55 +828,16 @@ int walk_plan(bool shared, bool exchange, int det_nn, int64_t n_tallies, int n_s
     W.n_sm = n_sm;
     W.reserve_sms = 0;
     W.exchange = exchange;
-    cudaError_t e;
-    for (int tally = 0; tally < 2; tally++) {
-        int blocks = 0, n_pairs = 0;
-        size_t smem = 0;
-#define MCB_PLAN(T_, S_, E_) plan_instance<T_, S_, E_>(W.det_nn, W.priv_tallies, n_sm, blocks, smem, n_pairs)
-        if (exchange) {
-            if (tally) e = shared ? MCB_PLAN(true, true, true) : MCB_PLAN(true, false, true);
-            else e = shared ? MCB_PLAN(false, true, true) : MCB_PLAN(false, false, true);
-        } else {
-            if (tally) e = shared ? MCB_PLAN(true, true, false) : MCB_PLAN(true, false, false);
-            else e = shared ? MCB_PLAN(false, true, false) : MCB_PLAN(false, false, false);
-        }
-#undef MCB_PLAN
-        if (e != cudaSuccess) return (int)e;
-        if (blocks < 1) return (int)cudaErrorInvalidConfiguration;
-        W.blocks_per_sm[tally] = std::min(blocks, MCB_WALK_MINB);
-        W.smem_bytes[tally] = smem;
-        W.n_pairs[tally] = n_pairs;
-    }
-    W.max_grid = n_sm * std::max(W.blocks_per_sm[0], W.blocks_per_sm[1]);
-    W.n_contexts = (int64_t)W.max_grid * WALK_SLOTS;
     W.shared = shared;
-    W.stack_records = shared ? (size_t)W.max_grid * (WALK_SLOTS + WALK_EXTRA) * STACK_CHUNK : 0;
-    W.chunk_tab_entries = shared ? (size_t)W.n_contexts * STACK_MAXCH : 0;
-    W.stack_max = STACK_MAXCH * STACK_CHUNK;
-#ifdef MCB_WALK_GLOBAL_STATE
-    W.gstate_pairs = (size_t)W.max_grid * std::max(W.n_pairs[0], W.n_pairs[1]) * WALK_SLOTS;
-#else
-    W.gstate_pairs = 0;
-#endif
-    return 0;
+    W.max_grid = 0; W.n_contexts = 0; W.stack_records = 0; W.chunk_tab_entries = 0; W.gstate_pairs = 0;
+    int rc = walk_plan_part0(W);
+    if (rc == 0) rc = walk_plan_part1(W);
+    return rc;
 }
 
 int walk_launch_info(const WalkPlan& W, bool tally, int out[4])
 {
-    cudaFuncAttributes a;
-    cudaError_t e;
-#define MCB_ATTR(T_, S_, E_) cudaFuncGetAttributes(&a, k_walk<T_, S_, E_>)
-    if (W.exchange) {
-        if (tally) e = W.shared ? MCB_ATTR(true, true, true) : MCB_ATTR(true, false, true);
-        else e = W.shared ? MCB_ATTR(false, true, true) : MCB_ATTR(false, false, true);
-    } else {
-        if (tally) e = W.shared ? MCB_ATTR(true, true, false) : MCB_ATTR(true, false, false);
-        else e = W.shared ? MCB_ATTR(false, true, false) : MCB_ATTR(false, false, false);
-    }
-#undef MCB_ATTR
-    if (e != cudaSuccess) return (int)e;
-    out[0] = a.numRegs; out[1] = W.n_sm * W.blocks_per_sm[tally ? 1 : 0]; out[2] = BLOCK; out[3] = (int)W.smem_bytes[tally ? 1 : 0];
-    return 0;
+    return tally ? walk_launch_info_part1(W, out) : walk_launch_info_part0(W, out);
 }
 
 void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, uint64_t end, Counters* C, const HistoryAcc& H,
@@ -791,28 +845,10 @@ void walk(cudaStream_t st, const DevProblem& P, const Bank& B, uint64_t begin, u
           const WalkSource& src)
 {
     if (end <= begin) return;
-    // persistent: every resident warp draws chunks of bank positions until the generation runs dry
-    const uint64_t n = end - begin;
-    const int ti = T.on ? 1 : 0;
-    const unsigned resident = (unsigned)(W.n_sm * W.blocks_per_sm[ti]);
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + BLOCK - 1) / BLOCK, resident));
-    const uint64_t warps = (uint64_t)grid * WARPS;
-    const uint32_t chunk = (uint32_t)std::max<uint64_t>(32, std::min<uint64_t>(128, n / (warps * 8)));
-    WalkRes R;
-    R.stack = stack; R.chunk_tab = chunk_tab; R.donq = donq; R.gstate = gstate; R.sm_limit = W.reserve_sms > 0 ? std::max(1, W.n_sm - W.reserve_sms) : 0; R.det_nn = W.det_nn; R.n_pairs = W.n_pairs[ti]; R.priv_tallies = ti ? W.priv_tallies : 0;
-    const size_t smem = W.smem_bytes[ti];
-    // four instances: cycles that score nothing carry no estimator code, problems where nothing is born in flight
-    // (k-eigenvalue without splitting) no secondary stack
-#define MCB_WALK(T_, S_, E_) k_walk<T_, S_, E_><<<grid, BLOCK, smem, st>>>(P, B, (unsigned long long)begin, (unsigned long long)end, chunk, C, H, T, reqs, site_cap, k_eff, R, src)
-    if (W.exchange) {
-        if (T.on) { if (W.shared) MCB_WALK(true, true, true); else MCB_WALK(true, false, true); }
-        else { if (W.shared) MCB_WALK(false, true, true); else MCB_WALK(false, false, true); }
-    } else {
-        if (T.on) { if (W.shared) MCB_WALK(true, true, false); else MCB_WALK(true, false, false); }
-        else { if (W.shared) MCB_WALK(false, true, false); else MCB_WALK(false, false, false); }
-    }
-#undef MCB_WALK
+    if (T.on) walk_part1(st, P, B, begin, end, C, H, T, reqs, site_cap, k_eff, W, stack, chunk_tab, donq, gstate, src);
+    else walk_part0(st, P, B, begin, end, C, H, T, reqs, site_cap, k_eff, W, stack, chunk_tab, donq, gstate, src);
     g_launches += 1;
 }
+#endif
 
 }  // namespace mcbk
