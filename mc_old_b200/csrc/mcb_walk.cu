@@ -368,6 +368,9 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
     unsigned long long chunk_begin = 0;
     uint64_t chunk_seed = 0;
     for (;;) {
+#if defined(MCB_WALK_SYNC) && MCB_WALK_SYNC >= 2
+        if (!EXCH) __syncthreads();
+#endif
         // ---- lanes without a history draw the next source particles
         unsigned idle = __ballot_sync(FULL, !have);
         while (idle && !exhausted) {

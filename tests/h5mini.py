@@ -1,5 +1,5 @@
 """Minimal reader for classic-layout HDF5 files (superblock v0/v1, v1 object headers, symbol-table groups, contiguous or
-compact datasets of f64 / integers / strings, variable-length strings in global heaps, v1-v3 attributes).
+compact datasets of f64 / integers / strings / complex numbers ({r, i} compounds), variable-length strings in global heaps, v1-v3 attributes).
 
 Test infrastructure: there is no h5py / libhdf5 in this image, so the output writer of the host program
 (mc_old_b200/host/h5lite.cpp) is checked by (i) reading the reference's own committed output.h5 files — written by the
@@ -174,6 +174,30 @@ class File:
             if size != 16:
                 raise H5Error("vlen element size %d" % size)
             return ("vstr", 16)
+        if cls == 6:  # compound: only {r: f64, i: f64} (how EigenHDF5 / h5py store complex numbers)
+            n_members = bits & 0xFFFF
+            p, members = 8, []
+            for _ in range(n_members):
+                e = data.index(b"\0", p)
+                name = data[p:e].decode()
+                p = (p + ((e + 1 - p + 7) & ~7)) if ver < 3 else e + 1
+                if ver < 3:
+                    off = struct.unpack_from("<I", data, p)[0]
+                    p += 4
+                    if ver == 1:
+                        p += 28  # dimensionality, reserved, permutation, reserved, 4 dimension sizes
+                else:
+                    nb = max(1, (size.bit_length() + 7) // 8)
+                    off = int.from_bytes(data[p:p + nb], "little")
+                    p += nb
+                mt = File._datatype(data[p:])
+                if mt != ("f64", 8):
+                    raise H5Error("compound member %s is not f64" % name)
+                p += 8 + 12  # an IEEE float datatype message: 8 header bytes + 12 property bytes
+                members.append((name, off))
+            if size != 16 or members != [("r", 0), ("i", 8)]:
+                raise H5Error("compound type %r of %d bytes is not a complex number" % (members, size))
+            return ("c128", 16)
         raise H5Error("datatype class %d" % cls)
 
     def _decode(self, dt, shape, raw):
@@ -181,6 +205,8 @@ class File:
         count = int(np.prod(shape)) if shape else 1
         if kind == "f64":
             a = np.frombuffer(raw, dtype="<f8", count=count)
+        elif kind == "c128":
+            a = np.frombuffer(raw, dtype="<c16", count=count)
         elif kind in ("int", "uint"):
             a = np.frombuffer(raw, dtype="<%s%d" % ("i" if kind == "int" else "u", size), count=count)
         elif kind == "str":
