@@ -62,6 +62,17 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
 int mcbh_trm_assemble(mcbh_deck* d, const double* tally_mean, double* TRM, double* inverse_speed, double* C_initial,
                       double* psi_initial);
 
+/* The reference's TRMM.exe (TRMM.cpp:10-81), a post-processing step on the host: reads "TRM" and "inverse_speed" from
+ * the run's output file `output_h5`, solves the eigen-problems of TRM and of the adjoint matrix and writes alpha,
+ * alpha_adj (N x 1), phi_mode, phi_mode_adj (N x N, column = mode) as complex {r, i} datasets to output_TRMM.h5 in the
+ * same directory.  Eigenvalues come sorted by descending real part, eigenvectors with unit norm (Eigen::EigenSolver's
+ * order and phase are artefacts of its iteration; consumers sort).  Returns 0, or -1 with mcbh_last_error(). */
+int mcbh_trmm_postprocess(const char* output_h5);
+
+/* the solver behind it: A n x n row-major; w_pairs 2n doubles (re, im); v_pairs 2 n n doubles, row-major, column j the
+ * eigenvector of eigenvalue j.  Returns 0, or -1 with mcbh_last_error(). */
+int mcbh_eigen_general(int32_t n, const double* A, double* w_pairs, double* v_pairs);
+
 /* self-check of the device lookup structure (union grid + map + hash, built by the same code mcb_create uses):
  * idx_out[i*Nn + k] = row index the device lookup uses for nuclide k of `material` at E[i]; must equal the
  * reference's binary_search(E, n_E) = #{n_E < E} - 1 (Algorithm.cpp:46-64).  Returns Nn; stats = nU, n_hash,

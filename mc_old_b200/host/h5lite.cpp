@@ -25,6 +25,16 @@ Dataset& Group::dataset_f64(const std::string& n, const std::vector<uint64_t>& d
     return d;
 }
 Dataset& Group::dataset_f64(const std::string& n, double scalar) { return dataset_f64(n, {}, &scalar); }
+Dataset& Group::dataset_c128(const std::string& n, const std::vector<uint64_t>& dims, const double* re_im_pairs)
+{
+    datasets.emplace_back();
+    Dataset& d = datasets.back();
+    d.name = n; d.type = Type::C128; d.dims = dims;
+    uint64_t count = 2;
+    for (uint64_t v : dims) count *= v;
+    d.f64.assign(re_im_pairs, re_im_pairs + count);
+    return d;
+}
 Dataset& Group::dataset_u64(const std::string& n, uint64_t scalar)
 {
     datasets.emplace_back();
@@ -98,6 +108,20 @@ struct Writer {
             p32(8);
             p16(0); p16(64);
             break;
+        case Type::C128: {  // class 6 (compound) version 1, two members: "r" at 0, "i" at 8, both IEEE f64 (TRMM.cpp:75-78
+                            // through EigenHDF5::save of complex matrices); the layout libhdf5 1.10 gives it
+            m = {0x16, 0x02, 0x00, 0x00};
+            p32(16);
+            const std::vector<uint8_t> f64 = datatype(Type::F64);
+            for (int k = 0; k < 2; k++) {
+                m.push_back(k == 0 ? 'r' : 'i');
+                for (int i = 0; i < 7; i++) m.push_back(0);   // name, null-terminated, padded to 8 bytes
+                p32(8 * k);                                    // byte offset of the member
+                for (int i = 0; i < 28; i++) m.push_back(0);  // dimensionality 0, reserved, permutation, reserved, 4 sizes
+                m.insert(m.end(), f64.begin(), f64.end());
+            }
+            break;
+        }
         case Type::VLEN_STRING:  // class 9 version 1; type = string (1), null-terminated, ASCII; base = 1-byte C string
             m = {0x19, 0x01, 0x00, 0x00};
             p32(16);
@@ -169,6 +193,7 @@ struct Writer {
         for (uint64_t v : d.dims) count *= v;
         std::vector<uint8_t> raw;
         if (d.type == Type::F64) { raw.resize(count * 8); if (count) memcpy(raw.data(), d.f64.data(), count * 8); }
+        else if (d.type == Type::C128) { raw.resize(count * 16); if (count) memcpy(raw.data(), d.f64.data(), count * 16); }
         else if (d.type == Type::U64) { raw.resize(count * 8); if (count) memcpy(raw.data(), d.u64.data(), count * 8); }
         else raw = vlen_ref(d.str);
         d.data_addr = raw.empty() ? UNDEF : img.alloc(raw.size());
@@ -320,6 +345,141 @@ bool File::write(const std::string& path, std::string& error)
     const bool ok = n == w.img.b.size() && fclose(fp) == 0;
     if (!ok) error = "short write to " + path;
     return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reader (see h5lite.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Reader {
+    std::vector<uint8_t> b;
+    std::string err;
+
+    bool fail(const std::string& m) { if (err.empty()) err = m; return false; }
+    bool in(uint64_t at, uint64_t n) const { return at <= b.size() && n <= b.size() - at; }
+    uint64_t u(uint64_t at, int n)
+    {
+        if (!in(at, (uint64_t)n)) { fail("read past the end of the file"); return 0; }
+        uint64_t v = 0;
+        for (int i = 0; i < n; i++) v |= (uint64_t)b[at + i] << (8 * i);
+        return v;
+    }
+    bool magic(uint64_t at, const char* m) { return in(at, 4) && !memcmp(b.data() + at, m, 4); }
+
+    struct Msg { uint16_t type; uint64_t at, size; };
+    // the messages of a version-1 object header, continuation blocks included
+    bool messages(uint64_t addr, std::vector<Msg>& out)
+    {
+        if (u(addr, 1) != 1) return fail("object header version " + std::to_string(u(addr, 1)) + " (only version 1 is read)");
+        const uint64_t n_msg = u(addr + 2, 2);
+        std::vector<std::pair<uint64_t, uint64_t>> blocks{{addr + 16, u(addr + 8, 4)}};
+        for (size_t k = 0; k < blocks.size() && err.empty(); k++) {
+            uint64_t p = blocks[k].first;
+            const uint64_t end = p + blocks[k].second;
+            if (!in(p, blocks[k].second)) return fail("object header block outside the file");
+            while (p + 8 <= end && out.size() < n_msg) {
+                const Msg m{(uint16_t)u(p, 2), p + 8, u(p + 2, 2)};
+                if (m.at + m.size > end) return fail("object header message runs past its block");
+                if (m.type == 0x0010) blocks.push_back({u(m.at, 8), u(m.at + 8, 8)});
+                out.push_back(m);
+                p += 8 + m.size;
+            }
+        }
+        return err.empty();
+    }
+    // object header address of `name` in the group whose B-tree / local heap are given; 0 if absent
+    uint64_t lookup(uint64_t btree, uint64_t heap, const std::string& name, int depth = 0)
+    {
+        if (depth > 16 || !magic(btree, "TREE") || u(btree + 4, 1) != 0) { fail("bad group B-tree node"); return 0; }
+        if (!magic(heap, "HEAP")) { fail("bad local heap"); return 0; }
+        const uint64_t level = u(btree + 5, 1), used = u(btree + 6, 2);
+        const uint64_t heap_size = u(heap + 8, 8), heap_data = u(heap + 24, 8);
+        for (uint64_t i = 0; i < used && err.empty(); i++) {
+            const uint64_t child = u(btree + 24 + 8 + 16 * i, 8);
+            if (level > 0) { const uint64_t h = lookup(child, heap, name, depth + 1); if (h) return h; continue; }
+            if (!magic(child, "SNOD")) { fail("bad symbol table node"); return 0; }
+            const uint64_t n_sym = u(child + 6, 2);
+            for (uint64_t s = 0; s < n_sym; s++) {
+                const uint64_t name_off = u(child + 8 + 40 * s, 8), header = u(child + 8 + 40 * s + 8, 8);
+                if (name_off >= heap_size || !in(heap_data + name_off, 1)) { fail("symbol name outside the heap"); return 0; }
+                const char* c = reinterpret_cast<const char*>(b.data() + heap_data + name_off);
+                const size_t max_len = (size_t)std::min<uint64_t>(heap_size - name_off, b.size() - (heap_data + name_off));
+                if (strnlen(c, max_len) == name.size() && !memcmp(c, name.data(), name.size())) return header;
+            }
+        }
+        return 0;
+    }
+};
+
+}  // namespace
+
+bool read_root_f64(const std::string& path, const std::string& name, std::vector<uint64_t>& dims, std::vector<double>& data,
+                   std::string& error)
+{
+    Reader r;
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) { error = "cannot open " + path; return false; }
+    uint8_t buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) r.b.insert(r.b.end(), buf, buf + n);
+    fclose(fp);
+    auto bad = [&](const std::string& m) { error = path + ": " + (r.err.empty() ? m : r.err); return false; };
+    static const uint8_t SIG[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (r.b.size() < 96 || memcmp(r.b.data(), SIG, 8)) return bad("not an HDF5 file");
+    const uint64_t ver = r.b[8];
+    if (ver > 1) return bad("superblock version " + std::to_string(ver) + " (only the classic versions 0 and 1 are read)");
+    if (r.b[13] != 8 || r.b[14] != 8) return bad("offsets / lengths are not 8 bytes");
+    const uint64_t root_entry = (ver == 0 ? 24 : 28) + 32;  // the root group's symbol table entry
+    const uint64_t root_header = r.u(root_entry + 8, 8);
+    uint64_t btree = 0, heap = 0;
+    if (r.u(root_entry + 16, 4) == 1) { btree = r.u(root_entry + 24, 8); heap = r.u(root_entry + 32, 8); }
+    else {
+        std::vector<Reader::Msg> msgs;
+        if (!r.messages(root_header, msgs)) return bad("");
+        for (const auto& m : msgs) if (m.type == 0x0011) { btree = r.u(m.at, 8); heap = r.u(m.at + 8, 8); }
+        if (!btree) return bad("the root group has no symbol table");
+    }
+    const uint64_t header = r.lookup(btree, heap, name);
+    if (!r.err.empty()) return bad("");
+    if (!header) return bad("no dataset \"" + name + "\" in the root group");
+    std::vector<Reader::Msg> msgs;
+    if (!r.messages(header, msgs)) return bad("");
+    bool have_space = false, have_type = false, have_layout = false;
+    uint64_t addr = 0, nbytes = 0;
+    dims.clear();
+    for (const auto& m : msgs) {
+        if (m.type == 0x0001) {  // dataspace, version 1 or 2
+            const uint64_t v = r.u(m.at, 1), rank = r.u(m.at + 1, 1);
+            if (v != 1 && v != 2) return bad("dataspace version " + std::to_string(v));
+            if (v == 2 && r.u(m.at + 3, 1) == 2) return bad("dataset \"" + name + "\" has a null dataspace");
+            const uint64_t p = m.at + (v == 1 ? 8 : 4);
+            for (uint64_t i = 0; i < rank; i++) dims.push_back(r.u(p + 8 * i, 8));
+            have_space = true;
+        } else if (m.type == 0x0003) {  // datatype: little-endian IEEE f64 and nothing else
+            const uint64_t cls = r.u(m.at, 1) & 0x0f, bits0 = r.u(m.at + 1, 1), size = r.u(m.at + 4, 4);
+            if (cls != 1 || (bits0 & 1) || size != 8 || r.u(m.at + 10, 2) != 64 || r.u(m.at + 12, 1) != 52 || r.u(m.at + 13, 1) != 11 ||
+                r.u(m.at + 15, 1) != 52 || r.u(m.at + 16, 4) != 1023)
+                return bad("dataset \"" + name + "\" is not little-endian IEEE f64");
+            have_type = true;
+        } else if (m.type == 0x0008) {  // data layout version 3: compact (0) or contiguous (1)
+            if (r.u(m.at, 1) != 3) return bad("data layout version " + std::to_string(r.u(m.at, 1)));
+            const uint64_t cls = r.u(m.at + 1, 1);
+            if (cls == 0) { nbytes = r.u(m.at + 2, 2); addr = m.at + 4; }
+            else if (cls == 1) { addr = r.u(m.at + 2, 8); nbytes = r.u(m.at + 10, 8); }
+            else return bad("dataset \"" + name + "\" is chunked (not read)");
+            have_layout = true;
+        } else if (m.type == 0x000B) return bad("dataset \"" + name + "\" is filtered (not read)");
+    }
+    if (!r.err.empty()) return bad("");
+    if (!have_space || !have_type || !have_layout) return bad("dataset \"" + name + "\" lacks a dataspace, datatype or layout message");
+    uint64_t count = 1;
+    for (uint64_t d : dims) { if (d && count > (1ull << 40) / d) return bad("dataset too large"); count *= d; }
+    if (nbytes != count * 8) return bad("dataset \"" + name + "\": " + std::to_string(nbytes) + " bytes stored for " + std::to_string(count) + " elements");
+    if (count && (addr == UNDEF || !r.in(addr, nbytes))) return bad("dataset \"" + name + "\" has no storage in the file");
+    data.resize(count);
+    if (count) memcpy(data.data(), r.b.data() + addr, nbytes);
+    return true;
 }
 
 }  // namespace h5lite

@@ -5,8 +5,8 @@
 // host program carries its own writer.  It emits the classic, most widely readable layout —
 // the one the reference's committed output files have: superblock v0, v1 object
 // headers, symbol-table groups (B-tree v1 "TREE" + local heap "HEAP" + "SNOD" nodes),
-// contiguous little-endian datasets (IEEE f64, u64), variable-length strings in one global
-// heap collection ("GCOL"), v1 attribute messages.
+// contiguous little-endian datasets (IEEE f64, u64, {r, i} compounds of f64), variable-length
+// strings in one global heap collection ("GCOL"), v1 attribute messages.
 //
 // Usage: build the tree in memory, then write():
 //   h5lite::File f;  auto& g = f.root.group("summary");  g.dataset_u64("Ncycle", 200);
@@ -21,7 +21,7 @@
 
 namespace h5lite {
 
-enum class Type { F64, U64, VLEN_STRING };
+enum class Type { F64, U64, VLEN_STRING, C128 };  // C128: complex numbers as the compound {r: f64, i: f64} (EigenHDF5 / h5py)
 
 struct Attribute {
     std::string name;
@@ -32,7 +32,7 @@ struct Dataset {
     std::string name;
     Type type = Type::F64;
     std::vector<uint64_t> dims;        // empty = scalar
-    std::vector<double> f64;
+    std::vector<double> f64;           // C128: (re, im) pairs
     std::vector<uint64_t> u64;
     std::string str;                   // VLEN_STRING scalar
     std::vector<Attribute> attrs;
@@ -50,6 +50,7 @@ struct Group {
     Group& group(const std::string& n);
     Dataset& dataset_f64(const std::string& n, const std::vector<uint64_t>& dims, const double* data);
     Dataset& dataset_f64(const std::string& n, double scalar);
+    Dataset& dataset_c128(const std::string& n, const std::vector<uint64_t>& dims, const double* re_im_pairs);
     Dataset& dataset_u64(const std::string& n, uint64_t scalar);
     Dataset& dataset_string(const std::string& n, const std::string& v);
     void attr_string(const std::string& n, const std::string& v) { attrs.push_back({n, v}); }
@@ -61,6 +62,12 @@ struct File {
     Group root;
     bool write(const std::string& path, std::string& error);
 };
+
+// Reader for what the TRMM post-processor needs (reference TRMM.cpp:20-24,48): one f64 dataset of the ROOT group of a
+// classic-layout file (superblock v0/v1, v1 object headers, symbol-table groups, contiguous or compact layout) — the
+// files h5lite writes and the ones the reference's libhdf5 wrote.  Anything else is an error, not a guess.
+bool read_root_f64(const std::string& path, const std::string& name, std::vector<uint64_t>& dims, std::vector<double>& data,
+                   std::string& error);
 
 }  // namespace h5lite
 #endif

@@ -5,6 +5,7 @@
 #include "mcb200_host.h"
 #include "mcb_tables.h"
 #include "h5lite.h"
+#include "trmm_eigen.h"
 
 struct mcbh_deck { mcb::Deck deck; };
 
@@ -208,6 +209,21 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
         f.root.dataset_f64("psi_initial", {(uint64_t)G}, psi.data());
     }
     return f.write(path, g_error) ? 0 : -1;
+}
+
+int mcbh_trmm_postprocess(const char* output_h5)
+{
+    return mcbhost::trmm_postprocess(output_h5 ? output_h5 : "", g_error) ? 0 : -1;
+}
+
+int mcbh_eigen_general(int32_t n, const double* A, double* w_pairs, double* v_pairs)
+{
+    std::vector<std::complex<double>> w, V;
+    if (!A || !w_pairs || !v_pairs) { g_error = "mcbh_eigen_general: null argument"; return -1; }
+    if (!mcbhost::eigen_general(n, A, w, V, g_error)) return -1;
+    for (size_t i = 0; i < w.size(); i++) { w_pairs[2 * i] = w[i].real(); w_pairs[2 * i + 1] = w[i].imag(); }
+    for (size_t i = 0; i < V.size(); i++) { v_pairs[2 * i] = V[i].real(); v_pairs[2 * i + 1] = V[i].imag(); }
+    return 0;
 }
 
 int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, int32_t* idx_out, int64_t stats[4])
