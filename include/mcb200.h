@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 2
+#define MCB_ABI_VERSION 3
 #define MCB_MAX_MAT_NUCLIDES 8 /* nuclides per material handled in registers */
 #define MCB_XS_ROW 6           /* doubles per xs row: E, sigma_s, sigma_c, sigma_f, nu, beta */
 
@@ -100,7 +100,8 @@ enum { MCB_SCORE_FLUX = 0, MCB_SCORE_ABSORPTION, MCB_SCORE_SCATTER, MCB_SCORE_CA
        MCB_SCORE_NU_FISSION, MCB_SCORE_TOTAL, MCB_SCORE_INVERSE_VELOCITY,
        MCB_SCORE_SCATTER_OLD, MCB_SCORE_NU_FISSION_OLD, MCB_SCORE_NU_FISSION_PROMPT_OLD,
        MCB_SCORE_NU_FISSION_DELAYED_OLD, MCB_SCORE_NU_FISSION_DELAYED_DECAY_OLD };
-enum { MCB_FILTER_SURFACE = 0, MCB_FILTER_CELL, MCB_FILTER_ENERGY, MCB_FILTER_ENERGY_OLD, MCB_FILTER_TIME };
+enum { MCB_FILTER_SURFACE = 0, MCB_FILTER_CELL, MCB_FILTER_ENERGY, MCB_FILTER_ENERGY_OLD, MCB_FILTER_TIME,
+       MCB_FILTER_TDMC /* FilterTDMC (Estimator.cpp:247-263): bin = the census the particle has just reached, else none */ };
 enum { MCB_ATTACH_SURFACE = 0, MCB_ATTACH_CELL_TL = 1, MCB_ATTACH_CELL_C = 2 };
 /* simulate-then-score estimators of the TRMM tally set (Estimator.cpp:441-482): a copy of the particle scatters /
  * fissions before the generic scoring.  MCB_SIM_FISSION_DELAYED + g = delayed group g (0..5) */
@@ -167,6 +168,14 @@ typedef struct mcb_problem {
     /* particle comb (setup.cpp:57-67, population_control.cpp:55-84): after every random walk, a history whose particle
      * bank holds bank_max or more waiting particles is combed down to `teeth` particles of equal weight */
     int32_t comb_on, comb_bank_max, comb_teeth, reserved2;
+    /* time-dependent mode (<tdmc>, setup.cpp:133-169; time_dependent.cpp; general.cpp:187-195; fixed_source.cpp:25-40):
+     * particles stop at the census times tdmc_time[0..n_tdmc) (a particle carries the index of the next one) and die at
+     * the last; delayed neutrons are forced to decay once in every remaining interval.  tdmc_interval[j] is the length
+     * the reference uses for interval j — it is computed from the previous INTERVAL, not the previous time
+     * (setup.cpp:146), and is passed through as the reference computes it */
+    int32_t tdmc_on, n_tdmc;
+    const double* tdmc_time;
+    const double* tdmc_interval;
 } mcb_problem;
 
 /* ---- per-process device context ---- */

@@ -150,6 +150,7 @@ struct mcb_ctx {
     DevBuf<mcb_estimator> d_estimators;
     DevBuf<mcb_score> d_scores;
     DevBuf<mcb_filter> d_filters;
+    DevBuf<double> d_tdmc_time, d_tdmc_interval;
     // shard
     uint64_t shard_begin = 0, shard_count = 0;
     // banks
@@ -415,7 +416,8 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
             for (int e = 0; e < p->n_estimators; e++) {
                 const mcb_estimator& E = p->estimators[e];
                 if (E.attach != kind) continue;
-                const mcb_filter& F0 = p->filters[E.filter_begin];
+                // the geometry filter: the estimator's first, or its second behind a TDMC filter (setup.cpp:703-741)
+                const mcb_filter& F0 = p->filters[E.filter_begin + (p->filters[E.filter_begin].type == MCB_FILTER_TDMC ? 1 : 0)];
                 for (int i = 0; i < F0.grid_n; i++)
                     if ((int)p->filter_grid[F0.grid_begin + i] == id) { list.push_back(e); break; }
             }
@@ -439,6 +441,14 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     P.track_old = track_old ? 1 : 0;
     P.track_time = track_time ? 1 : 0; P.pad = 0;
     P.comb_teeth = p->comb_on ? p->comb_teeth : 0; P.comb_bank_max = p->comb_bank_max;
+    P.n_tdmc = 0; P.tdmc_time = nullptr; P.tdmc_interval = nullptr;
+    if (p->tdmc_on) {
+        if (p->ksearch) return ctx->fail(MCB_ERR_ARG, "ksearch and tdmc could not coexist");
+        if (p->n_tdmc < 1 || !p->tdmc_time || !p->tdmc_interval) return ctx->fail(MCB_ERR_ARG, "tdmc_on without census times");
+        CK(ctx->d_tdmc_time.upload(p->tdmc_time, p->n_tdmc));
+        CK(ctx->d_tdmc_interval.upload(p->tdmc_interval, p->n_tdmc));
+        P.n_tdmc = p->n_tdmc; P.tdmc_time = ctx->d_tdmc_time.p; P.tdmc_interval = ctx->d_tdmc_interval.p;
+    }
     if (p->comb_on && (p->comb_teeth < 1 || p->comb_teeth > 256 || p->comb_bank_max < 1)) return ctx->fail(MCB_ERR_ARG, "particle comb: bank_max >= 1 and 1 <= teeth <= 256");
     P.wr = p->wr; P.ws = p->ws; P.seed0 = ctx->seed; P.n_sample = p->n_sample;
     P.materials = ctx->d_materials.p; P.nuclides = ctx->d_nuclides.p; P.mat_nuclide = ctx->d_mat_nuclide.p; P.mat_density = ctx->d_mat_density.p;
@@ -453,6 +463,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     mcb_shard_range(p->n_sample, ctx->rank, ctx->world, &ctx->shard_begin, &ctx->shard_count);
     if (ctx->shard_count >= (1ull << 31)) return ctx->fail(MCB_ERR_ARG, "more than 2^31 histories per GPU per generation");
     ctx->split_stages = (cfg && (cfg->reserved & 2)) || (getenv("MCB_MODE") && !strcmp(getenv("MCB_MODE"), "split"));
+    if (ctx->split_stages && p->tdmc_on) return ctx->fail(MCB_ERR_ARG, "the time-dependent mode runs in the walk kernel only (not with the event-queue stages)");
     ctx->walk_mode = !ctx->split_stages;
     {
         cudaDeviceProp prop;
@@ -527,7 +538,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         // walk kernel: launch shape on this device, per-context secondary stacks and tally tables
         int det_nn = 1;
         for (int m = 0; m < p->n_materials; m++) det_nn = std::max(det_nn, tabs[m].n_nuc);
-        const int rc = mcbk::walk_plan(P.shared_histories != 0, getenv("MCB_WALK_EXCHANGE") && atoi(getenv("MCB_WALK_EXCHANGE")) != 0, det_nn, p->n_tallies, ctx->n_sm, &ctx->plan);
+        const int rc = mcbk::walk_plan(P.shared_histories != 0, getenv("MCB_WALK_EXCHANGE") && atoi(getenv("MCB_WALK_EXCHANGE")) != 0 && !p->tdmc_on, det_nn, p->n_tallies, ctx->n_sm, &ctx->plan);
         if (rc != 0) return ctx->fail(MCB_ERR_CUDA, "walk kernel does not fit this device: %s", cudaGetErrorString((cudaError_t)rc));
         const size_t n_ctx = (size_t)ctx->plan.n_contexts;
         if (ctx->plan.gstate_pairs) CK(ctx->d_gstate.alloc(ctx->plan.gstate_pairs));

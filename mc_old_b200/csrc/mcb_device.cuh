@@ -41,6 +41,9 @@ struct DevProblem {
     int32_t shared_histories;    // several particles of one history can be in flight (secondaries / splitting)
     int32_t track_old;           // some estimator reads Particle::energy_old (TRMM tally set): Bank::Eold is maintained
     int32_t track_time;          // some estimator has a time filter: Bank::told (Particle::time_old) is maintained
+    int32_t n_tdmc;              // census times of the time-dependent mode (general.cpp:187-195), 0 = off
+    const double* tdmc_time;     // n_tdmc
+    const double* tdmc_interval; // n_tdmc, as the reference computes them (setup.cpp:146)
     int32_t comb_teeth;          // particle comb (population_control.cpp:55-84): 0 = off
     int32_t comb_bank_max, pad;
     double wr, ws;

@@ -111,6 +111,7 @@ struct ScoreState {   // the particle as Score / Filter / the simulating estimat
     double w, E, E_old, speed, t, t_old;
     double u, v, wd;  // direction
     int cell, surface_old, material, uidx;
+    int tdmc;         // index of the next census time (time-dependent mode)
     MacroXS X;        // macroscopic xs of `material` at E
 };
 
@@ -192,6 +193,10 @@ __device__ __noinline__ static int estimator_score_pieces(const DevProblem& P, c
             c.idx = mcb_binary_search(F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, g, F.grid_n);
             if (c.idx < 0 || c.idx >= F.grid_n - 1) return n_touched;
             break;
+        case MCB_FILTER_TDMC:
+            if (s.t != g[s.tdmc]) return n_touched;
+            c.idx = s.tdmc;
+            break;
         default: {                                                                                           // time :199-246
             const int Nbin = F.grid_n - 1;
             c.loc1 = mcb_binary_search(s.t_old, g, F.grid_n);
@@ -251,6 +256,10 @@ __device__ __forceinline__ void estimator_score_plain(const DevProblem& P, const
             switch (F.type) {
             case MCB_FILTER_SURFACE: idx = mcb_binary_search((double)s.surface_old, P.filter_grid + F.grid_begin, F.grid_n) + 1; break;
             case MCB_FILTER_CELL: idx = mcb_binary_search((double)s.cell, P.filter_grid + F.grid_begin, F.grid_n) + 1; break;
+            case MCB_FILTER_TDMC:  // only a particle that sits exactly on its census time scores (Estimator.cpp:247-263)
+                if (s.t != P.filter_grid[F.grid_begin + s.tdmc]) return;
+                idx = s.tdmc;
+                break;
             default:
                 idx = filter_bin(P, F.grid_begin, F.grid_n, F.type == MCB_FILTER_ENERGY ? s.E : s.E_old, CC);
                 if (idx < 0 || idx >= F.grid_n - 1) return;
@@ -326,6 +335,7 @@ struct Particle {
     int row;        // tally accumulator row of the history: context (walk kernel) or shard-local history index (dense rows)
     int n_touched;  // entries of the history's tally table in use (walk kernel)
     int drow;       // dense tally row of a history that is shared between lanes, -1 while a history is followed by one lane
+    int tdmc;       // time-dependent mode: index of the next census time (Particle::tdmc, Particle.cpp:29,82)
 };
 // all estimators attached to surface / cell `id` score one event of particle p.  Cold and out of line, with every
 // input BY VALUE (no address of a register-resident particle escapes), so that the transport kernels' register
@@ -336,9 +346,10 @@ struct ScoreRet { uint64_t rng; int n_touched; };
 static __device__ __noinline__ ScoreRet score_event(const DevProblem& P, const TallyAcc& T, Counters* C, int kind, int id, double w, double E, double E_old,
                                              double speed, double t, double t_old, double du, double dv, double dw, int cell, int row,
                                              int n_touched, uint64_t rng, int material, int uidx, bool have_X, double Xt, double Xs, double Xc,
-                                             double Xf, double Xnf, int surface_old, double l)
+                                             double Xf, double Xnf, int surface_old, double l, int tdmc)
 {
     ScoreState s;
+    s.tdmc = tdmc;
     s.w = w; s.E = E; s.speed = speed; s.u = du; s.v = dv; s.wd = dw;
     s.E_old = E_old;
     s.t = t; s.t_old = t_old;
@@ -358,7 +369,7 @@ static __device__ __noinline__ ScoreRet score_event(const DevProblem& P, const T
     do {                                                                                                                                   \
         const ScoreRet sr_ = score_event(P, T, C, kind, id, (p).wgt, (p).E, P.track_old ? (p).Eold : (p).E, (p).speed, (p).t,              \
                                          P.track_time ? (p).told : (p).t, (p).u, (p).v, (p).w, (p).cell, (p).row, (p).n_touched, (p).rng, \
-                                         material, uidx, have_X, (X).t, (X).s, (X).c, (X).f, (X).nf, surface_old, l);                     \
+                                         material, uidx, have_X, (X).t, (X).s, (X).c, (X).f, (X).nf, surface_old, l, P.n_tdmc ? (p).tdmc : 0); \
         (p).rng = sr_.rng; (p).n_touched = sr_.n_touched;                                                                                  \
     } while (0)
 
@@ -382,14 +393,16 @@ __device__ __forceinline__ bool ev_lookup(const DevProblem& P, const Particle& p
 }
 
 // flight event: surface_intersect + collision_distance + move_particle (general.cpp:40-83,177-207).
-// Returns true when the flight ends on a surface (S_hit), false when it ends in a collision.
 // A history that is followed by one lane at a time keeps its EstimatorK scores and its site count on registers
 // (HistLocal) and stores them once when it ends; otherwise they are bumped in memory with reductions.
 struct HistLocal { double kC, kTL; int nsite; };
 
-template <bool TALLY>
-__device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
-                                          const TallyAcc& T, Counters* C, int& S_hit, HistLocal* L = nullptr)
+// Returns the event the flight ends in: 0 collision, 1 surface, 2 census (time-dependent mode, TD instances only: the
+// particle stops at its next census time, general.cpp:187-195, and Simulator::time_hit moves it on to the next interval
+// or, after the last census, kills it, time_dependent.cpp:51-55).
+template <bool TALLY, bool TD = false>
+__device__ __forceinline__ int ev_flight(const DevProblem& P, Particle& p, const MacroXS& X, int uidx, const HistoryAcc& H,
+                                         const TallyAcc& T, Counters* C, int& S_hit, HistLocal* L = nullptr)
 {
     const int m = P.cells[p.cell].material;
     double dsurf;
@@ -397,8 +410,12 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, cons
     double dcol;
     if (m >= 0) dcol = -mcb_log(mcb_urand(p.rng)) / X.t;   // exponential_sample (Algorithm.cpp:123-126)
     else dcol = MCB_MAX_FLOAT_LESS;                      // vacuum (general.cpp:44-46)
-    const bool to_cross = dcol > dsurf;
-    const double l = to_cross ? dsurf : dcol;
+    int event = dcol > dsurf ? 1 : 0;
+    double l = event ? dsurf : dcol;
+    if (TD && P.n_tdmc) {
+        const double dbound = (P.tdmc_time[p.tdmc] - p.t) * p.speed;
+        if (l > dbound) { l = dbound; event = 2; }
+    }
     // Particle::move (Particle.cpp:66-76)
     p.x += p.u * l; p.y += p.v * l; p.z += p.w * l;
     if (TALLY) p.told = p.t;
@@ -410,7 +427,11 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, cons
     if (TALLY && T.on && has_attached(P, MCB_ATTACH_CELL_TL, p.cell)) {
         MCB_SCORE_EVENT(MCB_ATTACH_CELL_TL, p.cell, p, m, uidx, true, X, -1, l);
     }
-    return to_cross;
+    if (TD && event == 2) {
+        p.tdmc++;
+        if (p.tdmc == P.n_tdmc) p.wgt = 0.0;  // Particle::kill
+    }
+    return event;
 }
 
 // collide event, first half: Simulator::collision up to the fission dispatch (general.cpp:121-150): collision
@@ -419,6 +440,7 @@ __device__ __forceinline__ bool ev_flight(const DevProblem& P, Particle& p, cons
 struct CollideCtx {
     int m, N_fission;
     unsigned n_sites, n_second;
+    unsigned n_forced;  // time-dependent mode, delayed fission: fission neutrons, each forced to decay once per remaining interval
     double rXt;  // refined reciprocal of SigmaT: it divides three times in a collision (mcb_div_shared)
 };
 template <bool TALLY, class DET>
@@ -426,7 +448,7 @@ __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p,
                                                const TallyAcc& T, Counters* C, double k_eff, CollideCtx& c)
 {
     c.m = P.cells[p.cell].material;
-    c.N_fission = -1; c.n_sites = 0; c.n_second = 0;
+    c.N_fission = -1; c.n_sites = 0; c.n_second = 0; c.n_forced = 0;
     if (c.m < 0) { p.wgt = 0.0; return false; }  // vacuum: kill (general.cpp:124-128)
     if (TALLY && T.on && has_attached(P, MCB_ATTACH_CELL_C, p.cell)) {
         MCB_SCORE_EVENT(MCB_ATTACH_CELL_C, p.cell, p, c.m, uidx, true, X, -1, 0.0);
@@ -450,6 +472,10 @@ __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p,
             c.n_sites = bank_nu;
         } else if (prompt) {
             c.n_second = bank_nu;
+        } else if (P.n_tdmc) {
+            // delayed, time-dependent mode (fixed_source.cpp:25-40): room for one neutron per remaining interval
+            c.n_forced = bank_nu;
+            c.n_second = bank_nu * (unsigned)(P.n_tdmc - p.tdmc);
         } else {
             // delayed, non-TDMC branch: draws are consumed, no neutron is banked (fixed_source.cpp:41-63)
             (void)mcb_urand(p.rng);
@@ -482,7 +508,43 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Parti
             else C->overflow_sites = 1;
         }
     }
-    if (c.n_second) {
+    if (c.n_forced) {
+        // Simulator::forced_decay (time_dependent.cpp:16-45) for the rest of the current interval, then for every later
+        // one; each neutron is drawn from its own stream, its roulette (fixed_source.cpp:31,36) included
+        const DevNuclide& N = P.nuclides[c.N_fission];
+        for (unsigned i = 0; i < c.n_forced; i++) {
+            for (int j = p.tdmc - 1; j < P.n_tdmc - 1; j++) {
+                const bool rest = j < p.tdmc;
+                const double initial = rest ? p.t : P.tdmc_time[j];
+                const double interval = rest ? P.tdmc_time[p.tdmc] - p.t : P.tdmc_interval[j + 1];
+                seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
+                Particle q = p;
+                q.rng = seed;
+                q.tdmc = rest ? p.tdmc : j + 1;
+                q.t = initial + mcb_urand(q.rng) * interval;
+                double prob[6], w = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    prob[k] = N.fraction[k] * N.lambda[k] * exp(-N.lambda[k] * (q.t - p.t));  // f_lambda = fraction * lambda
+                    w += prob[k];
+                }
+                const double xi = mcb_urand(q.rng) * w;  // std::accumulate adds in the same order
+                int cg = 0;
+                double sum = 0.0;
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < 6; k++) { sum += prob[k]; if (!found && sum > xi) { cg = k; found = true; } }
+                q.E = chid_sample(N, cg, q.rng);
+                isotropic_direction(q.rng, q.u, q.v, q.w);
+                q.speed = mcb_speed_of_energy(q.E); q.wgt = w * interval; q.Eold = q.E; q.told = q.t;
+                if (q.wgt < P.wr) {  // weight_roulette (population_control.cpp:9-15)
+                    if (mcb_urand(q.rng) < q.wgt / P.ws) q.wgt = P.ws;
+                    else continue;
+                }
+                sink.push(q);
+            }
+        }
+    } else if (c.n_second) {
         const DevNuclide& N = P.nuclides[c.N_fission];
         for (unsigned b = 0; b < c.n_second; b++) {
             seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;

@@ -316,7 +316,7 @@ k_collide(const DevProblem P, Bank B, const uint32_t* __restrict__ evq, int cur,
         uint32_t i = 0;
         Particle p;
         MacroXS X = {0, 0, 0, 0, 0};
-        CollideCtx c = {-1, -1, 0, 0, 0.0};
+        CollideCtx c = {-1, -1, 0, 0, 0, 0.0};
         int uidx = -1;
         bool in_material = false;
         if (valid) {

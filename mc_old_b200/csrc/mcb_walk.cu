@@ -142,7 +142,7 @@ struct StackSink {
         r[0] = make_double2(q.x, q.y); r[1] = make_double2(q.z, q.u); r[2] = make_double2(q.v, q.w);
         r[3] = make_double2(q.E, q.speed); r[4] = make_double2(q.wgt, q.t);
         r[5] = make_double2(q.Eold, __longlong_as_double((long long)q.rng));
-        r[6] = make_double2(pack2i(q.cell, q.hist), pack2i(q.drow, 0));
+        r[6] = make_double2(pack2i(q.cell, q.hist), pack2i(q.drow, q.tdmc));
         sp++;
     }
     __device__ __forceinline__ void pop(Particle& p)
@@ -151,7 +151,7 @@ struct StackSink {
         const double2* r = reinterpret_cast<const double2*>(rec(sp));
         const double2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g = r[6];
         p.x = a.x; p.y = a.y; p.z = b.x; p.u = b.y; p.v = c.x; p.w = c.y; p.E = d.x; p.speed = d.y; p.wgt = e.x; p.t = e.y;
-        p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x);
+        p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x); p.tdmc = unpack_hi(g.y);
         p.told = p.t;
     }
 };
@@ -170,7 +170,7 @@ __device__ __forceinline__ bool donation_push(DonationQueue* D, const Particle& 
     __stcg(r + 0, make_double2(q.x, q.y)); __stcg(r + 1, make_double2(q.z, q.u)); __stcg(r + 2, make_double2(q.v, q.w));
     __stcg(r + 3, make_double2(q.E, q.speed)); __stcg(r + 4, make_double2(q.wgt, q.t));
     __stcg(r + 5, make_double2(q.Eold, __longlong_as_double((long long)q.rng)));
-    __stcg(r + 6, make_double2(pack2i(q.cell, q.hist), pack2i(q.drow, 0)));
+    __stcg(r + 6, make_double2(pack2i(q.cell, q.hist), pack2i(q.drow, q.tdmc)));
     __threadfence();
     *seq = pos + 1ull;
     atomicAdd(&D->avail, 1);
@@ -188,7 +188,7 @@ __device__ __forceinline__ bool donation_pop(DonationQueue* D, Particle& p, Coun
     const double2* r = reinterpret_cast<const double2*>(D->recs + cell);
     const double2 a = __ldcg(r + 0), b = __ldcg(r + 1), c = __ldcg(r + 2), d = __ldcg(r + 3), e = __ldcg(r + 4), f = __ldcg(r + 5), g = __ldcg(r + 6);
     p.x = a.x; p.y = a.y; p.z = b.x; p.u = b.y; p.v = c.x; p.w = c.y; p.E = d.x; p.speed = d.y; p.wgt = e.x; p.t = e.y;
-    p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x); p.hist = unpack_hi(g.x); p.drow = unpack_lo(g.y);
+    p.Eold = f.x; p.rng = (uint64_t)__double_as_longlong(f.y); p.cell = unpack_lo(g.x); p.hist = unpack_hi(g.x); p.drow = unpack_lo(g.y); p.tdmc = unpack_hi(g.y);
     p.told = p.t;
     __threadfence();
     *seq = pos + (unsigned long long)D->cap_mask + 1ull;
@@ -416,7 +416,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
                 }
                 p.Eold = p.E;  // the reference leaves energy_old uninitialised at birth; defined as E here
                 p.told = p.t;
-                p.n_touched = 0; p.drow = -1;
+                p.n_touched = 0; p.drow = -1; p.tdmc = 0;
                 L.kC = 0.0; L.kTL = 0.0; L.nsite = 0;
                 sp = 0; nch = 1;
                 have = true;
@@ -438,14 +438,16 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             __syncwarp();
         }
         // ---- common part of every track: xs lookup and flight; the particle is parked in its slot
-        bool to_cross = false;
+        bool to_cross = false, census = false;  // census: the flight ended at a census time (time-dependent mode), no event follows
         MacroXS X = {0, 0, 0, 0, 0};
         int uidx = -1, S = -1;
         if (have) {
             p.row = ctx_base + my_slot;
             const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
             if (ev_lookup(P, p, X, uidx, D)) lookups++;
-            to_cross = ev_flight<TALLY>(P, p, X, uidx, H, T, C, S, &L);
+            const int event = ev_flight<TALLY, SHARED>(P, p, X, uidx, H, T, C, S, &L);
+            to_cross = event == 1;
+            census = event == 2;
             tracks++;
         }
         if (EXCH && have) {
@@ -465,7 +467,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         }
         // ---- event queues: append what this warp holds, take one batch of a kind back out
         int kind = 0;  // 1 collide, 2 cross
-        if (!EXCH) kind = have ? (to_cross ? 2 : 1) : 0;
+        if (!EXCH) kind = have ? (census ? 3 : to_cross ? 2 : 1) : 0;
         if (EXCH) lock_acquire(Q, lane);
         if (EXCH) {
             const unsigned mC = __ballot_sync(FULL, have && !to_cross), mX = __ballot_sync(FULL, have && to_cross);
@@ -531,7 +533,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         }
         have = kind != 0;
         // ---- the event itself, on a batch of one kind (mixed only when the queues run low)
-        CollideCtx c = {-1, -1, 0, 0, 0.0};
+        CollideCtx c = {-1, -1, 0, 0, 0, 0.0};
         unsigned n_copy = 0;
         bool alive = false, in_material = false, unit_ended = false;
         const SlotDetail D = {st + SP_DET * WALK_SLOTS + my_slot, R.det_nn};
@@ -559,9 +561,11 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             if (kind == 1) {
                 in_material = ev_collide_pre<TALLY>(P, p, X, uidx, D, T, C, k_eff, c);
                 if (in_material) collisions++;
-            } else {
+            } else if (kind == 2) {
                 alive = ev_cross_pre<TALLY>(P, p, S, T, C, n_copy);
                 crossings++;
+            } else {
+                alive = p.wgt > 0.0;  // census: on to the next interval, or dead after the last (no roulette, general.cpp:193)
             }
         }
         __syncwarp();
@@ -576,7 +580,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             if (lane == 31) base = atomicAdd(&C->site_cursor, (unsigned long long)total);
             site0 = __shfl_sync(FULL, base, 31) + (v - c.n_sites);
         }
-        if (!SHARED) { c.n_second = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
+        if (!SHARED) { c.n_second = 0; c.n_forced = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
         unsigned short* const tab = SHARED ? R.chunk_tab + (size_t)(ctx_base + my_slot) * STACK_MAXCH : nullptr;
         if (SHARED) {  // room for the particles about to be born: borrow chunks (lane by lane; rare)
             const int need = (sp + (int)(c.n_second + n_copy) + STACK_CHUNK - 1) / STACK_CHUNK;

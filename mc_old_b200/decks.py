@@ -220,6 +220,64 @@ def gcr(samples=400, active=5, passive=2, trmm=False):
 """
 
 
+def gcr_td(samples=2500, times="3e-8 15e-8 4e-6 100e-6", linear=None, comb=None, groups=50):
+    """examples/infinite_GCR_TD/input.xml: the same medium in time-dependent mode (<tdmc>): a 14.1 MeV pulse at t = 0,
+    the spectrum scored at the census times through the <tdmc/> filter.  linear = "a n b" uses time_linear instead;
+    comb = (bank_max, teeth) adds the particle comb (examples/infinite_GCR_TD_sub)."""
+    grid = f'time_linear="{linear}"' if linear else f'time="{times}"'
+    ctrl = "" if comb is None else f"""
+<population_control>
+    <particle_comb bank_max="{comb[0]}" teeth="{comb[1]}"/>
+</population_control>"""
+    return HEAD + f"""
+<simulation>
+    <description name="Infinite GCR" samples="{samples:g}"/>
+    <tdmc {grid}/>
+</simulation>{ctrl}
+<distributions>
+    <isotropic name="dir" datatype="point" />
+    <delta name="enrg" datatype="double" val="14.1e6"/>
+</distributions>
+<nuclides>
+    <nuclide name="U-235" ZAID="092235"/>
+    <nuclide name="U-238" ZAID="092238"/>
+    <nuclide name="O-16"  ZAID="008016"/>
+    <nuclide name="C"     ZAID="006000"/>
+</nuclides>
+<materials>
+    <material name="Fuel">
+        <nuclide name="U-235" density="0.0000402"/>
+        <nuclide name="U-238" density="0.0009061"/>
+        <nuclide name="O-16"  density="0.0018927"/>
+        <nuclide name="C"     density="0.0757080"/>
+    </material>
+</materials>
+<surfaces>
+    <plane_x name="px1" x="100.0"  bc="reflective"/>
+    <plane_x name="px2" x="-100.0" bc="reflective"/>
+</surfaces>
+<cells>
+    <cell name="infinity" material="Fuel">
+        <surface name="px1" sense="-1" />
+        <surface name="px2" sense="+1" />
+    </cell>
+</cells>
+<sources>
+    <point x="0.0" y="0.0" z="0.0" direction="dir" energy="enrg"/>
+</sources>
+<estimators>
+    <estimator name="spectrum" scores="flux">
+        <cell name="infinity"/>
+        <filter type="energy" grid_lethargy="1E-5 2E7 {groups}"/>
+        <tdmc/>
+    </estimator>
+    <estimator name="rates" type="C" scores="flux fission">
+        <cell name="infinity"/>
+    </estimator>
+</estimators>
+"""
+
+
 def shielding(samples=20000, split=False):
     """examples/shielding_vReduction/input.xml: water/B4C shield with a He-3 detector (6 nuclides, 10 cells).
     split=True raises the importance of the cells towards the detector so that splitting is exercised."""

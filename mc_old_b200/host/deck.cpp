@@ -231,10 +231,36 @@ bool Deck::load_string(const std::string& xml_text, const std::string& xs_dir, i
         p.n_cycle = active + p.n_passive;
         mode = "k-eigenvalue";
     }
+    // ---- TDMC (setup.cpp:133-169) ----
     if (tdmc) {
+        p.tdmc_on = 1;
+        tdmc_interval.push_back(0.0);
+        if (tdmc->attribute("time")) {
+            std::istringstream iss(tdmc->attribute("time").value());
+            for (double s; iss >> s;) {
+                tdmc_time.push_back(s);
+                tdmc_interval.push_back(s - tdmc_interval.back());  // previous interval, not previous time (setup.cpp:146)
+            }
+            tdmc_interval.erase(tdmc_interval.begin());
+        } else if (tdmc->attribute("time_linear")) {
+            double a = 0.0, b = 0.0, step = 0.0;
+            std::istringstream iss(tdmc->attribute("time_linear").value());
+            iss >> a >> step >> b;
+            step = (b - a) / step;
+            if (!(step > 0.0)) { error = "[INPUT ERROR] <tdmc time_linear=\"a n b\"> needs b > a and n > 0"; return false; }
+            tdmc_time.push_back(a);
+            tdmc_interval.push_back(a - tdmc_interval.back());
+            while (tdmc_time.back() < b) {
+                tdmc_time.push_back(tdmc_time.back() + step);
+                tdmc_interval.push_back(tdmc_time.back() - tdmc_interval.back());
+            }
+            tdmc_interval.erase(tdmc_interval.begin());
+            tdmc_time.pop_back();
+            tdmc_time.push_back(b);
+        }
         if (ksearch) { error = "ksearch and tdmc could not coexist"; return false; }
-        error = "unsupported: tdmc (time-dependent mode is out of scope; SURVEY.md §2)";
-        return false;
+        if (tdmc_time.empty()) { error = "[INPUT ERROR] <tdmc> needs a time grid (the reference reads past the end of an empty one)"; return false; }
+        mode = "time-dependent";
     }
 
     // ---- user distributions, resolved iteratively (setup.cpp:174-305) ----
@@ -417,6 +443,7 @@ bool Deck::load_string(const std::string& xml_text, const std::string& xs_dir, i
         if (e_type == "TL") kernel = MCB_KERNEL_TRACK;
         else if (e_type == "C") kernel = MCB_KERNEL_COLLISION;
         else { error = "[ERROR] Unsupported score type in estimator " + e_name; return false; }
+        if (p.tdmc_on) kernel = MCB_KERNEL_VELOCITY;  // every estimator of a time-dependent run scores w * v (setup.cpp:659-661)
         if (!e->attribute("scores")) { error = "[ERROR] There is no score in estimator " + e_name; return false; }
         E.score_begin = (int32_t)scores.size();
         std::istringstream iss(e->attribute("scores").value());
@@ -437,11 +464,19 @@ bool Deck::load_string(const std::string& xml_text, const std::string& xs_dir, i
             scores.push_back(S);
         }
         E.n_scores = (int32_t)scores.size() - E.score_begin;
-        if (e->child("tdmc")) { error = "unsupported: tdmc filter"; return false; }
 
-        // attach to geometries; their IDs form the first filter's grid (setup.cpp:709-741)
         E.filter_begin = (int32_t)filters.size();
         std::vector<double> grid;
+        // TDMC filter: first in the index order (setup.cpp:703-708)
+        if (e->child("tdmc")) {
+            mcb_filter F;
+            std::memset(&F, 0, sizeof(F));
+            F.type = MCB_FILTER_TDMC;
+            F.grid_begin = (int32_t)filter_grid.size(); F.grid_n = (int32_t)tdmc_time.size(); F.size = F.grid_n;
+            filter_grid.insert(filter_grid.end(), tdmc_time.begin(), tdmc_time.end());
+            filters.push_back(F);
+        }
+        // attach to geometries; their IDs form the next filter's grid (setup.cpp:709-741)
         for (const XmlNode* s : e->children("surface")) {
             const int id = find_name(surface_names, s->attribute("name").value());
             if (id < 0) { error = "[ERROR] Unknown surface label " + s->attribute("name").value() + " in estimator " + e_name; return false; }
@@ -650,6 +685,9 @@ const mcb_problem* Deck::view()
     p.filters = filters.data();
     p.filter_grid = filter_grid.data();
     p.entropy_grid = entropy_grid.data();
+    p.n_tdmc = (int32_t)tdmc_time.size();
+    p.tdmc_time = tdmc_time.data();
+    p.tdmc_interval = tdmc_interval.data();
     return &p;
 }
 

@@ -43,6 +43,7 @@ struct Deck {
     std::vector<mcb_filter> filters;
     std::vector<double> filter_grid;
     std::vector<double> entropy_grid;
+    std::vector<double> tdmc_time, tdmc_interval;
 
     mcb_problem p{};  // scalar fields are filled by load(); pointers by view()
 

@@ -164,8 +164,9 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
     h5lite::Group& roulette = summary.group("survival_roulette");
     roulette.dataset_f64("wr", p->wr);
     roulette.dataset_f64("ws", p->ws);
-    static const char* const f_name[] = {"surface", "cell", "energy", "energy_initial", "time"};  // Estimator.h:307-369
-    static const char* const f_unit[] = {"id#", "id#", "eV", "eV", "s"};
+    if (p->tdmc_on) summary.group("tdmc").dataset_f64("time", {(uint64_t)p->n_tdmc}, p->tdmc_time);  // report.cpp:40-46
+    static const char* const f_name[] = {"surface", "cell", "energy", "energy_initial", "time", "time"};  // Estimator.h:307-369
+    static const char* const f_unit[] = {"id#", "id#", "eV", "eV", "s", "s"};
     for (size_t e = 0; e < d->deck.estimators.size(); e++) {
         const mcb_estimator& E = d->deck.estimators[e];
         h5lite::Group& g = f.root.group(E.name);

@@ -13,7 +13,7 @@ Artefacts
   oracle/_ref/MC_ref           unmodified reference sources + h5stub (text output.h5)
   oracle/_ref/MC_ref_patched   same + oracle patches A/B/C so that the
                                slab_analytic / shielding decks run instead of segfaulting
-  oracle/_ref/libref_harness.so  reference objects (all but Main/Random/time_dependent)
+  oracle/_ref/libref_harness.so  reference objects (all but Main/Random)
                                + oracle/ref_harness.cpp: function-level access with injected xi
   oracle/_ref/xs_library/      the reference's cross-section text files (data, read at run time)
 
@@ -42,9 +42,8 @@ SRC = ["src/Algorithm.cpp", "src/Distribution.cpp", "src/Entropy.cpp", "src/Esti
        "src/Material.cpp", "src/Nuclide.cpp", "src/Particle.cpp", "src/Random.cpp", "src/Reaction.cpp",
        "src/Source.cpp", "src/XSec.cpp", "src/simulator/fixed_source.cpp", "src/simulator/general.cpp",
        "src/simulator/handler.cpp", "src/simulator/ksearch.cpp", "src/simulator/population_control.cpp",
-       "src/simulator/report.cpp", "src/simulator/setup.cpp", "Main.cpp"]
-# src/simulator/time_dependent.cpp is left out (TDMC is out of scope and it includes Eigen); h5stub/ref_stubs.cpp
-# provides the two members it defines.
+       "src/simulator/report.cpp", "src/simulator/setup.cpp", "src/simulator/time_dependent.cpp", "Main.cpp"]
+# src/simulator/time_dependent.cpp includes <Eigen/Dense> without using it: h5stub/Eigen/Dense is an empty shadow.
 
 
 def run(cmd):

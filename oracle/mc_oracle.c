@@ -48,6 +48,7 @@ typedef struct particle {
     int alive;
     double E, E_old, speed, w, t, t_old;
     int cell, cell_old, surface_old;
+    int tdmc; /* index of the next census time (Particle::tdmc, Particle.cpp:29,82) */
     uint64_t rng; /* MCO_RNG_HISTORY: this particle's stream */
 } particle;
 
@@ -594,6 +595,10 @@ static void filter_idx_l(const mco_ctx* c, const mcb_filter* F, const particle* 
         out->idx[0] = i; out->l[0] = l; out->n = 1;
         break;
     }
+    case MCB_FILTER_TDMC: /* FilterTDMC (Estimator.cpp:247-263): only a particle sitting exactly on its census time scores */
+        if (P->t != g[P->tdmc]) return;
+        out->idx[0] = P->tdmc; out->l[0] = l; out->n = 1;
+        break;
     default: { /* FilterTime (Estimator.cpp:199-246) */
         const int loc1 = mco_binary_search(P->t_old, g, F->grid_n);
         const int loc2 = mco_binary_search(P->t, g, F->grid_n);
@@ -705,6 +710,7 @@ static void score_attached(mco_ctx* c, int attach, int id, particle* P, double l
         const mcb_filter* F0;
         if (E->attach != attach) continue;
         F0 = &p->filters[E->filter_begin];
+        if (F0->type == MCB_FILTER_TDMC) F0++; /* the geometry filter follows the TDMC filter (setup.cpp:703-741) */
         for (i = 0; i < F0->grid_n; i++) {
             if ((int)p->filter_grid[F0->grid_begin + i] == id) { estimator_score(c, e, P, l); break; }
         }
@@ -846,6 +852,7 @@ static particle fission_neutron(mco_ctx* c, particle* P, int nuc, int b)
         const double E = watt_sample(N->watt_a, N->watt_b, N->watt_g, P->E, &r);
         isotropic_direction(&r, dir);
         Q = p_make(P->pos, dir, E, P->t, 1.0, P->cell);
+        Q.tdmc = P->tdmc;
         Q.rng = s;
         c->n_draws += 0;
         return Q;
@@ -853,8 +860,42 @@ static particle fission_neutron(mco_ctx* c, particle* P, int nuc, int b)
         rng_ref r = {c, P, 0};
         const double E = watt_sample(N->watt_a, N->watt_b, N->watt_g, P->E, &r);
         isotropic_direction(&r, dir);
-        return p_make(P->pos, dir, E, P->t, 1.0, P->cell);
+        {
+            particle Q = p_make(P->pos, dir, E, P->t, 1.0, P->cell);
+            Q.tdmc = P->tdmc;
+            return Q;
+        }
     }
+}
+static void weight_roulette(mco_ctx* c, particle* P);
+/* Simulator::forced_decay (time_dependent.cpp:16-45): a delayed neutron of the fission at P, forced to appear inside
+ * [initial, initial + interval) with the weight of the expected emission there.  Draws, in order: emission time, precursor
+ * group, ChiD, direction (2).  MCO_RNG_HISTORY: the neutron is child number `q` of this collision and everything about
+ * it, its roulette included, is drawn from its own stream. */
+static particle forced_decay(mco_ctx* c, particle* P, int nuc, double initial, double interval, int p_tdmc, int q)
+{
+    const mcb_nuclide* N = &c->p->nuclides[nuc];
+    uint64_t s = 0;
+    rng_ref r = {c, P, 0};
+    double prob[6], p_weight = 0.0, total = 0.0, sum = 0.0, p_time, xi, E, dir[3];
+    int k, cg = 0;
+    particle Q;
+    if (c->rng_mode == MCO_RNG_HISTORY) { s = mco_lcg_skip(P->rng, ((uint64_t)(q + 1)) << 40); r.c = 0; r.P = 0; r.raw = &s; }
+    p_time = initial + draw(&r) * interval;
+    for (k = 0; k < 6; k++) {
+        prob[k] = N->fraction[k] * N->lambda[k] * exp(-N->lambda[k] * (p_time - P->t)); /* f_lambda(k) = fraction * lambda */
+        p_weight += prob[k];
+    }
+    p_weight *= interval;
+    for (k = 0; k < 6; k++) total += prob[k]; /* std::accumulate */
+    xi = draw(&r) * total;
+    for (k = 0; k < 6; k++) { sum += prob[k]; if (sum > xi) { cg = k; break; } }
+    E = chid_sample(c->p, nuc, cg, &r);
+    isotropic_direction(&r, dir);
+    Q = p_make(P->pos, dir, E, p_time, p_weight, P->cell);
+    Q.tdmc = p_tdmc;
+    if (c->rng_mode == MCO_RNG_HISTORY) Q.rng = s;
+    return Q;
 }
 static void collision(mco_ctx* c, particle* P) /* general.cpp:121-163 */
 {
@@ -894,11 +935,27 @@ static void collision(mco_ctx* c, particle* P) /* general.cpp:121-163 */
                 push(&c->Pbank, &c->Pn, &c->Pcap, &Q);
             }
         } else {
+            if (p->tdmc_on) {
+                /* combined and forced decay (fixed_source.cpp:25-40): per fission neutron one delayed neutron in the rest of
+                 * the current interval and one in every later interval, each through the roulette on its own */
+                int q = 0, j;
+                for (i = 0; i < bank_nu; i++) {
+                    particle Q = forced_decay(c, P, N_fission, P->t, p->tdmc_time[P->tdmc] - P->t, P->tdmc, q++);
+                    weight_roulette(c, &Q);
+                    if (Q.alive) push(&c->Pbank, &c->Pn, &c->Pcap, &Q);
+                    for (j = P->tdmc; j < p->n_tdmc - 1; j++) {
+                        Q = forced_decay(c, P, N_fission, p->tdmc_time[j], p->tdmc_interval[j + 1], j + 1, q++);
+                        weight_roulette(c, &Q);
+                        if (Q.alive) push(&c->Pbank, &c->Pn, &c->Pcap, &Q);
+                    }
+                }
+            } else {
             /* delayed, non-TDMC branch (fixed_source.cpp:41-63): one draw for the precursor group, then per
              * neutron one draw for ChiD and one for the emission time; the loop over tdmc_time (:54-61) is empty
              * without a <tdmc> block, so NO particle is banked — delayed neutrons are dropped (reference bug 20) */
             (void)urand(c, P);
             for (i = 0; i < bank_nu; i++) { (void)urand(c, P); (void)urand(c, P); }
+            }
         }
     }
     /* implicit absorption (general.cpp:154-156) */
@@ -951,6 +1008,15 @@ static int random_walk(mco_ctx* c, particle* P) /* general.cpp:177-211 */
         c->child_counter = 0;
         if (m >= 0) dcol = -log(urand(c, P)) / macro_(p, m, X_T, P->E); /* general.cpp:40-48, Algorithm.cpp:123-126 */
         else dcol = 0.9 * MAX_float;
+        if (p->tdmc_on) { /* general.cpp:187-195; Simulator::time_hit (time_dependent.cpp:51-55); no roulette on this path */
+            const double dbound = (p->tdmc_time[P->tdmc] - P->t) * P->speed;
+            if ((dsurf < dcol ? dsurf : dcol) > dbound) {
+                move_particle(c, P, dbound);
+                P->tdmc++;
+                if (P->tdmc == p->n_tdmc) p_kill(P);
+                continue;
+            }
+        }
         if (dcol > dsurf) {
             move_particle(c, P, dsurf);
             if (S < 0) { p_kill(P); } /* cannot happen with Sigma_t > 0; the reference would dereference null */

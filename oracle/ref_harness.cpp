@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): function-level access to the compiled
 // reference (ilhamv/MC-old) for differential tests.  Linked by
 // oracle/build_ref.py against the reference's own objects (everything except
-// Main.cpp, src/Random.cpp and src/simulator/time_dependent.cpp) into
+// Main.cpp and src/Random.cpp) into
 // oracle/_ref/libref_harness.so.  Our code here only *calls* the reference.
 //
 // Urand() is re-provided here (instead of the reference's src/Random.cpp) so

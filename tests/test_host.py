@@ -114,8 +114,10 @@ def test_deck_error_messages():
         mcb.Deck(xml=decks.slab(samples=10).replace("<point ", "<disk_z ").replace("/>\n</sources>", "/>\n</sources>"))
     with pytest.raises(ValueError, match="Unknown nuclide"):
         mcb.Deck(xml=decks.slab(samples=10).replace('<nuclide name="nuc3" density="0.1"/>', '<nuclide name="nope" density="0.1"/>'))
-    with pytest.raises(ValueError, match="tdmc"):
-        mcb.Deck(xml=decks.slab(samples=10).replace("</simulation>", '<tdmc time="1.0 2.0"/></simulation>'))
+    with pytest.raises(ValueError, match="ksearch and tdmc could not coexist"):   # setup.cpp:166-169
+        mcb.Deck(xml=decks.gcr(samples=10).replace("</simulation>", '<tdmc time="1.0 2.0"/></simulation>'))
+    with pytest.raises(ValueError, match="needs a time grid"):
+        mcb.Deck(xml=decks.slab(samples=10).replace("</simulation>", '<tdmc/></simulation>'))
     with pytest.raises(ValueError, match="TRMM should be run in ksearch mode"):
         mcb.Deck(xml=decks.slab(samples=10) + '<trmm><cell name="slab 1"/><filter type="energy" grid="1 2"/></trmm>')
     assert mcb.Deck(xml=decks.gcr(samples=10, trmm=True), flags=mcb.IGNORE_TRMM).info["n_estimators"] == 0
@@ -128,15 +130,14 @@ def test_deck_error_messages():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree not present")
 @pytest.mark.parametrize("example", ["slab_analytic", "HEU_sphere_criticality", "shielding_vReduction", "UCube", "infinite_GCR_TRMM",
                                      "infinite_GCR_TRMM_100", "infinite_GCR_TRMM_critical", "infinite_GCR_TRMM_critical2",
-                                     "infinite_GCR_Ttmp", "HEU_sphere_leakage"])
+                                     "infinite_GCR_Ttmp", "HEU_sphere_leakage", "infinite_GCR_TD", "infinite_GCR_TD_sub"])
 def test_reference_example_decks_load_unchanged(example):
-    """the reference's own input.xml files parse as they are, TRMM tally sets and time filters included (the four
-    decks left are TDMC / particle-comb studies, out of scope, and sphere_detection, whose <disk_z> source the
-    reference itself rejects)"""
+    """the reference's own input.xml files parse as they are, TRMM tally sets, time filters, time-dependent mode and
+    particle comb included (the one deck left is sphere_detection, whose <disk_z> source the reference itself rejects)"""
     deck = mcb.Deck(io_dir="/root/reference/examples/" + example)
     i = deck.info
     assert i["n_sample"] > 0 and i["n_cells"] > 0 and i["n_sources"] > 0
-    assert deck.mode == ("k-eigenvalue" if i["ksearch"] else "fixed source")
+    assert deck.mode == ("k-eigenvalue" if i["ksearch"] else "time-dependent" if "_TD" in example else "fixed source")
 
 
 def test_estimator_layout_matches_reference_order():
