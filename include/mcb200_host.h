@@ -62,6 +62,10 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
 int mcbh_trm_assemble(mcbh_deck* d, const double* tally_mean, double* TRM, double* inverse_speed, double* C_initial,
                       double* psi_initial);
 
+/* census times of a time-dependent deck (<tdmc>, setup.cpp:133-169) and the interval lengths as the reference computes
+ * them; returns their number (0: not a time-dependent deck).  Either output may be NULL. */
+int mcbh_tdmc(const mcbh_deck* d, double* time_out, double* interval_out);
+
 /* The reference's TRMM.exe (TRMM.cpp:10-81), a post-processing step on the host: reads "TRM" and "inverse_speed" from
  * the run's output file `output_h5`, solves the eigen-problems of TRM and of the adjoint matrix and writes alpha,
  * alpha_adj (N x 1), phi_mode, phi_mode_adj (N x N, column = mode) as complex {r, i} datasets to output_TRMM.h5 in the

@@ -230,6 +230,16 @@ class Deck:
     def mode(self) -> str:
         return host_lib().mcbh_mode(self._h).decode()
 
+    def tdmc(self):
+        """(census times, interval lengths as the reference computes them) of a time-dependent deck, else two empty arrays"""
+        L = host_lib()
+        L.mcbh_tdmc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        n = L.mcbh_tdmc(self._h, None, None)
+        t = np.zeros(n); dt = np.zeros(n)
+        if n:
+            L.mcbh_tdmc(self._h, t.ctypes.data, dt.ctypes.data)
+        return t, dt
+
     def search_cell(self, x, y, z) -> int:
         return host_lib().mcbh_search_cell(self._h, x, y, z)
 

@@ -212,6 +212,17 @@ int mcbh_write_output(mcbh_deck* d, const char* path, uint64_t n_track, const do
     return f.write(path, g_error) ? 0 : -1;
 }
 
+int mcbh_tdmc(const mcbh_deck* d, double* time_out, double* interval_out)
+{
+    if (!d) return 0;
+    const size_t n = d->deck.tdmc_time.size();
+    for (size_t i = 0; i < n; i++) {
+        if (time_out) time_out[i] = d->deck.tdmc_time[i];
+        if (interval_out) interval_out[i] = d->deck.tdmc_interval[i];
+    }
+    return (int)n;
+}
+
 int mcbh_trmm_postprocess(const char* output_h5)
 {
     return mcbhost::trmm_postprocess(output_h5 ? output_h5 : "", g_error) ? 0 : -1;
