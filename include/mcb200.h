@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCB_ABI_VERSION 3
+#define MCB_ABI_VERSION 4
 #define MCB_MAX_MAT_NUCLIDES 8 /* nuclides per material handled in registers */
 #define MCB_XS_ROW 6           /* doubles per xs row: E, sigma_s, sigma_c, sigma_f, nu, beta */
 
@@ -75,6 +75,12 @@ typedef struct mcb_nuclide {
 /* ---- sources and distributions (setup.cpp:174-305,1020-1066; src/Distribution.cpp) ---- */
 enum { MCB_DIST_DELTA = 0, MCB_DIST_UNIFORM = 1, MCB_DIST_WATT = 2 };
 enum { MCB_DIR_DELTA = 0, MCB_DIR_ISOTROPIC = 1, MCB_DIR_XYZ = 2 };
+/* source shapes.  POINT: SourcePoint (Source.cpp:20-24).  DISK_Z: the <disk_z x y z r> element of
+ * examples/sphere_detection/input.xml:106 — the deck behind the reference's MCNP6 integral test
+ * (test/test_integral_Simulator.cpp:10-19) — which the reference's own loader rejects (setup.cpp:1051-1063):
+ * positions uniform on the disk of radius r around (x, y, z) in the plane z = const: after energy and direction,
+ * rho = r sqrt(xi1), phi = 2 pi xi2, (x + rho cos phi, y + rho sin phi, z); the cell is searched per particle. */
+enum { MCB_SRC_POINT = 0, MCB_SRC_DISK_Z = 1 };
 typedef struct mcb_dist1 {
     int32_t kind, reserved;
     double a, b; /* delta: a=value; uniform: a, b */
@@ -88,6 +94,8 @@ typedef struct mcb_source {
     mcb_dist1 dir_xyz[3]; /* MCB_DIR_XYZ */
     mcb_dist1 energy;
     double prob;          /* parsed and ignored at sampling, like Source.cpp:42-46 */
+    int32_t kind, reserved; /* MCB_SRC_*; cell = the cell of the centre for a disk */
+    double radius;        /* MCB_SRC_DISK_Z */
 } mcb_source;
 
 /* ---- estimators (include/Estimator.h, src/Estimator.cpp, setup.cpp:637-805) ---- */

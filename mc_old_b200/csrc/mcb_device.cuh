@@ -125,6 +125,17 @@ __device__ __forceinline__ void direction_from_draws(double mu, double xi, doubl
     dx = mu;
 }
 
+// sin / cos of the azimuth 2 pi xi, the way direction_from_draws forms them
+__device__ __forceinline__ void circle_from_draw(double xi, double& sa, double& ca)
+{
+#ifdef MCB_FAST_TRIG
+    sincospi(2.0 * xi, &sa, &ca);
+#else
+    const double azi = MCB_PI_2 * xi;
+    sincos(azi, &sa, &ca);
+#endif
+}
+
 // The source bank a generation samples from.  Single GPU / a bank handed in from the host: one flat array.
 // Multi-GPU: the global bank is the rank-order concatenation of every rank's canonical slice; the slices stay where
 // they were written and are read in place over NVLink through peer pointers (CUDA IPC), so the bank is never

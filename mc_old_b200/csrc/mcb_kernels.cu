@@ -173,6 +173,15 @@ k_source(const DevProblem P, Bank B, uint32_t* active, int32_t first_hist, uint3
         else if (S.dir_kind == MCB_DIR_ISOTROPIC) isotropic_direction(rng, u, v, w);
         else { w = dist1_sample(S.dir_xyz[2], rng); v = dist1_sample(S.dir_xyz[1], rng); u = dist1_sample(S.dir_xyz[0], rng); }
         x = S.pos[0]; y = S.pos[1]; z = S.pos[2]; t = 0.0; cell = S.cell;
+        if (S.kind == MCB_SRC_DISK_Z) {  // uniform on the disk around (x, y, z) in the plane z = const (mcb200.h)
+            const double rho = S.radius * sqrt(mcb_urand(rng));
+            double sa, ca;
+            circle_from_draw(mcb_urand(rng), sa, ca);
+            x += rho * ca; y += rho * sa;
+            const int cs = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, x, y, z);
+            if (cs >= 0) cell = cs;
+            else if (atomicExch(&C->lost, 1) == 0) { C->lost_pos[0] = x; C->lost_pos[1] = y; C->lost_pos[2] = z; }  // general.cpp:31-33
+        }
     }
     B.x[q] = x; B.y[q] = y; B.z[q] = z; B.u[q] = u; B.v[q] = v; B.w[q] = w;
     B.E[q] = E; B.speed[q] = mcb_speed_of_energy(E); B.wgt[q] = 1.0; B.t[q] = t;

@@ -174,12 +174,13 @@ def ucube(samples=1000, active=5, passive=3):
 """
 
 
-def gcr(samples=400, active=5, passive=2, trmm=False):
-    """examples/infinite_GCR_TRMM/input.xml: infinite graphite-moderated medium (4 nuclides), reflective planes."""
-    t = """
+def gcr(samples=400, active=5, passive=2, trmm=False, groups=20):
+    """examples/infinite_GCR_TRMM/input.xml: infinite graphite-moderated medium (4 nuclides), reflective planes.
+    groups=100 is examples/infinite_GCR_TRMM_100 (8 * 100^2 + 15 * 100 = 81500 tallies)."""
+    t = f"""
 <trmm>
     <cell name="infinity"/>
-    <filter type="energy" grid_lethargy="1E-5 2E7 20"/>
+    <filter type="energy" grid_lethargy="1E-5 2E7 {groups}"/>
 </trmm>""" if trmm else ""
     return HEAD + f"""
 <simulation>
@@ -487,3 +488,96 @@ def write(dirpath, text):
     with open(os.path.join(dirpath, "input.xml"), "w") as f:
         f.write(text)
     return dirpath
+
+
+def sphere_detection(samples=100000):
+    """examples/sphere_detection/input.xml: a graphite sphere lit by a mono-directional 1 MeV disk source, seen by a He-3
+    tube inside a polyethylene moderator.  The deck of the reference's MCNP6 integral test
+    (test/test_integral_Simulator.cpp:10-19: detector_TL absorption = 6.9276e-5 per source particle); its <disk_z> source is
+    rejected by the reference's own loader (setup.cpp:1051-1063) and sampled here as include/mcb200.h says."""
+    return HEAD + f"""
+<simulation>
+    <description name="Detecting a Sphere" samples="{samples:g}"/>
+</simulation>
+<nuclides>
+    <nuclide name="C0"  ZAID="006000"/>
+    <nuclide name="H1"  ZAID="001001"/>
+    <nuclide name="He3" ZAID="002003"/>
+</nuclides>
+<materials>
+    <material name="polyethylene">
+        <nuclide name="C0" density="0.039929"/>
+        <nuclide name="H1" density="0.079855"/>
+    </material>
+    <material name="helium3">
+        <nuclide name="He3" density="0.00002501"/>
+    </material>
+    <material name="graphite">
+        <nuclide name="C0" density="0.100280"/>
+    </material>
+</materials>
+<surfaces>
+    <sphere     name="sp1"  x="0.0" y="0.0" z="0.0" r="4.0"/>
+    <plane_x    name="px1"  x="9.0"/>
+    <plane_x    name="px2"  x="24.0"/>
+    <cylinder_x name="cx1"  y="0.0" z="0.0" r="5.5"/>
+    <plane_x    name="px11" x="14.0"/>
+    <plane_x    name="px22" x="19.0"/>
+    <cylinder_x name="cx11" y="0.0" z="0.0" r="0.5"/>
+</surfaces>
+<cells>
+    <cell name="sphere" material="graphite">
+        <surface name="sp1" sense="-1"/>
+    </cell>
+    <cell name="detector" material="helium3">
+        <surface name="px11" sense="+1"/>
+        <surface name="px22" sense="-1"/>
+        <surface name="cx11" sense="-1"/>
+    </cell>
+    <cell name="moderator left" material="polyethylene">
+        <surface name="px1"  sense="+1"/>
+        <surface name="px11" sense="-1"/>
+        <surface name="cx1"  sense="-1"/>
+    </cell>
+    <cell name="moderator mid" material="polyethylene">
+        <surface name="px11" sense="+1"/>
+        <surface name="px22" sense="-1"/>
+        <surface name="cx1" sense="-1"/>
+        <surface name="cx11" sense="+1"/>
+    </cell>
+    <cell name="moderator right" material="polyethylene">
+        <surface name="px22" sense="+1"/>
+        <surface name="px2"  sense="-1"/>
+        <surface name="cx1"  sense="-1"/>
+    </cell>
+    <cell name="left vacuum">
+        <surface name="sp1" sense="+1"/>
+        <surface name="px1" sense="-1"/>
+    </cell>
+    <cell name="middle vacuum" importance="0.0">
+        <surface name="cx1" sense="+1"/>
+        <surface name="px1" sense="+1"/>
+        <surface name="px2" sense="-1"/>
+    </cell>
+    <cell name="right vacuum" importance="0.0">
+        <surface name="px2" sense="+1"/>
+    </cell>
+</cells>
+<estimators>
+    <estimator name="detector_TL" scores="flux absorption" type="TL">
+        <cell name="detector"/>
+    </estimator>
+</estimators>
+<estimators>
+    <estimator name="detector_C" scores="flux absorption" type="C">
+        <cell name="detector"/>
+    </estimator>
+</estimators>
+<distributions>
+    <delta name="dir" datatype="point" x = "0.0" y = "0.0" z = "1.0"/>
+    <delta name="enrg" datatype="double" val="1.0e6"/>
+</distributions>
+<sources>
+    <disk_z x="-1.0"  y="0.0" z="-5.0" r="2.0" direction="dir" energy="enrg"/>
+</sources>
+"""

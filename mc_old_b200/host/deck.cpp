@@ -640,6 +640,13 @@ bool Deck::load_string(const std::string& xml_text, const std::string& xs_dir, i
             for (auto& q : distp) if (q.name == s.attribute("position").value()) { d = &q; break; }
             if (!d || d->kind != MCB_DIR_DELTA) { error = "[INPUT ERROR] <source position=...> needs a delta point distribution"; return false; }
             std::memcpy(S.pos, d->xyz, sizeof(S.pos));
+        } else if (s.name == "disk_z") {
+            // superset of the reference: examples/sphere_detection/input.xml:106 (the deck of the MCNP6 integral test,
+            // test/test_integral_Simulator.cpp:10-19) uses it, setup.cpp:1051-1063 rejects it.  Sampling: mcb200.h
+            S.kind = MCB_SRC_DISK_Z;
+            S.pos[0] = s.attribute("x").as_double(); S.pos[1] = s.attribute("y").as_double(); S.pos[2] = s.attribute("z").as_double();
+            S.radius = s.attribute("r").as_double();
+            if (!(S.radius > 0.0)) { error = "[INPUT ERROR] <disk_z> needs a radius r > 0"; return false; }
         } else {
             error = "[INPUT ERROR] Unknown source type: " + s.name; return false;
         }

@@ -70,6 +70,7 @@ struct mco_ctx {
     particle* Fbank; size_t Fn, Fcap;   /* fission bank being filled */
     particle* Sbank; size_t Sn;         /* sample bank of SourceDelta sites (cycle > 0) */
     int S_is_deck;                      /* first cycle / fixed source: sample the deck's sources */
+    int src_lost;                       /* a <disk_z> source particle fell outside every cell */
     double* cdf; size_t cdf_n;          /* SourceBank::p */
     /* estimators */
     tally* tallies;
@@ -1070,6 +1071,19 @@ static particle deck_source(mco_ctx* c, const mcb_source* S, particle* stream)
         dir[1] = dist1_sample(&S->dir_xyz[1], &r);
         dir[0] = dist1_sample(&S->dir_xyz[0], &r);
     }
+    if (S->kind == MCB_SRC_DISK_Z) { /* no reference counterpart (setup.cpp:1051-1063 rejects the element): mcb200.h */
+        double pos[3];
+        const double rho = S->radius * sqrt(draw(&r));
+        const double phi = 2.0 * PI_ * draw(&r);
+        int cell;
+        pos[0] = S->pos[0] + rho * cos(phi); pos[1] = S->pos[1] + rho * sin(phi); pos[2] = S->pos[2];
+        cell = mco_search_cell(c->p, pos);
+        if (cell < 0) {
+            printf("[WARNING] A particle is lost:\n( x, y, z )  (%g, %g, %g )\n", pos[0], pos[1], pos[2]);
+            c->src_lost = 1; cell = S->cell;
+        }
+        return p_make(pos, dir, E, 0.0, 1.0, cell);
+    }
     return p_make(S->pos, dir, E, 0.0, 1.0, S->cell);
 }
 
@@ -1122,7 +1136,7 @@ int mco_transport_cycle(mco_ctx* c)
         memset(&stream, 0, sizeof(stream));
         if (c->rng_mode == MCO_RNG_HISTORY) stream.rng = mco_lcg_skip(c->seed, (c->icycle * p->n_sample + h) * RN_STRIDE);
         j = pick_source(c, &stream, nsrc);                /* handler.cpp:20, Source.cpp:42-46 */
-        if (c->S_is_deck) src = deck_source(c, &p->sources[j], &stream);
+        if (c->S_is_deck) { src = deck_source(c, &p->sources[j], &stream); if (c->src_lost) return -1; }
         else src = c->Sbank[j];
         src.rng = stream.rng;
         c->child_counter = 0;

@@ -82,14 +82,15 @@ def test_heu_entropy_history_parity():
 
 
 @pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("fsf_comb", 20000),
-                                    ("heu_tallies", 10000), ("gcr_trmm", 400), ("leak_time", 20000), ("gcr_td", 3000),
-                                    ("gcr_td_comb", 3000)])
+                                    ("heu_tallies", 10000), ("gcr_trmm", 400), ("gcr_trmm_100", 150), ("leak_time", 20000), ("gcr_td", 3000),
+                                    ("gcr_td_comb", 3000), ("sphere_det", 200000)])
 def test_tallies_history_parity(name, n):
     """Estimator::score / end_history / end_cycle / end_simulation (Estimator.cpp:298-367) on every deck family:
     surface, cell-TL and cell-C estimators, energy filters, splitting (cell_importance, population_control.cpp:21-49)
     and same-history fission secondaries (fixed_source.cpp:12-22); the TRMM tally set of infinite_GCR_TRMM (3500 bins:
     energy_initial x energy matrices filled by simulate-then-score estimators, Estimator.cpp:441-482, delayed-neutron
-    scores at energy_old); time filters that split a track over the bins it spans (examples/HEU_sphere_leakage,
+    scores at energy_old), also with the 100 groups of infinite_GCR_TRMM_100 (81500 tallies: more than a grid dimension holds,
+    and the keyed form of the per-history tally tables); the <disk_z> source and the cylinder / sphere / plane cells of examples/sphere_detection; time filters that split a track over the bins it spans (examples/HEU_sphere_leakage,
     Estimator.cpp:199-246); the particle comb (population_control.cpp:55-84, fsf_comb: banks of 3 or more waiting particles
     combed to 2); the time-dependent mode (examples/infinite_GCR_TD, _TD_sub: census stops, forced decay of delayed
     neutrons, the <tdmc/> filter; general.cpp:187-195, time_dependent.cpp, fixed_source.cpp:25-40).  Same per-history streams on both sides, so the
@@ -99,7 +100,8 @@ def test_tallies_history_parity(name, n):
            "fsf_comb": lambda: decks.fixed_source_fissile(samples=n, comb=(3, 2)),
            "heu_tallies": lambda: decks.heu_sphere(samples=n, active=1, passive=0, estimators=True),
            "gcr_trmm": lambda: decks.gcr(samples=n, active=1, passive=0, trmm=True),
-           "leak_time": lambda: decks.heu_leakage(samples=n), "gcr_td": lambda: decks.gcr_td(samples=n),
+           "gcr_trmm_100": lambda: decks.gcr(samples=n, active=1, passive=0, trmm=True, groups=100),
+           "leak_time": lambda: decks.heu_leakage(samples=n), "sphere_det": lambda: decks.sphere_detection(samples=n), "gcr_td": lambda: decks.gcr_td(samples=n),
            "gcr_td_comb": lambda: decks.gcr_td(samples=n, linear="1e-8 6 2e-5", comb=(8, 4), groups=10)}[name]()
     deck = mcb.Deck(xml=xml)
     ctx = mcb.Context(deck, device=0)
@@ -329,6 +331,34 @@ def test_slab_analytic_1e7():
     assert r.n_histories == 10_000_000
     assert abs(m[0] - np.exp(-4.2)) <= 3 * u[0], (m[0], u[0])
     assert 3.0e-5 < u[0] < 4.5e-5   # sqrt(p(1-p)/N) = 3.84e-5
+
+
+def test_sphere_detection_mcnp6_1e7():
+    """test/test_integral_Simulator.cpp:10-19: examples/sphere_detection at its own 1e7 histories against MCNP6's
+    6.9276e-5 absorptions per source particle in the He-3 tube, with the reference's own acceptance (uncer + 1.15e-6)
+    widened to 3 sigma; the <disk_z> source is a superset of the reference's loader (include/mcb200.h)"""
+    deck = mcb.Deck(xml=decks.sphere_detection(samples=10_000_000))
+    ctx = mcb.Context(deck, device=0)
+    r = ctx.run_cycle()
+    m, u = ctx.tallies()
+    ctx.close()
+    assert r.n_histories == 10_000_000
+    assert abs(m[1] - 6.9276e-5) <= 3 * u[1] + 1.15e-6, (m, u)
+    assert 0.8e-6 < u[1] < 1.6e-6   # 1.82e-6 at 4e6 histories (oracle)
+
+
+def test_disk_source_outside_every_cell_is_a_lost_particle():
+    xml = decks.sphere_detection(samples=2000).replace('<disk_z x="-1.0"  y="0.0" z="-5.0" r="2.0"', '<disk_z x="7.5"  y="0.0" z="-5.0" r="2.0"')
+    assert 'x="7.5"' in xml                     # the disk now straddles x = 9 at z = -5: beside the moderator, in "middle vacuum"
+    deck = mcb.Deck(xml=xml)                    # ... which exists, so this still loads and runs
+    ctx = mcb.Context(deck, device=0); ctx.run_cycle(); ctx.close()
+    xml = xml.replace('<cell name="middle vacuum" importance="0.0">\n        <surface name="cx1" sense="+1"/>\n        <surface name="px1" sense="+1"/>\n'
+                      '        <surface name="px2" sense="-1"/>\n    </cell>', "")
+    assert "middle vacuum" not in xml
+    ctx = mcb.Context(mcb.Deck(xml=xml), device=0)
+    with pytest.raises(RuntimeError, match="particle is lost"):
+        ctx.run_cycle()
+    ctx.close()
 
 
 # ---------------------------------------------------------------------------------------------------------------

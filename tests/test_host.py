@@ -111,7 +111,7 @@ def test_deck_source_forms():
 def test_deck_error_messages():
     """the reference's messages where it has one (it prints and exits; the loader returns them)"""
     with pytest.raises(ValueError, match="Unknown source type"):
-        mcb.Deck(xml=decks.slab(samples=10).replace("<point ", "<disk_z ").replace("/>\n</sources>", "/>\n</sources>"))
+        mcb.Deck(xml=decks.slab(samples=10).replace("<point ", "<ring_z "))
     with pytest.raises(ValueError, match="Unknown nuclide"):
         mcb.Deck(xml=decks.slab(samples=10).replace('<nuclide name="nuc3" density="0.1"/>', '<nuclide name="nope" density="0.1"/>'))
     with pytest.raises(ValueError, match="ksearch and tdmc could not coexist"):   # setup.cpp:166-169
@@ -130,10 +130,12 @@ def test_deck_error_messages():
 @pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree not present")
 @pytest.mark.parametrize("example", ["slab_analytic", "HEU_sphere_criticality", "shielding_vReduction", "UCube", "infinite_GCR_TRMM",
                                      "infinite_GCR_TRMM_100", "infinite_GCR_TRMM_critical", "infinite_GCR_TRMM_critical2",
-                                     "infinite_GCR_Ttmp", "HEU_sphere_leakage", "infinite_GCR_TD", "infinite_GCR_TD_sub"])
+                                     "infinite_GCR_Ttmp", "HEU_sphere_leakage", "infinite_GCR_TD", "infinite_GCR_TD_sub",
+                                     "sphere_detection"])
 def test_reference_example_decks_load_unchanged(example):
     """the reference's own input.xml files parse as they are, TRMM tally sets, time filters, time-dependent mode and
-    particle comb included (the one deck left is sphere_detection, whose <disk_z> source the reference itself rejects)"""
+    particle comb included - every example of the tree, sphere_detection (whose <disk_z> source the reference itself
+    rejects, setup.cpp:1051-1063) among them"""
     deck = mcb.Deck(io_dir="/root/reference/examples/" + example)
     i = deck.info
     assert i["n_sample"] > 0 and i["n_cells"] > 0 and i["n_sources"] > 0

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import golden_cases as gc
+import mc_old_b200 as mcb
 import oracle_lib as ol
 from mc_old_b200 import decks
 
@@ -229,3 +230,22 @@ def test_slab_analytic(golden_runs):
     rec = golden_runs["slab"]
     m = rec["/leak_rate/cross/mean"][0]; u = rec["/leak_rate/cross/uncertainty"][0]
     assert abs(m - np.exp(-4.2)) < 3 * u
+
+
+def test_sphere_detection_mcnp6_golden():
+    """test/test_integral_Simulator.cpp:10-19: absorption in the He-3 tube of examples/sphere_detection = 6.9276e-5 per source
+    particle (MCNP6), asked for within uncer + 1.15e-6.  The reference's loader rejects the deck's <disk_z> source
+    (setup.cpp:1051-1063), so there is no reference run to pin the disk sampling to ("parity unpinned" for this one
+    element); the MCNP6 number is the external anchor: 3 sigma of a 1e6-history oracle run + MCNP6's own 1.15e-6"""
+    deck = mcb.Deck(xml=decks.sphere_detection(samples=1_000_000))
+    assert deck.info["n_sources"] == 1 and deck.info["n_estimators"] == 1   # the second <estimators> block is never read
+    orc = ol.Oracle(deck, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF)
+    orc.run_cycle(); orc.end_simulation()
+    m, u = orc.tallies()
+    assert abs(m[1] - 6.9276e-5) <= 3 * u[1] + 1.15e-6, (m, u)
+    assert 2e-6 < u[1] < 6e-6
+
+
+def test_disk_source_needs_a_radius():
+    with pytest.raises(Exception, match="radius"):
+        mcb.Deck(xml=decks.sphere_detection(samples=10).replace('r="2.0" direction', 'r="0.0" direction'))
