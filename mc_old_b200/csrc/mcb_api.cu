@@ -310,15 +310,18 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
             track_old = true;
             if (p->scores[k].group < 0 || p->scores[k].group > 5) return ctx->fail(MCB_ERR_ARG, "score %d: precursor group %d", k, p->scores[k].group);
         }
+    trace_mark("create: begin");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ctx->fail(MCB_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
     ctx->device = cfg ? cfg->device : 0;
     ctx->rank = cfg ? cfg->rank : 0;
     ctx->world = cfg && cfg->world > 0 ? cfg->world : 1;
     if (ctx->rank < 0 || ctx->rank >= ctx->world) return ctx->fail(MCB_ERR_ARG, "rank %d outside world %d", ctx->rank, ctx->world);
+    trace_mark("create: device count known (driver initialised)");
     CK(cudaSetDevice(ctx->device));
     if (cfg && cfg->stream) ctx->stream = (cudaStream_t)cfg->stream;
     else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    trace_mark("create: device context and stream");
     ctx->timer.on = (cfg && (cfg->reserved & 1)) || getenv("MCB_STAGE_TIMES");
 
     ctx->ksearch = p->ksearch; ctx->entropy_on = p->entropy_on;
@@ -343,6 +346,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         for (int g = 0; g < 6; g++) { D.chid_cdf[g] = ctx->d_delayed.p ? ctx->d_delayed.p + N.chid_cdf_begin[g] : nullptr; D.chid_cdf_n[g] = N.chid_cdf_n[g]; }
     }
     CK(ctx->d_nuclides.upload(nuc.data(), nuc.size()));
+    trace_mark("create: nuclear data uploaded");
     std::vector<mcb::MaterialTables> tabs(p->n_materials);
     size_t nU = 0, nmap = 0, nhash = 0;
     for (int m = 0; m < p->n_materials; m++) {
@@ -350,6 +354,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         nU += tabs[m].U.size(); nmap += tabs[m].map.size(); nhash += tabs[m].hash.size();
         ctx->mat_n_nuc.push_back(tabs[m].n_nuc);
     }
+    trace_mark("create: union grids / hash tables built (host)");
     std::vector<double> U; std::vector<int32_t> map, hash, hrec;
     U.reserve(nU); map.reserve(nmap); hash.reserve(nhash);
     std::vector<DevMaterial> mats(p->n_materials);
@@ -459,6 +464,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     for (int a = 0; a < 3; a++) P.entropy_n[a] = p->entropy_n[a];
     P.entropy_bins = entropy_bins; P.entropy_grid = ctx->d_entropy_grid.p;
 
+    trace_mark("create: problem description uploaded");
     // ---- shard and banks ----
     mcb_shard_range(p->n_sample, ctx->rank, ctx->world, &ctx->shard_begin, &ctx->shard_count);
     if (ctx->shard_count >= (1ull << 31)) return ctx->fail(MCB_ERR_ARG, "more than 2^31 histories per GPU per generation");
@@ -596,6 +602,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         ctx->tally_mean.assign(p->n_tallies, 0.0);
         ctx->tally_uncer.assign(p->n_tallies, 0.0);
     }
+    trace_mark("create: banks, stacks and tally tables allocated");
     if (ctx->world > MCB_MAX_WORLD) return ctx->fail(MCB_ERR_ARG, "world %d > %d", ctx->world, MCB_MAX_WORLD);
     ctx->vec_len = 16 + (size_t)entropy_bins + 2 * (size_t)std::max<int64_t>(p->n_tallies, 0);
     CK(ctx->d_send.alloc(ctx->vec_len));
@@ -622,8 +629,10 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     }
     // Kernels are loaded lazily, and loading one waits for every running kernel to end: a kernel first launched BESIDE a
     // persistent kernel that waits for it would never start.  Everything the side stream launches is launched once here.
+    trace_mark("create: before kernel preload");
     mcbk::preload_side_kernels(ctx->stream, &ctx->d_counters.p->src_ready);
     CK(cudaStreamSynchronize(ctx->stream));
+    trace_mark("create: done");
     return MCB_OK;
 }
 

@@ -7,6 +7,7 @@
 // or a shell loop provide); the histories of every generation are sharded over the ranks, rank 0 prints and writes
 // the output.  The 128-byte NCCL id travels through a file (MCB_ID_FILE, default
 // $XDG_RUNTIME_DIR|$TMPDIR|/tmp/mcb_nccl_id.<run id>.<MASTER_PORT>.<uid>, tagged with the job so that a stale one is refused).
+#include <chrono>
 #include <unistd.h>
 
 #include <cstdio>
@@ -23,8 +24,17 @@
 
 #include "mcb200_host.h"
 
+// MCB_TIMING=1: wall seconds of the program's phases on stderr (deck, context, first cycle, the other cycles, output)
+static double wall_s()
+{
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 int main(int argc, char* argv[])
 {
+    const bool timing = getenv("MCB_TIMING") != nullptr;
+    double t_mark[6] = {wall_s(), 0, 0, 0, 0, 0};
     if (argc == 1) {
         std::cout << "[ERROR] Please provide input.xml directory...\n";
         std::exit(EXIT_FAILURE);
@@ -36,12 +46,19 @@ int main(int argc, char* argv[])
     mcbh_deck* deck = mcbh_load_deck(io_dir.c_str(), xs, flags);
     if (!deck) { std::cout << mcbh_last_error() << "\n"; std::exit(EXIT_FAILURE); }
     const mcb_problem* p = mcbh_problem(deck);
+    t_mark[1] = wall_s();
     mcb_config cfg;
     memset(&cfg, 0, sizeof(cfg));
     const int world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
     const int rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
     const bool root = rank == 0;
     cfg.device = getenv("MCB_DEVICE") ? atoi(getenv("MCB_DEVICE")) : (getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : 0);
+    if (world <= 1 && !getenv("CUDA_VISIBLE_DEVICES")) {
+        // One process, one GPU: the driver initialises every GPU it can see (measured on an 8-GPU box: 0.6-1.6 s of the
+        // ~1 s a shipped-size deck takes from start to output.h5), so only the one in use is left visible
+        setenv("CUDA_VISIBLE_DEVICES", std::to_string(cfg.device).c_str(), 1);
+        cfg.device = 0;
+    }
     cfg.rank = rank; cfg.world = world > 1 ? world : 1;
     mcb_ctx* ctx = nullptr;
     if (mcb_create(p, &cfg, &ctx) != MCB_OK) { std::cout << mcb_last_error(nullptr) << "\n"; std::exit(EXIT_FAILURE); }
@@ -82,6 +99,7 @@ int main(int argc, char* argv[])
         if (mcb_comm_init(ctx, id) != MCB_OK) { std::cout << mcb_last_error(ctx) << "\n"; std::exit(EXIT_FAILURE); }
         if (root) std::remove(id_file.c_str());
     }
+    t_mark[2] = wall_s();
     if (root) std::cout << "\nSimulation setup done,\nNow running the simulation...\n\n";
 
     std::vector<double> k_cycle, H_cycle, k_avg, k_uncer;
@@ -89,6 +107,7 @@ int main(int argc, char* argv[])
     for (uint64_t icycle = 0; icycle < p->n_cycle; icycle++) {  // handler.cpp:14
         mcb_cycle_result r;
         if (mcb_run_cycle(ctx, &r) != MCB_OK) { std::cout << mcb_last_error(ctx) << "\n"; std::exit(EXIT_FAILURE); }
+        if (icycle == 0) t_mark[3] = wall_s();
         n_track += r.n_tracks;  // general.cpp:76
         if (p->ksearch) {       // EstimatorK::report_cycle (Estimator.cpp:526-561)
             k_cycle.push_back(r.k_cycle); H_cycle.push_back(r.H);
@@ -100,6 +119,7 @@ int main(int argc, char* argv[])
             if (root) std::cout << "   (" << r.H << ")" << std::endl;
         }
     }
+    t_mark[4] = wall_s();
     if (!root) {  // every rank holds the same global results; rank 0 reports them
         mcb_destroy(ctx);
         mcbh_free_deck(deck);
@@ -115,6 +135,11 @@ int main(int argc, char* argv[])
         std::exit(EXIT_FAILURE);
     }
     std::cout << "Simulation output done!\n";
+    t_mark[5] = wall_s();
+    if (timing)
+        fprintf(stderr, "[mcb timing] deck %.3f s  context %.3f s  first cycle %.3f s  other %llu cycles %.3f s  output %.3f s\n",
+                t_mark[1] - t_mark[0], t_mark[2] - t_mark[1], t_mark[3] - t_mark[2], (unsigned long long)(p->n_cycle - 1),
+                t_mark[4] - t_mark[3], t_mark[5] - t_mark[4]);
     mcb_destroy(ctx);
     mcbh_free_deck(deck);
     return 0;

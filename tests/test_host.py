@@ -261,3 +261,31 @@ def test_gloo_world2_sharded_generations_match_one_rank():
         assert ns == ns1 and nt == nt1             # integer results do not depend on the number of ranks
         assert es == pytest.approx(es1, rel=1e-13)  # same sites, same order (summation order is the same too)
         assert k == pytest.approx(k1, rel=1e-12)   # double sums of two partials vs one running sum
+
+
+def test_xml_reader_covers_the_grammar_pugixml_accepts():
+    """the host keeps its own small XML reader (host/xml_lite.cpp) where the reference links pugixml: everything a deck
+    author may legally write around the deck grammar must load the same problem - comments (also with markup inside),
+    single-quoted attributes, the five named entities and character references, a DOCTYPE, CDATA, free white space
+    inside tags, explicit end tags, a byte-order mark - and malformed input is an error with a line number, never a
+    half-read deck"""
+    base = decks.slab(samples=10)
+    ref = mcb.Deck(xml=base).info
+    same = {
+        "comments": base.replace("<surfaces>", "<!-- a comment with <tags> & ampersands -->\n<surfaces><!-- inside -->"),
+        "single quotes": base.replace('name="px1" x="0.0"', "name='px1' x='0.0'"),
+        "entities": base.replace('name="Simple Slabs"', 'name="Simple &amp; &lt;Slabs&gt; &quot;&apos; &#65;&#x42;"'),
+        "doctype": base.replace("<simulation>", "<!DOCTYPE simulation>\n<simulation>", 1),
+        "cdata": base.replace("</simulation>", "<![CDATA[ junk <x> ]]></simulation>"),
+        "white space": base.replace('<plane_x name="px1" x="0.0"/>', '<plane_x   name = "px1"\n   x = "0.0"   />'),
+        "end tag": base.replace('<plane_x name="px1" x="0.0"/>', '<plane_x name="px1" x="0.0"></plane_x>'),
+        "byte-order mark": "﻿" + base,
+    }
+    for what, xml in same.items():
+        assert xml != base, what
+        assert mcb.Deck(xml=xml).info == ref, what
+    for what, xml, msg in [("missing end tag", base.replace("</cells>", ""), r"missing </cells> \(line \d+\)"),
+                           ("mismatched end tag", base.replace("</cells>", "</cell>"), r"mismatched </cell>, open <cells> \(line \d+\)"),
+                           ("unquoted attribute", base.replace('x="0.0"/>', "x=0.0/>", 1), r"value not quoted \(line \d+\)")]:
+        with pytest.raises(ValueError, match=msg):
+            mcb.Deck(xml=xml)
