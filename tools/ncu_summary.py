@@ -14,7 +14,9 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_th
         'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
         'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__icc_request_hit_rate.pct',
-        'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed', 'sm__icc_requests.sum.pct_of_peak_sustained_elapsed']
+        'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed', 'sm__icc_requests.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum']
 
 
 def launches(path):
