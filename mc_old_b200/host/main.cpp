@@ -142,5 +142,9 @@ int main(int argc, char* argv[])
                 t_mark[4] - t_mark[3], t_mark[5] - t_mark[4]);
     mcb_destroy(ctx);
     mcbh_free_deck(deck);
+    if (timing) {
+        const double now = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
+        fprintf(stderr, "[mcb timing] epoch main %.3f  epoch end %.3f  (teardown %.3f s)\n", now - wall_s(), now, wall_s() - t_mark[5]);
+    }
     return 0;
 }

@@ -6,6 +6,11 @@
  * (including the right-to-left evaluation of constructor arguments, SURVEY
  * App. D-4), so that in MCO_RNG_GLOBAL mode the whole run is bit-identical to
  * oracle/_ref/MC_ref.  Compile without FMA contraction (-ffp-contract=off).
+ *
+ * Parity: pinned (every fixture of tests/golden/ comes from the compiled reference) with ONE exception, stated here
+ * as the rules ask: the <disk_z> source (deck_source, MCB_SRC_DISK_Z) has no reference implementation - the
+ * reference's loader rejects the element (setup.cpp:1051-1063) - so that sampling is "parity unpinned"; it is
+ * anchored on the MCNP6 number of the reference's own integral test (test/test_integral_Simulator.cpp:10-19).
  */
 #include "mc_oracle.h"
 
