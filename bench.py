@@ -426,7 +426,7 @@ def main():
                                "io_GBps": n_e * 48 / (best * 1e-3) / 1e9, "io_frac_of_hbm_peak": n_e * 48 / (best * 1e-3) / 1e9 / peak}
         # the roofline fraction of this kernel is its real I/O (8 B in + 40 B out per lookup) against the HBM peak; the
         # SURVEY 8(d) algorithmic figure counts table bytes that L2 / L1 serve and is not a roofline (it can exceed the peak)
-        xs_micro["bound"] = ("L1 gather pipe: l1tex__data_pipe_lsu_wavefronts 88 % of peak (profiles/r2f_k_xs_lookup_ncu_full_summary.txt); "
+        xs_micro["bound"] = ("L1 gather pipe: l1tex__data_pipe_lsu_wavefronts 89 % of peak (profiles/r2f_k_xs_lookup_ncu_full_summary.txt); "
                              "every lane gathers 16-byte pieces of its own table rows from a different line")
         del out5
     ctx.close()

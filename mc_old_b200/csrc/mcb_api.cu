@@ -350,7 +350,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     std::vector<mcb::MaterialTables> tabs(p->n_materials);
     size_t nU = 0, nmap = 0, nhash = 0;
     for (int m = 0; m < p->n_materials; m++) {
-        mcb::build_material_tables(p, m, getenv("MCB_HASH_BITS") ? atoi(getenv("MCB_HASH_BITS")) : 14, tabs[m]);
+        mcb::build_material_tables(p, m, getenv("MCB_HASH_BITS") ? atoi(getenv("MCB_HASH_BITS")) : MCB_HASH_BITS_DEFAULT, tabs[m]);
         nU += tabs[m].U.size(); nmap += tabs[m].map.size(); nhash += tabs[m].hash.size();
         ctx->mat_n_nuc.push_back(tabs[m].n_nuc);
     }

@@ -1,6 +1,7 @@
 #include "mcb_tables.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace mcb {
 
@@ -52,8 +53,11 @@ void build_material_tables(const mcb_problem* p, int material, int max_mant_bits
         for (int r = 0; r < 2; r++) for (int n = 0; n < T.n_nuc; n++) T.hrec[(size_t)r * T.hrec_stride + 2 + n] = -1;
         return;
     }
-    // hash on the bit pattern; keep the table at most ~4 entries per grid point
-    const int64_t cap = std::max<int64_t>(4 * (int64_t)nU + 1024, 4096);
+    // hash on the bit pattern; the table may hold up to ~16 entries per grid point (measured on HEU, one B200: a walk step
+    // costs more than a bin - 14 bits / 4 per point 5.75 ms per generation, 16 bits / 16 per point 5.65 ms, 18 / 64 the same,
+    // 12 bits 5.90, 8 bits 6.25; profiles/r2f_hash_bits.txt).  MCB_HASH_PER_POINT / MCB_HASH_BITS are tuning knobs.
+    const int64_t per_point = getenv("MCB_HASH_PER_POINT") ? std::max(1, atoi(getenv("MCB_HASH_PER_POINT"))) : 16;
+    const int64_t cap = std::max<int64_t>(per_point * (int64_t)nU + 1024, 4096);
     int bits = std::min(std::max(max_mant_bits, 0), 20);
     for (;; bits--) {
         T.shift = 52 - bits;

@@ -20,6 +20,7 @@
 
 #include "mcb200.h"
 
+#define MCB_HASH_BITS_DEFAULT 16 /* mantissa bits of the hash key at most (bins per octave = 2^bits), see mcb_tables.cpp */
 #define MCB_MAP_BISECT (-2) /* map entry of a nuclide whose grid is not ascending: bisect its rows like the reference */
 
 #if defined(__CUDACC__)

@@ -244,7 +244,7 @@ int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, i
     const mcb_problem* p = d->deck.view();
     if (material < 0 || material >= p->n_materials) return -1;
     mcb::MaterialTables T;
-    mcb::build_material_tables(p, material, 14, T);
+    mcb::build_material_tables(p, material, MCB_HASH_BITS_DEFAULT, T);
     for (int64_t i = 0; i < n; i++) {
         const int u = mcb_union_count_less(T.U.data(), T.hash.data(), T.key_min, T.n_hash, T.shift, (int32_t)T.U.size(), E[i]) - 1;
         // the device reads the indices through the bin records (mcb_union_lookup): both routes must agree

@@ -9,7 +9,7 @@ echo "pytest exit $?"; grep -v "^$" gpurun_out/pytest_r2f.log | tail -4
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err
 echo "bench exit $?"; cut -c1-300 gpurun_out/r2f_bench.json
-timeout 600 python tools/shipped_decks.py --ref-timeout 75 > gpurun_out/r2f_shipped_decks.jsonl 2> gpurun_out/r2f_shipped_decks.err
+[ -n "${SKIP_SHIPPED:-}" ] || timeout 600 python tools/shipped_decks.py --ref-timeout 75 > gpurun_out/r2f_shipped_decks.jsonl 2> gpurun_out/r2f_shipped_decks.err
 echo "shipped exit $?"; cut -c1-420 gpurun_out/r2f_shipped_decks.jsonl | head -9
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r2f_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-xs > gpurun_out/bench_under_ncu.log 2>&1
