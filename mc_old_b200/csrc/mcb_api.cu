@@ -143,7 +143,7 @@ struct mcb_ctx {
     DevBuf<DevNuclide> d_nuclides;
     DevBuf<double> d_xs_rows, d_union, d_mat_density, d_filter_grid, d_entropy_grid, d_delayed, d_bank_eold, d_bank_told;
     DevBuf<int32_t> d_hrec;
-    DevBuf<int32_t> d_map, d_hash, d_mat_nuclide, d_cell_surface, d_cell_sense, d_attach_begin[3], d_attach_list[3];
+    DevBuf<int32_t> d_map, d_hash, d_mat_nuclide, d_cell_surface, d_cell_sense, d_cross_neighbor, d_attach_begin[3], d_attach_list[3];
     DevBuf<mcb_surface> d_surfaces;
     DevBuf<mcb_cell> d_cells;
     DevBuf<mcb_source> d_sources;
@@ -387,6 +387,29 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     CK(ctx->d_cells.upload(p->cells, p->n_cells));
     CK(ctx->d_cell_surface.upload(p->cell_surface, p->n_cell_surface));
     CK(ctx->d_cell_sense.upload(p->cell_sense, p->n_cell_surface));
+    {
+        // The cell behind a surface, where search_cell's answer (general.cpp:26-34: the FIRST cell in deck order that
+        // contains the point) can be told beforehand: leaving cell c through its entry (s, g) the point lies on side -g of
+        // s.  Every cell that holds (s, g) is ruled out by that one evaluation; if the first cell in deck order that the
+        // side does not rule out consists of (s, -g) alone, it contains every such point and is the answer.  The crossing
+        // code still evaluates s at the nudged point and takes the shortcut only when the sign is strictly the new side's
+        // (the same arithmetic as test_point, so the same cell), and searches otherwise.  Typical hit: the one-surface
+        // "outside" / graveyard cells every leaking particle enters.
+        std::vector<int32_t> nb((size_t)std::max(p->n_cell_surface, 1), -1);
+        for (int c = 0; c < p->n_cells; c++)
+            for (int i = p->cells[c].surf_begin; i < p->cells[c].surf_end; i++) {
+                const int s = p->cell_surface[i], side = -p->cell_sense[i];
+                for (int b = 0; b < p->n_cells; b++) {
+                    const mcb_cell& B = p->cells[b];
+                    bool ruled_out = false;
+                    for (int j = B.surf_begin; j < B.surf_end; j++) if (p->cell_surface[j] == s && p->cell_sense[j] != side) ruled_out = true;
+                    if (ruled_out) continue;
+                    if (B.surf_end - B.surf_begin == 1 && p->cell_surface[B.surf_begin] == s && p->cell_sense[B.surf_begin] == side) nb[(size_t)i] = b;
+                    break;
+                }
+            }
+        CK(ctx->d_cross_neighbor.upload(nb.data(), (size_t)std::max(p->n_cell_surface, 1)));
+    }
     CK(ctx->d_sources.upload(p->sources, p->n_sources));
     CK(ctx->d_estimators.upload(p->estimators, p->n_estimators));
     CK(ctx->d_scores.upload(p->scores, p->n_scores));
@@ -457,7 +480,7 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     if (p->comb_on && (p->comb_teeth < 1 || p->comb_teeth > 256 || p->comb_bank_max < 1)) return ctx->fail(MCB_ERR_ARG, "particle comb: bank_max >= 1 and 1 <= teeth <= 256");
     P.wr = p->wr; P.ws = p->ws; P.seed0 = ctx->seed; P.n_sample = p->n_sample;
     P.materials = ctx->d_materials.p; P.nuclides = ctx->d_nuclides.p; P.mat_nuclide = ctx->d_mat_nuclide.p; P.mat_density = ctx->d_mat_density.p;
-    P.surfaces = ctx->d_surfaces.p; P.cells = ctx->d_cells.p; P.cell_surface = ctx->d_cell_surface.p; P.cell_sense = ctx->d_cell_sense.p;
+    P.surfaces = ctx->d_surfaces.p; P.cells = ctx->d_cells.p; P.cell_surface = ctx->d_cell_surface.p; P.cell_sense = ctx->d_cell_sense.p; P.cross_neighbor = ctx->d_cross_neighbor.p;
     P.sources = ctx->d_sources.p; P.estimators = ctx->d_estimators.p; P.scores = ctx->d_scores.p; P.filters = ctx->d_filters.p;
     P.filter_grid = ctx->d_filter_grid.p;
     for (int kind = 0; kind < 3; kind++) { P.attach_begin[kind] = ctx->d_attach_begin[kind].p; P.attach_list[kind] = ctx->d_attach_list[kind].p; }

@@ -590,7 +590,10 @@ __device__ __forceinline__ bool ev_collide_scatter(const DevProblem& P, Particle
 
 // cross event, first half: surface_hit + cell_importance up to the split (general.cpp:89-115,
 // population_control.cpp:21-43).  n_copy = split copies the second half will write.
-template <bool TALLY>
+// LEAN (walk kernel, instances that neither score nor keep secondaries): a particle that dies at the crossing ends its
+// history, and nothing reads its stream again - the draws the reference still makes for it (importance roulette against
+// a ratio of 0, weight roulette of a particle already killed) are skipped, with the same generation bit for bit
+template <bool TALLY, bool LEAN = false>
 __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, int S, const TallyAcc& T, Counters* C, unsigned& n_copy)
 {
     n_copy = 0;
@@ -602,7 +605,17 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
         p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
         if (TALLY) p.told = p.t;
         p.t += MCB_EPSILON_FLOAT / p.speed;
-        const int cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, p.x, p.y, p.z);
+        int cn = -1;
+        {   // the cell behind the surface where it is known beforehand (cross_neighbor, mcb_api.cu), else the search
+            const mcb_cell Co = P.cells[cell_old];
+            for (int i = Co.surf_begin; i < Co.surf_end; i++)
+                if (__ldg(&P.cell_surface[i]) == S) {
+                    const int nb = __ldg(&P.cross_neighbor[i]);
+                    if (nb >= 0 && mcb_surf_eval(Sf, p.x, p.y, p.z) * (double)(-__ldg(&P.cell_sense[i])) > 0) cn = nb;
+                    break;
+                }
+        }
+        if (cn < 0) cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, p.x, p.y, p.z);
         if (cn < 0) {  // "[WARNING] A particle is lost" (general.cpp:31-33)
             if (atomicExch(&C->lost, 1) == 0) { C->lost_pos[0] = p.x; C->lost_pos[1] = p.y; C->lost_pos[2] = p.z; }
             alive = false; p.wgt = 0.0;
@@ -619,7 +632,9 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
         const MacroXS X0 = {0, 0, 0, 0, 0};
         MCB_SCORE_EVENT(MCB_ATTACH_SURFACE, S, p, P.cells[p.cell].material, -1, false, X0, S, 0.0);
     }
+    if (LEAN && !alive) return false;
     const double Iold = P.cells[cell_old].importance, Inew = P.cells[p.cell].importance;
+    if (LEAN && Inew == 0.0 && Iold > 0.0) { p.wgt = 0.0; return false; }  // ratio 0: killed whatever the draw
     if (Inew != Iold) {
         // a leaking particle enters importance 0: 0 / Iold is decided without dividing (a zero numerator sends the
         // IEEE division routine down its slow path); same value, same draw

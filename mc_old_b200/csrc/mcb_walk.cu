@@ -562,7 +562,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
                 in_material = ev_collide_pre<TALLY>(P, p, X, uidx, D, T, C, k_eff, c);
                 if (in_material) collisions++;
             } else if (kind == 2) {
-                alive = ev_cross_pre<TALLY>(P, p, S, T, C, n_copy);
+                alive = ev_cross_pre<TALLY, !TALLY && !SHARED>(P, p, S, T, C, n_copy);
                 crossings++;
             } else {
                 alive = p.wgt > 0.0;  // census: on to the next interval, or dead after the last (no roulette, general.cpp:193)
@@ -595,7 +595,7 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         StackSink sink = {SHARED ? R.stack + (size_t)blockIdx.x * (WALK_SLOTS + WALK_EXTRA) * STACK_CHUNK : nullptr, tab, my_slot, sp, nch, C};
         if (c.n_sites | c.n_second) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, &L);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
-        if (have && kind == 2) alive = ev_cross_post(P, p, alive, n_copy, sink);
+        if (have && kind == 2 && (TALLY || SHARED || alive)) alive = ev_cross_post(P, p, alive, n_copy, sink);  // (lean instances: see ev_cross_pre)
         if (in_material) alive = ev_collide_scatter<TALLY>(P, p, X, uidx, D, c, H, &L);
         __syncwarp();
         if (have && !alive) {
