@@ -492,9 +492,22 @@ __device__ __forceinline__ bool ev_collide_pre(const DevProblem& P, Particle& p,
 template <class SINK>
 __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Particle& p, const CollideCtx& c, const HistoryAcc& H,
                                                 Counters* C, SiteReq* reqs, uint64_t site_cap, unsigned long long site0, SINK& sink,
+                                                HistLocal* L, double E_in, uint64_t seed_in);
+template <class SINK>
+__device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Particle& p, const CollideCtx& c, const HistoryAcc& H,
+                                                Counters* C, SiteReq* reqs, uint64_t site_cap, unsigned long long site0, SINK& sink,
                                                 HistLocal* L = nullptr)
 {
-    uint64_t seed = p.rng;
+    ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, L, p.E, p.rng);
+}
+// E_in / seed_in: the particle's energy and stream state at the collision, for callers that bank after the scatter
+// kinematics have moved both on (the walk kernel's lean instances: the slot reservation's round trip is hidden that way)
+template <class SINK>
+__device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Particle& p, const CollideCtx& c, const HistoryAcc& H,
+                                                Counters* C, SiteReq* reqs, uint64_t site_cap, unsigned long long site0, SINK& sink,
+                                                HistLocal* L, double E_in, uint64_t seed_in)
+{
+    uint64_t seed = seed_in;
     if (c.n_sites) {
         int seq0;
         if (L) { seq0 = L->nsite; L->nsite += (int)c.n_sites; }
@@ -502,7 +515,7 @@ __device__ __forceinline__ void ev_collide_bank(const DevProblem& P, const Parti
         for (unsigned b = 0; b < c.n_sites; b++) {
             seed = (seed * MCB_RN_JUMP40) & MCB_RN_MASK;
             SiteReq r;
-            r.x = p.x; r.y = p.y; r.z = p.z; r.t = p.t; r.E_in = p.E; r.seed = seed;
+            r.x = p.x; r.y = p.y; r.z = p.z; r.t = p.t; r.E_in = E_in; r.seed = seed;
             r.cell = p.cell; r.seq = seq0 + (int)b; r.hist = p.hist; r.nuclide = c.N_fission;
             if (site0 + b < site_cap) reqs[site0 + b] = r;
             else C->overflow_sites = 1;

@@ -570,16 +570,24 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
         }
         __syncwarp();
         // fission-site requests: one reservation per warp
-        unsigned long long site0 = 0;
-        if (__any_sync(FULL, c.n_sites != 0u)) {
+        // Lean instances (no tallies, no secondaries) bank AFTER the scatter kinematics: the reservation is one atomic on
+        // a device-wide cursor, and its round trip to L2 (ncu, round 2f: the shuffle that waits for it owned 2.2 % of all
+        // stall samples, at one lane) passes under the ~1000 instructions of the scatter instead of in front of them
+        constexpr bool BANK_LATE = !TALLY && !SHARED && !EXCH;
+        unsigned long long site0 = 0, site_base = 0;
+        unsigned site_incl = 0;
+        const bool any_sites = __any_sync(FULL, c.n_sites != 0u);
+        if (any_sites) {
             unsigned v = c.n_sites;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const unsigned t = __shfl_up_sync(FULL, v, d); if (lane >= (unsigned)d) v += t; }
             const unsigned total = __shfl_sync(FULL, v, 31);
-            unsigned long long base = 0;
-            if (lane == 31) base = atomicAdd(&C->site_cursor, (unsigned long long)total);
-            site0 = __shfl_sync(FULL, base, 31) + (v - c.n_sites);
+            if (lane == 31) site_base = atomicAdd(&C->site_cursor, (unsigned long long)total);
+            site_incl = v;
+            if (!BANK_LATE) site0 = __shfl_sync(FULL, site_base, 31) + (v - c.n_sites);
         }
+        const double E_coll = p.E;        // energy and stream state at the collision (what the site requests record)
+        const uint64_t rng_coll = p.rng;
         if (!SHARED) { c.n_second = 0; c.n_forced = 0; n_copy = 0; }  // k-eigenvalue without splitting: nothing is ever born in flight
         unsigned short* const tab = SHARED ? R.chunk_tab + (size_t)(ctx_base + my_slot) * STACK_MAXCH : nullptr;
         if (SHARED) {  // room for the particles about to be born: borrow chunks (lane by lane; rare)
@@ -593,11 +601,16 @@ k_walk(const DevProblem P, const Bank B, unsigned long long begin, unsigned long
             }
         }
         StackSink sink = {SHARED ? R.stack + (size_t)blockIdx.x * (WALK_SLOTS + WALK_EXTRA) * STACK_CHUNK : nullptr, tab, my_slot, sp, nch, C};
-        if (c.n_sites | c.n_second) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, &L);
+        if (!BANK_LATE && (c.n_sites | c.n_second)) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, &L);
         __syncwarp();  // the banking lanes rejoin the warp before the scatter kinematics
         if (have && kind == 2 && (TALLY || SHARED || alive)) alive = ev_cross_post(P, p, alive, n_copy, sink);  // (lean instances: see ev_cross_pre)
         if (in_material) alive = ev_collide_scatter<TALLY>(P, p, X, uidx, D, c, H, &L);
         __syncwarp();
+        if (BANK_LATE && any_sites) {
+            site0 = __shfl_sync(FULL, site_base, 31) + (site_incl - c.n_sites);
+            if (c.n_sites) ev_collide_bank(P, p, c, H, C, reqs, site_cap, site0, sink, &L, E_coll, rng_coll);
+            __syncwarp();
+        }
         if (have && !alive) {
             if (SHARED && sp > 0) {
                 if (P.comb_teeth && sp >= P.comb_bank_max) {  // handler.cpp:27-28
