@@ -389,26 +389,25 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
     CK(ctx->d_cell_sense.upload(p->cell_sense, p->n_cell_surface));
     {
         // The cell behind a surface, where search_cell's answer (general.cpp:26-34: the FIRST cell in deck order that
-        // contains the point) can be told beforehand: leaving cell c through its entry (s, g) the point lies on side -g of
-        // s.  Every cell that holds (s, g) is ruled out by that one evaluation; if the first cell in deck order that the
-        // side does not rule out consists of (s, -g) alone, it contains every such point and is the answer.  The crossing
-        // code still evaluates s at the nudged point and takes the shortcut only when the sign is strictly the new side's
-        // (the same arithmetic as test_point, so the same cell), and searches otherwise.  Typical hit: the one-surface
-        // "outside" / graveyard cells every leaking particle enters.
-        std::vector<int32_t> nb((size_t)std::max(p->n_cell_surface, 1), -1);
-        for (int c = 0; c < p->n_cells; c++)
-            for (int i = p->cells[c].surf_begin; i < p->cells[c].surf_end; i++) {
-                const int s = p->cell_surface[i], side = -p->cell_sense[i];
+        // contains the point) can be told beforehand: a point on side g of surface s is outside every cell that holds
+        // (s, -g); if the first cell in deck order that the side does not rule out consists of (s, g) alone, it contains
+        // every such point and is the answer.  The crossing code evaluates s at the nudged point (the same arithmetic as
+        // test_point, so the same decision), takes the table's cell when the value is strictly on one side, and searches
+        // otherwise.  Typical hit: the one-surface "outside" / graveyard cells every leaking particle enters.
+        std::vector<int32_t> nb((size_t)std::max(2 * p->n_surfaces, 2), -1);  // [2 s] side -1, [2 s + 1] side +1
+        for (int s = 0; s < p->n_surfaces; s++)
+            for (int k = 0; k < 2; k++) {
+                const int side = k ? 1 : -1;
                 for (int b = 0; b < p->n_cells; b++) {
                     const mcb_cell& B = p->cells[b];
                     bool ruled_out = false;
                     for (int j = B.surf_begin; j < B.surf_end; j++) if (p->cell_surface[j] == s && p->cell_sense[j] != side) ruled_out = true;
                     if (ruled_out) continue;
-                    if (B.surf_end - B.surf_begin == 1 && p->cell_surface[B.surf_begin] == s && p->cell_sense[B.surf_begin] == side) nb[(size_t)i] = b;
+                    if (B.surf_end - B.surf_begin == 1 && p->cell_surface[B.surf_begin] == s && p->cell_sense[B.surf_begin] == side) nb[(size_t)(2 * s + k)] = b;
                     break;
                 }
             }
-        CK(ctx->d_cross_neighbor.upload(nb.data(), (size_t)std::max(p->n_cell_surface, 1)));
+        CK(ctx->d_cross_neighbor.upload(nb.data(), nb.size()));
     }
     CK(ctx->d_sources.upload(p->sources, p->n_sources));
     CK(ctx->d_estimators.upload(p->estimators, p->n_estimators));

@@ -56,7 +56,7 @@ struct DevProblem {
     const mcb_cell* cells;
     const int32_t* cell_surface;
     const int32_t* cell_sense;
-    const int32_t* cross_neighbor;        // per cell_surface entry: the cell behind that surface when it is provably unique, else -1 (mcb_api.cu)
+    const int32_t* cross_neighbor;        // [2 s + (side > 0)]: the cell on that side of surface s when search_cell's answer is provably that cell, else -1 (mcb_api.cu)
     const mcb_source* sources;
     const mcb_estimator* estimators;
     const mcb_score* scores;

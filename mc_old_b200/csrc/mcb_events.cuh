@@ -619,15 +619,15 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
         if (TALLY) p.told = p.t;
         p.t += MCB_EPSILON_FLOAT / p.speed;
         int cn = -1;
+#ifndef MCB_NO_CROSS_NEIGHBOR
         {   // the cell behind the surface where it is known beforehand (cross_neighbor, mcb_api.cu), else the search
-            const mcb_cell Co = P.cells[cell_old];
-            for (int i = Co.surf_begin; i < Co.surf_end; i++)
-                if (__ldg(&P.cell_surface[i]) == S) {
-                    const int nb = __ldg(&P.cross_neighbor[i]);
-                    if (nb >= 0 && mcb_surf_eval(Sf, p.x, p.y, p.z) * (double)(-__ldg(&P.cell_sense[i])) > 0) cn = nb;
-                    break;
-                }
+            const int2 nb = __ldg(reinterpret_cast<const int2*>(P.cross_neighbor) + S);
+            if ((nb.x & nb.y) != -1) {   // (both -1: nothing known about this surface)
+                const double e = mcb_surf_eval(Sf, p.x, p.y, p.z);
+                if (e > 0.0) cn = nb.y; else if (e < 0.0) cn = nb.x;
+            }
         }
+#endif
         if (cn < 0) cn = mcb_search_cell(P.cells, P.n_cells, P.surfaces, P.cell_surface, P.cell_sense, p.x, p.y, p.z);
         if (cn < 0) {  // "[WARNING] A particle is lost" (general.cpp:31-33)
             if (atomicExch(&C->lost, 1) == 0) { C->lost_pos[0] = p.x; C->lost_pos[1] = p.y; C->lost_pos[2] = p.z; }
