@@ -617,7 +617,7 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
     if (Sf.bc == MCB_BC_TRANSMISSION) {
         p.x += p.u * MCB_EPSILON_FLOAT; p.y += p.v * MCB_EPSILON_FLOAT; p.z += p.w * MCB_EPSILON_FLOAT;
         if (TALLY) p.told = p.t;
-        p.t += MCB_EPSILON_FLOAT / p.speed;
+        if (!LEAN) p.t += MCB_EPSILON_FLOAT / p.speed;   // (lean instances: below, for the particles that live on)
         int cn = -1;
 #ifndef MCB_NO_CROSS_NEIGHBOR
         {   // the cell behind the surface where it is known beforehand (cross_neighbor, mcb_api.cu), else the search
@@ -648,6 +648,7 @@ __device__ __forceinline__ bool ev_cross_pre(const DevProblem& P, Particle& p, i
     if (LEAN && !alive) return false;
     const double Iold = P.cells[cell_old].importance, Inew = P.cells[p.cell].importance;
     if (LEAN && Inew == 0.0 && Iold > 0.0) { p.wgt = 0.0; return false; }  // ratio 0: killed whatever the draw
+    if (LEAN && Sf.bc == MCB_BC_TRANSMISSION) p.t += MCB_EPSILON_FLOAT / p.speed;  // the time of a dead particle is never read
     if (Inew != Iold) {
         // a leaking particle enters importance 0: 0 / Iold is decided without dividing (a zero numerator sends the
         // IEEE division routine down its slow path); same value, same draw
