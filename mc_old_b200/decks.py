@@ -581,3 +581,19 @@ def sphere_detection(samples=100000):
     <disk_z x="-1.0"  y="0.0" z="-5.0" r="2.0" direction="dir" energy="enrg"/>
 </sources>
 """
+
+
+def slab_overlap(samples=20000):
+    """The slab of slab_analytic with a void cell that OVERLAPS the one-surface outside cell and comes before it in deck
+    order: a particle leaving through x = 5 is found by search_cell (general.cpp:26-34, first match in deck order) in
+    "catch", flies on to y = 1000 and only there enters "right outside".  A crossing shortcut that took the one-surface
+    cell behind x = 5 for granted would end the history at x = 5 and the second estimator would stay empty."""
+    x = slab(samples)
+    for old, new in [('<plane_x name="px3" x="5.0"/>', '<plane_x name="px3" x="5.0"/>\n    <plane_y name="py" y="1000.0"/>'),
+                     ('<cell name="left outside" importance="0.0">',
+                      '<cell name="catch">\n        <surface name="py" sense="-1"/>\n    </cell>\n    <cell name="left outside" importance="0.0">'),
+                     ('x = "1.0" y = "0.0" z = "0.0"', 'x = "0.8" y = "0.6" z = "0.0"'),
+                     ('</estimators>', '    <estimator name="far_plane" scores="cross">\n        <surface name="py"/>\n    </estimator>\n</estimators>')]:
+        assert old in x, old
+        x = x.replace(old, new)
+    return x

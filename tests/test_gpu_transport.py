@@ -81,7 +81,7 @@ def test_heu_entropy_history_parity():
     ctx.close()
 
 
-@pytest.mark.parametrize("name,n", [("slab", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("fsf_comb", 20000),
+@pytest.mark.parametrize("name,n", [("slab", 50000), ("slab_overlap", 50000), ("shield", 20000), ("shield_split", 10000), ("fsf", 20000), ("fsf_comb", 20000),
                                     ("heu_tallies", 10000), ("gcr_trmm", 400), ("gcr_trmm_100", 150), ("leak_time", 20000), ("gcr_td", 3000),
                                     ("gcr_td_comb", 3000), ("sphere_det", 200000)])
 def test_tallies_history_parity(name, n):
@@ -89,13 +89,14 @@ def test_tallies_history_parity(name, n):
     surface, cell-TL and cell-C estimators, energy filters, splitting (cell_importance, population_control.cpp:21-49)
     and same-history fission secondaries (fixed_source.cpp:12-22); the TRMM tally set of infinite_GCR_TRMM (3500 bins:
     energy_initial x energy matrices filled by simulate-then-score estimators, Estimator.cpp:441-482, delayed-neutron
-    scores at energy_old), also with the 100 groups of infinite_GCR_TRMM_100 (81500 tallies: more than a grid dimension holds,
+    scores at energy_old); slab_overlap: a void cell overlapping the one-surface outside cell and preceding it in the deck (search_cell's
+    first-match rule against the crossing shortcut of ev_cross_pre: every leaked particle must still reach the far plane), also with the 100 groups of infinite_GCR_TRMM_100 (81500 tallies: more than a grid dimension holds,
     and the keyed form of the per-history tally tables); the <disk_z> source and the cylinder / sphere / plane cells of examples/sphere_detection; time filters that split a track over the bins it spans (examples/HEU_sphere_leakage,
     Estimator.cpp:199-246); the particle comb (population_control.cpp:55-84, fsf_comb: banks of 3 or more waiting particles
     combed to 2); the time-dependent mode (examples/infinite_GCR_TD, _TD_sub: census stops, forced decay of delayed
     neutrons, the <tdmc/> filter; general.cpp:187-195, time_dependent.cpp, fixed_source.cpp:25-40).  Same per-history streams on both sides, so the
     per-bin means agree far inside their statistical error: |gpu - oracle| <= 0.2 sigma + 1e-9 relative."""
-    xml = {"slab": lambda: decks.slab(samples=n), "shield": lambda: decks.shielding(samples=n),
+    xml = {"slab": lambda: decks.slab(samples=n), "slab_overlap": lambda: decks.slab_overlap(samples=n), "shield": lambda: decks.shielding(samples=n),
            "shield_split": lambda: decks.shielding(samples=n, split=True), "fsf": lambda: decks.fixed_source_fissile(samples=n),
            "fsf_comb": lambda: decks.fixed_source_fissile(samples=n, comb=(3, 2)),
            "heu_tallies": lambda: decks.heu_sphere(samples=n, active=1, passive=0, estimators=True),
@@ -109,6 +110,8 @@ def test_tallies_history_parity(name, n):
     g = ctx.run_cycle(); o = orc.run_cycle()
     orc.end_simulation()
     gm, gu = ctx.tallies(); om, ou = orc.tallies()
+    if name == "slab_overlap":
+        assert gm[0] > 0 and gm[1] == gm[0]
     assert abs(int(g.n_tracks) - int(o.n_tracks)) <= 0.01 * o.n_tracks
     scored = ou > 0
     assert scored.any()

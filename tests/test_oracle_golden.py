@@ -249,3 +249,21 @@ def test_sphere_detection_mcnp6_golden():
 def test_disk_source_needs_a_radius():
     with pytest.raises(Exception, match="radius"):
         mcb.Deck(xml=decks.sphere_detection(samples=10).replace('r="2.0" direction', 'r="0.0" direction'))
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built")
+def test_search_cell_takes_the_first_match_in_deck_order_like_the_reference():
+    """general.cpp:26-34 on overlapping cells: a void cell that overlaps the one-surface outside cell and precedes it in
+    the deck catches every particle leaving the slab; they cross a far plane before they die.  The compiled reference
+    (patched build: capture-only nuclides) and the oracle give the same two tallies bit for bit - the semantics the
+    GPU's crossing shortcut has to preserve (tests/test_gpu_transport.py: slab_overlap)"""
+    xml = decks.slab_overlap(samples=20000)
+    d = decks.write(tempfile.mkdtemp(prefix="mcb_t_"), xml)
+    _, parsed = ol.run_ref(d, patched=True)
+    deck = mcb.Deck(xml=xml)
+    orc = ol.Oracle(deck, rng_mode=ol.RNG_GLOBAL, pick_mode=ol.PICK_CDF)
+    orc.run_cycle(); orc.end_simulation()
+    m, u = orc.tallies()
+    assert m[0] > 0 and m[1] == m[0]                                   # every leaked particle reaches the far plane
+    assert parsed["/leak_rate/cross/mean"][0] == m[0] and parsed["/far_plane/cross/mean"][0] == m[1]
+    assert parsed["/far_plane/cross/uncertainty"][0] == u[1]
