@@ -82,6 +82,11 @@ int mcbh_eigen_general(int32_t n, const double* A, double* w_pairs, double* v_pa
  * reference's binary_search(E, n_E) = #{n_E < E} - 1 (Algorithm.cpp:46-64).  Returns Nn; stats = nU, n_hash,
  * shift, largest hash bin. */
 int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, int32_t* idx_out, int64_t stats[4]);
+/* The crossing shortcut of the walk kernel (test / inspection): out[2 s + (side > 0)] = the cell that search_cell
+ * (general.cpp:26-34) is bound to return for any point strictly on that side of surface s, or -1 where it has to search.
+ * Returns the number of entries (2 * surfaces), -1 on error. */
+int mcbh_cross_neighbors(mcbh_deck* d, int32_t* out, int32_t max_n);
+
 
 #ifdef __cplusplus
 }

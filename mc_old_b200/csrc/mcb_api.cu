@@ -394,19 +394,8 @@ static int create_impl(mcb_ctx* ctx, const mcb_problem* p, const mcb_config* cfg
         // every such point and is the answer.  The crossing code evaluates s at the nudged point (the same arithmetic as
         // test_point, so the same decision), takes the table's cell when the value is strictly on one side, and searches
         // otherwise.  Typical hit: the one-surface "outside" / graveyard cells every leaking particle enters.
-        std::vector<int32_t> nb((size_t)std::max(2 * p->n_surfaces, 2), -1);  // [2 s] side -1, [2 s + 1] side +1
-        for (int s = 0; s < p->n_surfaces; s++)
-            for (int k = 0; k < 2; k++) {
-                const int side = k ? 1 : -1;
-                for (int b = 0; b < p->n_cells; b++) {
-                    const mcb_cell& B = p->cells[b];
-                    bool ruled_out = false;
-                    for (int j = B.surf_begin; j < B.surf_end; j++) if (p->cell_surface[j] == s && p->cell_sense[j] != side) ruled_out = true;
-                    if (ruled_out) continue;
-                    if (B.surf_end - B.surf_begin == 1 && p->cell_surface[B.surf_begin] == s && p->cell_sense[B.surf_begin] == side) nb[(size_t)(2 * s + k)] = b;
-                    break;
-                }
-            }
+        std::vector<int32_t> nb;
+        mcb::build_cross_neighbors(p, nb);   // mcb_tables.cpp
         CK(ctx->d_cross_neighbor.upload(nb.data(), nb.size()));
     }
     CK(ctx->d_sources.upload(p->sources, p->n_sources));

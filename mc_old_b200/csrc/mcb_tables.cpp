@@ -93,4 +93,22 @@ void build_material_tables(const mcb_problem* p, int material, int max_mant_bits
                 if (T.hrec[(size_t)r * T.hrec_stride] > 0) T.hrec[(size_t)r * T.hrec_stride + 2 + n] = MCB_MAP_BISECT;
 }
 
+void build_cross_neighbors(const mcb_problem* p, std::vector<int32_t>& nb)
+{
+    nb.assign((size_t)std::max(2 * p->n_surfaces, 2), -1);  // [2 s] side -1, [2 s + 1] side +1
+    for (int s = 0; s < p->n_surfaces; s++)
+        for (int k = 0; k < 2; k++) {
+            const int side = k ? 1 : -1;
+            for (int b = 0; b < p->n_cells; b++) {
+                const mcb_cell& B = p->cells[b];
+                bool ruled_out = false;  // the cell holds (s, -side): test_point puts every point of this side outside it
+                for (int j = B.surf_begin; j < B.surf_end; j++) if (p->cell_surface[j] == s && p->cell_sense[j] != side) ruled_out = true;
+                if (ruled_out) continue;
+                // the first cell in deck order that the side does not rule out: the answer if it is (s, side) and nothing else
+                if (B.surf_end - B.surf_begin == 1 && p->cell_surface[B.surf_begin] == s && p->cell_sense[B.surf_begin] == side) nb[(size_t)(2 * s + k)] = b;
+                break;
+            }
+        }
+}
+
 }  // namespace mcb

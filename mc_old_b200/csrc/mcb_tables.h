@@ -117,6 +117,10 @@ struct MaterialTables {
 // max_mant_bits: mantissa bits kept in the key at most (bins per octave = 2^bits)
 void build_material_tables(const mcb_problem* p, int material, int max_mant_bits, MaterialTables& out);
 
+// out[2 s + (side > 0)] = the cell search_cell (general.cpp:26-34) is bound to return for ANY point strictly on that side
+// of surface s, or -1 where that cannot be told beforehand (see mcb_api.cu / ev_cross_pre); 2 * max(n_surfaces, 1) entries
+void build_cross_neighbors(const mcb_problem* p, std::vector<int32_t>& out);
+
 }  // namespace mcb
 #endif
 #endif

@@ -1,4 +1,5 @@
 // C entry points of libmcbhost.so (include/mcb200_host.h).
+#include <algorithm>
 #include <string>
 
 #include "deck.h"
@@ -264,6 +265,16 @@ int mcbh_union_indices(mcbh_deck* d, int material, const double* E, int64_t n, i
     }
     if (stats) { stats[0] = (int64_t)T.U.size(); stats[1] = T.n_hash; stats[2] = T.shift; stats[3] = T.max_bin; }
     return T.n_nuc;
+}
+
+int mcbh_cross_neighbors(mcbh_deck* d, int32_t* out, int32_t max_n)
+{
+    if (!d || !out) return -1;
+    std::vector<int32_t> nb;
+    mcb::build_cross_neighbors(d->deck.view(), nb);
+    if ((int64_t)nb.size() > max_n) return -1;
+    std::copy(nb.begin(), nb.end(), out);
+    return (int)nb.size();
 }
 
 }  // extern "C"

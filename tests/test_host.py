@@ -289,3 +289,39 @@ def test_xml_reader_covers_the_grammar_pugixml_accepts():
                            ("unquoted attribute", base.replace('x="0.0"/>', "x=0.0/>", 1), r"value not quoted \(line \d+\)")]:
         with pytest.raises(ValueError, match=msg):
             mcb.Deck(xml=xml)
+
+
+def _cross_neighbors(deck):
+    """{(surface name, side): cell name or None} from mcbh_cross_neighbors (the table the walk kernel's crossing uses)"""
+    L = mcb.host_lib()
+    L.mcbh_cross_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    n = deck.info["n_surfaces"]
+    out = np.full(2 * max(n, 1), -7, dtype=np.int32)
+    assert L.mcbh_cross_neighbors(deck._h, out.ctypes.data, out.size) == 2 * max(n, 1)
+    return {(deck.name(2, s), side): (deck.name(3, int(out[2 * s + k])) if out[2 * s + k] >= 0 else None)
+            for s in range(n) for k, side in enumerate((-1, +1))}
+
+
+def test_crossing_shortcut_is_taken_only_where_search_cell_has_one_possible_answer():
+    """search_cell returns the FIRST cell in deck order that contains the point (general.cpp:26-34).  The kernel may
+    take the cell behind a surface from a table only where that answer is forced: every cell before it holds the
+    surface with the other sense, and the cell itself consists of that one surface"""
+    # bare sphere + graveyard: leaving the sphere can only end in the graveyard; entering it is never tabulated
+    # (the sphere cell comes first and consists of (sphere, -1) alone: also forced)
+    t = _cross_neighbors(mcb.Deck(xml=decks.heu_sphere(samples=10)))
+    (sname, _), = {k for k in t if k[1] == +1}
+    assert t[(sname, +1)] is not None and t[(sname, -1)] is not None and t[(sname, +1)] != t[(sname, -1)]
+    # slab: behind px1 (x < 0) lies "left outside", but slab2 precedes it in the deck and does not mention px1 at all, so
+    # the side does not rule it out: not forced (the kernel searches, as before)
+    t = _cross_neighbors(mcb.Deck(xml=decks.slab(samples=10)))
+    assert t[("px1", -1)] is None and t[("px3", +1)] is None
+    assert all(v is None for v in t.values())
+    # the overlap deck: "catch" (one surface: py, -1) precedes the outside cells and mentions neither px1 nor px3:
+    # nothing about the x planes is forced; y > 1000 rules "catch" out, but slab1 / slab2 do not mention py: not forced
+    t = _cross_neighbors(mcb.Deck(xml=decks.slab_overlap(samples=10)))
+    assert all(v is None for v in t.values())
+    # a one-cell world behind a single plane, listed first: forced on its side only
+    xml = decks.slab(samples=10).replace('<cells>', '<cells>\n    <cell name="beyond" importance="0.0">\n        <surface name="px3" sense="+1"/>\n    </cell>') \
+        .replace('<cell name="right outside" importance="0.0">\n        <surface name="px3" sense="+1"/>\n    </cell>', "")
+    t = _cross_neighbors(mcb.Deck(xml=xml))
+    assert t[("px3", +1)] == "beyond" and t[("px3", -1)] is None and t[("px1", -1)] is None
