@@ -227,6 +227,9 @@ int mcb_create(const mcb_problem* problem, const mcb_config* config, mcb_ctx** o
 void mcb_destroy(mcb_ctx* ctx);
 const char* mcb_last_error(const mcb_ctx* ctx); /* ctx may be NULL for a failed mcb_create */
 int mcb_device_count(void);
+/* Starts the CUDA driver and the primary context of `device` (what the first mcb_create would otherwise wait for: 0.6-1.6 s
+ * on the boxes measured).  A host program calls it on a second thread while it parses the deck; MCB.exe does. */
+int mcb_warm_up(int device);
 
 /* multi-GPU plumbing: one process per GPU; id is an opaque 128-byte NCCL unique id made on rank 0 */
 int mcb_comm_unique_id(char id[128]);

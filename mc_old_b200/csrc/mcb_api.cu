@@ -279,6 +279,12 @@ void mcb_shard_range(uint64_t n, int32_t rank, int32_t world, uint64_t* begin, u
     if (count) *count = e - b;
 }
 
+int mcb_warm_up(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); return MCB_ERR_CUDA; }
+    return MCB_OK;
+}
+
 int mcb_device_count(void)
 {
     int n = 0;

@@ -8,6 +8,7 @@
 // the output.  The 128-byte NCCL id travels through a file (MCB_ID_FILE, default
 // $XDG_RUNTIME_DIR|$TMPDIR|/tmp/mcb_nccl_id.<run id>.<MASTER_PORT>.<uid>, tagged with the job so that a stale one is refused).
 #include <chrono>
+#include <thread>
 #include <unistd.h>
 
 #include <cstdio>
@@ -43,10 +44,6 @@ int main(int argc, char* argv[])
     const char* xs = getenv("MCB_XS_LIBRARY") ? getenv("MCB_XS_LIBRARY") : "./xs_library";
     int flags = 0;
     for (int i = 2; i < argc; i++) if (!strcmp(argv[i], "--ignore-trmm")) flags |= MCBH_IGNORE_TRMM;
-    mcbh_deck* deck = mcbh_load_deck(io_dir.c_str(), xs, flags);
-    if (!deck) { std::cout << mcbh_last_error() << "\n"; std::exit(EXIT_FAILURE); }
-    const mcb_problem* p = mcbh_problem(deck);
-    t_mark[1] = wall_s();
     mcb_config cfg;
     memset(&cfg, 0, sizeof(cfg));
     const int world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
@@ -60,6 +57,14 @@ int main(int argc, char* argv[])
         cfg.device = 0;
     }
     cfg.rank = rank; cfg.world = world > 1 ? world : 1;
+    // the CUDA driver and context start on a second thread while the deck and the xs_library are read (0.2 s of the ~1 s
+    // they take); a failure shows up in mcb_create with its message
+    std::thread warm([dev = cfg.device] { mcb_warm_up(dev); });
+    mcbh_deck* deck = mcbh_load_deck(io_dir.c_str(), xs, flags);
+    if (!deck) { warm.join(); std::cout << mcbh_last_error() << "\n"; std::exit(EXIT_FAILURE); }
+    const mcb_problem* p = mcbh_problem(deck);
+    t_mark[1] = wall_s();
+    warm.join();
     mcb_ctx* ctx = nullptr;
     if (mcb_create(p, &cfg, &ctx) != MCB_OK) { std::cout << mcb_last_error(nullptr) << "\n"; std::exit(EXIT_FAILURE); }
     if (world > 1) {
