@@ -325,3 +325,48 @@ def test_crossing_shortcut_is_taken_only_where_search_cell_has_one_possible_answ
         .replace('<cell name="right outside" importance="0.0">\n        <surface name="px3" sense="+1"/>\n    </cell>', "")
     t = _cross_neighbors(mcb.Deck(xml=xml))
     assert t[("px3", +1)] == "beyond" and t[("px3", -1)] is None and t[("px1", -1)] is None
+
+
+def _surface_sides(xml, pts):
+    """sign of Surface*::eval (Geometry.cpp:29-69) of every surface of the deck at every point: {name: array of -1/0/+1}"""
+    import xml.etree.ElementTree as ET
+    root = ET.fromstring("<r>" + xml.split("?>", 1)[1] + "</r>")
+    x, y, z = pts.T
+    out = {}
+    for s in root.find("surfaces"):
+        a = {k: float(v) for k, v in s.attrib.items() if k not in ("name", "bc")}
+        e = {"plane_x": lambda: x - a["x"], "plane_y": lambda: y - a["y"], "plane_z": lambda: z - a["z"],
+             "plane": lambda: a["a"] * x + a["b"] * y + a["c"] * z - a["d"],
+             "sphere": lambda: (x - a["x"]) ** 2 + (y - a["y"]) ** 2 + (z - a["z"]) ** 2 - a["r"] ** 2,
+             "cylinder_x": lambda: (y - a["y"]) ** 2 + (z - a["z"]) ** 2 - a["r"] ** 2,
+             "cylinder_z": lambda: (x - a["x"]) ** 2 + (y - a["y"]) ** 2 - a["r"] ** 2}[s.tag]()
+        out[s.attrib["name"]] = np.sign(e).astype(int)
+    return out
+
+
+@pytest.mark.parametrize("name", ["heu", "slab", "slab_overlap", "shield", "fsf", "ucube", "sphere_det", "leak"])
+def test_crossing_shortcut_agrees_with_search_cell_everywhere(name):
+    """property behind the walk kernel's crossing shortcut: wherever the table names a cell for (surface, side), search_cell
+    (mcbh_search_cell: general.cpp:26-34 on the host) returns that very cell at EVERY point strictly on that side - checked on
+    2e4 random points per deck, half of them close to the surfaces' scale"""
+    xml = {"heu": decks.heu_sphere(samples=10), "slab": decks.slab(samples=10), "slab_overlap": decks.slab_overlap(samples=10),
+           "shield": decks.shielding(samples=10), "fsf": decks.fixed_source_fissile(samples=10), "ucube": decks.ucube(samples=10),
+           "sphere_det": decks.sphere_detection(samples=10), "leak": decks.heu_leakage(samples=10)}[name]
+    deck = mcb.Deck(xml=xml)
+    table = _cross_neighbors(deck)
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.uniform(-30, 30, (10000, 3)), rng.uniform(-1200, 1200, (2000, 3)), rng.normal(0, 6, (8000, 3))])
+    sides = _surface_sides(xml, pts)
+    L = mcb.host_lib()
+    L.mcbh_search_cell.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    found = np.array([L.mcbh_search_cell(deck._h, *p) for p in pts])
+    cells = {deck.name(3, i): i for i in range(deck.info["n_cells"])}
+    n_checked = 0
+    for (sname, side), cname in table.items():
+        if cname is None:
+            continue
+        on_side = sides[sname] == side
+        n_checked += int(on_side.sum())
+        assert np.all(found[on_side] == cells[cname]), (sname, side, cname)
+    if name in ("heu", "leak"):
+        assert n_checked > 10000   # both sides of the sphere are forced there
